@@ -1,0 +1,142 @@
+"""CPU: the oracle restatements against golden outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by oracle/make_golden.py in the build container)."""
+import numpy as np
+import pytest
+import scipy.stats
+
+from conftest import golden, split_cases
+from oracle import ffn as offn
+from oracle import prgls as oprgls
+from oracle import unet as ounet
+
+
+@pytest.mark.parametrize("case", ["worm3_single", "worm3_ensemble", "small", "nomatch"])
+def test_pr_gls_quick_matches_reference(case):
+    c = split_cases(golden("pr_gls_quick.npz"))[case]
+    P, TX, C = oprgls.pr_gls_quick(c["X"], c["Y"], c["corr"], BETA=float(c["BETA"]),
+                                   max_iteration=int(c["max_iteration"]), LAMBDA=float(c["LAMBDA"]))
+    np.testing.assert_allclose(TX, c["T_X"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(P, c["P"], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(C, c["C"], rtol=1e-6, atol=1e-9 * np.abs(c["C"]).max())
+
+
+def test_predict_one_rep_matches_reference():
+    g = golden("predict_one_rep.npz")
+    post = oprgls.predict_one_rep(g["pre"], g["inter"], float(g["beta"]), g["C"])
+    np.testing.assert_allclose(post, g["post"], rtol=1e-12, atol=1e-10)
+
+
+def test_trackerlite_em_matches_reference():
+    g = golden("trackerlite_em.npz")
+    prior, pairs = oprgls.simple_match(g["corr"])
+    assert prior.dtype == g["prior"].dtype == np.float32
+    np.testing.assert_array_equal(prior, g["prior"])
+    np.testing.assert_array_equal(pairs, g["pairs"])
+    p64, pr64 = oprgls.simple_match(g["sm64__corr"], threshold=0.3)
+    np.testing.assert_array_equal(p64, g["sm64__prior"])
+    np.testing.assert_array_equal(pr64, g["sm64__pairs"])
+    for tag in ("b3l3", "b1l01"):
+        pred, post = oprgls.prgls_with_two_ref(g["prior"], g["tgt_norm"], g["ref_norm"], g["conf_norm"],
+                                               beta=float(g[f"{tag}__beta"]), lambda_=float(g[f"{tag}__lambda"]))
+        np.testing.assert_allclose(pred, g[f"{tag}__pred"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(post, g[f"{tag}__post"], rtol=1e-7, atol=1e-13)
+    pred, post = oprgls.prgls_quick(g["prior"], g["tgt_norm"], g["ref_norm"], 3.0, 3.0)
+    np.testing.assert_allclose(pred, g["quick__pred"], rtol=1e-9, atol=1e-11)
+    ep = oprgls.estimate_posterior(g["prior"], 0.01, g["ref_norm"], g["tgt_norm"], 0.05)
+    np.testing.assert_allclose(ep, g["estep__post"], rtol=1e-12, atol=1e-300)
+    C = oprgls.solve_movements_ref(0.01, 3.0, g["estep__post"], g["ref_norm"], g["tgt_norm"],
+                                   oprgls.gaussian_kernel(g["ref_norm"], g["ref_norm"], 9.0))
+    np.testing.assert_allclose(C, g["mstep__C"], rtol=1e-7, atol=1e-12)
+
+
+def test_normalize_points_matches_reference():
+    g = golden("trackerlite_em.npz")
+    norm, (mean, scale) = offn.normalize_points(g["points"], return_para=True)
+    np.testing.assert_allclose(norm, g["ref_norm"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(mean, g["mean"], rtol=1e-14)
+    np.testing.assert_allclose(scale, g["scale"], rtol=1e-12)
+    with pytest.raises(ValueError):
+        offn.normalize_points(np.zeros((4, 2)))
+    with pytest.raises(ValueError):
+        offn.normalize_points(np.zeros((4,)))
+
+
+def test_ffn_feature_grid_matches_reference():
+    g = golden("ffn_features.npz")
+
+    class Rec:
+        def predict(self, x, batch_size=None):
+            if isinstance(x, (list, tuple)):
+                x = np.concatenate(x, axis=1)
+            self.x = x
+            return np.zeros((x.shape[0], 1), np.float32)
+
+    r = Rec()
+    offn.initial_matching_ffn(r, g["ref_s"], g["tgt_s"], 20)
+    assert r.x.dtype == np.float32 and r.x.shape == g["grid_s"].shape
+    np.testing.assert_allclose(r.x, g["grid_s"], rtol=2e-6, atol=1e-7)
+    r2 = Rec()
+    offn.initial_matching_quick(r2, g["ref_q"], g["tgt_q"], 20)
+    np.testing.assert_allclose(r2.x, g["grid_q"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(offn.knn_features(g["ref_full"]), g["feat_ref_full"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(offn.knn_features(g["tgt_full"]), g["feat_tgt_full"], rtol=2e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        offn.knn_features(np.zeros((20, 3)))
+
+
+def test_schedules_match_reference():
+    g = golden("schedules.npz")
+    for key in g.files:
+        parts = key.split("_")
+        if parts[0] == "ref":
+            ens, vol, adj = int(parts[1]), int(parts[2]), bool(int(parts[3]))
+            got = oprgls.get_reference_vols(ens, vol, adjacent=adj)
+        else:
+            cur, samp, adj, start = int(parts[1]), int(parts[2]), bool(int(parts[3])), int(parts[4])
+            got = oprgls.get_volumes_list(cur, [4, 7], samp, adj, start)
+        assert list(g[key]) == list(got), key
+    # docstring known answers, tracker.py:818-821
+    assert oprgls.get_reference_vols(10, 101) == list(range(1, 100, 10))
+    assert oprgls.get_reference_vols(10, 101, adjacent=True) == list(range(91, 101))
+
+
+def test_trim_mean_matches_scipy():
+    rng = np.random.default_rng(3)
+    for e in (1, 2, 9, 10, 19, 20, 21):
+        a = rng.normal(size=(e, 17, 3))
+        np.testing.assert_allclose(oprgls.trim_mean(a, 0.1), scipy.stats.trim_mean(a, 0.1, axis=0), rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_unet_tiling_matches_reference(case):
+    c = split_cases(golden("unet_tiling.npz"))[case]
+    tin = tuple(int(v) for v in c["tin"])
+
+    class Duck:
+        input_shape = (None,) + tin + (1,)
+        output_shape = (None,) + tin + (1,)
+        g = np.meshgrid(*[np.arange(s) for s in tin], indexing="ij")
+        ramp = (0.001 * g[0] + 0.01 * g[1] + 0.1 * g[2]).astype(np.float32)
+
+        def predict(self, x):
+            return (x * 0.5 + self.ramp[None, ..., None]).astype(np.float32)
+
+    out = ounet.unet3_prediction(c["img"], Duck(), tuple(int(v) for v in c["shrink"]))
+    np.testing.assert_array_equal(out, c["out"])
+
+
+def test_unet_oracle_shapes_and_flops():
+    for variant, gmac in (("a", 17.786), ("b", 97.976), ("c", 6.06)):
+        spec = ounet.unet_spec(variant)
+        layers = ounet.conv_layers(spec)
+        ws = ounet.random_weights(variant, 0)
+        assert len(ws) == 6 * len(layers) + 2
+    layers = ounet.conv_layers(ounet.unet_spec("a"))
+    assert layers == [(1, 8), (8, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 64),
+                      (128, 32), (32, 32), (64, 16), (16, 16), (32, 8), (8, 8)]
+    assert sum(int(np.prod(w.shape)) for w in ounet.random_weights("a", 0)) == 512025
+    m = ounet.UNetOracle("c", ounet.random_weights("c", 1))
+    x = np.random.default_rng(0).normal(size=(1, 64, 64, 64, 1)).astype(np.float32)
+    # small smoke of the graph on a crop is impossible (fixed pools) -> run variant c at reduced size
+    y = m.predict(x[:, :16, :16, :16])
+    assert y.shape == (1, 16, 16, 16, 1) and np.all((y > 0) & (y < 1))
