@@ -1,0 +1,74 @@
+// Shared helpers for libct3d (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <atomic>
+
+#include "../../include/ct3d.h"
+
+namespace ct {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+
+inline int check_cuda(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+// Count a kernel launch and check the launch status (asynchronous errors surface later).
+#define CT_LAUNCHED(name)                                                        \
+    do {                                                                         \
+        ::ct::g_launches.fetch_add(1, std::memory_order_relaxed);                \
+        if (::ct::check_cuda(cudaGetLastError(), name)) return 1;                \
+    } while (0)
+
+#define CT_CUDA(expr)                                                            \
+    do {                                                                         \
+        if (::ct::check_cuda((expr), #expr)) return 1;                           \
+    } while (0)
+
+#define CT_REQUIRE(cond, ...)                                                    \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            ::ct::set_error(__VA_ARGS__);                                        \
+            return 1;                                                            \
+        }                                                                        \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Bump allocator over a caller-provided workspace.
+struct Arena {
+    char* base;
+    size_t size;
+    size_t off = 0;
+    Arena(void* p, size_t n) : base(static_cast<char*>(p)), size(n) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= size; }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ct

@@ -1,0 +1,298 @@
+// LCN normalisation for the U-Net input (sm_100a, memory-bound CUDA-core kernels).
+//
+// Replaces preprocess.py:170-188 (_normalize_image), :136-167 (lcn_gpu) and :117-133 (conv3d_keras):
+//   v   = max(raw - median(raw), 0)
+//   avg = box27x27x1(v) / 729            (zero padded, float32 like the Keras Conv3D output)
+//   std = sqrt(box27x27x1((v-avg)^2)/729)
+//   out = (v - avg) / (std + noise_level)
+//
+// The exact median (np.median: mean of the two middle order statistics for even counts) is found by
+// an 8-bit-digit radix select over order-preserving integer keys: 2 passes for uint16/uint8 input,
+// 4 for float32.  Histograms are privatised per warp in shared memory; lanes that hit the same bin are
+// merged with __match_any_sync before the shared-memory atomic, because microscopy stacks put most
+// voxels into a handful of background bins.
+#include "common.cuh"
+
+namespace ct {
+
+// ---------------------------------------------------------------------------------------------
+// keys
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct KeyOf;
+template <> struct KeyOf<uint16_t> {
+    static constexpr int bits = 16;
+    __device__ static uint32_t key(uint16_t v) { return v; }
+    __device__ static double value(uint32_t k) { return (double)k; }
+};
+template <> struct KeyOf<uint8_t> {
+    static constexpr int bits = 8;
+    __device__ static uint32_t key(uint8_t v) { return v; }
+    __device__ static double value(uint32_t k) { return (double)k; }
+};
+template <> struct KeyOf<float> {
+    static constexpr int bits = 32;
+    __device__ static uint32_t key(float f) {
+        uint32_t u = __float_as_uint(f);
+        return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    }
+    __device__ static double value(uint32_t k) {
+        uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+        return (double)__uint_as_float(u);
+    }
+};
+
+struct SelectState {
+    unsigned long long rank[2];    // remaining rank inside the current prefix bucket
+    uint32_t prefix[2];            // key bits fixed so far (high bits)
+    uint32_t hist[2][256];
+};
+
+__global__ void select_init(SelectState* st, long long count) {
+    int t = threadIdx.x;
+    if (t == 0) {
+        st->rank[0] = (unsigned long long)((count - 1) / 2);
+        st->rank[1] = (unsigned long long)(count / 2);
+        st->prefix[0] = st->prefix[1] = 0;
+    }
+    for (int i = t; i < 512; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+}
+
+// One digit pass: histogram of digit `shift` for keys whose higher bits equal prefix[r].
+template <typename T>
+__global__ void __launch_bounds__(256) select_hist(const T* __restrict__ data, long long count,
+                                                   SelectState* st, int shift, int key_bits) {
+    __shared__ uint32_t sh[8][2][256];
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * 2 * 256; i += 256) (&sh[0][0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t p0 = st->prefix[0], p1 = st->prefix[1];
+    const bool same = (p0 == p1);
+    const int hi_shift = shift + 8;                       // bits above the current digit
+    const bool top = hi_shift >= key_bits;                // first pass: no prefix to match
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_iter = (count + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long it = 0; it < n_iter; ++it, i += stride) {
+        bool valid = i < count;
+        uint32_t k = valid ? KeyOf<T>::key(data[i]) : 0u;
+        uint32_t digit = (k >> shift) & 0xffu;
+        uint32_t hi = top ? 0u : (k >> hi_shift);
+        bool m0 = valid && (top || hi == (p0 >> hi_shift));
+        bool m1 = valid && !same && (top || hi == (p1 >> hi_shift));
+        // merge lanes with the same (bucket, digit)
+        uint32_t tag = m0 ? digit : (m1 ? 256u + digit : 0xffffu);
+        uint32_t peers = __match_any_sync(0xffffffffu, tag);
+        if (tag != 0xffffu && (__ffs(peers) - 1) == (threadIdx.x & 31)) {
+            atomicAdd(&sh[warp][tag >> 8][tag & 0xffu], __popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 512; b += 256) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += (&sh[w][0][0])[b];
+        if (s) atomicAdd(&(&st->hist[0][0])[b], s);
+    }
+}
+
+// Pick the digit holding the wanted rank, update prefix / rank, clear histograms for the next pass.
+__global__ void select_scan(SelectState* st, int shift) {
+    if (threadIdx.x < 2) {
+        int r = threadIdx.x;
+        bool same = st->prefix[0] == st->prefix[1];
+        const uint32_t* h = st->hist[(r == 1 && same) ? 0 : r];
+        unsigned long long rank = st->rank[r];
+        uint32_t d = 0;
+        for (; d < 255; ++d) {
+            if (rank < h[d]) break;
+            rank -= h[d];
+        }
+        st->rank[r] = rank;
+        // defer the prefix write until both lanes have read `same`
+        __syncwarp(0x3);
+        st->prefix[r] |= d << shift;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&st->hist[0][0])[i] = 0;
+}
+
+template <typename T>
+__global__ void select_finish(const SelectState* st, double* median_out) {
+    *median_out = 0.5 * (KeyOf<T>::value(st->prefix[0]) + KeyOf<T>::value(st->prefix[1]));
+}
+
+template <typename T>
+static int median_impl(const T* data, long long count, double* median_out, SelectState* st, cudaStream_t s) {
+    const int bits = KeyOf<T>::bits;
+    select_init<<<1, 256, 0, s>>>(st, count);
+    CT_LAUNCHED("select_init");
+    int blocks = (int)((count + 256 * 16 - 1) / (256 * 16));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    for (int shift = bits - 8; shift >= 0; shift -= 8) {
+        select_hist<T><<<blocks, 256, 0, s>>>(data, count, st, shift, bits);
+        CT_LAUNCHED("select_hist");
+        select_scan<<<1, 256, 0, s>>>(st, shift);
+        CT_LAUNCHED("select_scan");
+    }
+    select_finish<T><<<1, 1, 0, s>>>(st, median_out);
+    CT_LAUNCHED("select_finish");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// box filters.  Layout (x, y, z), z fastest; the filter spans x and y only.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float clamped(const T* __restrict__ raw, long long idx, double med) {
+    // med is NaN when the caller asked for plain lcn_gpu (no median subtraction, no clamp)
+    if (med != med) return (float)raw[idx];
+    double v = (double)raw[idx] - med;
+    return v > 0.0 ? (float)v : 0.0f;       // keras casts the float64 array to float32 (exact here)
+}
+
+// pass 1: T1 = sum over dy of v   (float32; exact for integer-valued input)
+template <typename T>
+__global__ void __launch_bounds__(256) box_y_v(const T* __restrict__ raw, const double* __restrict__ med_p,
+                                               float* __restrict__ t1, int X, int Y, int Z, int ry) {
+    const long long plane = (long long)Y * Z;
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // index inside the (y,z) plane
+    if (f >= plane) return;
+    const int x = blockIdx.y;
+    const int y = (int)(f / Z);
+    const double med = *med_p;
+    const T* base = raw + (long long)x * plane;
+    const int y0 = max(y - ry, 0), y1 = min(y + ry, Y - 1);
+    float acc = 0.f;
+    for (int yy = y0; yy <= y1; ++yy) acc += clamped(base, f + (long long)(yy - y) * Z, med);
+    t1[(long long)x * plane + f] = acc;
+}
+
+// pass 2: avg = float32(sum over dx of T1) / volume
+__global__ void __launch_bounds__(256) box_x_avg(const float* __restrict__ t1, float* __restrict__ avg,
+                                                 int X, int Y, int Z, int rx, float volume) {
+    const long long plane = (long long)Y * Z;
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= plane) return;
+    const int x = blockIdx.y;
+    const int x0 = max(x - rx, 0), x1 = min(x + rx, X - 1);
+    double acc = 0.0;
+    for (int xx = x0; xx <= x1; ++xx) acc += (double)t1[(long long)xx * plane + f];
+    avg[(long long)x * plane + f] = (float)acc / volume;
+}
+
+// pass 3: T2 = sum over dy of float32((v-avg)^2)
+template <typename T>
+__global__ void __launch_bounds__(256) box_y_sq(const T* __restrict__ raw, const double* __restrict__ med_p,
+                                                const float* __restrict__ avg, float* __restrict__ t2,
+                                                int X, int Y, int Z, int ry) {
+    const long long plane = (long long)Y * Z;
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= plane) return;
+    const int x = blockIdx.y;
+    const int y = (int)(f / Z);
+    const double med = *med_p;
+    const long long off = (long long)x * plane;
+    const int y0 = max(y - ry, 0), y1 = min(y + ry, Y - 1);
+    double acc = 0.0;
+    for (int yy = y0; yy <= y1; ++yy) {
+        long long i = off + f + (long long)(yy - y) * Z;
+        double d = (double)clamped(raw, i, med) - (double)avg[i];
+        acc += (double)(float)(d * d);
+    }
+    t2[off + f] = (float)acc;
+}
+
+// pass 4: std, normalise
+template <typename T>
+__global__ void __launch_bounds__(256) box_x_norm(const T* __restrict__ raw, const double* __restrict__ med_p,
+                                                  const float* __restrict__ avg, const float* __restrict__ t2,
+                                                  float* __restrict__ out, int X, int Y, int Z, int rx,
+                                                  float volume, float noise) {
+    const long long plane = (long long)Y * Z;
+    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= plane) return;
+    const int x = blockIdx.y;
+    const int x0 = max(x - rx, 0), x1 = min(x + rx, X - 1);
+    double acc = 0.0;
+    for (int xx = x0; xx <= x1; ++xx) acc += (double)t2[(long long)xx * plane + f];
+    const long long i = (long long)x * plane + f;
+    const float sd = sqrtf((float)acc / volume);
+    const float den = sd + noise;
+    const double d = (double)clamped(raw, i, *med_p) - (double)avg[i];
+    out[i] = (float)(d / (double)den);
+}
+
+__global__ void set_nan(double* p) { *p = __longlong_as_double(0x7ff8000000000000LL); }
+
+template <typename T>
+static int normalize_impl(const T* raw, float* out, int X, int Y, int Z, float noise, int fx, int fy,
+                          int subtract_median, void* ws, size_t ws_bytes, cudaStream_t s) {
+    const long long n = (long long)X * Y * Z;
+    Arena a(ws, ws_bytes);
+    SelectState* st = a.take<SelectState>(1);
+    double* med = a.take<double>(1);
+    float* t1 = a.take<float>(n);
+    float* avg = a.take<float>(n);
+    float* t2 = t1;     // t1 is dead after pass 2
+    CT_REQUIRE(a.ok(), "ct_normalize_image: workspace too small (%zu < %zu)", ws_bytes, a.off);
+    if (subtract_median) {
+        if (median_impl<T>(raw, n, med, st, s)) return 1;
+    } else {
+        set_nan<<<1, 1, 0, s>>>(med);
+        CT_LAUNCHED("set_nan");
+    }
+    const long long plane = (long long)Y * Z;
+    dim3 grid((unsigned)((plane + 255) / 256), X);
+    const float volume = (float)(fx * fy);
+    box_y_v<T><<<grid, 256, 0, s>>>(raw, med, t1, X, Y, Z, fy / 2);
+    CT_LAUNCHED("box_y_v");
+    box_x_avg<<<grid, 256, 0, s>>>(t1, avg, X, Y, Z, fx / 2, volume);
+    CT_LAUNCHED("box_x_avg");
+    box_y_sq<T><<<grid, 256, 0, s>>>(raw, med, avg, t2, X, Y, Z, fy / 2);
+    CT_LAUNCHED("box_y_sq");
+    box_x_norm<T><<<grid, 256, 0, s>>>(raw, med, avg, t2, out, X, Y, Z, fx / 2, volume, noise);
+    CT_LAUNCHED("box_x_norm");
+    return 0;
+}
+
+}  // namespace ct
+
+extern "C" {
+
+size_t ct_normalize_workspace_bytes(int x, int y, int z) {
+    size_t n = (size_t)x * y * z;
+    return 2 * ct::align_up(n * sizeof(float), 256) + ct::align_up(sizeof(ct::SelectState), 256) + 1024;
+}
+
+int ct_median(const void* raw, int dtype, long long count, double* median_out, void* ws, size_t ws_bytes,
+              void* stream) {
+    CT_REQUIRE(count > 0, "ct_median: empty input");
+    CT_REQUIRE(ws_bytes >= sizeof(ct::SelectState) + 256, "ct_median: workspace too small");
+    ct::Arena a(ws, ws_bytes);
+    ct::SelectState* st = a.take<ct::SelectState>(1);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case 0: return ct::median_impl<uint16_t>((const uint16_t*)raw, count, median_out, st, s);
+        case 1: return ct::median_impl<float>((const float*)raw, count, median_out, st, s);
+        case 2: return ct::median_impl<uint8_t>((const uint8_t*)raw, count, median_out, st, s);
+    }
+    ct::set_error("ct_median: unsupported dtype %d", dtype);
+    return 1;
+}
+
+int ct_normalize_image(const void* raw, int dtype, float* out, int x, int y, int z, float noise_level,
+                       int filter_x, int filter_y, int subtract_median, void* ws, size_t ws_bytes, void* stream) {
+    CT_REQUIRE(x > 0 && y > 0 && z > 0, "ct_normalize_image: empty volume");
+    CT_REQUIRE((filter_x & 1) && (filter_y & 1), "ct_normalize_image: filter sizes must be odd");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case 0: return ct::normalize_impl<uint16_t>((const uint16_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, ws, ws_bytes, s);
+        case 1: return ct::normalize_impl<float>((const float*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, ws, ws_bytes, s);
+        case 2: return ct::normalize_impl<uint8_t>((const uint8_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, ws, ws_bytes, s);
+    }
+    ct::set_error("ct_normalize_image: unsupported dtype %d", dtype);
+    return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,559 @@
+// Greedy prior + PR-GLS / coherent-point-drift EM as ONE persistent CTA per problem (fp64).
+//
+// Reference: track.py:11-114 (pr_gls_quick), trackerlite.py:242-259 (simple_match), :262-358
+// (prgls_quick / prgls_with_two_ref), :361-382 (dist_squares, gaussian_kernel, estimate_posterior),
+// :409-417 (solve_movements_ref), tracker.py:1269-1289 (_predict_one_rep).
+//
+// The reference drives every EM iteration from Python (about ten NumPy dispatches building (M,N,3)
+// temporaries plus one LAPACK gesv).  Here a whole problem -- greedy prior, Gram matrix, all EM
+// iterations with the convergence test -- runs inside one 1024-thread CTA with no host round trip;
+// a batch (ensemble members x repetitions) is one launch with one CTA per problem.  The N x N system
+//      (G diag(p) + lambda sigma^2 I)^T C^T = (Y^T P - X^T diag(p))^T
+// is non-symmetric, so it is solved like LAPACK gesv does: LU with partial pivoting (first maximum),
+// reciprocal-scaled multipliers, then back substitution.  The matrix lives in shared memory when
+// N <= 168 (N^2 * 8 B <= 220.5 KiB) and in the L2-resident workspace otherwise.
+#include "common.cuh"
+#include <vector>
+
+namespace ct {
+
+constexpr int EM_THREADS = 1024;
+constexpr int EM_WARPS = EM_THREADS / 32;
+constexpr int SMEM_N_MAX = 168;
+
+struct DevProblem {
+    CtPrglsProblem p;
+    double* gram;       // (N,N)
+    double* gram_nl;    // (N,L)   LITE
+    double* sys;        // (N,N)   only when N > SMEM_N_MAX
+    double* prior;      // (M,N)
+    double* colsum;     // (N)     p_n
+    double* ytp;        // (N,3)   sum_m P[m,n] Y[m]
+    double* colpart;    // (R*N,4) partial column moments, R*N <= max(N, 1024)
+    double* rhs;        // (N,3)   right-hand side, overwritten by the solution W = C^T
+    double* mult;       // (N)     multipliers of the current LU column
+    double* cur;        // (N,3)   T_X / predicted ref
+    double* cur_l;      // (L,3)   predicted tracked
+    double* rowmax;     // (M)     greedy scratch
+    int* rowarg;        // (M)
+    int* match;         // (M)     matched ref index per target row or -1
+    unsigned char* col_dead;  // (N)
+    int* pairs;         // (min(M,N), 2)
+    int* n_pairs;       // (1)
+};
+
+struct Scratch {
+    double red[EM_WARPS];
+    int redi[EM_WARPS];
+    double bc[4];
+    int bci[4];
+};
+
+__device__ __forceinline__ double block_sum(double v, Scratch& s) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s.red[w] = v;
+    __syncthreads();
+    double t = (threadIdx.x < EM_WARPS) ? s.red[threadIdx.x] : 0.0;
+    if (w == 0) {
+        t = warp_sum(t);
+        if (lane == 0) s.bc[0] = t;
+    }
+    __syncthreads();
+    return s.bc[0];
+}
+
+// argmax with "first occurrence" tie-break (smallest index among equal values)
+__device__ __forceinline__ void better(double& v, int& i, double ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__device__ __forceinline__ void warp_argmax(double& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        better(v, i, ov, oi);
+    }
+}
+__device__ __forceinline__ void block_argmax(double& v, int& i, Scratch& s) {
+    warp_argmax(v, i);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { s.red[w] = v; s.redi[w] = i; }
+    __syncthreads();
+    if (w == 0) {
+        double tv = s.red[lane];
+        int ti = s.redi[lane];
+        warp_argmax(tv, ti);
+        if (lane == 0) { s.bc[0] = tv; s.bci[0] = ti; }
+    }
+    __syncthreads();
+    v = s.bc[0]; i = s.bci[0];
+}
+
+__device__ __forceinline__ double corr_at(const DevProblem& d, int m, int n) {
+    const size_t idx = (size_t)m * d.p.n_ref + n;
+    return d.p.corr_is_f64 ? static_cast<const double*>(d.p.corr)[idx]
+                           : (double)static_cast<const float*>(d.p.corr)[idx];
+}
+
+__device__ __forceinline__ double dist2(const double* a, const double* b) {
+    const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// ---------------------------------------------------------------------------------------------
+// greedy one-to-one assignment -> prior.   track.py:58-70 / trackerlite.py:242-259
+// Row maxima are cached; a round is: argmax over the M cached maxima, retire row m* and column n*,
+// rescan only the rows whose cached argmax was n* (zeroed entries count as 0, like the reference).
+// ---------------------------------------------------------------------------------------------
+__device__ void scan_row(const DevProblem& d, int m, bool row_dead, int lane) {
+    const int N = d.p.n_ref;
+    double v = -INFINITY;
+    int i = 0x7fffffff;
+    for (int n = lane; n < N; n += 32) {
+        const double c = (row_dead || d.col_dead[n]) ? 0.0 : corr_at(d, m, n);
+        better(v, i, c, n);
+    }
+    warp_argmax(v, i);
+    if (lane == 0) { d.rowmax[m] = v; d.rowarg[m] = i; }
+}
+
+__device__ void greedy_prior(const DevProblem& d, int mode, double threshold, Scratch& s) {
+    const int N = d.p.n_ref, M = d.p.n_tgt;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int n = tid; n < N; n += EM_THREADS) d.col_dead[n] = 0;
+    for (int m = tid; m < M; m += EM_THREADS) d.match[m] = -1;
+    __syncthreads();
+    for (int m = w; m < M; m += EM_WARPS) scan_row(d, m, false, lane);
+    __syncthreads();
+    int n_pairs = 0;
+    for (int round = 0; round < N; ++round) {
+        double v = -INFINITY;
+        int i = 0x7fffffff;
+        for (int m = tid; m < M; m += EM_THREADS) better(v, i, d.rowmax[m], m);
+        // ties between rows: smallest m wins, which is the row-major first maximum of np.argmax
+        block_argmax(v, i, s);
+        if (v < threshold) break;
+        const int ms = i, ns = d.rowarg[ms];
+        __syncthreads();
+        if (tid == 0) {
+            d.match[ms] = ns;
+            d.col_dead[ns] = 1;
+            if (d.pairs) { d.pairs[2 * n_pairs] = ms; d.pairs[2 * n_pairs + 1] = ns; }
+        }
+        ++n_pairs;
+        __syncthreads();
+        // retired row: all zeros.  Rows that pointed at column ns (or whose maximum is <= 0, for which a
+        // newly zeroed entry at a smaller index could now be the first maximum) are rescanned.
+        for (int m = w; m < M; m += EM_WARPS) {
+            const bool dead = d.match[m] >= 0;
+            if (m == ms || (!dead && (d.rowarg[m] == ns || d.rowmax[m] <= 0.0))) scan_row(d, m, dead, lane);
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && d.n_pairs) *d.n_pairs = n_pairs;
+    // fill the prior
+    const double lo64 = 0.1 / (double)(N - 1);
+    double lo, hi, unmatched;
+    if (mode == CT_PRGLS_LITE) {
+        // np.full_like(match_matrix, 0.1/(N-1)) keeps corr's dtype (trackerlite.py:256)
+        lo = d.p.corr_is_f64 ? lo64 : (double)(float)lo64;
+        hi = d.p.corr_is_f64 ? 0.9 : (double)0.9f;
+        unmatched = lo;
+    } else {
+        lo = lo64; hi = 0.9; unmatched = 1.0 / (double)N;
+    }
+    for (size_t e = tid; e < (size_t)M * N; e += EM_THREADS) {
+        const int m = (int)(e / N), n = (int)(e % N);
+        const int mt = d.match[m];
+        d.prior[e] = (mt < 0) ? unmatched : (n == mt ? hi : lo);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// LU with partial pivoting + back substitution on S (ld = N), 3 right-hand sides in rhs (N,3).
+// ---------------------------------------------------------------------------------------------
+__device__ void lu_solve(double* __restrict__ S, int N, double* __restrict__ rhs, double* __restrict__ mult,
+                         Scratch& s) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int k = 0; k < N; ++k) {
+        // pivot: first maximum of |S[i][k]|, i >= k   (LAPACK idamax)
+        double v = -1.0;
+        int pi = 0x7fffffff;
+        for (int i = k + tid; i < N; i += EM_THREADS) better(v, pi, fabs(S[(size_t)i * N + k]), i);
+        block_argmax(v, pi, s);
+        if (pi != k) {
+            for (int j = k + tid; j < N; j += EM_THREADS) {
+                const double a = S[(size_t)k * N + j], b = S[(size_t)pi * N + j];
+                S[(size_t)k * N + j] = b; S[(size_t)pi * N + j] = a;
+            }
+            if (tid < 3) {
+                const double a = rhs[3 * k + tid], b = rhs[3 * pi + tid];
+                rhs[3 * k + tid] = b; rhs[3 * pi + tid] = a;
+            }
+            __syncthreads();
+        }
+        const double rinv = 1.0 / S[(size_t)k * N + k];
+        for (int i = k + 1 + tid; i < N; i += EM_THREADS) mult[i] = S[(size_t)i * N + k] * rinv;
+        __syncthreads();
+        // trailing update: warp w takes rows k+1+w, k+1+w+32, ...; lanes run along the row
+        for (int i = k + 1 + w; i < N; i += EM_WARPS) {
+            const double l = mult[i];
+            double* __restrict__ row = S + (size_t)i * N;
+            const double* __restrict__ piv = S + (size_t)k * N;
+            for (int j = k + 1 + lane; j < N; j += 32) row[j] = fma(-l, piv[j], row[j]);
+            if (lane < 3) rhs[3 * i + lane] = fma(-l, rhs[3 * k + lane], rhs[3 * i + lane]);
+        }
+        __syncthreads();
+    }
+    // back substitution: warp d solves column d
+    if (w < 3) {
+        for (int k = N - 1; k >= 0; --k) {
+            const double x = rhs[3 * k + w] / S[(size_t)k * N + k];
+            __syncwarp();
+            if (lane == 0) rhs[3 * k + w] = x;
+            for (int i = lane; i < k; i += 32) rhs[3 * i + w] = fma(-S[(size_t)i * N + k], x, rhs[3 * i + w]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// the EM kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EM_THREADS, 1)
+prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
+    extern __shared__ double dyn_smem[];
+    __shared__ Scratch s;
+    const DevProblem d = probs[blockIdx.x];
+    const int N = d.p.n_ref, M = d.p.n_tgt, L = d.p.n_tracked;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool lite = prm.mode == CT_PRGLS_LITE;
+    const double* X = d.p.ref;
+    const double* Y = d.p.tgt;
+    double* P = d.p.post;
+    double* S = (N <= SMEM_N_MAX) ? dyn_smem : d.sys;
+    const double two_b2 = 2.0 * prm.beta * prm.beta;
+
+    // ---- prior
+    if (d.p.prior_given) {
+        for (size_t e = tid; e < (size_t)M * N; e += EM_THREADS)
+            d.prior[e] = d.p.corr_is_f64 ? static_cast<const double*>(d.p.corr)[e]
+                                         : (double)static_cast<const float*>(d.p.corr)[e];
+        __syncthreads();
+    } else {
+        greedy_prior(d, prm.mode, prm.threshold, s);
+    }
+
+    // ---- Gram matrices (track.py:44-46, trackerlite.py:319-320), sigma^2 (track.py:53-56, trackerlite.py:321)
+    for (size_t e = tid; e < (size_t)N * N; e += EM_THREADS) {
+        const int i = (int)(e / N), j = (int)(e % N);
+        d.gram[e] = exp(-dist2(X + 3 * j, X + 3 * i) / two_b2);
+    }
+    if (lite) {
+        for (size_t e = tid; e < (size_t)N * L; e += EM_THREADS) {
+            const int n = (int)(e / L), l = (int)(e % L);
+            d.gram_nl[e] = exp(-dist2(d.p.tracked + 3 * l, X + 3 * n) / two_b2);
+        }
+        for (int e = tid; e < 3 * L; e += EM_THREADS) d.cur_l[e] = d.p.tracked[e];
+    }
+    for (int e = tid; e < 3 * N; e += EM_THREADS) d.cur[e] = X[e];
+    double acc = 0.0;
+    for (size_t e = tid; e < (size_t)M * N; e += EM_THREADS) {
+        const int m = (int)(e / N), n = (int)(e % N);
+        acc += dist2(X + 3 * n, Y + 3 * m);
+    }
+    double sigma2 = block_sum(acc, s);
+    sigma2 = lite ? (sigma2 / ((double)M * (double)N)) / 3.0 : sigma2 / (3.0 * (double)N * (double)M);
+    double gamma = lite ? 0.05 : 0.1;
+    const double PI = 3.141592653589793;
+    int iterations = 0;
+
+    for (int it = 1; it < prm.max_iteration; ++it) {
+        iterations = it;
+        // ---------------- E-step (track.py:81-88 / trackerlite.py:375-382): one warp per target row
+        const double two_s2 = 2.0 * sigma2;
+        const double norm15 = pow(2.0 * PI * sigma2, 1.5);
+        const double outlier = lite ? gamma / prm.vol : gamma * norm15 / ((1.0 - gamma) * prm.vol);
+        const double one_m_g = 1.0 - gamma;
+        for (int m = w; m < M; m += EM_WARPS) {
+            const double* y = Y + 3 * m;
+            double rs = 0.0;
+            for (int n = lane; n < N; n += 32) {
+                const double like = exp(-dist2(d.cur + 3 * n, y) / two_s2);
+                const double pr = d.prior[(size_t)m * N + n];
+                const double v = lite ? (one_m_g * pr) * like / norm15 : pr * like;
+                P[(size_t)m * N + n] = v;
+                rs += v;
+            }
+            rs = warp_sum(rs);
+            const double den = rs + outlier;
+            for (int n = lane; n < N; n += 32) P[(size_t)m * N + n] /= den;
+        }
+        __syncthreads();
+        // ---------------- column moments: p_n = sum_m P[m,n], ytp_n = sum_m P[m,n] Y[m]
+        // R = 1024/N row groups work in parallel; partials are combined in a fixed order (deterministic).
+        {
+            const int R = (N >= EM_THREADS) ? 1 : EM_THREADS / N;
+            for (int t = tid; t < R * N; t += EM_THREADS) {
+                const int g = t / N, n = t % N;
+                double c0 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                for (int m = g; m < M; m += R) {
+                    const double pv = P[(size_t)m * N + n];
+                    c0 += pv;
+                    a0 = fma(pv, Y[3 * m], a0); a1 = fma(pv, Y[3 * m + 1], a1); a2 = fma(pv, Y[3 * m + 2], a2);
+                }
+                double* o = d.colpart + 4 * (size_t)t;
+                o[0] = c0; o[1] = a0; o[2] = a1; o[3] = a2;
+            }
+            __syncthreads();
+            for (int n = tid; n < N; n += EM_THREADS) {
+                double c0 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                for (int g = 0; g < R; ++g) {
+                    const double* o = d.colpart + 4 * ((size_t)g * N + n);
+                    c0 += o[0]; a0 += o[1]; a1 += o[2]; a2 += o[3];
+                }
+                d.colsum[n] = c0;
+                d.ytp[3 * n] = a0; d.ytp[3 * n + 1] = a1; d.ytp[3 * n + 2] = a2;
+            }
+        }
+        __syncthreads();
+        // ---------------- M-step assembly (track.py:91-96 / trackerlite.py:411-415)
+        //   S = a^T:  S[i][j] = p_i G[i][j] + lambda sigma^2 [i==j]     (G symmetric)
+        //   rhs[i]  = ytp_i - p_i * base_i,  base = X (TRACK) or the current prediction (LITE)
+        const double reg = prm.lambda * sigma2;
+        for (size_t e = tid; e < (size_t)N * N; e += EM_THREADS) {
+            const int i = (int)(e / N), j = (int)(e % N);
+            // the reference adds lambda*sigma^2*I to the dense product: same two roundings here
+            double v = d.gram[e] * d.colsum[i];
+            if (i == j) v += reg;
+            S[e] = v;
+        }
+        const double* base = lite ? d.cur : X;
+        for (int e = tid; e < 3 * N; e += EM_THREADS) d.rhs[e] = d.ytp[e] - base[e] * d.colsum[e / 3];
+        __syncthreads();
+        lu_solve(S, N, d.rhs, d.mult, s);      // rhs now holds W = C^T (N,3)
+        // ---------------- apply: move = G W   (track.py:100 / trackerlite.py:337-341)
+        double move2 = 0.0;
+        for (int i = w; i < N; i += EM_WARPS) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            const double* g = d.gram + (size_t)i * N;
+            for (int j = lane; j < N; j += 32) {
+                const double gv = g[j];
+                a0 = fma(gv, d.rhs[3 * j], a0); a1 = fma(gv, d.rhs[3 * j + 1], a1); a2 = fma(gv, d.rhs[3 * j + 2], a2);
+            }
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+            if (lane == 0) {
+                if (lite) {
+                    move2 += a0 * a0 + a1 * a1 + a2 * a2;
+                    if (it > 1) { d.cur[3 * i] += a0; d.cur[3 * i + 1] += a1; d.cur[3 * i + 2] += a2; }
+                } else {
+                    d.cur[3 * i] = X[3 * i] + a0; d.cur[3 * i + 1] = X[3 * i + 1] + a1; d.cur[3 * i + 2] = X[3 * i + 2] + a2;
+                }
+            }
+        }
+        if (lite && it > 1) {
+            // tracked points: move_l = (C G_nl)^T, thread per (l, dim) running down the N rows (coalesced in l)
+            for (int e = tid; e < 3 * L; e += EM_THREADS) {
+                const int l = e / 3, dim = e % 3;
+                double a = 0.0;
+                for (int n = 0; n < N; ++n) a = fma(d.gram_nl[(size_t)n * L + l], d.rhs[3 * n + dim], a);
+                d.cur_l[e] += a;
+            }
+        }
+        if (lite) move2 = block_sum(move2, s); else __syncthreads();
+        // ---------------- gamma, sigma^2 (track.py:103-112 / trackerlite.py:342-350)
+        double cs = 0.0;
+        for (int n = tid; n < N; n += EM_THREADS) cs += d.colsum[n];
+        const double sumP = block_sum(cs, s);
+        gamma = 1.0 - sumP / (double)M;
+        if (lite && gamma < 1e-4) gamma = 1e-4;
+        double q = 0.0;
+        for (int m = w; m < M; m += EM_WARPS) {
+            const double* y = Y + 3 * m;
+            for (int n = lane; n < N; n += 32) q = fma(P[(size_t)m * N + n], dist2(d.cur + 3 * n, y), q);
+        }
+        sigma2 = block_sum(q, s) / (3.0 * sumP);
+        if (!lite && sigma2 < 1.0) sigma2 = 1.0;
+        if (lite && sqrt(move2) < 1e-3) break;
+    }
+
+    // ---- outputs
+    for (int e = tid; e < 3 * N; e += EM_THREADS) {
+        if (d.p.ref_out) d.p.ref_out[e] = d.cur[e];
+        if (d.p.coef) d.p.coef[(size_t)(e % 3) * N + e / 3] = (iterations > 0) ? d.rhs[e] : 0.0;
+    }
+    if (lite && d.p.tracked_out)
+        for (int e = tid; e < 3 * L; e += EM_THREADS) d.p.tracked_out[e] = d.cur_l[e];
+    if (tid == 0 && d.p.iterations) *d.p.iterations = iterations;
+}
+
+__global__ void __launch_bounds__(EM_THREADS, 1)
+greedy_kernel(const DevProblem* __restrict__ probs, int mode, double threshold) {
+    __shared__ Scratch s;
+    greedy_prior(probs[blockIdx.x], mode, threshold, s);
+}
+
+// tracker.py:1269-1289: post = pre + (C G)^T,  G[n,l] = exp(-|pre_l - inter_n|^2 / (2 beta^2))
+__global__ void __launch_bounds__(128)
+predict_one_rep_kernel(const double* __restrict__ pre, int L, const double* __restrict__ inter, int N,
+                       double two_b2, const double* __restrict__ coef, double* __restrict__ post) {
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (l >= L) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int n = lane; n < N; n += 32) {
+        const double g = exp(-dist2(pre + 3 * l, inter + 3 * n) / two_b2);
+        a0 = fma(coef[n], g, a0); a1 = fma(coef[N + n], g, a1); a2 = fma(coef[2 * N + n], g, a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { post[3 * l] = pre[3 * l] + a0; post[3 * l + 1] = pre[3 * l + 1] + a1; post[3 * l + 2] = pre[3 * l + 2] + a2; }
+}
+
+// scipy.stats.trim_mean(axis=0): per output element sort the E samples, drop int(p*E) at both ends.
+__global__ void __launch_bounds__(128)
+trim_mean_kernel(const double* __restrict__ stack, int E, int count, int cut, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    // rank-based selection (E is small, <= a few dozen): an element is kept when its rank is in [cut, E-cut)
+    double sum = 0.0;
+    for (int a = 0; a < E; ++a) {
+        const double va = stack[(size_t)a * count + i];
+        int rank = 0;
+        for (int b = 0; b < E; ++b) {
+            const double vb = stack[(size_t)b * count + i];
+            rank += (vb < va) || (vb == va && b < a);
+        }
+        if (rank >= cut && rank < E - cut) sum += va;
+    }
+    out[i] = sum / (double)(E - 2 * cut);
+}
+
+struct Layout {
+    size_t gram, gram_nl, sys, prior, colsum, ytp, colpart, rhs, mult, cur, cur_l, rowmax, rowarg, match, col_dead, pairs, n_pairs, total;
+};
+
+static Layout layout_for(int N, int M, int L) {
+    Layout o{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
+    o.gram = take((size_t)N * N * 8);
+    o.gram_nl = take((size_t)N * (L > 0 ? L : 1) * 8);
+    o.sys = take(N > SMEM_N_MAX ? (size_t)N * N * 8 : 8);
+    o.prior = take((size_t)M * N * 8);
+    o.colsum = take((size_t)N * 8);
+    o.ytp = take((size_t)N * 24);
+    o.colpart = take((size_t)(N > EM_THREADS ? N : EM_THREADS) * 32);
+    o.rhs = take((size_t)N * 24);
+    o.mult = take((size_t)N * 8);
+    o.cur = take((size_t)N * 24);
+    o.cur_l = take((size_t)(L > 0 ? L : 1) * 24);
+    o.rowmax = take((size_t)M * 8);
+    o.rowarg = take((size_t)M * 4);
+    o.match = take((size_t)M * 4);
+    o.col_dead = take((size_t)N);
+    o.pairs = take((size_t)(M < N ? M : N) * 8 + 8);
+    o.n_pairs = take(8);
+    o.total = off;
+    return o;
+}
+
+static void bind(DevProblem& d, char* base, const Layout& o) {
+    d.gram = (double*)(base + o.gram); d.gram_nl = (double*)(base + o.gram_nl); d.sys = (double*)(base + o.sys);
+    d.prior = (double*)(base + o.prior); d.colsum = (double*)(base + o.colsum); d.ytp = (double*)(base + o.ytp); d.colpart = (double*)(base + o.colpart);
+    d.rhs = (double*)(base + o.rhs); d.mult = (double*)(base + o.mult); d.cur = (double*)(base + o.cur);
+    d.cur_l = (double*)(base + o.cur_l); d.rowmax = (double*)(base + o.rowmax); d.rowarg = (int*)(base + o.rowarg);
+    d.match = (int*)(base + o.match); d.col_dead = (unsigned char*)(base + o.col_dead);
+    d.pairs = (int*)(base + o.pairs); d.n_pairs = (int*)(base + o.n_pairs);
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+extern "C" size_t ct_prgls_workspace_bytes(int n_ref, int n_tgt, int n_tracked) {
+    return layout_for(n_ref, n_tgt, n_tracked).total + align_up(sizeof(DevProblem), 256) + 256;
+}
+
+extern "C" size_t ct_greedy_workspace_bytes(int n_ref, int n_tgt) { return ct_prgls_workspace_bytes(n_ref, n_tgt, 0); }
+
+extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems, int batch,
+                        void* ws, size_t ws_bytes, void* stream) {
+    CT_REQUIRE(prm && problems && ws, "ct_prgls: null argument");
+    CT_REQUIRE(prm->mode == CT_PRGLS_TRACK || prm->mode == CT_PRGLS_LITE, "ct_prgls: unknown mode %d", prm->mode);
+    if (batch == 0) return 0;
+    CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_prgls: workspace must be 256-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<DevProblem> host(batch);
+    char* base = static_cast<char*>(ws);
+    size_t off = align_up((size_t)batch * sizeof(DevProblem), 256);
+    int max_n = 0;
+    for (int b = 0; b < batch; ++b) {
+        const CtPrglsProblem& p = problems[b];
+        CT_REQUIRE(p.n_ref >= 2 && p.n_tgt >= 1 && p.n_tracked >= 0, "ct_prgls: problem %d has bad sizes", b);
+        CT_REQUIRE(p.ref && p.tgt && p.corr && p.post, "ct_prgls: problem %d has a null required pointer", b);
+        CT_REQUIRE(prm->mode != CT_PRGLS_LITE || p.n_tracked == 0 || (p.tracked && p.tracked_out),
+                   "ct_prgls: problem %d needs tracked / tracked_out", b);
+        Layout o = layout_for(p.n_ref, p.n_tgt, p.n_tracked);
+        host[b].p = p;
+        bind(host[b], base + off, o);
+        if (!(prm->mode == CT_PRGLS_LITE)) host[b].p.n_tracked = 0;
+        off += o.total;
+        if (p.n_ref > max_n) max_n = p.n_ref;
+    }
+    CT_REQUIRE(off <= ws_bytes, "ct_prgls: workspace too small (%zu < %zu)", ws_bytes, off);
+    CT_CUDA(cudaMemcpyAsync(ws, host.data(), (size_t)batch * sizeof(DevProblem), cudaMemcpyHostToDevice, s));
+    const size_t smem = (max_n <= SMEM_N_MAX) ? (size_t)max_n * max_n * 8 : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CT_CUDA(cudaFuncSetAttribute(prgls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SMEM_N_MAX * SMEM_N_MAX * 8));
+        attr_set = true;
+    }
+    prgls_kernel<<<batch, EM_THREADS, smem, s>>>(static_cast<const DevProblem*>(ws), *prm);
+    CT_LAUNCHED("prgls_kernel");
+    return 0;
+}
+
+extern "C" int ct_greedy_prior(const void* corr, int corr_is_f64, int n_tgt, int n_ref, int mode, double threshold,
+                               double* prior, int* pairs, int* n_pairs, void* ws, size_t ws_bytes, void* stream) {
+    CT_REQUIRE(corr && prior && ws, "ct_greedy_prior: null argument");
+    CT_REQUIRE(n_ref >= 2 && n_tgt >= 1, "ct_greedy_prior: bad sizes");
+    CT_REQUIRE(ws_bytes >= ct_greedy_workspace_bytes(n_ref, n_tgt), "ct_greedy_prior: workspace too small");
+    CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_greedy_prior: workspace must be 256-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    DevProblem d{};
+    d.p.corr = corr; d.p.corr_is_f64 = corr_is_f64; d.p.n_ref = n_ref; d.p.n_tgt = n_tgt;
+    Layout o = layout_for(n_ref, n_tgt, 0);
+    char* base = static_cast<char*>(ws) + align_up(sizeof(DevProblem), 256);
+    bind(d, base, o);
+    d.prior = prior;
+    d.pairs = pairs;
+    d.n_pairs = n_pairs;
+    CT_CUDA(cudaMemcpyAsync(ws, &d, sizeof(d), cudaMemcpyHostToDevice, s));
+    greedy_kernel<<<1, EM_THREADS, 0, s>>>(static_cast<const DevProblem*>(ws), mode, threshold);
+    CT_LAUNCHED("greedy_kernel");
+    return 0;
+}
+
+extern "C" int ct_predict_one_rep(const double* pre, int L, const double* inter, int N, double beta,
+                                  const double* coef, double* post, void* stream) {
+    CT_REQUIRE(pre && inter && coef && post, "ct_predict_one_rep: null argument");
+    if (L == 0) return 0;
+    predict_one_rep_kernel<<<cdiv(L, 4), 128, 0, (cudaStream_t)stream>>>(pre, L, inter, N, 2.0 * beta * beta, coef, post);
+    CT_LAUNCHED("predict_one_rep_kernel");
+    return 0;
+}
+
+extern "C" int ct_trim_mean(const double* stack, int e, int count, double proportion, double* out, void* stream) {
+    CT_REQUIRE(stack && out && e >= 1, "ct_trim_mean: bad argument");
+    const int cut = (int)(proportion * e);
+    CT_REQUIRE(e - 2 * cut > 0, "ct_trim_mean: proportion too big");
+    if (count == 0) return 0;
+    trim_mean_kernel<<<cdiv(count, 128), 128, 0, (cudaStream_t)stream>>>(stack, e, count, cut, out);
+    CT_LAUNCHED("trim_mean_kernel");
+    return 0;
+}

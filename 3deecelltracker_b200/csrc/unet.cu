@@ -1,0 +1,442 @@
+// U-Net engine: weight packing, the per-tile op plan, tile gather / scatter and the element-wise
+// kernels between convolutions.
+//
+// Reference semantics reproduced here:
+//   unet3d.py:84-98   graph of _unet3_depth3 (and :40-67 unet3_b): two convs per level, MaxPooling3D,
+//                     two convs on the LOWER level, UpSampling3D, concatenate([up, skip]), ..., 1x1x1 head
+//   unet3d.py:203-256 unet3_prediction: reflect pre-pad, tiles of the model input size at a stride of the
+//                     centre size, centre crop, scatter, final crop to the original size
+// Every tile is convolved with its own zero 'same' padding (tiles are batch entries, never merged), so
+// results depend on the tile grid exactly as in the reference.
+#include "unet_common.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace ct {
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_index(int j, int n) {
+    // numpy.pad(mode='reflect') for arbitrarily wide pads: triangle wave of period 2(n-1)
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    j %= period;
+    if (j < 0) j += period;
+    return j < n ? j : period - j;
+}
+
+// Tile gather.  mode 0: tile t of the volume's tile grid, reflect-padded (unet3d.py:235,247-249).
+//               mode 1: tiles are given explicitly as (B, x, y, z) (Keras model.predict).
+// Output: [tile][1 chunk][TX][TY][TZ][4] with channels 1..3 = 0.
+__global__ void __launch_bounds__(256)
+gather_tiles(const float* __restrict__ src, float4* __restrict__ slab, size_t slab_stride4, size_t in_off4,
+             int mode, int tile_first, int X, int Y, int Z, int TX, int TY, int TZ,
+             int ny, int nz, int cx, int cy, int cz, int bx, int by, int bz) {
+    const int t = blockIdx.y;
+    const size_t tile_vox = (size_t)TX * TY * TZ;
+    float4* out = slab + (size_t)t * slab_stride4 + in_off4;
+    int gi = tile_first + t;
+    const int k = gi % nz; gi /= nz;
+    const int j = gi % ny; gi /= ny;
+    const int i = gi;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < tile_vox; v += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(v % TZ);
+        size_t r = v / TZ;
+        const int b = (int)(r % TY);
+        const int a = (int)(r / TY);
+        float val;
+        if (mode == 0) {
+            const int sx = reflect_index(i * cx + a - bx, X);
+            const int sy = reflect_index(j * cy + b - by, Y);
+            const int sz = reflect_index(k * cz + c - bz, Z);
+            val = src[((size_t)sx * Y + sy) * Z + sz];
+        } else {
+            val = src[(size_t)(tile_first + t) * tile_vox + v];
+        }
+        out[v] = make_float4(val, 0.f, 0.f, 0.f);
+    }
+}
+
+// MaxPooling3D(pool) on c4-blocked buffers (unet3d.py:168).
+__global__ void __launch_bounds__(256)
+pool_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, size_t slab_stride4,
+            size_t src_off4, size_t dst_off4, int src_c4off, int c4, int SXs, int SYs, int SZs,
+            int DX, int DY, int DZ, int px, int py, int pz) {
+    const int t = blockIdx.y;
+    const size_t dvol = (size_t)DX * DY * DZ, svol = (size_t)SXs * SYs * SZs;
+    const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4 + (size_t)src_c4off * svol;
+    float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4;
+    const size_t total = dvol * c4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t ck = idx / dvol, v = idx % dvol;
+        const int z = (int)(v % DZ);
+        const size_t r = v / DZ;
+        const int y = (int)(r % DY), x = (int)(r / DY);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int a = 0; a < px; ++a)
+            for (int b = 0; b < py; ++b)
+                for (int c = 0; c < pz; ++c) {
+                    const float4 q = src[ck * svol + ((size_t)(x * px + a) * SYs + (y * py + b)) * SZs + (z * pz + c)];
+                    m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y); m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
+                }
+        dst[idx] = m;
+    }
+}
+
+// UpSampling3D(size) nearest, written into the first channels of the concat buffer (unet3d.py:199).
+__global__ void __launch_bounds__(256)
+upsample_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, size_t slab_stride4,
+                size_t src_off4, size_t dst_off4, int dst_c4off, int c4, int SXs, int SYs, int SZs,
+                int DX, int DY, int DZ, int px, int py, int pz) {
+    const int t = blockIdx.y;
+    const size_t dvol = (size_t)DX * DY * DZ, svol = (size_t)SXs * SYs * SZs;
+    const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4;
+    float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4 + (size_t)dst_c4off * dvol;
+    const size_t total = dvol * c4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t ck = idx / dvol, v = idx % dvol;
+        const int z = (int)(v % DZ);
+        const size_t r = v / DZ;
+        const int y = (int)(r % DY), x = (int)(r / DY);
+        dst[idx] = src[ck * svol + ((size_t)(x / px) * SYs + (y / py)) * SZs + (z / pz)];
+    }
+}
+
+// Head: Conv3D(1, 1, activation='sigmoid') (unet3d.py:96) + centre crop + scatter (unet3d.py:250-255).
+// mode 0: write the centre window of tile (i,j,k) into prob (X,Y,Z), clipped to the volume.
+// mode 1: write the whole tile to prob (B, TX, TY, TZ).
+__global__ void __launch_bounds__(256)
+head_scatter(const float4* __restrict__ slab, size_t slab_stride4, size_t last_off4, int c4,
+             const float* __restrict__ head_w, float head_b, float* __restrict__ prob,
+             int mode, int tile_first, int X, int Y, int Z, int TX, int TY, int TZ,
+             int ny, int nz, int cx, int cy, int cz, int bx, int by, int bz) {
+    const int t = blockIdx.y;
+    const size_t tile_vox = (size_t)TX * TY * TZ;
+    const float4* in = slab + (size_t)t * slab_stride4 + last_off4;
+    int gi = tile_first + t;
+    const int k = gi % nz; gi /= nz;
+    const int j = gi % ny; gi /= ny;
+    const int i = gi;
+    const int wx = mode == 0 ? cx : TX, wy = mode == 0 ? cy : TY, wz = mode == 0 ? cz : TZ;
+    const int ox = mode == 0 ? bx : 0, oy = mode == 0 ? by : 0, oz = mode == 0 ? bz : 0;
+    const size_t win = (size_t)wx * wy * wz;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < win; v += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(v % wz);
+        const size_t r = v / wz;
+        const int b = (int)(r % wy), a = (int)(r / wy);
+        const size_t tv = ((size_t)(a + ox) * TY + (b + oy)) * TZ + (c + oz);
+        float acc = head_b;
+        for (int ck = 0; ck < c4; ++ck) {
+            const float4 q = in[(size_t)ck * tile_vox + tv];
+            acc = fmaf(q.x, head_w[ck * 4 + 0], acc);
+            acc = fmaf(q.y, head_w[ck * 4 + 1], acc);
+            acc = fmaf(q.z, head_w[ck * 4 + 2], acc);
+            acc = fmaf(q.w, head_w[ck * 4 + 3], acc);
+        }
+        const float p = 1.f / (1.f + expf(-acc));
+        if (mode == 0) {
+            const int gx = i * cx + a, gy = j * cy + b, gz = k * cz + c;
+            if (gx < X && gy < Y && gz < Z) prob[((size_t)gx * Y + gy) * Z + gz] = p;
+        } else {
+            prob[(size_t)(tile_first + t) * tile_vox + tv] = p;
+        }
+    }
+}
+
+static int grid_for(size_t work) {
+    size_t b = (work + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+// ---------------------------------------------------------------------------------------------
+// plan + weights
+// ---------------------------------------------------------------------------------------------
+static void conv_list(const CtUNetSpec* sp, std::vector<std::pair<int, int>>& out) {
+    int c = 1;
+    std::vector<int> skips;
+    for (int l = 0; l < sp->levels; ++l) {
+        out.push_back({c, sp->down[l][0]});
+        out.push_back({sp->down[l][0], sp->down[l][1]});
+        skips.push_back(sp->down[l][1]);
+        c = sp->down[l][1];
+    }
+    for (int u = 0; u < sp->levels; ++u) {
+        out.push_back({c, sp->up[u][0]});
+        out.push_back({sp->up[u][0], sp->up[u][1]});
+        c = sp->up[u][1] + skips[sp->levels - 1 - u];
+    }
+    out.push_back({c, sp->out[0]});
+    out.push_back({sp->out[0], sp->out[1]});
+}
+
+extern "C" size_t ct_unet_weight_count(const CtUNetSpec* sp) {
+    std::vector<std::pair<int, int>> convs;
+    conv_list(sp, convs);
+    size_t n = 0;
+    for (auto& c : convs) n += (size_t)27 * c.first * c.second + 5 * (size_t)c.second;
+    return n + sp->out[1] + 1;
+}
+
+static int validate_spec(const CtUNetSpec* sp) {
+    CT_REQUIRE(sp->levels >= 1 && sp->levels <= CT_UNET_MAX_LEVELS, "unet: levels %d out of range", sp->levels);
+    int dx = sp->in_x, dy = sp->in_y, dz = sp->in_z;
+    for (int l = 0; l < sp->levels; ++l) {
+        CT_REQUIRE(dx % sp->pool_x == 0 && dy % sp->pool_y == 0 && dz % sp->pool_z == 0,
+                   "unet: input %dx%dx%d not divisible by the pool size at level %d", sp->in_x, sp->in_y, sp->in_z, l);
+        dx /= sp->pool_x; dy /= sp->pool_y; dz /= sp->pool_z;
+        for (int q = 0; q < 2; ++q) {
+            CT_REQUIRE(sp->down[l][q] % 8 == 0 && sp->up[l][q] % 8 == 0, "unet: filter counts must be multiples of 8");
+        }
+    }
+    CT_REQUIRE(sp->out[0] % 8 == 0 && sp->out[1] % 4 == 0, "unet: output filter counts must be multiples of 8 / 4");
+    return 0;
+}
+
+extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_floats, CtUNet** out) {
+    CT_REQUIRE(sp && w && out, "ct_unet_create: null argument");
+    if (validate_spec(sp)) return 1;
+    CT_REQUIRE(n_floats == ct_unet_weight_count(sp), "ct_unet_create: expected %zu weights, got %zu",
+               ct_unet_weight_count(sp), n_floats);
+    CtUNet* net = new CtUNet();
+    net->spec = *sp;
+    net->alpha = sp->act_relu ? 0.f : 0.3f;     // keras LeakyReLU() default alpha
+    net->engine = 0;
+    std::vector<std::pair<int, int>> convs;
+    conv_list(sp, convs);
+
+    // ---- pack weights on the host into one staging vector, then one device allocation
+    std::vector<float> host;
+    struct Offs { size_t wd, wt, b, sc, sh; };
+    std::vector<Offs> offs;
+    const float* p = w;
+    const float eps = 1e-3f;                    // keras BatchNormalization default epsilon
+    for (auto& c : convs) {
+        const int cin = c.first, cout = c.second, cin_pad = (cin + 3) / 4 * 4;
+        Offs o;
+        auto take = [&](size_t n) { size_t at = (host.size() + 63) / 64 * 64; host.resize(at + n, 0.f); return at; };
+        o.wd = take((size_t)cin_pad * 27 * cout);
+        // keras kernel (kx,ky,kz,ci,co) -> [ci/4][tap][co][ci%4]
+        for (int tap = 0; tap < 27; ++tap)
+            for (int ci = 0; ci < cin; ++ci)
+                for (int co = 0; co < cout; ++co)
+                    host[o.wd + (((size_t)(ci / 4) * 27 + tap) * cout + co) * 4 + (ci % 4)] =
+                        p[((size_t)tap * cin + ci) * cout + co];
+        const size_t tcn = tc_weight_floats(cin_pad, cout);
+        o.wt = take(tcn);
+        if (tcn) tc_pack_weights(p, cin, cin_pad, cout, &host[o.wt]);
+        p += (size_t)27 * cin * cout;
+        o.b = take(cout); o.sc = take(cout); o.sh = take(cout);
+        const float *bias = p, *gamma = p + cout, *beta = p + 2 * cout, *mean = p + 3 * cout, *var = p + 4 * cout;
+        for (int co = 0; co < cout; ++co) {
+            const float s = gamma[co] / std::sqrt(var[co] + eps);
+            host[o.b + co] = bias[co];
+            host[o.sc + co] = s;
+            host[o.sh + co] = beta[co] - mean[co] * s;
+        }
+        p += 5 * (size_t)cout;
+        offs.push_back(o);
+    }
+    net->last_c = sp->out[1];
+    size_t head_at = (host.size() + 63) / 64 * 64;
+    host.resize(head_at + net->last_c, 0.f);
+    for (int c = 0; c < net->last_c; ++c) host[head_at + c] = p[c];
+    net->head_b = p[net->last_c];
+
+    if (check_cuda(cudaMalloc(&net->all_dev, host.size() * sizeof(float)), "cudaMalloc(weights)") ||
+        check_cuda(cudaMemcpy(net->all_dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice),
+                   "cudaMemcpy(weights)")) {
+        delete net;
+        return 1;
+    }
+    for (size_t i = 0; i < convs.size(); ++i) {
+        ConvLayer L;
+        L.cin = convs[i].first; L.cout = convs[i].second; L.cin_pad = (L.cin + 3) / 4 * 4;
+        L.w_direct = net->all_dev + offs[i].wd;
+        L.w_tc = tc_weight_floats(L.cin_pad, L.cout) ? net->all_dev + offs[i].wt : nullptr;
+        L.bias = net->all_dev + offs[i].b; L.scale = net->all_dev + offs[i].sc; L.shift = net->all_dev + offs[i].sh;
+        net->layers.push_back(L);
+    }
+    net->head_w = net->all_dev + head_at;
+
+    // ---- op plan over one tile's slab
+    int lx[CT_UNET_MAX_LEVELS + 1], ly[CT_UNET_MAX_LEVELS + 1], lz[CT_UNET_MAX_LEVELS + 1];
+    lx[0] = sp->in_x; ly[0] = sp->in_y; lz[0] = sp->in_z;
+    for (int l = 1; l <= sp->levels; ++l) { lx[l] = lx[l - 1] / sp->pool_x; ly[l] = ly[l - 1] / sp->pool_y; lz[l] = lz[l - 1] / sp->pool_z; }
+    size_t off = 0;
+    auto buf = [&](int c, int l) { size_t at = off; off += (size_t)c * lx[l] * ly[l] * lz[l]; off = (off + 63) / 64 * 64; return at; };
+    double flops = 0;
+    int li = 0;
+    auto conv = [&](size_t s_off, int s_c, size_t d_off, int d_c, int d_coff, int l) {
+        Op o{}; o.kind = OP_CONV; o.layer = li; o.src_off = s_off; o.dst_off = d_off; o.src_c = s_c; o.dst_c = d_c;
+        o.src_coff = 0; o.dst_coff = d_coff; o.c = net->layers[li].cout;
+        o.sx = o.dx = lx[l]; o.sy = o.dy = ly[l]; o.sz = o.dz = lz[l];
+        flops += 2.0 * 27 * net->layers[li].cin * net->layers[li].cout * (double)lx[l] * ly[l] * lz[l];
+        net->ops.push_back(o); ++li;
+    };
+    net->in_off = buf(4, 0);
+    size_t x_off = net->in_off; int x_c = 4;
+    size_t cat_off[CT_UNET_MAX_LEVELS]; int cat_c[CT_UNET_MAX_LEVELS];
+    for (int l = 0; l < sp->levels; ++l) {
+        const int f1 = sp->down[l][0], f2 = sp->down[l][1];
+        const int upc = sp->up[sp->levels - 1 - l][1];
+        size_t t = buf(f1, l);
+        conv(x_off, x_c, t, f1, 0, l);
+        cat_c[l] = upc + f2; cat_off[l] = buf(cat_c[l], l);
+        conv(t, f1, cat_off[l], cat_c[l], upc, l);
+        size_t pl = buf(f2, l + 1);
+        Op o{}; o.kind = OP_POOL; o.src_off = cat_off[l]; o.dst_off = pl; o.src_c = cat_c[l]; o.dst_c = f2;
+        o.src_coff = upc; o.dst_coff = 0; o.c = f2;
+        o.sx = lx[l]; o.sy = ly[l]; o.sz = lz[l]; o.dx = lx[l + 1]; o.dy = ly[l + 1]; o.dz = lz[l + 1];
+        net->ops.push_back(o);
+        x_off = pl; x_c = f2;
+    }
+    for (int u = 0; u < sp->levels; ++u) {
+        const int l = sp->levels - 1 - u;      // level the result is upsampled INTO; convs run at l+1
+        const int f1 = sp->up[u][0], f2 = sp->up[u][1];
+        size_t t1 = buf(f1, l + 1), t2 = buf(f2, l + 1);
+        conv(x_off, x_c, t1, f1, 0, l + 1);
+        conv(t1, f1, t2, f2, 0, l + 1);
+        Op o{}; o.kind = OP_UPSAMPLE; o.src_off = t2; o.dst_off = cat_off[l]; o.src_c = f2; o.dst_c = cat_c[l];
+        o.src_coff = 0; o.dst_coff = 0; o.c = f2;
+        o.sx = lx[l + 1]; o.sy = ly[l + 1]; o.sz = lz[l + 1]; o.dx = lx[l]; o.dy = ly[l]; o.dz = lz[l];
+        net->ops.push_back(o);
+        x_off = cat_off[l]; x_c = cat_c[l];
+    }
+    size_t o1 = buf(sp->out[0], 0), o2 = buf(sp->out[1], 0);
+    conv(x_off, x_c, o1, sp->out[0], 0, 0);
+    conv(o1, sp->out[0], o2, sp->out[1], 0, 0);
+    flops += 2.0 * sp->out[1] * (double)lx[0] * ly[0] * lz[0];
+    net->last_off = o2;
+    net->slab_floats = off;
+    net->flops_per_tile = flops;
+    *out = net;
+    return 0;
+}
+
+extern "C" void ct_unet_destroy(CtUNet* net) {
+    if (!net) return;
+    cudaFree(net->all_dev);
+    delete net;
+}
+
+extern "C" int ct_unet_set_engine(CtUNet* net, int engine) {
+    CT_REQUIRE(net && engine >= 0 && engine <= 2, "ct_unet_set_engine: bad argument");
+    net->engine = engine;
+    return 0;
+}
+
+extern "C" double ct_unet_flops_per_tile(const CtUNet* net) { return net ? net->flops_per_tile : 0.0; }
+
+extern "C" size_t ct_unet_workspace_bytes(const CtUNet* net, int tiles_per_batch) {
+    if (!net || tiles_per_batch < 1) return 0;
+    return net->slab_floats * sizeof(float) * (size_t)tiles_per_batch + 256;
+}
+
+static int tile_geometry(const CtUNet* net, int x, int y, int z, const int shrink[3], int centre[3], int num[3]) {
+    const int in[3] = {net->spec.in_x, net->spec.in_y, net->spec.in_z};
+    const int sz[3] = {x, y, z};
+    for (int a = 0; a < 3; ++a) {
+        centre[a] = in[a] - 2 * shrink[a];
+        CT_REQUIRE(shrink[a] >= 0 && centre[a] > 0, "unet3_prediction: shrink %d too large for input size %d", shrink[a], in[a]);
+        CT_REQUIRE(sz[a] > 0, "unet3_prediction: empty volume");
+        num[a] = (sz[a] + centre[a] - 1) / centre[a];
+    }
+    return 0;
+}
+
+extern "C" int ct_unet_tile_count(const CtUNet* net, int x, int y, int z, const int shrink[3], int counts_out[3]) {
+    int centre[3], num[3];
+    if (!net || tile_geometry(net, x, y, z, shrink, centre, num)) return -1;
+    if (counts_out) { counts_out[0] = num[0]; counts_out[1] = num[1]; counts_out[2] = num[2]; }
+    return num[0] * num[1] * num[2];
+}
+
+// Runs the op plan on `tiles` slabs that already hold their padded input.
+static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) {
+    const size_t stride = net->slab_floats;
+    for (const Op& op : net->ops) {
+        if (op.kind == OP_CONV) {
+            int rc = 2;
+            if (net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s);
+            if (rc == 1) return 1;
+            if (rc == 2) {
+                CT_REQUIRE(net->engine != 2 || net->layers[op.layer].cin == 1,
+                           "unet: tcgen05 engine forced but layer %d (cin %d, cout %d) is unsupported",
+                           op.layer, net->layers[op.layer].cin, net->layers[op.layer].cout);
+                if (launch_conv_direct(net, op, slab0, stride, tiles, s)) return 1;
+            }
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(slab0);
+            float4* dst = reinterpret_cast<float4*>(slab0);
+            const size_t work = (size_t)op.dx * op.dy * op.dz * (op.c / 4);
+            dim3 grid(grid_for(work), tiles);
+            if (op.kind == OP_POOL) {
+                pool_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.src_coff / 4,
+                                                 op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
+                                                 net->spec.pool_x, net->spec.pool_y, net->spec.pool_z);
+                CT_LAUNCHED("pool_kernel");
+            } else {
+                upsample_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.dst_coff / 4,
+                                                     op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
+                                                     net->spec.pool_x, net->spec.pool_y, net->spec.pool_z);
+                CT_LAUNCHED("upsample_kernel");
+            }
+        }
+    }
+    return 0;
+}
+
+static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode, int first, int last,
+                     int X, int Y, int Z, const int centre[3], const int num[3], const int shrink[3],
+                     void* ws, size_t ws_bytes, int tiles_per_batch, cudaStream_t s) {
+    CT_REQUIRE(tiles_per_batch >= 1, "unet: tiles_per_batch must be >= 1");
+    CT_REQUIRE(ws_bytes >= ct_unet_workspace_bytes(net, tiles_per_batch), "unet: workspace too small (%zu < %zu)",
+               ws_bytes, ct_unet_workspace_bytes(net, tiles_per_batch));
+    CT_REQUIRE(((uintptr_t)ws & 255) == 0, "unet: workspace must be 256-byte aligned");
+    float* slab0 = static_cast<float*>(ws);
+    const int TX = net->spec.in_x, TY = net->spec.in_y, TZ = net->spec.in_z;
+    const size_t tile_vox = (size_t)TX * TY * TZ;
+    for (int t0 = first; t0 < last; t0 += tiles_per_batch) {
+        const int nt = (last - t0 < tiles_per_batch) ? last - t0 : tiles_per_batch;
+        dim3 g(grid_for(tile_vox), nt);
+        gather_tiles<<<g, 256, 0, s>>>(src, reinterpret_cast<float4*>(slab0), net->slab_floats / 4, net->in_off / 4, mode, t0,
+                                       X, Y, Z, TX, TY, TZ, num[1], num[2], centre[0], centre[1], centre[2],
+                                       shrink[0], shrink[1], shrink[2]);
+        CT_LAUNCHED("gather_tiles");
+        if (run_plan(net, slab0, nt, s)) return 1;
+        head_scatter<<<g, 256, 0, s>>>(reinterpret_cast<const float4*>(slab0), net->slab_floats / 4, net->last_off / 4,
+                                       net->last_c / 4, net->head_w, net->head_b, prob, mode, t0, X, Y, Z, TX, TY, TZ,
+                                       num[1], num[2], centre[0], centre[1], centre[2], shrink[0], shrink[1], shrink[2]);
+        CT_LAUNCHED("head_scatter");
+    }
+    return 0;
+}
+
+extern "C" int ct_unet_predict_tiles(const CtUNet* net, const float* tiles, float* prob, int batch,
+                                     void* ws, size_t ws_bytes, int tiles_per_batch, void* stream) {
+    CT_REQUIRE(net && tiles && prob && batch >= 0, "ct_unet_predict_tiles: bad argument");
+    const int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
+    const int num[3] = {batch, 1, 1};
+    return run_tiles(net, tiles, prob, 1, 0, batch, 0, 0, 0, one, num, zero, ws, ws_bytes, tiles_per_batch,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int ct_unet3_prediction(const CtUNet* net, const float* vol_norm, float* prob, int x, int y, int z,
+                                   const int shrink[3], int tile_begin, int tile_end,
+                                   void* ws, size_t ws_bytes, int tiles_per_batch, void* stream) {
+    CT_REQUIRE(net && vol_norm && prob && shrink, "ct_unet3_prediction: null argument");
+    int centre[3], num[3];
+    if (tile_geometry(net, x, y, z, shrink, centre, num)) return 1;
+    const int total = num[0] * num[1] * num[2];
+    CT_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= total,
+               "ct_unet3_prediction: tile range [%d,%d) outside [0,%d)", tile_begin, tile_end, total);
+    return run_tiles(net, vol_norm, prob, 0, tile_begin, tile_end, x, y, z, centre, num, shrink, ws, ws_bytes,
+                     tiles_per_batch, (cudaStream_t)stream);
+}

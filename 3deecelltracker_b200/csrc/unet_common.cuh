@@ -1,0 +1,63 @@
+// Internal structures of the U-Net engine (shared by the CUDA-core and tcgen05 convolution paths).
+//
+// Activation layout in HBM ("c4 blocked"): [tile][C/4][X][Y][Z][4] float32, i.e. channel chunks of 4 are
+// the slowest per-tile dimension and the 4 channels of a chunk are interleaved per voxel (16 B).  z is the
+// fastest spatial axis, as in the reference's (x, y, z) arrays.  One voxel-chunk is one 16-byte vector:
+// it is the unit of coalesced global access, of shared-memory staging, and -- for the tensor-core path --
+// exactly one row of a no-swizzle K-major UMMA core matrix (8 rows x 16 B).
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace ct {
+
+struct ConvLayer {
+    int cin, cout;            // logical channels (cin of the first layer is 1, stored padded to 4)
+    int cin_pad;              // multiple of 4
+    float* w_direct;          // device: [cin_pad/4][27][cout][4]   (CUDA-core kernel)
+    float* w_tc;              // device: tcgen05 layout (see unet_tc.cu), may be null
+    float* bias;              // device [cout]
+    float* scale;             // device [cout]  gamma / sqrt(var + eps)
+    float* shift;             // device [cout]  beta - mean * scale
+};
+
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_UPSAMPLE = 2 };
+
+struct Op {
+    OpKind kind;
+    int layer;                // OP_CONV: index into layers
+    size_t src_off, dst_off;  // float offsets inside one tile's workspace slab
+    int src_c, dst_c;         // total channels of the src / dst buffers
+    int src_coff, dst_coff;   // channel offset inside the buffer (multiple of 4)
+    int c;                    // channels moved (pool / upsample) or cout (conv)
+    int sx, sy, sz;           // spatial size of src
+    int dx, dy, dz;           // spatial size of dst
+};
+
+}  // namespace ct
+
+struct CtUNet {
+    CtUNetSpec spec;
+    std::vector<ct::ConvLayer> layers;
+    std::vector<ct::Op> ops;
+    size_t slab_floats;       // workspace floats per tile
+    size_t in_off, last_off;  // offsets of the padded input buffer and of the last conv output
+    int last_c;
+    float* head_w;            // device [last_c]
+    float head_b;
+    float alpha;              // 0.3 (LeakyReLU) or 0 (ReLU)
+    int engine;               // 1 direct, 2 tcgen05
+    double flops_per_tile;
+    float* all_dev;           // one allocation holding every device array
+};
+
+namespace ct {
+// implemented in unet_direct.cu
+int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
+                       cudaStream_t s);
+// implemented in unet_tc.cu (returns 2 when the layer shape is not supported by the tensor-core path)
+int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
+                   cudaStream_t s);
+size_t tc_weight_floats(int cin_pad, int cout);
+void tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
+}  // namespace ct

@@ -1,0 +1,150 @@
+// CUDA-core fp32 3x3x3 'same' convolution with fused bias -> LeakyReLU/ReLU -> BatchNorm(eval).
+//
+// Replaces one Conv3D + LeakyReLU + BatchNormalization block of unet3d.py:117-119 (or the ReLU variant
+// :139-140) for a batch of independent tiles.  This is the exact-fp32 engine: it serves the layers the
+// tensor-core path does not take (Cin = 1) and is the numerical cross-check for the 3xTF32 path.
+//
+// CTA = 256 threads = 2 (x groups of 4) x 8 (y) x 16 (z) -> output block 8 x 8 x 16 voxels, CO output
+// channels.  Each thread owns 4 consecutive-x voxels x CO channels (register tile).  Per 4-channel input
+// chunk the 10 x 10 x 18 halo block (zero filled outside the tile = Keras 'same' padding) and the
+// 27 x CO x 4 weights are staged in shared memory; lanes run along z so every activation LDS.128 of a
+// quarter warp touches 128 contiguous bytes, and weight reads are warp-uniform broadcasts.
+#include "unet_common.cuh"
+
+namespace ct {
+
+constexpr int BX = 8, BY = 8, BZ = 16;
+constexpr int SX = BX + 2, SY = BY + 2, SZ = BZ + 2;
+
+template <int CO>
+__global__ void __launch_bounds__(256, 2)
+conv3_direct_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                    const float4* __restrict__ wts,      // [cin4][27][cout][1] float4 (4 cin)
+                    const float* __restrict__ bias, const float* __restrict__ scale,
+                    const float* __restrict__ shift, float alpha,
+                    int cin4, int cout, int X, int Y, int Z, int nbx, int nby,
+                    size_t src_tile_stride4, size_t dst_tile_stride4, int dst_c4off) {
+    __shared__ float4 in_s[SX][SY][SZ];
+    __shared__ float4 w_s[27][CO];
+
+    const int tid = threadIdx.x;
+    const int tz = tid & 15, ty = (tid >> 4) & 7, tx = (tid >> 7) * 4;
+    int b = blockIdx.x;
+    const int bxi = b % nbx; b /= nbx;
+    const int byi = b % nby; b /= nby;
+    const int bzi = b;
+    const int x0 = bxi * BX, y0 = byi * BY, z0 = bzi * BZ;
+    const int co0 = blockIdx.y * CO;
+    const int tile = blockIdx.z;
+    const size_t vol = (size_t)X * Y * Z;
+    const float4* s_tile = src + (size_t)tile * src_tile_stride4;
+
+    float acc[4][CO];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[v][c] = 0.f;
+
+    for (int ck = 0; ck < cin4; ++ck) {
+        __syncthreads();
+        const float4* s_ck = s_tile + (size_t)ck * vol;
+        for (int i = tid; i < SX * SY * SZ; i += 256) {
+            int sz = i % SZ, r = i / SZ;
+            int sy = r % SY, sx = r / SY;
+            int gx = x0 + sx - 1, gy = y0 + sy - 1, gz = z0 + sz - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gx >= 0 && gx < X && gy >= 0 && gy < Y && gz >= 0 && gz < Z)
+                v = s_ck[((size_t)gx * Y + gy) * Z + gz];
+            in_s[sx][sy][sz] = v;
+        }
+        const float4* w_ck = wts + ((size_t)ck * 27) * cout;
+        for (int i = tid; i < 27 * CO; i += 256) {
+            int t = i / CO, c = i % CO;
+            w_s[t][c] = w_ck[(size_t)t * cout + co0 + c];
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+            for (int dz = 0; dz < 3; ++dz) {
+                float4 a[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) a[i] = in_s[tx + i][ty + dy][tz + dz];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int tap = (dx * 3 + dy) * 3 + dz;
+#pragma unroll
+                    for (int c = 0; c < CO; ++c) {
+                        const float4 w = w_s[tap][c];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            acc[v][c] = fmaf(a[v + dx].x, w.x, acc[v][c]);
+                            acc[v][c] = fmaf(a[v + dx].y, w.y, acc[v][c]);
+                            acc[v][c] = fmaf(a[v + dx].z, w.z, acc[v][c]);
+                            acc[v][c] = fmaf(a[v + dx].w, w.w, acc[v][c]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // epilogue: bias -> activation -> BN affine, written as 16-byte channel chunks
+    const int gy = y0 + ty, gz = z0 + tz;
+    if (gy < Y && gz < Z) {
+        float4* d_tile = dst + (size_t)tile * dst_tile_stride4;
+#pragma unroll
+        for (int c4 = 0; c4 < CO / 4; ++c4) {
+            float bs[4], sc[4], sh[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int co = co0 + c4 * 4 + j;
+                bs[j] = bias[co]; sc[j] = scale[co]; sh[j] = shift[co];
+            }
+            float4* d_ck = d_tile + (size_t)(dst_c4off + (co0 >> 2) + c4) * vol;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                int gx = x0 + tx + v;
+                if (gx < X) {
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = acc[v][c4 * 4 + j] + bs[j];
+                        t = t > 0.f ? t : alpha * t;
+                        o[j] = fmaf(t, sc[j], sh[j]);
+                    }
+                    d_ck[((size_t)gx * Y + gy) * Z + gz] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+}
+
+int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
+                       cudaStream_t s) {
+    const ConvLayer& L = net->layers[op.layer];
+    const int X = op.sx, Y = op.sy, Z = op.sz;
+    const int nbx = cdiv(X, BX), nby = cdiv(Y, BY), nbz = cdiv(Z, BZ);
+    const float4* src = reinterpret_cast<const float4*>(slab0 + op.src_off);
+    float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
+    CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
+    CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
+    dim3 grid(nbx * nby * nbz, 1, tiles);
+    if (L.cout % 16 == 0) {
+        grid.y = L.cout / 16;
+        conv3_direct_kernel<16><<<grid, 256, 0, s>>>(src, dst, reinterpret_cast<const float4*>(L.w_direct), L.bias,
+                                                    L.scale, L.shift, net->alpha, L.cin_pad / 4, L.cout, X, Y, Z,
+                                                    nbx, nby, slab_stride / 4, slab_stride / 4, op.dst_coff / 4);
+    } else {
+        CT_REQUIRE(L.cout % 8 == 0, "conv: cout %d must be a multiple of 8", L.cout);
+        grid.y = L.cout / 8;
+        conv3_direct_kernel<8><<<grid, 256, 0, s>>>(src, dst, reinterpret_cast<const float4*>(L.w_direct), L.bias,
+                                                   L.scale, L.shift, net->alpha, L.cin_pad / 4, L.cout, X, Y, Z,
+                                                   nbx, nby, slab_stride / 4, slab_stride / 4, op.dst_coff / 4);
+    }
+    CT_LAUNCHED("conv3_direct_kernel");
+    return 0;
+}
+
+}  // namespace ct

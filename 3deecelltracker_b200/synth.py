@@ -1,0 +1,49 @@
+"""Seeded synthetic inputs for tests and bench.py: uint16 stacks of Gaussian blobs, point sets
+with affine motion + dropped / added cells.  Pure NumPy, host side; nothing here is on the timed path."""
+import numpy as np
+
+
+def blob_centres(shape_xyz, k, seed, margin=8):
+    rng = np.random.default_rng(seed)
+    lo = np.array([margin, margin, min(margin, shape_xyz[2] // 4)], dtype=np.float64)
+    hi = np.array(shape_xyz, dtype=np.float64) - lo
+    return rng.uniform(lo, hi, (k, 3))
+
+
+def blob_stack(shape_xyz, centres, seed, z_xy_ratio=1.0, sigma_xy=4.0):
+    """uint16 (x,y,z): background N(100,10^2) clipped at 0 + Gaussian blobs of amplitude U(300,3000)."""
+    rng = np.random.default_rng(seed)
+    x, y, z = shape_xyz
+    img = rng.normal(100.0, 10.0, shape_xyz).astype(np.float32)
+    sigma_z = max(1.0, sigma_xy / z_xy_ratio)
+    amp = rng.uniform(300, 3000, len(centres))
+    rx, rz = int(3 * sigma_xy) + 1, int(3 * sigma_z) + 1
+    for (cx, cy, cz), a in zip(centres, amp):
+        x0, x1 = max(int(cx) - rx, 0), min(int(cx) + rx + 1, x)
+        y0, y1 = max(int(cy) - rx, 0), min(int(cy) + rx + 1, y)
+        z0, z1 = max(int(cz) - rz, 0), min(int(cz) + rz + 1, z)
+        gx = np.exp(-0.5 * ((np.arange(x0, x1) - cx) / sigma_xy) ** 2)
+        gy = np.exp(-0.5 * ((np.arange(y0, y1) - cy) / sigma_xy) ** 2)
+        gz = np.exp(-0.5 * ((np.arange(z0, z1) - cz) / sigma_z) ** 2)
+        img[x0:x1, y0:y1, z0:z1] += (a * gx[:, None, None] * gy[None, :, None] * gz[None, None, :]).astype(np.float32)
+    return np.clip(img, 0, 65535).astype(np.uint16)
+
+
+def move_points(points, seed, affine_level=0.05, noise=0.002, drop=0.05, add=0.05):
+    """Affine-perturbed copy with dropped / added points (semantics of ffn.py:29-54 in normalised coordinates)."""
+    rng = np.random.default_rng(seed)
+    mean = points.mean(axis=0)
+    c = points - mean
+    scale = np.abs(c).max()
+    a = np.eye(3) + (rng.random((3, 3)) - 0.5) * affine_level
+    t = (c / scale) @ a + (rng.random(c.shape) - 0.5) * 4 * noise
+    t = t * scale + mean
+    t = t[rng.random(len(t)) > drop]
+    extra = rng.uniform(points.min(axis=0), points.max(axis=0), (int(add * len(points)), 3))
+    t = np.concatenate([t, extra], axis=0)
+    return t[rng.permutation(len(t))]
+
+
+def random_points(n, seed, extent=(512.0, 512.0, 320.0)):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(0, 1, (n, 3)) * np.asarray(extent)

@@ -1,0 +1,167 @@
+/*
+ * ct3d.h -- C ABI of libct3d.so: the B200 (sm_100a) hot path of a 3DeeCellTracker-compatible
+ * segment-and-track engine.
+ *
+ * The reference (WenChentao/3DeeCellTracker) is pure Python; it has no FFI layer.  The seams this
+ * library plugs into are the reference's Python operator functions; every entry point below names the
+ * reference function (file:line under CellTracker/) whose arithmetic it replaces.  The Python package
+ * `3deecelltracker_b200` binds these symbols with ctypes and keeps the reference's signatures.
+ *
+ * Conventions
+ *   - plain C types only; every data pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns every buffer, including workspaces (query with ct_*_workspace_bytes);
+ *   - all work is enqueued on the CUDA stream passed as `stream` (a cudaStream_t cast to void*);
+ *     no entry point synchronises the device unless documented;
+ *   - return value 0 = success, non-zero = error; ct_last_error() returns a thread-local message;
+ *   - the library never falls back to a CPU implementation.
+ *   - volumes are C-ordered (x, y, z) arrays (z fastest), as in the reference (unet3d.py:210).
+ */
+#ifndef CT3D_H_
+#define CT3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CT3D_ABI_VERSION 1
+
+int ct_abi_version(void);
+const char* ct_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench.py "gpu_launches"). */
+unsigned long long ct_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * LCN normalisation.  Replaces preprocess.py:170-188 (_normalize_image) + :136-167 (lcn_gpu) +
+ * :117-133 (conv3d_keras): median subtract, clamp at 0, 27x27x1 zero-padded box mean / std,
+ * (x-avg)/(std+noise_level).
+ * dtype: 0 = uint16, 1 = float32, 2 = uint8.   out: float32 (x,y,z).
+ * ---------------------------------------------------------------------------------------------- */
+size_t ct_normalize_workspace_bytes(int x, int y, int z);
+/* subtract_median = 1: _normalize_image (median subtract + clamp + LCN); 0: lcn_gpu alone (no clamp). */
+int ct_normalize_image(const void* raw, int dtype, float* out, int x, int y, int z, float noise_level,
+                       int filter_x, int filter_y, int subtract_median, void* ws, size_t ws_bytes,
+                       void* stream);
+/* The median alone (what np.median returns; mean of the two middle values for even counts).
+ * Writes one double to median_out (device). */
+int ct_median(const void* raw, int dtype, long long count, double* median_out, void* ws, size_t ws_bytes,
+              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3D U-Net.  Replaces the Keras graphs of unet3d.py:26-98 (unet3_a/b/c), the blocks :101-200 and the
+ * tiled prediction unet3_prediction (unet3d.py:203-256).
+ * ---------------------------------------------------------------------------------------------- */
+#define CT_UNET_MAX_LEVELS 4
+typedef struct CtUNetSpec {
+    int in_x, in_y, in_z;              /* model input tile, e.g. 160,160,16 (unet3d.py:36) */
+    int pool_x, pool_y, pool_z;        /* MaxPooling3D / UpSampling3D size (unet3d.py:35) */
+    int act_relu;                      /* 0: Conv->LeakyReLU(0.3)->BN (:117-119); 1: Conv(relu)->BN (:139-140) */
+    int levels;                        /* number of _downscale blocks */
+    int down[CT_UNET_MAX_LEVELS][2];   /* filters of the two convs of each _downscale (:88-90) */
+    int up[CT_UNET_MAX_LEVELS][2];     /* filters of the two convs of each _upscale, deepest first (:91-93) */
+    int out[2];                        /* output_m2 / output_m1 filters (:94-95) */
+} CtUNetSpec;
+
+typedef struct CtUNet CtUNet;
+
+/* weights_host: float32 arrays concatenated in Keras Model.get_weights() order: per Conv3D+BN block
+ * kernel(3,3,3,Cin,Cout), bias, gamma, beta, moving_mean, moving_var; head kernel(1,1,1,C,1), bias. */
+size_t ct_unet_weight_count(const CtUNetSpec* spec);
+int ct_unet_create(const CtUNetSpec* spec, const float* weights_host, size_t n_floats, CtUNet** out);
+void ct_unet_destroy(CtUNet* net);
+/* engine: 0 = auto, 1 = CUDA-core fp32 direct convolution, 2 = tcgen05 implicit GEMM (3xTF32). */
+int ct_unet_set_engine(CtUNet* net, int engine);
+double ct_unet_flops_per_tile(const CtUNet* net);
+
+size_t ct_unet_workspace_bytes(const CtUNet* net, int tiles_per_batch);
+/* Keras `model.predict(tiles)`: tiles (B, x, y, z) float32 -> prob (B, x, y, z) float32. */
+int ct_unet_predict_tiles(const CtUNet* net, const float* tiles, float* prob, int batch,
+                          void* ws, size_t ws_bytes, int tiles_per_batch, void* stream);
+/* Number of tiles unet3_prediction visits for a volume (unet3d.py:226-228,259-279). */
+int ct_unet_tile_count(const CtUNet* net, int x, int y, int z, const int shrink[3], int counts_out[3]);
+/* unet3_prediction over tiles [tile_begin, tile_end) of the (i,j,k) row-major tile grid: reflect
+ * pre-pad, per-tile zero 'same' padding, centre crop, scatter into prob (x,y,z).  Voxels of prob not
+ * covered by the tile range are left untouched (multi-GPU tile sharding). */
+int ct_unet3_prediction(const CtUNet* net, const float* vol_norm, float* prob, int x, int y, int z,
+                        const int shrink[3], int tile_begin, int tile_end,
+                        void* ws, size_t ws_bytes, int tiles_per_batch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FFN match.  Replaces ffn.py:225-265 (FFN.call), ffn.py:268-327 (initial_matching_ffn) and
+ * track.py:117-178 (initial_matching_quick).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct CtFFN CtFFN;
+/* weights_host: W1(61,512), bn1 gamma,beta,mean,var, W2(1024,512), bn2 gamma,beta,mean,var, W3(512,1), b3(1). */
+size_t ct_ffn_weight_count(void);
+int ct_ffn_create(const float* weights_host, size_t n_floats, CtFFN** out);
+void ct_ffn_destroy(CtFFN* ffn);
+/* k-NN features (ffn.py:288-304): pts (n,3) float64 -> feat (n, 3k+1) float32.  n >= k+1 required. */
+int ct_knn_features(const double* pts, int n, int k, float* feat, void* stream);
+size_t ct_ffn_match_workspace_bytes(int n_ref, int n_tgt);
+/* corr (M,N) float32 = FFN([feat(ref n) | feat(tgt m)]) for every pair. */
+int ct_ffn_match(const CtFFN* ffn, const double* ref, int n_ref, const double* tgt, int n_tgt, int k,
+                 float* corr, void* ws, size_t ws_bytes, void* stream);
+/* Keras FFN.predict on arbitrary rows: x (rows,122) float32 -> out (rows) float32. */
+size_t ct_ffn_predict_workspace_bytes(int rows);
+int ct_ffn_predict(const CtFFN* ffn, const float* x, int rows, float* out, void* ws, size_t ws_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Greedy prior + PR-GLS / CPD EM.  Replaces track.py:11-114 (pr_gls_quick), trackerlite.py:242-259
+ * (simple_match), :262-358 (prgls_quick, prgls_with_two_ref), :361-382, :409-417, and
+ * tracker.py:1269-1289 (_predict_one_rep).
+ * ---------------------------------------------------------------------------------------------- */
+#define CT_PRGLS_TRACK 0     /* track.py flavour: gamma0 0.1, vol 1e8, sigma^2 >= 1, fixed iteration count */
+#define CT_PRGLS_LITE 1      /* trackerlite.py flavour: gamma0 0.05, vol 1, increments, convergence test */
+
+typedef struct CtPrglsParams {
+    int mode;                /* CT_PRGLS_TRACK | CT_PRGLS_LITE */
+    int max_iteration;       /* loop runs iterations 1 .. max_iteration-1 */
+    double beta;
+    double lambda;
+    double vol;              /* 1e8 (track.py:11) or 1 (trackerlite.py:376) */
+    double threshold;        /* greedy threshold: 0.5 (track.py:63) or 0.1 (trackerlite.py:242) */
+} CtPrglsParams;
+
+typedef struct CtPrglsProblem {
+    const double* ref;       /* (N,3)  X / prts_ref_nx3 */
+    const double* tgt;       /* (M,3)  Y / ptrs_tgt_mx3 */
+    const void* corr;        /* (M,N)  FFN output (float32 or float64), or a ready prior if prior_given */
+    const double* tracked;   /* (L,3)  LITE only: tracked_ref_lx3 (may be NULL when L == 0) */
+    double* post;            /* (M,N)  out: P / posterior_mxn (required; also used as scratch) */
+    double* ref_out;         /* (N,3)  out: T_X (TRACK) / predicted_coord_ref_nx3 (LITE) */
+    double* coef;            /* (3,N)  out: C of the last iteration */
+    double* tracked_out;     /* (L,3)  out, LITE only */
+    int* iterations;         /* out: number of EM iterations executed (1 int), may be NULL */
+    int n_ref, n_tgt, n_tracked;
+    int corr_is_f64;         /* dtype of corr: 0 float32, 1 float64 */
+    int prior_given;         /* 1: corr already holds the prior (skip the greedy step) */
+} CtPrglsProblem;
+
+/* Greedy prior alone.  mode TRACK: rows default 1/N, matched rows 0.1/(N-1) & 0.9 (track.py:58-70);
+ * mode LITE: everything 0.1/(N-1), matched 0.9, values rounded to corr's dtype (trackerlite.py:256).
+ * prior (M,N) float64; pairs (min(M,N),2) int32 (tgt m, ref n) in pick order, n_pairs 1 int (may be NULL). */
+size_t ct_greedy_workspace_bytes(int n_ref, int n_tgt);
+int ct_greedy_prior(const void* corr, int corr_is_f64, int n_tgt, int n_ref, int mode, double threshold,
+                    double* prior, int* pairs, int* n_pairs, void* ws, size_t ws_bytes, void* stream);
+
+/* Workspace for one problem of the given size; a batch needs the sum over its problems. */
+size_t ct_prgls_workspace_bytes(int n_ref, int n_tgt, int n_tracked);
+/* Runs `batch` independent EM problems (one persistent CTA each, no host round trips).
+ * problems_host: array of descriptors in HOST memory (copied to the device inside the workspace). */
+int ct_prgls(const CtPrglsParams* params, const CtPrglsProblem* problems_host, int batch,
+             void* ws, size_t ws_bytes, void* stream);
+
+/* _predict_one_rep: post(L,3) = pre(L,3) + (C G)^T, G[n,l] = exp(-|pre_l - inter_n|^2 / 2 beta^2). */
+int ct_predict_one_rep(const double* pre, int n_tracked, const double* inter, int n_ref, double beta,
+                       const double* coef, double* post, void* stream);
+
+/* trim_mean(stack (E,L,3), proportion, axis=0) -> (L,3)  (tracker.py:1507, trackerlite.py:123). */
+int ct_trim_mean(const double* stack, int e, int count, double proportion, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CT3D_H_ */

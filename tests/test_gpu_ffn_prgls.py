@@ -1,0 +1,204 @@
+"""GPU parity: FFN match, greedy prior and the PR-GLS / CPD EM kernels (through the C ABI) against the
+golden outputs of the unmodified reference and against the CPU oracle.
+
+Tolerances: displacements / coordinates 1e-4 relative is the north_star bar; fp64 kernels are held to
+1e-8 here.  Index work (greedy pairs, priors) is bit-exact."""
+import importlib
+
+import numpy as np
+import pytest
+import scipy.stats
+import torch
+
+from conftest import golden, load_pkg, split_cases
+from oracle import ffn as offn
+from oracle import prgls as oprgls
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m():
+    load_pkg()
+    names = ["ffn", "track", "trackerlite", "coord_image_transformer", "synth", "tracker"]
+    return {n: importlib.import_module("3deecelltracker_b200." + n) for n in names}
+
+
+# ------------------------------------------------------------------------------------------- FFN
+def test_knn_features_match_reference_golden(m):
+    g = golden("ffn_features.npz")
+    for pts, want in ((g["ref_full"], g["feat_ref_full"]), (g["tgt_full"], g["feat_tgt_full"]),
+                      (g["ref_q"], g["grid_q"][:33, :61])):
+        got = m["ffn"].knn_features(pts, 20)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        m["ffn"].knn_features(np.zeros((20, 3)), 20)
+
+
+@pytest.mark.parametrize("n,mm,seed", [(40, 35, 0), (180, 171, 1), (21, 64, 2), (333, 290, 3)])
+def test_initial_matching_matches_oracle(m, n, mm, seed):
+    ws = offn.random_weights(seed)
+    ref = m["synth"].random_points(n, seed + 10, extent=(1.0, 1.0, 0.6)) - 0.5
+    tgt = m["synth"].random_points(mm, seed + 20, extent=(1.0, 1.0, 0.6)) - 0.5
+    want = offn.initial_matching_ffn(offn.FFNOracle(ws), ref, tgt, 20)
+    model = m["ffn"].FFN(ws)
+    got = m["ffn"].initial_matching_ffn(model, ref, tgt, 20)
+    assert got.shape == (mm, n) and got.dtype == np.float32
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6)
+    got2 = m["track"].initial_matching_quick(model, ref, tgt, 20)
+    np.testing.assert_array_equal(got, got2)
+
+
+def test_ffn_predict_rows_matches_oracle(m):
+    ws = offn.random_weights(5)
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 0.7, (1500, 122)).astype(np.float32)
+    want = offn.FFNOracle(ws).predict(x)
+    model = m["ffn"].FFN(ws)
+    np.testing.assert_allclose(model.predict(x), want, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(model.predict([x[:, :61], x[:, 61:]]), want, rtol=1e-4, atol=1e-6)
+    assert model.predict(x[:0]).shape == (0, 1)
+    with pytest.raises(ValueError):
+        model.predict(x[:, :100])
+
+
+# ------------------------------------------------------------------------------------------- greedy prior
+def test_simple_match_bit_exact_vs_reference(m):
+    g = golden("trackerlite_em.npz")
+    prior, pairs = m["trackerlite"].simple_match(g["corr"])
+    assert prior.dtype == np.float32
+    np.testing.assert_array_equal(prior, g["prior"])
+    np.testing.assert_array_equal(pairs, g["pairs"])
+    p64, pr64 = m["trackerlite"].simple_match(g["sm64__corr"], threshold=0.3)
+    np.testing.assert_array_equal(p64, g["sm64__prior"])
+    np.testing.assert_array_equal(pr64, g["sm64__pairs"])
+
+
+def test_simple_match_ties_and_empty(m):
+    # ties: np.argmax takes the first maximum in row-major order
+    corr = np.full((6, 5), 0.7, dtype=np.float64)
+    want_p, want_pairs = oprgls.simple_match(corr)
+    got_p, got_pairs = m["trackerlite"].simple_match(corr)
+    np.testing.assert_array_equal(got_p, want_p)
+    np.testing.assert_array_equal(got_pairs, want_pairs)
+    # nothing above threshold
+    corr = np.full((4, 7), 0.05, dtype=np.float32)
+    got_p, got_pairs = m["trackerlite"].simple_match(corr)
+    np.testing.assert_array_equal(got_p, oprgls.simple_match(corr)[0])
+    assert len(got_pairs) == 0
+    rng = np.random.default_rng(9)
+    for shape in ((50, 80), (80, 50), (200, 300)):
+        c = rng.random(shape).astype(np.float32)
+        c[rng.random(shape) < 0.3] = 0.0
+        want_p, want_pairs = oprgls.simple_match(c, threshold=0.2)
+        got_p, got_pairs = m["trackerlite"].simple_match(c, threshold=0.2)
+        np.testing.assert_array_equal(got_pairs, want_pairs)
+        np.testing.assert_array_equal(got_p, want_p)
+
+
+# ------------------------------------------------------------------------------------------- EM
+@pytest.mark.parametrize("case", ["worm3_single", "worm3_ensemble", "small", "nomatch"])
+def test_pr_gls_quick_vs_reference_golden(m, case):
+    c = split_cases(golden("pr_gls_quick.npz"))[case]
+    P, TX, C = m["track"].pr_gls_quick(c["X"], c["Y"], c["corr"], BETA=float(c["BETA"]),
+                                       max_iteration=int(c["max_iteration"]), LAMBDA=float(c["LAMBDA"]))
+    np.testing.assert_allclose(TX, c["T_X"], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(P, c["P"], rtol=1e-6, atol=1e-12)
+    scale = np.abs(c["C"]).max()
+    np.testing.assert_allclose(C, c["C"], rtol=1e-4, atol=1e-7 * scale)
+
+
+def test_prgls_with_two_ref_vs_reference_golden(m):
+    g = golden("trackerlite_em.npz")
+    for tag in ("b3l3", "b1l01"):
+        pred, post = m["trackerlite"].prgls_with_two_ref(g["prior"], g["tgt_norm"], g["ref_norm"], g["conf_norm"],
+                                                         beta=float(g[f"{tag}__beta"]), lambda_=float(g[f"{tag}__lambda"]))
+        np.testing.assert_allclose(pred, g[f"{tag}__pred"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(post, g[f"{tag}__post"], rtol=1e-6, atol=1e-13)
+    pred, post = m["trackerlite"].prgls_quick(g["prior"], g["tgt_norm"], g["ref_norm"], 3.0, 3.0)
+    np.testing.assert_allclose(pred, g["quick__pred"], rtol=1e-8, atol=1e-10)
+
+
+def test_estep_single_iteration(m):
+    """One EM iteration = estimate_posterior (trackerlite.py:375) with the initial sigma^2 and gamma."""
+    g = golden("trackerlite_em.npz")
+    ref, tgt = g["ref_norm"], g["tgt_norm"]
+    s2 = oprgls.dist_squares(ref, tgt).mean() / 3
+    want = oprgls.estimate_posterior(g["prior"], s2, ref, tgt, 0.05)
+    _, post = m["trackerlite"].prgls_with_two_ref(g["prior"], tgt, ref, ref[:30], 3.0, 3.0, max_iteration=2)
+    np.testing.assert_allclose(post, want, rtol=1e-10, atol=1e-300)
+
+
+@pytest.mark.parametrize("n,mm", [(169, 200), (300, 260)])
+def test_pr_gls_quick_large_n_vs_oracle(m, n, mm):
+    """N > 168: the N x N system no longer fits shared memory and runs from the L2-resident workspace."""
+    ref = m["synth"].random_points(n, 1)
+    tgt = m["synth"].move_points(ref, 2)[:mm]
+    rng = np.random.default_rng(3)
+    d2 = ((ref[None] - tgt[:, None]) ** 2).sum(axis=2)
+    corr = np.clip(np.exp(-d2 / 50.0) * 0.95 + rng.random(d2.shape) * 0.3, 0, 1)
+    want = oprgls.pr_gls_quick(ref, tgt, corr, BETA=300, max_iteration=8, LAMBDA=0.1)
+    got = m["track"].pr_gls_quick(ref, tgt, corr, BETA=300, max_iteration=8, LAMBDA=0.1)
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-6, atol=1e-12)
+
+
+def test_em_batch_equals_singles(m):
+    """A batched launch (ensemble members) gives bit-identical results to one launch per problem."""
+    tr = m["track"]
+    probs, singles = [], []
+    for e in range(5):
+        ref = m["synth"].random_points(60 + 7 * e, 10 + e)
+        tgt = m["synth"].move_points(ref, 20 + e)
+        rng = np.random.default_rng(e)
+        corr = rng.random((len(tgt), len(ref)))
+        probs.append(tr.EmProblem(ref, tgt, corr))
+        singles.append(tr.pr_gls_quick(ref, tgt, corr, BETA=250, max_iteration=6, LAMBDA=0.1))
+    tr.run_em(probs, tr.MODE_TRACK, 250, 0.1, 6, 1e8, 0.5)
+    for p, s in zip(probs, singles):
+        np.testing.assert_array_equal(p.ref_out.cpu().numpy(), s[1])
+        np.testing.assert_array_equal(p.post.cpu().numpy(), s[0])
+
+
+def test_predict_one_rep_and_trim_mean(m):
+    g = golden("predict_one_rep.npz")
+    tr = m["track"]
+    post = tr.predict_one_rep_device(torch.from_numpy(g["pre"]).cuda(), torch.from_numpy(g["inter"]).cuda(),
+                                     float(g["beta"]), torch.from_numpy(g["C"]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(post, g["post"], rtol=1e-10, atol=1e-9)
+    rng = np.random.default_rng(3)
+    for e in (1, 2, 9, 10, 19, 20, 21):
+        a = rng.normal(size=(e, 17, 3))
+        got = tr.trim_mean_device(torch.from_numpy(a).cuda(), 0.1).cpu().numpy()
+        np.testing.assert_allclose(got, scipy.stats.trim_mean(a, 0.1, axis=0), rtol=1e-12, atol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------- class API
+def test_trackerlite_predict_cell_positions(m, tmp_path):
+    g = golden("trackerlite_em.npz")
+    Coordinates = m["coord_image_transformer"].Coordinates
+    voxel = np.array([1.0, 1.0, 1.0])
+    pts1 = g["points"].astype(np.float32).astype(np.float64)          # Coordinates stores float32
+    pts2 = m["synth"].move_points(pts1, 7).astype(np.float32).astype(np.float64)
+    (tmp_path / "seg").mkdir()
+    np.save(tmp_path / "seg" / "coords000001.npy", pts1)
+    np.save(tmp_path / "seg" / "coords000002.npy", pts2)
+    ws = offn.random_weights(1)
+    model = m["ffn"].FFN(ws)
+    proof = Coordinates(pts1, 1, voxel, dtype="raw")
+    lite = m["trackerlite"].TrackerLite(str(tmp_path), model, proof)
+    got = lite.predict_cell_positions(1, 2, beta=3.0, lambda_=3.0)
+    # oracle pipeline (trackerlite.py:70-109)
+    conf_norm, (mean, scale) = offn.normalize_points(pts1, return_para=True)
+    s2 = (pts2 - mean) / scale
+    s1 = (pts1 - mean) / scale
+    corr = offn.initial_matching_ffn(offn.FFNOracle(ws), s1, s2, 20)
+    prior, _ = oprgls.simple_match(corr)
+    pred, _ = oprgls.prgls_with_two_ref(prior, s2, s1, conf_norm, 3.0, 3.0)
+    want = pred * scale + mean
+    np.testing.assert_allclose(got.real, want.astype(np.float32), rtol=1e-4, atol=1e-3)
+    with pytest.raises(AssertionError):
+        m["trackerlite"].TrackerLite(str(tmp_path), model, proof, miss_frame=[2]).predict_cell_positions(1, 2)
+    with pytest.raises(TypeError):
+        m["trackerlite"].TrackerLite(str(tmp_path), model, proof, miss_frame=(2,))
