@@ -238,6 +238,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
     double* P = d.p.post;
     double* S = (N <= SMEM_N_MAX) ? dyn_smem : d.sys;
     const double two_b2 = 2.0 * prm.beta * prm.beta;
+    const bool prior_f32 = lite && !d.p.corr_is_f64;
 
     // ---- prior
     if (d.p.prior_given) {
@@ -286,7 +287,10 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             for (int n = lane; n < N; n += 32) {
                 const double like = exp(-dist2(d.cur + 3 * n, y) / two_s2);
                 const double pr = d.prior[(size_t)m * N + n];
-                const double v = lite ? (one_m_g * pr) * like / norm15 : pr * like;
+                // NumPy dtype rule kept: a float32 prior times the scalar (1 - gamma) is a float32 product
+                // (trackerlite.py:377-378 with prior from simple_match on the float32 FFN output)
+                const double w1 = prior_f32 ? (double)((float)one_m_g * (float)pr) : one_m_g * pr;
+                const double v = lite ? w1 * like / norm15 : pr * like;
                 P[(size_t)m * N + n] = v;
                 rs += v;
             }

@@ -90,6 +90,8 @@ class FFN:
         arr = np.asarray(x)
         if arr.ndim != 2 or arr.shape[1] != 2 * NUMBER_FEATURES:
             raise ValueError(f"expected input of shape (rows, 122), got {arr.shape}")
+        if arr.shape[0] == 0:
+            return np.zeros((0, 1), np.float32)
         dev = to_device(arr.astype(np.float32, copy=False), torch.float32)
         rows = int(dev.shape[0])
         out = torch.empty(rows, dtype=torch.float32, device=dev.device)

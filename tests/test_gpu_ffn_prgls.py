@@ -164,8 +164,8 @@ def test_em_batch_equals_singles(m):
 def test_predict_one_rep_and_trim_mean(m):
     g = golden("predict_one_rep.npz")
     tr = m["track"]
-    post = tr.predict_one_rep_device(torch.from_numpy(g["pre"]).cuda(), torch.from_numpy(g["inter"]).cuda(),
-                                     float(g["beta"]), torch.from_numpy(g["C"]).cuda()).cpu().numpy()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()      # golden C is a transposed view
+    post = tr.predict_one_rep_device(dev(g["pre"]), dev(g["inter"]), float(g["beta"]), dev(g["C"])).cpu().numpy()
     np.testing.assert_allclose(post, g["post"], rtol=1e-10, atol=1e-9)
     rng = np.random.default_rng(3)
     for e in (1, 2, 9, 10, 19, 20, 21):
