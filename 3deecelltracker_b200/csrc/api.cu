@@ -1,6 +1,7 @@
 // Error reporting, ABI version and launch accounting for libct3d.
 #include "common.cuh"
 #include <cstring>
+#include <vector>
 
 namespace ct {
 static thread_local char g_err[512] = "";
@@ -14,7 +15,65 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace ct
 
+// ---------------------------------------------------------------------------------------------
+// opt-in device-side profiler: CUDA events around tagged launches on the launching stream
+// ---------------------------------------------------------------------------------------------
+namespace ct {
+struct ProfRec { int tag; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(int tag, cudaStream_t s) : tag_(tag), s_(s), on_(g_prof_on) {
+    if (!on_) return;
+    a_ = prof_event();
+    cudaEventRecord(a_, s_);
+}
+ProfScope::~ProfScope() {
+    if (!on_) return;
+    cudaEvent_t b = prof_event();
+    cudaEventRecord(b, s_);
+    g_prof.push_back({tag_, a_, b});
+}
+}  // namespace ct
+
 extern "C" {
+int ct_profile_enable(int on) {
+    ct::g_prof_on = on != 0;
+    return 0;
+}
+
+int ct_profile_read(int tag, double* total_ms, unsigned long long* count, int reset) {
+    double ms = 0.0;
+    unsigned long long n = 0;
+    for (auto& r : ct::g_prof) {
+        if (r.tag != tag) continue;
+        if (cudaEventSynchronize(r.b) != cudaSuccess) { ct::set_error("ct_profile_read: event sync failed"); return 1; }
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms += t;
+        ++n;
+    }
+    if (total_ms) *total_ms = ms;
+    if (count) *count = n;
+    if (reset) {
+        std::vector<ct::ProfRec> keep;
+        for (auto& r : ct::g_prof) {
+            if (r.tag == tag) { ct::g_prof_pool.push_back(r.a); ct::g_prof_pool.push_back(r.b); }
+            else keep.push_back(r);
+        }
+        ct::g_prof.swap(keep);
+    }
+    return 0;
+}
+
 int ct_abi_version(void) { return CT3D_ABI_VERSION; }
 const char* ct_last_error(void) { return ct::g_err; }
 unsigned long long ct_launch_count(void) { return ct::g_launches.load(); }

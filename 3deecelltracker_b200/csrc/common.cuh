@@ -41,6 +41,17 @@ inline int check_cuda(cudaError_t e, const char* what) {
         }                                                                        \
     } while (0)
 
+// Profiler tags (ct_profile_read)
+enum ProfTag { PROF_CONV = 1, PROF_EM = 2, PROF_FFN = 3, PROF_LCN = 4, PROF_UNET_AUX = 5 };
+struct ProfScope {
+    ProfScope(int tag, cudaStream_t s);
+    ~ProfScope();
+    int tag_;
+    cudaStream_t s_;
+    bool on_;
+    cudaEvent_t a_;
+};
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

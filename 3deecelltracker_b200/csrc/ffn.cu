@@ -266,6 +266,7 @@ extern "C" int ct_ffn_match(const CtFFN* f, const double* ref, int N, const doub
     cudaStream_t s = (cudaStream_t)stream;
     Arena a(ws, ws_bytes);
     const int rows = N + M;
+    ProfScope prof(PROF_FFN, s);
     float* feat = a.take<float>((size_t)rows * FEAT);
     float* F = a.take<float>((size_t)rows * HID);
     float* AB = a.take<float>((size_t)rows * HID);

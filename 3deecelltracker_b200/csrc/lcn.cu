@@ -229,6 +229,7 @@ template <typename T>
 static int normalize_impl(const T* raw, float* out, int X, int Y, int Z, float noise, int fx, int fy,
                           int subtract_median, void* ws, size_t ws_bytes, cudaStream_t s) {
     const long long n = (long long)X * Y * Z;
+    ProfScope prof(PROF_LCN, s);
     Arena a(ws, ws_bytes);
     SelectState* st = a.take<SelectState>(1);
     double* med = a.take<double>(1);

@@ -517,6 +517,7 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
                                      SMEM_N_MAX * SMEM_N_MAX * 8));
         attr_set = true;
     }
+    ProfScope prof(PROF_EM, s);
     prgls_kernel<<<batch, EM_THREADS, smem, s>>>(static_cast<const DevProblem*>(ws), *prm);
     CT_LAUNCHED("prgls_kernel");
     return 0;

@@ -131,6 +131,7 @@ int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t sla
     CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
     CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
     dim3 grid(nbx * nby * nbz, 1, tiles);
+    ProfScope prof(PROF_CONV, s);
     if (L.cout % 16 == 0) {
         grid.y = L.cout / 16;
         conv3_direct_kernel<16><<<grid, 256, 0, s>>>(src, dst, reinterpret_cast<const float4*>(L.w_direct), L.bias,

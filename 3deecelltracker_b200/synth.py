@@ -47,3 +47,41 @@ def move_points(points, seed, affine_level=0.05, noise=0.002, drop=0.05, add=0.0
 def random_points(n, seed, extent=(512.0, 512.0, 320.0)):
     rng = np.random.default_rng(seed)
     return rng.uniform(0, 1, (n, 3)) * np.asarray(extent)
+
+
+def unet_weights(variant="a", seed=0):
+    """Seeded random-init U-Net weights in Keras order (He-normal kernels, non-trivial BatchNorm statistics) for
+    benchmarks: throughput does not depend on the weight values."""
+    import math
+    from .unet3d import _SPECS, _conv_layers
+    rng = np.random.default_rng(seed)
+    spec = _SPECS[variant]
+    ws = []
+    for cin, cout in _conv_layers(spec):
+        ws.append((rng.standard_normal((3, 3, 3, cin, cout)) * math.sqrt(2.0 / (27 * cin))).astype(np.float32))
+        ws.append((rng.standard_normal(cout) * 0.05).astype(np.float32))
+        ws.append(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+        ws.append((rng.standard_normal(cout) * 0.1).astype(np.float32))
+        ws.append((rng.standard_normal(cout) * 0.1).astype(np.float32))
+        ws.append(rng.uniform(0.5, 1.5, cout).astype(np.float32))
+    c = spec["out"][1]
+    ws.append((rng.standard_normal((1, 1, 1, c, 1)) * math.sqrt(2.0 / c)).astype(np.float32))
+    ws.append((rng.standard_normal(1) * 0.05).astype(np.float32))
+    return ws
+
+
+def ffn_weights(seed=0):
+    """Seeded random-init FFN weights in Keras order (Glorot-uniform kernels, non-trivial BatchNorm statistics)."""
+    import math
+    rng = np.random.default_rng(seed)
+
+    def glorot(fi, fo):
+        lim = math.sqrt(6.0 / (fi + fo))
+        return rng.uniform(-lim, lim, (fi, fo)).astype(np.float32)
+
+    def bn(c):
+        return [rng.uniform(0.5, 1.5, c).astype(np.float32), (rng.standard_normal(c) * 0.1).astype(np.float32),
+                (rng.standard_normal(c) * 0.1).astype(np.float32), rng.uniform(0.5, 1.5, c).astype(np.float32)]
+
+    return [glorot(61, 512)] + bn(512) + [glorot(1024, 512)] + bn(512) + \
+           [glorot(512, 1), (rng.standard_normal(1) * 0.05).astype(np.float32)]

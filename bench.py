@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the segment-and-track hot path (contract in the task statement).
+
+One "step" = one frame of BASELINE.json configs[1] (worm1 single mode, 512 x 512 x 35 uint16 stack, 164 cells):
+    LCN normalise -> tiled 3D U-Net (unet3_a, 75 tiles) -> 5 x (FFN match + PR-GLS EM, 19 iterations) -> replay of the
+    5 fitted transforms on the tracked cells -> trimmed mean.
+The host watershed between segmentation and matching is outside SURVEY section 8 (row f-1); point sets are the
+synthetic ground-truth centres, so the step is "segment + match + track without the host watershed stage".
+
+metric  voxels/s = input-volume voxels (x*y*z) per second through the whole step (whole job, all GPUs).
+value   inputs resident in HBM when the timed region starts.
+e2e     same step through the public Python API with HOST buffers: pinned uint16 stack H2D, probability map
+        and tracked coordinates D2H, all inside the timed region.
+N > 1   frames shard one per GPU (weak scaling, no data-path collective); timing is max over ranks.
+
+`--impl reference` times the CPU oracle (torch/oneDNN fp32 restatement of the Keras graphs + NumPy EM; TensorFlow is
+not installable in this image) on a bounded sample of the same workload with all host threads.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPE = (512, 512, 35)
+N_CELLS = 164
+Z_XY_RATIO = 9.2
+NOISE_LEVEL = 20
+BETA_TK, LAMBDA_TK, MAXITER_TK = 300, 0.1, 20       # single_mode_worm1-clear.ipynb:151
+REP_NUM_PRGLS = 5
+SHRINK = (24, 24, 2)
+FLOP_PER_TILE = 35.573e9
+WORKLOAD = "worm1 single-mode 512x512x35, unet3_a seg (75 tiles) + 5x(FFN match + PR-GLS 19 it) @164 cells"
+
+
+def mod(name):
+    return importlib.import_module("3deecelltracker_b200." + name)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------
+def make_inputs(frame):
+    synth = mod("synth")
+    centres0 = synth.blob_centres(SHAPE, N_CELLS, 1234)
+    real0 = centres0 * np.array([1.0, 1.0, Z_XY_RATIO])
+    real_t = synth.move_points(real0, 1234 + frame, affine_level=0.05, noise=0.002)
+    centres_t = real_t / np.array([1.0, 1.0, Z_XY_RATIO])
+    centres_t = np.clip(centres_t, 0, np.array(SHAPE) - 1)
+    raw = synth.blob_stack(SHAPE, centres_t, 1234 + frame, z_xy_ratio=Z_XY_RATIO)
+    return raw, real0, real_t
+
+
+class Step:
+    """Device pipeline of one frame; mirrors Tracker.track_one_vol's hot-path calls."""
+
+    def __init__(self, unet, ffn):
+        self.unet, self.ffn = unet, ffn
+        self.pre, self.track = mod("preprocess"), mod("track")
+
+    def run(self, raw_dev, ref_dev, tgt_dev, tracked_dev):
+        import torch
+        norm = self.pre.normalize_image_device(raw_dev, NOISE_LEVEL)
+        prob = self.unet.prediction_device(norm, SHRINK)
+        tr = self.track
+        inter, pred = ref_dev, tracked_dev
+        for i in range(REP_NUM_PRGLS):
+            beta = BETA_TK * (0.8 ** i)
+            corr = self.ffn.match_device(inter, tgt_dev, 20)
+            p = tr.run_em([tr.EmProblem(inter, tgt_dev, corr)], tr.MODE_TRACK, beta, LAMBDA_TK, MAXITER_TK, 1e8, 0.5)[0]
+            pred = tr.predict_one_rep_device(pred, inter, beta, p.coef)
+            inter = p.ref_out
+        out = tr.trim_mean_device(pred[None], 0.1)
+        return prob, out
+
+
+def gpu_main(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = mod("_lib")
+    lib = L.lib()
+    synth = mod("synth")
+    unet = mod("unet3d").UNet3("a", weights=synth.unet_weights("a", 0), tiles_per_batch=args.tiles_per_batch,
+                               engine=args.engine)
+    ffn = mod("ffn").FFN(synth.ffn_weights(0))
+    step = Step(unet, ffn)
+    n_tiles, _ = unet.tile_count(SHAPE, SHRINK)
+
+    raw, real0, real_t = make_inputs(frame=1 + rank)
+    dev = torch.device("cuda", local_rank)
+    raw_pinned = torch.from_numpy(raw.view(np.int16)).pin_memory()
+    ref_pinned = torch.from_numpy(real0).pin_memory()
+    tgt_pinned = torch.from_numpy(real_t).pin_memory()
+    raw_dev = raw_pinned.to(dev).view(torch.uint16)
+    ref_dev, tgt_dev = ref_pinned.to(dev), tgt_pinned.to(dev)
+    tracked_dev = ref_dev.clone()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        step.run(raw_dev, ref_dev, tgt_dev, tracked_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.ct_profile_enable(1)
+    launches0 = lib.ct_launch_count()
+    times = []
+    for _ in range(args.steps):
+        flush.zero_()                                            # flush L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step.run(raw_dev, ref_dev, tgt_dev, tracked_dev)
+        e1.record()
+        times.append((e0, e1))
+    barrier()
+    launches = lib.ct_launch_count() - launches0
+    lib.ct_profile_enable(0)
+    dev_ms = sum(a.elapsed_time(b) for a, b in times)
+    import ctypes as C
+    prof = {}
+    for tag, name in ((1, "conv"), (2, "em"), (3, "ffn"), (4, "lcn")):
+        ms, cnt = C.c_double(), C.c_ulonglong()
+        lib.ct_profile_read(tag, C.byref(ms), C.byref(cnt), 1)
+        prof[name] = (ms.value, cnt.value)
+
+    # ---- end-to-end arm: host buffers in, host results out, every step
+    prob_host = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    out_host = torch.empty((N_CELLS, 3), dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        r = raw_pinned.to(dev, non_blocking=True).view(torch.uint16)
+        a = ref_pinned.to(dev, non_blocking=True)
+        b = tgt_pinned.to(dev, non_blocking=True)
+        prob, out = step.run(r, a, b, a)
+        prob_host.copy_(prob, non_blocking=True)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        voxels = SHAPE[0] * SHAPE[1] * SHAPE[2]
+        pk = peaks()
+        conv_ms, conv_n = prof["conv"]
+        conv_flops = n_tiles * FLOP_PER_TILE * args.steps
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        peak = pk["bf16_sustained"]
+        line = {
+            "metric": "voxels/s", "value": voxels * world * args.steps / (dev_ms * 1e-3), "unit": "voxels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (U-Net/FFN, reference arithmetic) + f64 (PR-GLS EM)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "unet_tiles": n_tiles,
+                       "unet_engine": args.engine, "tiles_per_batch": args.tiles_per_batch,
+                       "l2": "flushed between timed iterations (256 MiB write)",
+                       "sharding": "frames, one per GPU" if world > 1 else "single GPU",
+                       "host_watershed": "excluded (SURVEY 8f-1)"},
+            "frames_per_s": world * args.steps / (dev_ms * 1e-3),
+            "e2e": {"value": voxels * world * args.steps / (e2e_ms * 1e-3), "unit": "voxels/s",
+                    "frames_per_s": world * args.steps / (e2e_ms * 1e-3),
+                    "h2d_bytes_per_step": int(raw.nbytes + real0.nbytes + real_t.nbytes),
+                    "d2h_bytes_per_step": int(prob_host.numel() * 4 + out_host.numel() * 8)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "unet 3x3x3 conv (%s engine)" % args.engine,
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": pk["source"] + ", bf16 dense sustained",
+                         "launches": int(conv_n), "avg_launch_ms": conv_ms / max(conv_n, 1),
+                         "share_of_step": conv_ms / dev_ms if dev_ms else None, "traffic": None},
+            "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(sample_tiles=2, threads=None)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm (oracle)
+# --------------------------------------------------------------------------------------------------
+def cpu_step(sample_tiles, model, ffn_model, norm_tiles, ref, tgt):
+    """Bounded sample of one frame on the CPU oracle with the reference's control flow: `sample_tiles` U-Net tiles
+    (one predict per tile, batch 1) + ONE of the five (FFN match + PR-GLS) repetitions.  Returns seconds for a
+    whole frame, extrapolated: tiles * 75 / sample_tiles + 5 * rep."""
+    from oracle import ffn as offn
+    from oracle import prgls as oprgls
+    t0 = time.perf_counter()
+    for i in range(sample_tiles):
+        model.predict(norm_tiles[i:i + 1])
+    t_tiles = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    corr = offn.initial_matching_quick(ffn_model, ref, tgt, 20)
+    oprgls.pr_gls_quick(ref, tgt, corr, BETA=BETA_TK, max_iteration=MAXITER_TK, LAMBDA=LAMBDA_TK)
+    t_rep = time.perf_counter() - t0
+    return t_tiles, t_rep
+
+
+def cpu_baseline(sample_tiles=2, threads=None, steps=1, warmup=0):
+    import torch
+    from oracle import ffn as offn
+    from oracle import unet as ounet
+    cores = os.cpu_count() or 1
+    if threads:
+        torch.set_num_threads(threads)
+    used = torch.get_num_threads()
+    model = ounet.UNetOracle("a", ounet.random_weights("a", 0))
+    ffn_model = offn.FFNOracle(offn.random_weights(0))
+    rng = np.random.default_rng(0)
+    tiles = rng.normal(0, 1, (sample_tiles, 160, 160, 16, 1)).astype(np.float32)
+    real0, real_t = make_points()
+    for _ in range(warmup):
+        cpu_step(1, model, ffn_model, tiles, real0, real_t)
+    tt, tr = 0.0, 0.0
+    for _ in range(steps):
+        a, b = cpu_step(sample_tiles, model, ffn_model, tiles, real0, real_t)
+        tt += a; tr += b
+    tt /= steps; tr /= steps
+    n_tiles = 75
+    frame_s = tt * n_tiles / sample_tiles + REP_NUM_PRGLS * tr
+    voxels = SHAPE[0] * SHAPE[1] * SHAPE[2]
+    return {"value": voxels / frame_s, "unit": "voxels/s", "cores": used, "host_cores": cores, "kind": "port",
+            "frame_seconds_extrapolated": frame_s, "unet_s_per_tile": tt / sample_tiles, "ffn_prgls_s_per_rep": tr,
+            "sample": f"{sample_tiles} of 75 U-Net tiles (torch/oneDNN fp32, batch 1 per tile as unet3d.py:253) + 1 of 5 "
+                      f"FFN+PR-GLS repetitions (NumPy fp64, dense (M*N,122) grid as ffn.py:320), extrapolated to one "
+                      f"frame; LCN excluded (<1% of the CPU frame)",
+            "note": "CPU restatement (torch/oneDNN) -- TensorFlow is not installable in this image"}
+
+
+def make_points():
+    synth = mod("synth")
+    centres0 = synth.blob_centres(SHAPE, N_CELLS, 1234)
+    real0 = centres0 * np.array([1.0, 1.0, Z_XY_RATIO])
+    real_t = synth.move_points(real0, 1235, affine_level=0.05, noise=0.002)
+    return real0, real_t
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline(sample_tiles=2, threads=None, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    voxels = SHAPE[0] * SHAPE[1] * SHAPE[2]
+    line = {"impl": "reference", "metric": "voxels/s", "value": base["value"], "unit": "voxels/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": base["frame_seconds_extrapolated"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (U-Net/FFN) + f64 (PR-GLS EM)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": base["sample"]},
+            "frames_per_s": 1.0 / base["frame_seconds_extrapolated"],
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    assert voxels > 0
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05"])
+    ap.add_argument("--tiles-per-batch", type=int, default=15)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_main(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        gpu_main(args)
+
+
+if __name__ == "__main__":
+    main()

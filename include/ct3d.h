@@ -32,6 +32,11 @@ int ct_abi_version(void);
 const char* ct_last_error(void);
 /* Number of kernels this library has launched in the calling process (for bench.py "gpu_launches"). */
 unsigned long long ct_launch_count(void);
+/* Opt-in profiler used by bench.py: CUDA events are recorded on the launching stream around every launch of a
+ * kernel family.  tag: 1 = U-Net convolutions, 2 = PR-GLS EM, 3 = FFN match, 4 = LCN, 5 = U-Net pool/upsample/
+ * gather/head.  ct_profile_read synchronises on the recorded events and returns their summed duration. */
+int ct_profile_enable(int on);
+int ct_profile_read(int tag, double* total_ms, unsigned long long* count, int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * LCN normalisation.  Replaces preprocess.py:170-188 (_normalize_image) + :136-167 (lcn_gpu) +
