@@ -10,8 +10,9 @@
 // a batch (ensemble members x repetitions) is one launch with one CTA per problem.  The N x N system
 //      (G diag(p) + lambda sigma^2 I)^T C^T = (Y^T P - X^T diag(p))^T
 // is non-symmetric, so it is solved like LAPACK gesv does: LU with partial pivoting (first maximum),
-// reciprocal-scaled multipliers, then back substitution.  The matrix lives in shared memory when
-// N <= 168 (N^2 * 8 B <= 220.5 KiB) and in the L2-resident workspace otherwise.
+// reciprocal-scaled multipliers, then back substitution.  The system matrix and the five per-point vectors
+// live in shared memory when they fit (N <= 164: 8 N (N|1) + 88 N bytes <= 226 KiB), otherwise the matrix
+// moves to the L2-resident workspace (vectors stay in shared memory up to N ~ 2600).
 #include "common.cuh"
 #include <vector>
 
@@ -19,7 +20,6 @@ namespace ct {
 
 constexpr int EM_THREADS = 1024;
 constexpr int EM_WARPS = EM_THREADS / 32;
-constexpr int SMEM_N_MAX = 168;
 
 struct DevProblem {
     CtPrglsProblem p;
@@ -174,36 +174,38 @@ __device__ void greedy_prior(const DevProblem& d, int mode, double threshold, Sc
 }
 
 // ---------------------------------------------------------------------------------------------
-// LU with partial pivoting + back substitution on S (ld = N), 3 right-hand sides in rhs (N,3).
+// LU with partial pivoting + back substitution on S (leading dimension ld), 3 right-hand sides in rhs (N,3).
+// Per elimination step: warp 0 does the panel work (pivot search = LAPACK idamax "first maximum", row swap,
+// reciprocal-scaled multipliers), one barrier, all 32 warps do the rank-1 trailing update, one barrier.
+// ld is odd when S is in shared memory, so column walks (stride ld doubles) are bank-conflict free.
 // ---------------------------------------------------------------------------------------------
-__device__ void lu_solve(double* __restrict__ S, int N, double* __restrict__ rhs, double* __restrict__ mult,
-                         Scratch& s) {
+__device__ void lu_solve(double* __restrict__ S, int N, int ld, double* __restrict__ rhs, double* __restrict__ mult) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int k = 0; k < N; ++k) {
-        // pivot: first maximum of |S[i][k]|, i >= k   (LAPACK idamax)
-        double v = -1.0;
-        int pi = 0x7fffffff;
-        for (int i = k + tid; i < N; i += EM_THREADS) better(v, pi, fabs(S[(size_t)i * N + k]), i);
-        block_argmax(v, pi, s);
-        if (pi != k) {
-            for (int j = k + tid; j < N; j += EM_THREADS) {
-                const double a = S[(size_t)k * N + j], b = S[(size_t)pi * N + j];
-                S[(size_t)k * N + j] = b; S[(size_t)pi * N + j] = a;
+        if (w == 0) {
+            double v = -1.0;
+            int pi = 0x7fffffff;
+            for (int i = k + lane; i < N; i += 32) better(v, pi, fabs(S[(size_t)i * ld + k]), i);
+            warp_argmax(v, pi);
+            if (pi != k) {
+                for (int j = k + lane; j < N; j += 32) {
+                    const double a = S[(size_t)k * ld + j], b = S[(size_t)pi * ld + j];
+                    S[(size_t)k * ld + j] = b; S[(size_t)pi * ld + j] = a;
+                }
+                if (lane < 3) {
+                    const double a = rhs[3 * k + lane], b = rhs[3 * pi + lane];
+                    rhs[3 * k + lane] = b; rhs[3 * pi + lane] = a;
+                }
+                __syncwarp();
             }
-            if (tid < 3) {
-                const double a = rhs[3 * k + tid], b = rhs[3 * pi + tid];
-                rhs[3 * k + tid] = b; rhs[3 * pi + tid] = a;
-            }
-            __syncthreads();
+            const double rinv = 1.0 / S[(size_t)k * ld + k];
+            for (int i = k + 1 + lane; i < N; i += 32) mult[i] = S[(size_t)i * ld + k] * rinv;
         }
-        const double rinv = 1.0 / S[(size_t)k * N + k];
-        for (int i = k + 1 + tid; i < N; i += EM_THREADS) mult[i] = S[(size_t)i * N + k] * rinv;
         __syncthreads();
-        // trailing update: warp w takes rows k+1+w, k+1+w+32, ...; lanes run along the row
         for (int i = k + 1 + w; i < N; i += EM_WARPS) {
             const double l = mult[i];
-            double* __restrict__ row = S + (size_t)i * N;
-            const double* __restrict__ piv = S + (size_t)k * N;
+            double* __restrict__ row = S + (size_t)i * ld;
+            const double* __restrict__ piv = S + (size_t)k * ld;
             for (int j = k + 1 + lane; j < N; j += 32) row[j] = fma(-l, piv[j], row[j]);
             if (lane < 3) rhs[3 * i + lane] = fma(-l, rhs[3 * k + lane], rhs[3 * i + lane]);
         }
@@ -212,15 +214,22 @@ __device__ void lu_solve(double* __restrict__ S, int N, double* __restrict__ rhs
     // back substitution: warp d solves column d
     if (w < 3) {
         for (int k = N - 1; k >= 0; --k) {
-            const double x = rhs[3 * k + w] / S[(size_t)k * N + k];
+            const double x = rhs[3 * k + w] / S[(size_t)k * ld + k];
             __syncwarp();
             if (lane == 0) rhs[3 * k + w] = x;
-            for (int i = lane; i < k; i += 32) rhs[3 * i + w] = fma(-S[(size_t)i * N + k], x, rhs[3 * i + w]);
+            for (int i = lane; i < k; i += 32) rhs[3 * i + w] = fma(-S[(size_t)i * ld + k], x, rhs[3 * i + w]);
             __syncwarp();
         }
     }
     __syncthreads();
 }
+
+// Shared-memory plan of one CTA (dynamic): the five small vectors (11 N doubles) first, then the N x ld system
+// when it fits.  EM_SMEM_BUDGET leaves room for the static Scratch.
+constexpr size_t EM_SMEM_BUDGET = 232448 - 1024;
+__host__ __device__ inline int sys_ld(int N) { return N | 1; }
+__host__ __device__ inline bool vec_fits(int N) { return (size_t)88 * N <= EM_SMEM_BUDGET; }
+__host__ __device__ inline bool sys_fits(int N) { return (size_t)88 * N + (size_t)8 * N * sys_ld(N) <= EM_SMEM_BUDGET; }
 
 // ---------------------------------------------------------------------------------------------
 // the EM kernel
@@ -236,7 +245,16 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
     const double* X = d.p.ref;
     const double* Y = d.p.tgt;
     double* P = d.p.post;
-    double* S = (N <= SMEM_N_MAX) ? dyn_smem : d.sys;
+    // small vectors in shared memory when they fit (N <= ~2600), else in the workspace
+    const bool vsm = vec_fits(N);
+    double* rhs = vsm ? dyn_smem : d.rhs;
+    double* mult = vsm ? dyn_smem + 3 * (size_t)N : d.mult;
+    double* cur = vsm ? dyn_smem + 4 * (size_t)N : d.cur;
+    double* colsum = vsm ? dyn_smem + 7 * (size_t)N : d.colsum;
+    double* ytp = vsm ? dyn_smem + 8 * (size_t)N : d.ytp;
+    const bool ssm = sys_fits(N);
+    double* S = ssm ? dyn_smem + 11 * (size_t)N : d.sys;
+    const int ld = ssm ? sys_ld(N) : N;
     const double two_b2 = 2.0 * prm.beta * prm.beta;
     const bool prior_f32 = lite && !d.p.corr_is_f64;
 
@@ -262,7 +280,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
         }
         for (int e = tid; e < 3 * L; e += EM_THREADS) d.cur_l[e] = d.p.tracked[e];
     }
-    for (int e = tid; e < 3 * N; e += EM_THREADS) d.cur[e] = X[e];
+    for (int e = tid; e < 3 * N; e += EM_THREADS) cur[e] = X[e];
     double acc = 0.0;
     for (size_t e = tid; e < (size_t)M * N; e += EM_THREADS) {
         const int m = (int)(e / N), n = (int)(e % N);
@@ -282,10 +300,12 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
         const double outlier = lite ? gamma / prm.vol : gamma * norm15 / ((1.0 - gamma) * prm.vol);
         const double one_m_g = 1.0 - gamma;
         for (int m = w; m < M; m += EM_WARPS) {
-            const double* y = Y + 3 * m;
+            const double y0 = Y[3 * m], y1 = Y[3 * m + 1], y2 = Y[3 * m + 2];
             double rs = 0.0;
             for (int n = lane; n < N; n += 32) {
-                const double like = exp(-dist2(d.cur + 3 * n, y) / two_s2);
+                const double dx = cur[3 * n] - y0, dy = cur[3 * n + 1] - y1, dz = cur[3 * n + 2] - y2;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                const double like = exp(-d2 / two_s2);
                 const double pr = d.prior[(size_t)m * N + n];
                 // NumPy dtype rule kept: a float32 prior times the scalar (1 - gamma) is a float32 product
                 // (trackerlite.py:377-378 with prior from simple_match on the float32 FFN output)
@@ -306,6 +326,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             for (int t = tid; t < R * N; t += EM_THREADS) {
                 const int g = t / N, n = t % N;
                 double c0 = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 4
                 for (int m = g; m < M; m += R) {
                     const double pv = P[(size_t)m * N + n];
                     c0 += pv;
@@ -321,8 +342,8 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
                     const double* o = d.colpart + 4 * ((size_t)g * N + n);
                     c0 += o[0]; a0 += o[1]; a1 += o[2]; a2 += o[3];
                 }
-                d.colsum[n] = c0;
-                d.ytp[3 * n] = a0; d.ytp[3 * n + 1] = a1; d.ytp[3 * n + 2] = a2;
+                colsum[n] = c0;
+                ytp[3 * n] = a0; ytp[3 * n + 1] = a1; ytp[3 * n + 2] = a2;
             }
         }
         __syncthreads();
@@ -330,17 +351,19 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
         //   S = a^T:  S[i][j] = p_i G[i][j] + lambda sigma^2 [i==j]     (G symmetric)
         //   rhs[i]  = ytp_i - p_i * base_i,  base = X (TRACK) or the current prediction (LITE)
         const double reg = prm.lambda * sigma2;
-        for (size_t e = tid; e < (size_t)N * N; e += EM_THREADS) {
-            const int i = (int)(e / N), j = (int)(e % N);
-            // the reference adds lambda*sigma^2*I to the dense product: same two roundings here
-            double v = d.gram[e] * d.colsum[i];
-            if (i == j) v += reg;
-            S[e] = v;
+        for (int i = w; i < N; i += EM_WARPS) {
+            const double pi_ = colsum[i];
+            const double* g = d.gram + (size_t)i * N;
+            double* srow = S + (size_t)i * ld;
+            for (int j = lane; j < N; j += 32) {
+                double v = g[j] * pi_;
+                if (i == j) v += reg;
+                srow[j] = v;
+            }
         }
-        const double* base = lite ? d.cur : X;
-        for (int e = tid; e < 3 * N; e += EM_THREADS) d.rhs[e] = d.ytp[e] - base[e] * d.colsum[e / 3];
+        for (int e = tid; e < 3 * N; e += EM_THREADS) rhs[e] = ytp[e] - (lite ? cur[e] : X[e]) * colsum[e / 3];
         __syncthreads();
-        lu_solve(S, N, d.rhs, d.mult, s);      // rhs now holds W = C^T (N,3)
+        lu_solve(S, N, ld, rhs, mult);      // rhs now holds W = C^T (N,3)
         // ---------------- apply: move = G W   (track.py:100 / trackerlite.py:337-341)
         double move2 = 0.0;
         for (int i = w; i < N; i += EM_WARPS) {
@@ -348,15 +371,15 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             const double* g = d.gram + (size_t)i * N;
             for (int j = lane; j < N; j += 32) {
                 const double gv = g[j];
-                a0 = fma(gv, d.rhs[3 * j], a0); a1 = fma(gv, d.rhs[3 * j + 1], a1); a2 = fma(gv, d.rhs[3 * j + 2], a2);
+                a0 = fma(gv, rhs[3 * j], a0); a1 = fma(gv, rhs[3 * j + 1], a1); a2 = fma(gv, rhs[3 * j + 2], a2);
             }
             a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
             if (lane == 0) {
                 if (lite) {
                     move2 += a0 * a0 + a1 * a1 + a2 * a2;
-                    if (it > 1) { d.cur[3 * i] += a0; d.cur[3 * i + 1] += a1; d.cur[3 * i + 2] += a2; }
+                    if (it > 1) { cur[3 * i] += a0; cur[3 * i + 1] += a1; cur[3 * i + 2] += a2; }
                 } else {
-                    d.cur[3 * i] = X[3 * i] + a0; d.cur[3 * i + 1] = X[3 * i + 1] + a1; d.cur[3 * i + 2] = X[3 * i + 2] + a2;
+                    cur[3 * i] = X[3 * i] + a0; cur[3 * i + 1] = X[3 * i + 1] + a1; cur[3 * i + 2] = X[3 * i + 2] + a2;
                 }
             }
         }
@@ -365,21 +388,25 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             for (int e = tid; e < 3 * L; e += EM_THREADS) {
                 const int l = e / 3, dim = e % 3;
                 double a = 0.0;
-                for (int n = 0; n < N; ++n) a = fma(d.gram_nl[(size_t)n * L + l], d.rhs[3 * n + dim], a);
+                for (int n = 0; n < N; ++n) a = fma(d.gram_nl[(size_t)n * L + l], rhs[3 * n + dim], a);
                 d.cur_l[e] += a;
             }
         }
         if (lite) move2 = block_sum(move2, s); else __syncthreads();
         // ---------------- gamma, sigma^2 (track.py:103-112 / trackerlite.py:342-350)
         double cs = 0.0;
-        for (int n = tid; n < N; n += EM_THREADS) cs += d.colsum[n];
+        for (int n = tid; n < N; n += EM_THREADS) cs += colsum[n];
         const double sumP = block_sum(cs, s);
         gamma = 1.0 - sumP / (double)M;
         if (lite && gamma < 1e-4) gamma = 1e-4;
         double q = 0.0;
         for (int m = w; m < M; m += EM_WARPS) {
-            const double* y = Y + 3 * m;
-            for (int n = lane; n < N; n += 32) q = fma(P[(size_t)m * N + n], dist2(d.cur + 3 * n, y), q);
+            const double y0 = Y[3 * m], y1 = Y[3 * m + 1], y2 = Y[3 * m + 2];
+            for (int n = lane; n < N; n += 32) {
+                const double dx = cur[3 * n] - y0, dy = cur[3 * n + 1] - y1, dz = cur[3 * n + 2] - y2;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                q = fma(P[(size_t)m * N + n], d2, q);
+            }
         }
         sigma2 = block_sum(q, s) / (3.0 * sumP);
         if (!lite && sigma2 < 1.0) sigma2 = 1.0;
@@ -388,8 +415,8 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
 
     // ---- outputs
     for (int e = tid; e < 3 * N; e += EM_THREADS) {
-        if (d.p.ref_out) d.p.ref_out[e] = d.cur[e];
-        if (d.p.coef) d.p.coef[(size_t)(e % 3) * N + e / 3] = (iterations > 0) ? d.rhs[e] : 0.0;
+        if (d.p.ref_out) d.p.ref_out[e] = cur[e];
+        if (d.p.coef) d.p.coef[(size_t)(e % 3) * N + e / 3] = (iterations > 0) ? rhs[e] : 0.0;
     }
     if (lite && d.p.tracked_out)
         for (int e = tid; e < 3 * L; e += EM_THREADS) d.p.tracked_out[e] = d.cur_l[e];
@@ -446,7 +473,7 @@ static Layout layout_for(int N, int M, int L) {
     auto take = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
     o.gram = take((size_t)N * N * 8);
     o.gram_nl = take((size_t)N * (L > 0 ? L : 1) * 8);
-    o.sys = take(N > SMEM_N_MAX ? (size_t)N * N * 8 : 8);
+    o.sys = take(sys_fits(N) ? 8 : (size_t)N * N * 8);
     o.prior = take((size_t)M * N * 8);
     o.colsum = take((size_t)N * 8);
     o.ytp = take((size_t)N * 24);
@@ -510,11 +537,16 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
     }
     CT_REQUIRE(off <= ws_bytes, "ct_prgls: workspace too small (%zu < %zu)", ws_bytes, off);
     CT_CUDA(cudaMemcpyAsync(ws, host.data(), (size_t)batch * sizeof(DevProblem), cudaMemcpyHostToDevice, s));
-    const size_t smem = (max_n <= SMEM_N_MAX) ? (size_t)max_n * max_n * 8 : 0;
+    // every CTA carves its own plan out of the same allocation: size it for the most demanding problem
+    size_t smem = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int n = problems[b].n_ref;
+        const size_t need = sys_fits(n) ? (size_t)88 * n + (size_t)8 * n * sys_ld(n) : (vec_fits(n) ? (size_t)88 * n : 0);
+        if (need > smem) smem = need;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        CT_CUDA(cudaFuncSetAttribute(prgls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SMEM_N_MAX * SMEM_N_MAX * 8));
+        CT_CUDA(cudaFuncSetAttribute(prgls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
         attr_set = true;
     }
     ProfScope prof(PROF_EM, s);
