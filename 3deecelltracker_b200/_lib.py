@@ -50,6 +50,9 @@ SIGNATURES = {
     "ct_unet_flops_per_tile": (c_double, [c_void_p]),
     "ct_unet_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "ct_unet_predict_tiles": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "ct_unet_conv_block_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "ct_unet_conv_block": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_size_t, c_void_p]),
     "ct_unet_tile_count": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(c_int * 3), C.POINTER(c_int * 3)]),
     "ct_unet3_prediction": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_int * 3),
                                     c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),

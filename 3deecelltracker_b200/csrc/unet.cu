@@ -144,6 +144,37 @@ head_scatter(const float4* __restrict__ slab, size_t slab_stride4, size_t last_o
     }
 }
 
+// Keras channels-last (B, X, Y, Z, C) <-> c4-blocked [B][C/4][X][Y][Z][4] (channel pad = 0); used by the
+// single-block operator ct_unet_conv_block.
+__global__ void __launch_bounds__(256)
+ndhwc_to_c4(const float* __restrict__ src, float4* __restrict__ dst, size_t vol, int c, int c4, size_t total) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = idx % vol;
+        const size_t r = idx / vol;
+        const int ck = (int)(r % c4);
+        const size_t b = r / c4;
+        const float* s = src + (b * vol + v) * c + ck * 4;
+        float q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = (ck * 4 + j < c) ? s[j] : 0.f;
+        dst[idx] = make_float4(q[0], q[1], q[2], q[3]);
+    }
+}
+__global__ void __launch_bounds__(256)
+c4_to_ndhwc(const float4* __restrict__ src, float* __restrict__ dst, size_t vol, int c, int c4, size_t total) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = idx % vol;
+        const size_t r = idx / vol;
+        const int ck = (int)(r % c4);
+        const size_t b = r / c4;
+        const float4 q = src[idx];
+        float* d = dst + (b * vol + v) * c + ck * 4;
+        const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (ck * 4 + j < c) d[j] = qq[j];
+    }
+}
+
 static int grid_for(size_t work) {
     size_t b = (work + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
@@ -415,6 +446,55 @@ static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode,
                                        net->last_c / 4, net->head_w, net->head_b, prob, mode, t0, X, Y, Z, TX, TY, TZ,
                                        num[1], num[2], centre[0], centre[1], centre[2], shrink[0], shrink[1], shrink[2]);
         CT_LAUNCHED("head_scatter");
+    }
+    return 0;
+}
+
+extern "C" size_t ct_unet_conv_block_workspace_bytes(const CtUNet* net, int layer, int batch, int x, int y, int z) {
+    if (!net || layer < 0 || layer >= (int)net->layers.size() || batch < 1) return 0;
+    const ConvLayer& L = net->layers[layer];
+    const size_t vol = (size_t)x * y * z;
+    return ((size_t)L.cin_pad + (size_t)L.cout) * vol * sizeof(float) * (size_t)batch + 512;
+}
+
+extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, const float* in, float* out, int batch,
+                                  int x, int y, int z, void* ws, size_t ws_bytes, void* stream) {
+    CT_REQUIRE(net && in && out && ws, "ct_unet_conv_block: null argument");
+    CT_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "ct_unet_conv_block: layer %d out of range", layer);
+    CT_REQUIRE(batch >= 1 && x > 0 && y > 0 && z > 0, "ct_unet_conv_block: bad shape");
+    CT_REQUIRE(engine == 1 || engine == 2, "ct_unet_conv_block: engine must be 1 (direct) or 2 (tcgen05)");
+    CT_REQUIRE(ws_bytes >= ct_unet_conv_block_workspace_bytes(net, layer, batch, x, y, z), "ct_unet_conv_block: workspace too small");
+    CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_unet_conv_block: workspace must be 256-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const ConvLayer& L = net->layers[layer];
+    const size_t vol = (size_t)x * y * z;
+    // one "slab" per batch entry: [cin_pad planes | cout planes]
+    const size_t stride = ((size_t)L.cin_pad + L.cout) * vol;
+    float* slab0 = static_cast<float*>(ws);
+    Op op{};
+    op.kind = OP_CONV; op.layer = layer; op.src_off = 0; op.dst_off = (size_t)L.cin_pad * vol;
+    op.src_c = L.cin_pad; op.dst_c = L.cout; op.src_coff = 0; op.dst_coff = 0; op.c = L.cout;
+    op.sx = op.dx = x; op.sy = op.dy = y; op.sz = op.dz = z;
+    const int cin4 = L.cin_pad / 4, cout4 = L.cout / 4;
+    for (int b = 0; b < batch; ++b) {
+        const size_t total = vol * cin4;
+        ndhwc_to_c4<<<grid_for(total), 256, 0, s>>>(in + (size_t)b * vol * L.cin, reinterpret_cast<float4*>(slab0 + b * stride),
+                                                     vol, L.cin, cin4, total);
+        CT_LAUNCHED("ndhwc_to_c4");
+    }
+    if (engine == 2) {
+        const int rc = launch_conv_tc(net, op, slab0, stride, batch, s);
+        CT_REQUIRE(rc != 2, "ct_unet_conv_block: layer %d (cin %d, cout %d, z %d) is not supported by the tcgen05 engine",
+                   layer, L.cin, L.cout, z);
+        if (rc) return 1;
+    } else if (launch_conv_direct(net, op, slab0, stride, batch, s)) {
+        return 1;
+    }
+    for (int b = 0; b < batch; ++b) {
+        const size_t total = vol * cout4;
+        c4_to_ndhwc<<<grid_for(total), 256, 0, s>>>(reinterpret_cast<const float4*>(slab0 + b * stride + op.dst_off),
+                                                     out + (size_t)b * vol * L.cout, vol, L.cout, cout4, total);
+        CT_LAUNCHED("c4_to_ndhwc");
     }
     return 0;
 }

@@ -1,9 +1,422 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the tensor-core engine lands; the CUDA-core
-// engine in unet_direct.cu takes every layer while this returns "unsupported").
+// tcgen05 implicit-GEMM 3x3x3 'same' convolution with fused bias -> LeakyReLU/ReLU -> BatchNorm(eval).
+//
+// Replaces one Conv3D + LeakyReLU + BatchNormalization block of unet3d.py:117-119 (or the ReLU variant
+// :139-140) for a batch of independent tiles, on the 5th-generation tensor cores.
+//
+// GEMM view.  M = output voxels, N = Cout, K = 27 taps x Cin.  One CTA owns an output block of
+// BX (x) x 16 (y) x 8 (z) voxels = BX UMMA tiles of M = 128 (row r of a tile is voxel y = r / 8, z = r % 8),
+// all Cout channels, accumulated in tensor memory.
+//
+// A operand = im2col WITHOUT materialisation.  Per 4-channel input chunk, TMA loads the haloed input block
+// (BX+2) x 18 x 10 voxels x 16 B straight from the c4-blocked activation tensor into shared memory
+// (5-D tensor map; out-of-bounds coordinates are zero filled, which IS the Keras 'same' padding of the tile).
+// A voxel-chunk is 16 bytes = one row of a no-swizzle K-major UMMA core matrix; 8 consecutive z voxels are
+// one core matrix, the 16 y rows of the block sit at a uniform stride of 160 B (SBO).  The A tile of tap
+// (dx,dy,dz) is therefore the SAME shared-memory block addressed from a shifted start address; the two K
+// halves of one K = 8 MMA are two different taps (LBO = address distance between the taps).
+//
+// Precision.  The reference computes in fp32 (TF-CPU); parity target 1e-4 on probabilities after 15 stacked
+// convolutions.  kind::tf32 alone (10-bit mantissa) cannot meet it, so both operands are split
+// x = hi + lo (hi = RN_tf32(x), lo = x - hi, exact) and the product uses every cross term:
+//   D[:, 0:N)  += (A_hi + A_lo) * B_hi,     D[:, N:2N) += (A_hi + A_lo) * B_lo
+// i.e. two MMAs per K step (A_hi, A_lo) against one B tile [B_hi | B_lo] of 2N columns; the epilogue adds the
+// two column halves.  Activations stay single fp32 tensors in HBM: four converter warps split the TMA-landed
+// block in place inside shared memory (hi overwrites the raw plane, lo goes to a second plane).
+//
+// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one lane),
+// warps 2-5 = hi/lo converters during the main loop, then epilogue (tcgen05.ld -> bias/activation/BN ->
+// 16-byte channel-chunk stores).  Stage ring: full (TMA landed) -> conv (split done) -> empty (MMAs retired).
 #include "unet_common.cuh"
+#include <cuda.h>
+#include <cstring>
+#include <mutex>
 
 namespace ct {
-size_t tc_weight_floats(int, int) { return 0; }
-void tc_pack_weights(const float*, int, int, int, float*) {}
-int launch_conv_tc(const CtUNet*, const Op&, float*, size_t, int, cudaStream_t) { return 2; }
+
+constexpr int TC_SYH = 18, TC_SZH = 10;          // haloed block extent in y and z (16 + 2, 8 + 2)
+constexpr int TC_PAIRS = 14;                     // 27 taps -> 14 K=8 steps (tap 0 is paired with a zero column)
+
+// voxel offset of tap t = (dx*3 + dy)*3 + dz inside the haloed block (x stride 180, y stride 10)
+__host__ __device__ constexpr int tap_off(int t) { return ((t / 9) * TC_SYH + (t / 3) % 3) * TC_SZH + t % 3; }
+// K step p covers taps (first, second); step 0 is (tap 0, zero weights read at tap 1's address)
+__host__ __device__ constexpr int pair_first(int p) { return p == 0 ? 0 : 2 * p - 1; }
+__host__ __device__ constexpr int pair_second(int p) { return p == 0 ? 1 : 2 * p; }
+
+template <int N, int BX, int STAGES>
+struct TcCfg {
+    static constexpr int NP = 2 * N;                                   // accumulator columns per M tile
+    static constexpr int SXH = BX + 2;
+    static constexpr int PLANE = SXH * TC_SYH * TC_SZH * 16;           // bytes of one (hi or lo) plane
+    static constexpr int B_BYTES = TC_PAIRS * NP * 32;                 // [pair][k half][2N rows][16 B]
+    static constexpr int STAGE = 2 * PLANE + B_BYTES;
+    static constexpr int COLS_NEEDED = BX * NP;
+    static constexpr int TMEM_COLS = COLS_NEEDED <= 32 ? 32 : COLS_NEEDED <= 64 ? 64 : COLS_NEEDED <= 128 ? 128
+                                     : COLS_NEEDED <= 256 ? 256 : 512;
+    static constexpr int SMEM = STAGES * STAGE + 1024;                 // + slack to align the ring to 1 KiB
+    static_assert(COLS_NEEDED <= 512, "accumulators exceed tensor memory");
+    static_assert(PLANE % 128 == 0 && B_BYTES % 128 == 0, "stage parts must stay 128-byte aligned");
+    static_assert(NP % 16 == 0 && NP <= 256, "UMMA N out of range for M = 128");
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every MMA issued so far by this thread has retired
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float rn_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major: ((8, m), 2) : ((16 B, SBO), LBO)   [units of 16 B]
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr_bytes, uint32_t lbo16, uint32_t sbo16) {
+    const uint32_t lo = ((addr_bytes >> 4) & 0x3FFFu) | ((lbo16 & 0x3FFFu) << 16);
+    const uint32_t hi = (sbo16 & 0x3FFFu) | (1u << 14);            // descriptor version 1 (sm_100)
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int N, int BX, int STAGES>
+__global__ void __launch_bounds__(192)
+conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
+                const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                float alpha, float4* __restrict__ dst, int cin4, int X, int Y, int Z, int nbx, int nby,
+                size_t dst_tile_stride4, int dst_c4off) {
+    using Cfg = TcCfg<N, BX, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float ep_s[3][N];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int b = blockIdx.x;
+    const int bxi = b % nbx; b /= nbx;
+    const int byi = b % nby; b /= nby;
+    const int x0 = bxi * BX, y0 = byi * 16, z0 = b * 8;
+    const int tile = blockIdx.y;
+    uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_conv[s], 4);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+    if (threadIdx.x >= 64) {
+        for (int i = threadIdx.x - 64; i < 3 * N; i += 128)
+            ep_s[i / N][i % N] = (i < N) ? bias[i] : (i < 2 * N ? scale[i - N] : shift[i - 2 * N]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ---------------- TMA producer
+        if (lane == 0) {
+            for (int c = 0; c < cin4; ++c) {
+                const int s = c % STAGES, use = c / STAGES;
+                if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1);
+                uint8_t* st = ring + (size_t)s * Cfg::STAGE;
+                mbar_expect_tx(&bar_full[s], Cfg::PLANE + Cfg::B_BYTES);
+                tma_load_5d(st, &tmap, &bar_full[s], (z0 - 1) * 4, y0 - 1, x0 - 1, c, tile);
+                bulk_load(st + 2 * Cfg::PLANE, wpack + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &bar_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 2N, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Cfg::NP >> 3) << 17) | (8u << 24);
+            const uint32_t ring_addr = smem_u32(ring);
+            for (int c = 0; c < cin4; ++c) {
+                const int s = c % STAGES, use = c / STAGES;
+                mbar_wait(&bar_conv[s], use & 1);
+                tc_fence_after();
+                const uint32_t a_hi = ring_addr + s * Cfg::STAGE, a_lo = a_hi + Cfg::PLANE, b_base = a_hi + 2 * Cfg::PLANE;
+#pragma unroll
+                for (int p = 0; p < TC_PAIRS; ++p) {
+                    const uint32_t off = (uint32_t)tap_off(pair_first(p)) * 16u;
+                    const uint32_t lbo = (uint32_t)(tap_off(pair_second(p)) - tap_off(pair_first(p)));
+                    const uint64_t bdesc = smem_desc(b_base + p * (Cfg::NP * 32), Cfg::NP, 8);
+#pragma unroll 2
+                    for (int i = 0; i < BX; ++i) {
+                        const uint32_t xo = off + (uint32_t)i * (TC_SYH * TC_SZH * 16);
+                        const uint32_t d = tmem_base + (uint32_t)i * Cfg::NP;
+                        umma_tf32(d, smem_desc(a_hi + xo, lbo, TC_SZH), bdesc, idesc, (c | p) != 0);
+                        umma_tf32(d, smem_desc(a_lo + xo, lbo, TC_SZH), bdesc, idesc, 1u);
+                    }
+                }
+                umma_commit(&bar_empty[s]);
+            }
+            umma_commit(&bar_acc);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- converters: split the landed block into tf32 hi / lo planes, in place
+        const int ct = threadIdx.x - 64;
+        for (int c = 0; c < cin4; ++c) {
+            const int s = c % STAGES, use = c / STAGES;
+            mbar_wait(&bar_full[s], use & 1);
+            float4* hi = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE);
+            float4* lo = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE + Cfg::PLANE);
+#pragma unroll 4
+            for (int i = ct; i < Cfg::PLANE / 16; i += 128) {
+                const float4 v = hi[i];
+                float4 h, l;
+                h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                hi[i] = h;
+                lo[i] = l;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_conv[s]);
+        }
+        // ---------------- epilogue
+        mbar_wait(&bar_acc, 0);
+        tc_fence_after();
+        const int q = warp & 3;                        // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const int y = y0 + (row >> 3), z = z0 + (row & 7);
+        const bool y_ok = y < Y;
+        const size_t vol = (size_t)X * Y * Z;
+        float4* d_tile = dst + (size_t)tile * dst_tile_stride4 + (size_t)dst_c4off * vol;
+#pragma unroll 1
+        for (int i = 0; i < BX; ++i) {
+            const int x = x0 + i;
+            if (x >= X) break;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)i * Cfg::NP;
+            const size_t vox = ((size_t)x * Y + y) * Z + z;
+#pragma unroll
+            for (int g = 0; g < N / 8; ++g) {
+                float a[8], c2[8];
+                tmem_ld8(taddr + g * 8, a);
+                tmem_ld8(taddr + N + g * 8, c2);
+                tmem_ld_wait();
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float t = (a[k] + c2[k]) + ep_s[0][g * 8 + k];
+                    t = t > 0.f ? t : alpha * t;
+                    o[k] = fmaf(t, ep_s[1][g * 8 + k], ep_s[2][g * 8 + k]);
+                }
+                if (y_ok) {
+                    d_tile[(size_t)(2 * g) * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
+                    d_tile[(size_t)(2 * g + 1) * vol + vox] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static float host_rn_tf32(float v) {
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return v;       // inf / nan pass through
+    u += 0x0FFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
+static bool tc_shape_ok(int cout) { return cout == 8 || cout == 16 || cout == 32 || cout == 64; }
+
+size_t tc_weight_floats(int cin_pad, int cout) {
+    if (!tc_shape_ok(cout)) return 0;
+    return (size_t)(cin_pad / 4) * TC_PAIRS * 2 * (2 * cout) * 4;
+}
+
+// keras kernel (kx,ky,kz,ci,co) -> [ci/4][pair][k half][row: co (hi) | cout + co (lo)][ci % 4]
+void tc_pack_weights(const float* w, int cin, int cin_pad, int cout, float* dst) {
+    const int np = 2 * cout;
+    std::memset(dst, 0, tc_weight_floats(cin_pad, cout) * sizeof(float));
+    for (int c = 0; c < cin_pad / 4; ++c)
+        for (int p = 0; p < TC_PAIRS; ++p)
+            for (int j = 0; j < 2; ++j) {
+                if (p == 0 && j == 1) continue;          // zero column paired with tap 0
+                const int tap = j == 0 ? pair_first(p) : pair_second(p);
+                float* blk = dst + ((((size_t)c * TC_PAIRS + p) * 2 + j) * np) * 4;
+                for (int co = 0; co < cout; ++co)
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const int ci = c * 4 + qd;
+                        if (ci >= cin) continue;
+                        const float v = w[((size_t)tap * cin + ci) * cout + co];
+                        const float h = host_rn_tf32(v);
+                        blk[(size_t)co * 4 + qd] = h;
+                        blk[(size_t)(cout + co) * 4 + qd] = v - h;
+                    }
+            }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+template <int N, int BX, int STAGES>
+static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, float4* dst, int X, int Y, int Z,
+                     size_t stride4, int dst_c4off, int tiles, cudaStream_t s) {
+    using Cfg = TcCfg<N, BX, STAGES>;
+    static bool attr = false;
+    if (!attr) {
+        CT_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr = true;
+    }
+    const int nbx = cdiv(X, BX), nby = cdiv(Y, 16), nbz = Z / 8;
+    dim3 grid(nbx * nby * nbz, tiles);
+    conv3_tc_kernel<N, BX, STAGES><<<grid, 192, Cfg::SMEM, s>>>(map, L.w_tc, L.bias, L.scale, L.shift, alpha, dst,
+                                                              L.cin_pad / 4, X, Y, Z, nbx, nby, stride4, dst_c4off);
+    return 0;
+}
+
+template <int BX>
+static int make_map(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, int tiles, size_t slab_stride) {
+    EncodeTiledFn enc = encode_fn();
+    CT_REQUIRE(enc, "unet: cuTensorMapEncodeTiled is unavailable in this driver");
+    const cuuint64_t dims[5] = {(cuuint64_t)Z * 4, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)c4, (cuuint64_t)tiles};
+    const cuuint64_t strides[4] = {(cuuint64_t)Z * 16, (cuuint64_t)Y * Z * 16, (cuuint64_t)X * Y * Z * 16,
+                                   (cuuint64_t)slab_stride * 4};
+    const cuuint32_t box[5] = {TC_SZH * 4, TC_SYH, BX + 2, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CT_REQUIRE(r == CUDA_SUCCESS, "unet: cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return 0;
+}
+
+int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
+    const ConvLayer& L = net->layers[op.layer];
+    const int X = op.sx, Y = op.sy, Z = op.sz;
+    if (!L.w_tc || !tc_shape_ok(L.cout) || Z % 8 != 0 || tiles > 65535) return 2;
+    CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
+    CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
+    float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
+    CUtensorMap map;
+    ProfScope prof(PROF_CONV, s);
+    int rc;
+    if (L.cout == 32) {
+        if (make_map<8>(&map, slab0 + op.src_off, X, Y, Z, L.cin_pad / 4, tiles, slab_stride)) return 1;
+        rc = launch_tc<32, 8, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
+    } else {
+        if (make_map<4>(&map, slab0 + op.src_off, X, Y, Z, L.cin_pad / 4, tiles, slab_stride)) return 1;
+        if (L.cout == 8) rc = launch_tc<8, 4, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
+        else if (L.cout == 16) rc = launch_tc<16, 4, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
+        else rc = launch_tc<64, 4, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
+    }
+    if (rc) return 1;
+    CT_LAUNCHED("conv3_tc_kernel");
+    return 0;
+}
+
 }  // namespace ct

@@ -169,6 +169,22 @@ class UNet3:
         dev = to_device(arr[..., 0].astype(np.float32, copy=False), torch.float32)
         return self.predict_device(dev).cpu().numpy()[..., None]
 
+    def conv_block_device(self, layer, x_dev, engine="tcgen05"):
+        """One Conv3D + LeakyReLU/ReLU + BatchNorm block (unet3d.py:101-141) on a channels-last CUDA tensor
+        (B, x, y, z, Cin) float32 -> (B, x, y, z, Cout) float32.  `layer` indexes the conv blocks in graph order."""
+        cin, cout = _conv_layers(self._spec)[layer]
+        b, x, y, z, c = (int(v) for v in x_dev.shape)
+        if c != cin:
+            raise ValueError(f"layer {layer} expects {cin} input channels, got {c}")
+        lib = _lib.lib()
+        x_dev = x_dev.contiguous()
+        out = torch.empty((b, x, y, z, cout), dtype=torch.float32, device=x_dev.device)
+        ws = WORKSPACE.get("unet_block", lib.ct_unet_conv_block_workspace_bytes(self._handle, layer, b, x, y, z))
+        wp = aligned_ptr(ws)
+        _lib.check(lib.ct_unet_conv_block(self._handle, int(layer), ENGINES[engine], x_dev.data_ptr(), out.data_ptr(),
+                                          b, x, y, z, wp, ws.numel() - (wp - ws.data_ptr()), stream_ptr()))
+        return out
+
     # ---- unet3_prediction on a device-resident normalised volume
     def tile_count(self, shape_xyz, shrink):
         sh = (C.c_int * 3)(*[int(s) for s in shrink])

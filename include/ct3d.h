@@ -76,7 +76,7 @@ typedef struct CtUNet CtUNet;
 size_t ct_unet_weight_count(const CtUNetSpec* spec);
 int ct_unet_create(const CtUNetSpec* spec, const float* weights_host, size_t n_floats, CtUNet** out);
 void ct_unet_destroy(CtUNet* net);
-/* engine: 0 = auto, 1 = CUDA-core fp32 direct convolution, 2 = tcgen05 implicit GEMM (3xTF32). */
+/* engine: 0 = auto, 1 = CUDA-core fp32 direct convolution, 2 = tcgen05 implicit GEMM (split TF32: hi/lo operands, all cross terms). */
 int ct_unet_set_engine(CtUNet* net, int engine);
 double ct_unet_flops_per_tile(const CtUNet* net);
 
@@ -84,6 +84,13 @@ size_t ct_unet_workspace_bytes(const CtUNet* net, int tiles_per_batch);
 /* Keras `model.predict(tiles)`: tiles (B, x, y, z) float32 -> prob (B, x, y, z) float32. */
 int ct_unet_predict_tiles(const CtUNet* net, const float* tiles, float* prob, int batch,
                           void* ws, size_t ws_bytes, int tiles_per_batch, void* stream);
+/* One Conv3D(3, 'same') + LeakyReLU/ReLU + BatchNormalization block (unet3d.py:101-141) of the network, on
+ * Keras channels-last tensors: in (B, x, y, z, Cin) float32 -> out (B, x, y, z, Cout) float32.  `layer` indexes the
+ * network's conv blocks in graph order; engine 1 = CUDA-core fp32, 2 = tcgen05 (split-TF32).  Any x, y; the tcgen05
+ * engine needs z % 8 == 0. */
+size_t ct_unet_conv_block_workspace_bytes(const CtUNet* net, int layer, int batch, int x, int y, int z);
+int ct_unet_conv_block(const CtUNet* net, int layer, int engine, const float* in, float* out, int batch,
+                       int x, int y, int z, void* ws, size_t ws_bytes, void* stream);
 /* Number of tiles unet3_prediction visits for a volume (unet3d.py:226-228,259-279). */
 int ct_unet_tile_count(const CtUNet* net, int x, int y, int z, const int shrink[3], int counts_out[3]);
 /* unet3_prediction over tiles [tile_begin, tile_end) of the (i,j,k) row-major tile grid: reflect
