@@ -49,13 +49,17 @@ struct TcCfg {
     static constexpr int PLANE = SXH * TC_SYH * TC_SZH * 16;           // bytes of one (hi or lo) plane
     static constexpr int B_BYTES = TC_PAIRS * NP * 32;                 // [pair][k half][2N rows][16 B]
     static constexpr int STAGE = 2 * PLANE + B_BYTES;
-    static constexpr int COLS_NEEDED = BX * NP;
+    static constexpr int SET_COLS = BX * NP;                           // one accumulator set
+    static constexpr int COLS_NEEDED = 2 * SET_COLS;                   // ping-pong sets
     static constexpr int TMEM_COLS = COLS_NEEDED <= 32 ? 32 : COLS_NEEDED <= 64 ? 64 : COLS_NEEDED <= 128 ? 128
                                      : COLS_NEEDED <= 256 ? 256 : 512;
     static constexpr int SMEM = STAGES * STAGE + 1024;                 // + slack to align the ring to 1 KiB
+    static constexpr int TILES_PER_HALF = BX / 2;                      // M tiles drained by one worker thread
+    static_assert(BX % 2 == 0, "BX must be even (two worker halves)");
     static_assert(COLS_NEEDED <= 512, "accumulators exceed tensor memory");
     static_assert(PLANE % 128 == 0 && B_BYTES % 128 == 0, "stage parts must stay 128-byte aligned");
     static_assert(NP % 16 == 0 && NP <= 256, "UMMA N out of range for M = 128");
+    static_assert(SMEM <= 232448, "shared memory ring too large");
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -157,39 +161,65 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr_bytes, uint32_t lbo1
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int TC_WORKERS = 256;                  // 8 worker warps: two per TMEM lane quarter
+constexpr int TC_THREADS = 64 + TC_WORKERS;
+
+struct TcGeom {
+    int cin4, X, Y, Z, nbx, nby, nbz, units;     // units = nbx * nby * nbz * tiles
+    int dst_c4off;
+    size_t dst_tile_stride4;
+};
+
+struct TcUnit { int x0, y0, z0, tile; };
+__device__ __forceinline__ TcUnit tc_unit(int u, const TcGeom& g, int bx) {
+    TcUnit r;
+    r.x0 = (u % g.nbx) * bx; u /= g.nbx;
+    r.y0 = (u % g.nby) * 16; u /= g.nby;
+    r.z0 = (u % g.nbz) * 8;
+    r.tile = u / g.nbz;
+    return r;
+}
+
+// Persistent CTA (one per SM).  Work unit = BX x 16 x 8 output voxels x all Cout of one tile; units are taken
+// round-robin.  `g` counts K stages (4-channel input chunks) across all units of the CTA: ring slot g % STAGES,
+// accumulator set g & 1.  Every stage accumulates into a FRESH tensor-memory set (28 MMAs per accumulator) that
+// the worker warps drain into fp32 registers while the next stage's MMAs run: the tensor core adds with
+// truncation, so long in-TMEM accumulation chains would bias the result by ~K/8 * 2^-25 (measured 2e-5 at
+// K = 3456); register accumulation rounds to nearest.
 template <int N, int BX, int STAGES>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
                 const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
-                float alpha, float4* __restrict__ dst, int cin4, int X, int Y, int Z, int nbx, int nby,
-                size_t dst_tile_stride4, int dst_c4off) {
+                float alpha, float4* __restrict__ dst, const TcGeom geo) {
     using Cfg = TcCfg<N, BX, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc;
+    __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float ep_s[3][N];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int b = blockIdx.x;
-    const int bxi = b % nbx; b /= nbx;
-    const int byi = b % nby; b /= nby;
-    const int x0 = bxi * BX, y0 = byi * 16, z0 = b * 8;
-    const int tile = blockIdx.y;
     uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int cin4 = geo.cin4;
+    const int n_units = ((int)blockIdx.x < geo.units) ? (geo.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_stages = n_units * cin4;
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_conv[s], 4);
+            mbar_init(&bar_conv[s], TC_WORKERS / 32);
             mbar_init(&bar_empty[s], 1);
         }
-        mbar_init(&bar_acc, 1);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_acc_full[a], 1);
+            mbar_init(&bar_acc_empty[a], TC_WORKERS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
     if (threadIdx.x >= 64) {
-        for (int i = threadIdx.x - 64; i < 3 * N; i += 128)
+        for (int i = threadIdx.x - 64; i < 3 * N; i += TC_WORKERS)
             ep_s[i / N][i % N] = (i < N) ? bias[i] : (i < 2 * N ? scale[i - N] : shift[i - 2 * N]);
     }
     tc_fence_before();
@@ -200,13 +230,17 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
     if (warp == 0) {
         // ---------------- TMA producer
         if (lane == 0) {
-            for (int c = 0; c < cin4; ++c) {
-                const int s = c % STAGES, use = c / STAGES;
-                if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1);
-                uint8_t* st = ring + (size_t)s * Cfg::STAGE;
-                mbar_expect_tx(&bar_full[s], Cfg::PLANE + Cfg::B_BYTES);
-                tma_load_5d(st, &tmap, &bar_full[s], (z0 - 1) * 4, y0 - 1, x0 - 1, c, tile);
-                bulk_load(st + 2 * Cfg::PLANE, wpack + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &bar_full[s]);
+            int g = 0;
+            for (int k = 0; k < n_units; ++k) {
+                const TcUnit un = tc_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+                for (int c = 0; c < cin4; ++c, ++g) {
+                    const int s = g % STAGES, use = g / STAGES;
+                    if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1);
+                    uint8_t* st = ring + (size_t)s * Cfg::STAGE;
+                    mbar_expect_tx(&bar_full[s], Cfg::PLANE + Cfg::B_BYTES);
+                    tma_load_5d(st, &tmap, &bar_full[s], (un.z0 - 1) * 4, un.y0 - 1, un.x0 - 1, c, un.tile);
+                    bulk_load(st + 2 * Cfg::PLANE, wpack + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &bar_full[s]);
+                }
             }
         }
         __syncwarp();
@@ -216,11 +250,13 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 2N, M = 128
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Cfg::NP >> 3) << 17) | (8u << 24);
             const uint32_t ring_addr = smem_u32(ring);
-            for (int c = 0; c < cin4; ++c) {
-                const int s = c % STAGES, use = c / STAGES;
+            for (int g = 0; g < n_stages; ++g) {
+                const int s = g % STAGES, use = g / STAGES, set = g & 1, use_a = g >> 1;
+                if (use_a > 0) mbar_wait(&bar_acc_empty[set], (use_a - 1) & 1);
                 mbar_wait(&bar_conv[s], use & 1);
                 tc_fence_after();
                 const uint32_t a_hi = ring_addr + s * Cfg::STAGE, a_lo = a_hi + Cfg::PLANE, b_base = a_hi + 2 * Cfg::PLANE;
+                const uint32_t d_set = tmem_base + (uint32_t)set * Cfg::SET_COLS;
 #pragma unroll
                 for (int p = 0; p < TC_PAIRS; ++p) {
                     const uint32_t off = (uint32_t)tap_off(pair_first(p)) * 16u;
@@ -229,70 +265,103 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
 #pragma unroll 2
                     for (int i = 0; i < BX; ++i) {
                         const uint32_t xo = off + (uint32_t)i * (TC_SYH * TC_SZH * 16);
-                        const uint32_t d = tmem_base + (uint32_t)i * Cfg::NP;
-                        umma_tf32(d, smem_desc(a_hi + xo, lbo, TC_SZH), bdesc, idesc, (c | p) != 0);
+                        const uint32_t d = d_set + (uint32_t)i * Cfg::NP;
+                        umma_tf32(d, smem_desc(a_hi + xo, lbo, TC_SZH), bdesc, idesc, p != 0);
                         umma_tf32(d, smem_desc(a_lo + xo, lbo, TC_SZH), bdesc, idesc, 1u);
                     }
                 }
                 umma_commit(&bar_empty[s]);
+                umma_commit(&bar_acc_full[set]);
             }
-            umma_commit(&bar_acc);
         }
         __syncwarp();
     } else {
-        // ---------------- converters: split the landed block into tf32 hi / lo planes, in place
-        const int ct = threadIdx.x - 64;
-        for (int c = 0; c < cin4; ++c) {
-            const int s = c % STAGES, use = c / STAGES;
-            mbar_wait(&bar_full[s], use & 1);
-            float4* hi = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE);
-            float4* lo = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE + Cfg::PLANE);
-#pragma unroll 4
-            for (int i = ct; i < Cfg::PLANE / 16; i += 128) {
-                const float4 v = hi[i];
-                float4 h, l;
-                h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
-                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                hi[i] = h;
-                lo[i] = l;
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_conv[s]);
-        }
-        // ---------------- epilogue
-        mbar_wait(&bar_acc, 0);
-        tc_fence_after();
+        // ---------------- workers: tf32 hi/lo split of the landed block, accumulator drain, epilogue
+        const int wt = threadIdx.x - 64;
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;              // which BX/2 M tiles this thread drains
         const int row = q * 32 + lane;
-        const int y = y0 + (row >> 3), z = z0 + (row & 7);
-        const bool y_ok = y < Y;
-        const size_t vol = (size_t)X * Y * Z;
-        float4* d_tile = dst + (size_t)tile * dst_tile_stride4 + (size_t)dst_c4off * vol;
-#pragma unroll 1
-        for (int i = 0; i < BX; ++i) {
-            const int x = x0 + i;
-            if (x >= X) break;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)i * Cfg::NP;
-            const size_t vox = ((size_t)x * Y + y) * Z + z;
+        const size_t vol = (size_t)geo.X * geo.Y * geo.Z;
+        float acc[Cfg::TILES_PER_HALF][N];
+
+        auto drain = [&](int g, bool first) {
+            const int set = g & 1, use_a = g >> 1;
+            mbar_wait(&bar_acc_full[set], use_a & 1);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * Cfg::SET_COLS +
+                                (uint32_t)(half * Cfg::TILES_PER_HALF) * Cfg::NP;
 #pragma unroll
-            for (int g = 0; g < N / 8; ++g) {
-                float a[8], c2[8];
-                tmem_ld8(taddr + g * 8, a);
-                tmem_ld8(taddr + N + g * 8, c2);
-                tmem_ld_wait();
-                float o[8];
+            for (int i = 0; i < Cfg::TILES_PER_HALF; ++i) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float t = (a[k] + c2[k]) + ep_s[0][g * 8 + k];
-                    t = t > 0.f ? t : alpha * t;
-                    o[k] = fmaf(t, ep_s[1][g * 8 + k], ep_s[2][g * 8 + k]);
-                }
-                if (y_ok) {
-                    d_tile[(size_t)(2 * g) * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
-                    d_tile[(size_t)(2 * g + 1) * vol + vox] = make_float4(o[4], o[5], o[6], o[7]);
+                for (int n8 = 0; n8 < N / 8; ++n8) {
+                    float a[8], b2[8];
+                    tmem_ld8(t0 + i * Cfg::NP + n8 * 8, a);
+                    tmem_ld8(t0 + i * Cfg::NP + N + n8 * 8, b2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float v = a[k] + b2[k];
+                        acc[i][n8 * 8 + k] = first ? v : acc[i][n8 * 8 + k] + v;
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_empty[set]);
+        };
+        auto store_unit = [&](const TcUnit& un) {
+            const int y = un.y0 + (row >> 3), z = un.z0 + (row & 7);
+            if (y >= geo.Y) return;
+            float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)geo.dst_c4off * vol;
+#pragma unroll
+            for (int i = 0; i < Cfg::TILES_PER_HALF; ++i) {
+                const int x = un.x0 + half * Cfg::TILES_PER_HALF + i;
+                if (x >= geo.X) break;
+                const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
+#pragma unroll
+                for (int c4 = 0; c4 < N / 4; ++c4) {
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float t = acc[i][c4 * 4 + k] + ep_s[0][c4 * 4 + k];
+                        t = t > 0.f ? t : alpha * t;
+                        o[k] = fmaf(t, ep_s[1][c4 * 4 + k], ep_s[2][c4 * 4 + k]);
+                    }
+                    d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        };
+
+        // flattened stage loop: stage g is split, then stage g - 1 is drained while the MMAs of stage g run
+        int c = 0, k = 0;                              // chunk / unit ordinal of stage g
+        int pc = 0;                                    // chunk of stage g - 1
+        TcUnit prev{};
+        for (int g = 0; g <= n_stages; ++g) {
+            if (g < n_stages) {
+                const int s = g % STAGES, use = g / STAGES;
+                mbar_wait(&bar_full[s], use & 1);
+                float4* hi = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE);
+                float4* lo = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE + Cfg::PLANE);
+#pragma unroll 4
+                for (int i = wt; i < Cfg::PLANE / 16; i += TC_WORKERS) {
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_conv[s]);
+            }
+            if (g > 0) {
+                drain(g - 1, pc == 0);
+                if (pc == cin4 - 1) store_unit(prev);
+            }
+            if (c == 0) prev = tc_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+            pc = c;
+            if (++c == cin4) { c = 0; ++k; }
         }
         tc_fence_before();
     }
@@ -363,6 +432,16 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int N, int BX, int STAGES>
 static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, float4* dst, int X, int Y, int Z,
                      size_t stride4, int dst_c4off, int tiles, cudaStream_t s) {
@@ -372,10 +451,13 @@ static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, fl
         CT_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr = true;
     }
-    const int nbx = cdiv(X, BX), nby = cdiv(Y, 16), nbz = Z / 8;
-    dim3 grid(nbx * nby * nbz, tiles);
-    conv3_tc_kernel<N, BX, STAGES><<<grid, 192, Cfg::SMEM, s>>>(map, L.w_tc, L.bias, L.scale, L.shift, alpha, dst,
-                                                              L.cin_pad / 4, X, Y, Z, nbx, nby, stride4, dst_c4off);
+    TcGeom g;
+    g.cin4 = L.cin_pad / 4; g.X = X; g.Y = Y; g.Z = Z;
+    g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
+    g.units = g.nbx * g.nby * g.nbz * tiles;
+    g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
+    const int grid = g.units < sm_count() ? g.units : sm_count();
+    conv3_tc_kernel<N, BX, STAGES><<<grid, TC_THREADS, Cfg::SMEM, s>>>(map, L.w_tc, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
 }
 
@@ -398,21 +480,28 @@ static int make_map(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, 
 int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;
-    if (!L.w_tc || !tc_shape_ok(L.cout) || Z % 8 != 0 || tiles > 65535) return 2;
+    if (!L.w_tc || !tc_shape_ok(L.cout) || Z % 8 != 0) return 2;
     CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
     CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
     float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
     CUtensorMap map;
     ProfScope prof(PROF_CONV, s);
     int rc;
-    if (L.cout == 32) {
-        if (make_map<8>(&map, slab0 + op.src_off, X, Y, Z, L.cin_pad / 4, tiles, slab_stride)) return 1;
-        rc = launch_tc<32, 8, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
+    const size_t st4 = slab_stride / 4;
+    const int co4 = op.dst_coff / 4, c4 = L.cin_pad / 4;
+    float* src = slab0 + op.src_off;
+    if (L.cout == 8) {
+        if (make_map<8>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
+        rc = launch_tc<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
+    } else if (L.cout == 16) {
+        if (make_map<8>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
+        rc = launch_tc<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
+    } else if (L.cout == 32) {
+        if (make_map<4>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
+        rc = launch_tc<32, 4, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
     } else {
-        if (make_map<4>(&map, slab0 + op.src_off, X, Y, Z, L.cin_pad / 4, tiles, slab_stride)) return 1;
-        if (L.cout == 8) rc = launch_tc<8, 4, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
-        else if (L.cout == 16) rc = launch_tc<16, 4, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
-        else rc = launch_tc<64, 4, 2>(map, L, net->alpha, dst, X, Y, Z, slab_stride / 4, op.dst_coff / 4, tiles, s);
+        if (make_map<2>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
+        rc = launch_tc<64, 2, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
     }
     if (rc) return 1;
     CT_LAUNCHED("conv3_tc_kernel");

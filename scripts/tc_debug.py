@@ -36,13 +36,28 @@ for li in only:
               f"tc err {np.abs(out['tcgen05']-ref).max()/sc:.2e}", flush=True)
 print("block checks done")
 # whole network, both engines
-tiles = rng.normal(0, 1, (2, 160, 160, 16, 1)).astype(np.float32)
+ntile = 15
+model = u.UNet3("a", weights=ws, tiles_per_batch=ntile)
+tiles = torch.from_numpy(rng.normal(0, 1, (ntile, 160, 160, 16)).astype(np.float32)).cuda()
 res = {}
 for eng in ("direct", "tcgen05"):
     model.set_engine(eng)
-    model.predict(tiles)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    res[eng] = model.predict(tiles)
-    torch.cuda.synchronize(); print(eng, "2 tiles", time.perf_counter() - t0, "s")
-d = np.abs(res["direct"].astype(np.float64) - res["tcgen05"]) / np.maximum(np.abs(res["direct"]), 1e-30)
+    for _ in range(2):
+        res[eng] = model.predict_device(tiles)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        model.predict_device(tiles)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"{eng}: {ntile} tiles {ms:.3f} ms -> {ntile * 35.573e9 / ms / 1e9:.1f} TFLOP/s, {ms / ntile * 75:.2f} ms per 75-tile volume")
+a_, b_ = res["direct"].double().cpu().numpy(), res["tcgen05"].double().cpu().numpy()
+d = np.abs(a_ - b_) / np.maximum(np.abs(a_), 1e-30)
 print("full net direct vs tc: max rel", d.max(), "q99.99", np.quantile(d, 0.9999))
+want64 = ounet.UNetOracle("a", ws, dtype=torch.float64)
+with torch.no_grad():
+    y64 = want64.forward(tiles[:1].cpu().double()[:, None]).numpy()[0, 0]
+for eng in ("direct", "tcgen05"):
+    r = np.abs(res[eng][0].double().cpu().numpy() - y64) / np.maximum(np.abs(y64), 1e-30)
+    print(eng, "vs fp64 oracle: max rel", r.max(), "q99.99", np.quantile(r, 0.9999))
