@@ -120,6 +120,20 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a converged warp.  The compiler recognises elect.sync and issues the uniform-datapath instructions
+// (UTCHMMA, UTMALDG) once; a `lane == 0` test instead wraps each of them in an ELECT/branch loop (~60 clk per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread for the CTA
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -229,7 +243,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
 
     if (warp == 0) {
         // ---------------- TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int g = 0;
             for (int k = 0; k < n_units; ++k) {
                 const TcUnit un = tc_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
@@ -246,28 +260,33 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         __syncwarp();
     } else if (warp == 1) {
         // ---------------- MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 2N, M = 128
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Cfg::NP >> 3) << 17) | (8u << 24);
-            const uint32_t ring_addr = smem_u32(ring);
+            // descriptor high words: SBO | version 1.  A: 16 y rows 160 B apart; B: 8-row groups 128 B apart
+            constexpr uint64_t a_hi_word = (uint64_t)((uint32_t)TC_SZH | (1u << 14)) << 32;
+            constexpr uint64_t b_hi_word = (uint64_t)(8u | (1u << 14)) << 32;
+            const uint32_t ring16 = smem_u32(ring) >> 4;           // everything below in 16-byte units (< 2^14)
             for (int g = 0; g < n_stages; ++g) {
                 const int s = g % STAGES, use = g / STAGES, set = g & 1, use_a = g >> 1;
                 if (use_a > 0) mbar_wait(&bar_acc_empty[set], (use_a - 1) & 1);
                 mbar_wait(&bar_conv[s], use & 1);
                 tc_fence_after();
-                const uint32_t a_hi = ring_addr + s * Cfg::STAGE, a_lo = a_hi + Cfg::PLANE, b_base = a_hi + 2 * Cfg::PLANE;
+                const uint32_t a_hi = ring16 + (uint32_t)s * (Cfg::STAGE / 16), a_lo = a_hi + Cfg::PLANE / 16;
+                const uint32_t b_base = a_hi + 2 * (Cfg::PLANE / 16);
                 const uint32_t d_set = tmem_base + (uint32_t)set * Cfg::SET_COLS;
 #pragma unroll
                 for (int p = 0; p < TC_PAIRS; ++p) {
-                    const uint32_t off = (uint32_t)tap_off(pair_first(p)) * 16u;
-                    const uint32_t lbo = (uint32_t)(tap_off(pair_second(p)) - tap_off(pair_first(p)));
-                    const uint64_t bdesc = smem_desc(b_base + p * (Cfg::NP * 32), Cfg::NP, 8);
-#pragma unroll 2
+                    const uint32_t lbo = (uint32_t)(tap_off(pair_second(p)) - tap_off(pair_first(p))) << 16;
+                    const uint32_t ah = (a_hi + (uint32_t)tap_off(pair_first(p))) | lbo;
+                    const uint32_t al = (a_lo + (uint32_t)tap_off(pair_first(p))) | lbo;
+                    const uint64_t bdesc = b_hi_word | (uint64_t)((b_base + (uint32_t)p * (Cfg::NP * 2)) | ((uint32_t)Cfg::NP << 16));
+#pragma unroll
                     for (int i = 0; i < BX; ++i) {
-                        const uint32_t xo = off + (uint32_t)i * (TC_SYH * TC_SZH * 16);
+                        const uint32_t xo = (uint32_t)i * (TC_SYH * TC_SZH);
                         const uint32_t d = d_set + (uint32_t)i * Cfg::NP;
-                        umma_tf32(d, smem_desc(a_hi + xo, lbo, TC_SZH), bdesc, idesc, p != 0);
-                        umma_tf32(d, smem_desc(a_lo + xo, lbo, TC_SZH), bdesc, idesc, 1u);
+                        umma_tf32(d, a_hi_word | (uint64_t)(ah + xo), bdesc, idesc, p != 0);
+                        umma_tf32(d, a_hi_word | (uint64_t)(al + xo), bdesc, idesc, 1u);
                     }
                 }
                 umma_commit(&bar_empty[s]);
