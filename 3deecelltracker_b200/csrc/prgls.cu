@@ -198,10 +198,20 @@ __device__ void greedy_prior(const DevProblem& d, int mode, double threshold, Sc
 // elimination because the right-hand sides are columns of S).
 // ---------------------------------------------------------------------------------------------
 constexpr int LU_NB = 8;
+constexpr int LU_PANEL_THREADS = 384;     // SM path: warps 0-5 = one thread per row, warps 6-11 = one per column
 
-__device__ void lu_solve(double* __restrict__ S, int N, int ld, double* __restrict__ sol) {
+__device__ __forceinline__ void panel_barrier(bool sm) {
+    if (sm) asm volatile("bar.sync 1, %0;" ::"n"(LU_PANEL_THREADS) : "memory");
+    else __syncthreads();
+}
+
+// SM = true: S is the shared-memory copy (N <= 164, so one thread per row / per column covers a panel step and
+// only the first 12 warps take part in phase A, on a named barrier).  SM = false: S is in the workspace (any N).
+template <bool SM>
+__device__ __forceinline__ void lu_solve(double* __restrict__ S, const int N, const int ld, double* __restrict__ sol) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int NC = N + 3;
+    const int TA = SM ? LU_PANEL_THREADS / 2 : EM_THREADS;        // stride of the row / column loops of phase A
     {   // scale row 0
         const double r = 1.0 / S[0];
         for (int c = 1 + tid; c < NC; c += EM_THREADS) S[c] *= r;
@@ -210,80 +220,118 @@ __device__ void lu_solve(double* __restrict__ S, int N, int ld, double* __restri
     for (int k0 = 0; k0 < N; k0 += LU_NB) {
         const int kend = (k0 + LU_NB < N) ? k0 + LU_NB : N;
         // ---------------- phase A
-        for (int j = k0; j + 1 < kend; ++j) {
-            const double* __restrict__ rowj = S + (size_t)j * ld;
-            double* __restrict__ rown = S + (size_t)(j + 1) * ld;       // row finished (and scaled) by this step
-            // region 1: one thread per row below j, panel columns (j, kend)
-            for (int i = j + 1 + tid; i < N; i += EM_THREADS) {
-                double* __restrict__ row = S + (size_t)i * ld;
-                const double l = row[j];
-                if (i == j + 1) {
-                    const double rn = 1.0 / fma(-l, rowj[j + 1], row[j + 1]);
-                    for (int c = j + 2; c < kend; ++c) row[c] = fma(-l, rowj[c], row[c]) * rn;
-                } else {
-                    for (int c = j + 1; c < kend; ++c) row[c] = fma(-l, rowj[c], row[c]);
+        if (!SM || tid < LU_PANEL_THREADS) {
+            const bool row_role = !SM || tid < TA, col_role = !SM || tid >= TA;
+            const int t = SM ? (tid < TA ? tid : tid - TA) : tid;
+            for (int j = k0; j + 1 < kend; ++j) {
+                double* rowj = S + j * ld;
+                double* rown = rowj + ld;                              // row j + 1: finished (and scaled) by this step
+                if (row_role) {
+                    // one thread per row below j: its remaining panel columns (j, kend)
+                    for (int i = j + 1 + t; i < N; i += TA) {
+                        double* row = S + i * ld;
+                        const double l = row[j];
+                        double v[LU_NB - 1];
+#pragma unroll
+                        for (int q = 0; q < LU_NB - 1; ++q) {
+                            const int c = j + 1 + q;
+                            v[q] = (c < kend) ? fma(-l, rowj[c], row[c]) : 0.0;
+                        }
+                        if (i == j + 1) {
+                            const double rn = 1.0 / v[0];              // the new pivot; its slot stays stale on purpose
+#pragma unroll
+                            for (int q = 1; q < LU_NB - 1; ++q)
+                                if (j + 1 + q < kend) row[j + 1 + q] = v[q] * rn;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < LU_NB - 1; ++q)
+                                if (j + 1 + q < kend) row[j + 1 + q] = v[q];
+                        }
+                    }
                 }
-            }
-            // region 2: one thread per column right of the panel, panel rows (j, kend); upper thread half
-            for (int c = kend + (tid ^ (EM_THREADS - 1)); c < NC; c += EM_THREADS) {
-                const double u = rowj[c];
-                const double ln = rown[j];
-                const double rn = 1.0 / fma(-ln, rowj[j + 1], rown[j + 1]);
-                rown[c] = fma(-ln, u, rown[c]) * rn;
-                for (int i = j + 2; i < kend; ++i) {
-                    double* __restrict__ row = S + (size_t)i * ld;
-                    row[c] = fma(-row[j], u, row[c]);
+                if (col_role) {
+                    // one thread per column right of the panel: the panel rows (j, kend)
+                    for (int c = kend + t; c < NC; c += TA) {
+                        const double u = rowj[c];
+                        const double rn = 1.0 / fma(-rown[j], rowj[j + 1], rown[j + 1]);
+                        double v[LU_NB - 1];
+#pragma unroll
+                        for (int q = 0; q < LU_NB - 1; ++q) {
+                            const int i = j + 1 + q;
+                            v[q] = (i < kend) ? fma(-rowj[(q + 1) * ld + j], u, rowj[(q + 1) * ld + c]) : 0.0;
+                        }
+                        rown[c] = v[0] * rn;
+#pragma unroll
+                        for (int q = 1; q < LU_NB - 1; ++q)
+                            if (j + 1 + q < kend) rown[q * ld + c] = v[q];
+                    }
                 }
+                panel_barrier(SM);
             }
-            __syncthreads();
         }
         if (kend >= N) break;
-        // ---------------- phase B: S[i][c] -= sum_j S[i][j] S[j][c], i >= kend, c >= kend
+        if (SM) __syncthreads();
+        // ---------------- phase B: S[i][c] -= sum_j S[i][j] S[j][c], i >= kend, c >= kend  (4 x 2 register tiles)
         {
             const int nb = kend - k0;
             const int rows = N - kend, cols = NC - kend;
             const int rblocks = (rows + 3) >> 2, cstrips = (cols + 63) >> 6;
-            for (int item = w; item < rblocks * cstrips; item += EM_WARPS) {
-                const int rb = item / cstrips, cs = item - rb * cstrips;
+            const int items = rblocks * cstrips;
+            int rb = w / cstrips, cs = w - rb * cstrips;                 // item = w, advanced incrementally
+            for (int item = w; item < items; item += EM_WARPS) {
                 const int i0 = kend + 4 * rb;
-                const int c0 = kend + 64 * cs + lane, c1 = c0 + 32;
-                const bool v0 = c0 < NC, v1 = c1 < NC;
+                const int c0 = kend + 64 * cs + lane;
+                const bool v0 = c0 < NC, v1 = c0 + 32 < NC;
+                const int cc0 = v0 ? c0 : kend, cc1 = v1 ? c0 + 32 : kend;     // clamped (reads only)
+                int ro[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) ro[a] = ((i0 + a < N) ? i0 + a : N - 1) * ld;
                 double acc[4][2];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int i = (i0 + a < N) ? i0 + a : N - 1;
-                    acc[a][0] = v0 ? S[(size_t)i * ld + c0] : 0.0;
-                    acc[a][1] = v1 ? S[(size_t)i * ld + c1] : 0.0;
-                }
-                for (int j = 0; j < nb; ++j) {
-                    const double* __restrict__ urow = S + (size_t)(k0 + j) * ld;
-                    const double u0 = v0 ? urow[c0] : 0.0, u1 = v1 ? urow[c1] : 0.0;
+                for (int a = 0; a < 4; ++a) { acc[a][0] = S[ro[a] + cc0]; acc[a][1] = S[ro[a] + cc1]; }
+                const double* __restrict__ up = S + k0 * ld;
+                const double* __restrict__ lp = S + k0;
+                if (nb == LU_NB) {
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const int i = (i0 + a < N) ? i0 + a : N - 1;
-                        const double l = S[(size_t)i * ld + k0 + j];
-                        acc[a][0] = fma(-l, u0, acc[a][0]);
-                        acc[a][1] = fma(-l, u1, acc[a][1]);
+                    for (int j = 0; j < LU_NB; ++j) {
+                        const double u0 = up[j * ld + cc0], u1 = up[j * ld + cc1];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const double l = lp[ro[a] + j];
+                            acc[a][0] = fma(-l, u0, acc[a][0]);
+                            acc[a][1] = fma(-l, u1, acc[a][1]);
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < nb; ++j) {
+                        const double u0 = up[j * ld + cc0], u1 = up[j * ld + cc1];
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const double l = lp[ro[a] + j];
+                            acc[a][0] = fma(-l, u0, acc[a][0]);
+                            acc[a][1] = fma(-l, u1, acc[a][1]);
+                        }
                     }
                 }
                 if (rb == 0) {
                     // row kend is final: scale it by its pivot (recomputed from entries nobody writes)
-                    const double* __restrict__ rk = S + (size_t)kend * ld;
+                    const double* __restrict__ rk = S + kend * ld;
                     double piv = rk[kend];
-                    for (int j = 0; j < nb; ++j) piv = fma(-rk[k0 + j], S[(size_t)(k0 + j) * ld + kend], piv);
+                    for (int j = 0; j < nb; ++j) piv = fma(-rk[k0 + j], up[j * ld + kend], piv);
                     const double rn = 1.0 / piv;
                     acc[0][0] *= rn;
                     acc[0][1] *= rn;
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    const int i = i0 + a;
-                    if (i < N) {
+                    if (i0 + a < N) {
                         // the (kend, kend) pivot entry stays stale on purpose (see above)
-                        if (v0 && !(i == kend && c0 == kend)) S[(size_t)i * ld + c0] = acc[a][0];
-                        if (v1) S[(size_t)i * ld + c1] = acc[a][1];
+                        if (v0 && !(a == 0 && rb == 0 && c0 == kend)) S[ro[a] + c0] = acc[a][0];
+                        if (v1) S[ro[a] + c0 + 32] = acc[a][1];
                     }
                 }
+                cs += EM_WARPS;
+                while (cs >= cstrips) { cs -= cstrips; ++rb; }
             }
         }
         __syncthreads();
@@ -291,13 +339,13 @@ __device__ void lu_solve(double* __restrict__ S, int N, int ld, double* __restri
     __syncthreads();
     // ---------------- back substitution with the unit upper factor: warp d solves right-hand side d
     if (w < 3) {
-        const int cd = N + w;
+        double* __restrict__ col = S + N + w;
         for (int k = N - 1; k > 0; --k) {
-            const double x = S[(size_t)k * ld + cd];
-            for (int i = lane; i < k; i += 32) S[(size_t)i * ld + cd] = fma(-S[(size_t)i * ld + k], x, S[(size_t)i * ld + cd]);
+            const double x = col[k * ld];
+            for (int i = lane; i < k; i += 32) col[i * ld] = fma(-S[i * ld + k], x, col[i * ld]);
             __syncwarp();
         }
-        for (int i = lane; i < N; i += 32) sol[3 * i + w] = S[(size_t)i * ld + cd];
+        for (int i = lane; i < N; i += 32) sol[3 * i + w] = col[i * ld];
     }
     __syncthreads();
 }
@@ -312,6 +360,8 @@ __host__ __device__ inline bool sys_fits(int N) { return (size_t)56 * N + (size_
 // ---------------------------------------------------------------------------------------------
 // the EM kernel
 // ---------------------------------------------------------------------------------------------
+// SM = true: every problem of the launch keeps its vectors and augmented system in shared memory (N <= 164).
+template <bool SM>
 __global__ void __launch_bounds__(EM_THREADS, 1)
 prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
     extern __shared__ double dyn_smem[];
@@ -324,13 +374,12 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
     const double* Y = d.p.tgt;
     double* P = d.p.post;
     // per-point vectors in shared memory when they fit (N <= ~4100), else in the workspace
-    const bool vsm = vec_fits(N);
-    double* rhs = vsm ? dyn_smem : d.rhs;                         // (N,3) solution W = C^T
-    double* cur = vsm ? dyn_smem + 3 * (size_t)N : d.cur;
-    double* colsum = vsm ? dyn_smem + 6 * (size_t)N : d.colsum;
+    const bool vsm = SM || vec_fits(N);
+    double* rhs = SM ? dyn_smem : (vsm ? dyn_smem : d.rhs);                         // (N,3) solution W = C^T
+    double* cur = SM ? dyn_smem + 3 * N : (vsm ? dyn_smem + 3 * (size_t)N : d.cur);
+    double* colsum = SM ? dyn_smem + 6 * N : (vsm ? dyn_smem + 6 * (size_t)N : d.colsum);
     double* ytp = d.ytp;
-    const bool ssm = sys_fits(N);
-    double* S = ssm ? dyn_smem + 7 * (size_t)N : d.sys;
+    double* S = SM ? dyn_smem + 7 * N : d.sys;
     const int ld = sys_ld(N);
     const double two_b2 = 2.0 * prm.beta * prm.beta;
     const bool prior_f32 = lite && !d.p.corr_is_f64;
@@ -443,7 +492,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             S[(size_t)i * ld + N + (e - 3 * i)] = ytp[e] - (lite ? cur[e] : X[e]) * colsum[i];
         }
         __syncthreads();
-        lu_solve(S, N, ld, rhs);            // rhs now holds W = C^T (N,3)
+        lu_solve<SM>(S, N, ld, rhs);        // rhs now holds W = C^T (N,3)
         // ---------------- apply: move = G W   (track.py:100 / trackerlite.py:337-341)
         double move2 = 0.0;
         for (int i = w; i < N; i += EM_WARPS) {
@@ -553,7 +602,7 @@ static Layout layout_for(int N, int M, int L) {
     auto take = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
     o.gram = take((size_t)N * N * 8);
     o.gram_nl = take((size_t)N * (L > 0 ? L : 1) * 8);
-    o.sys = take(sys_fits(N) ? 8 : (size_t)N * sys_ld(N) * 8);
+    o.sys = take((size_t)N * sys_ld(N) * 8);
     o.prior = take((size_t)M * N * 8);
     o.colsum = take((size_t)N * 8);
     o.ytp = take((size_t)N * 24);
@@ -624,13 +673,26 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
         const size_t need = sys_fits(n) ? (size_t)56 * n + (size_t)8 * n * sys_ld(n) : (vec_fits(n) ? (size_t)56 * n : 0);
         if (need > smem) smem = need;
     }
+    bool all_sm = true;
+    for (int b = 0; b < batch; ++b) all_sm = all_sm && sys_fits(problems[b].n_ref);
     static bool attr_set = false;
     if (!attr_set) {
-        CT_CUDA(cudaFuncSetAttribute(prgls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
+        CT_CUDA(cudaFuncSetAttribute(prgls_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
+        CT_CUDA(cudaFuncSetAttribute(prgls_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
         attr_set = true;
     }
     ProfScope prof(PROF_EM, s);
-    prgls_kernel<<<batch, EM_THREADS, smem, s>>>(static_cast<const DevProblem*>(ws), *prm);
+    if (all_sm) {
+        prgls_kernel<true><<<batch, EM_THREADS, smem, s>>>(static_cast<const DevProblem*>(ws), *prm);
+    } else {
+        // mixed / large problems: vectors in shared memory when they fit, system in the workspace
+        size_t vsmem = 0;
+        for (int b = 0; b < batch; ++b) {
+            const size_t need = vec_fits(problems[b].n_ref) ? (size_t)56 * problems[b].n_ref : 0;
+            if (need > vsmem) vsmem = need;
+        }
+        prgls_kernel<false><<<batch, EM_THREADS, vsmem, s>>>(static_cast<const DevProblem*>(ws), *prm);
+    }
     CT_LAUNCHED("prgls_kernel");
     return 0;
 }
