@@ -186,173 +186,263 @@ __device__ void greedy_prior(const DevProblem& d, int mode, double threshold, Sc
 // cond(S) = 1e4, worm4 parameters), which is what the parity tests pin.  Dropping the pivot search removes the
 // serial argmax + row swap from all N elimination steps.
 //
-// Right-looking blocked elimination, panel width 8, "row-scaled" form: after step j row j is divided by its
-// pivot (U has a unit diagonal, L carries the pivots), so the trailing updates and the back substitution contain
-// no division.  One barrier per column:
-//   phase A, step j in the panel: rows below j get their remaining PANEL columns updated (one thread per row),
-//            the panel rows below j get their columns right of the panel updated (one thread per column); the
-//            threads that finish row j+1 also scale it (each recomputes the pivot from values nobody writes).
-//   phase B: rank-8 update of the block below/right of the panel in 4 x 2 register tiles; the tiles holding the
-//            next panel's first row scale it on the way out.
-// The stale diagonal entries are never read again (unit-diagonal U, forward substitution is part of the
-// elimination because the right-hand sides are columns of S).
+// Right-looking blocked elimination, panel width 8, "row-scaled" form S = L U' with U' unit upper triangular
+// (every pivot row is divided by its pivot as soon as it is final), so only the 8 x 8 diagonal blocks see
+// divisions, and the right-hand sides -- being columns of S -- come out forward-substituted AND scaled.
+// Per panel [k0, k0+8):
+//   diag8   warp 0 eliminates the 8 x 8 diagonal block in registers (lane = (row, column pair), shuffles
+//           broadcast the pivot row).  This chain of 8 reciprocals per panel is the only serial part; it runs
+//           one panel AHEAD: in phase (3) warp 0 updates the tile holding the next diagonal block first and
+//           then factors it while the other warps finish the phase.
+//   (2)     one thread per row below the panel computes its 8 entries of L (forward substitution against U11'),
+//           one thread per column right of the panel its 8 entries of U' (forward substitution against L11,
+//           times the pivot reciprocals) -- no divisions, no communication, stores after the last load.
+//   (3)     the trailing block gets its rank-8 update on the FP64 tensor cores (mma.sync m16n8k8, K = panel
+//           width): same FMA rate as DFMA on B200 (measured 63.8 vs 62.7 FMA/clk/SM, scripts/micro/fp64_rate.cu)
+//           but a fraction of the shared-memory wavefronts of a register-tiled DFMA loop; rows and columns are
+//           permuted inside a tile so every fragment access is bank-conflict free for any odd ld.
+// Substitution (not explicit block inverses) keeps the result within ~1e-10 of LAPACK at cond(S) ~ 1e7.
+// Back substitution is blocked the same way (8 x 8 unit-upper solves in one warp + parallel updates).
+// The whole solve is bound by the FP64 pipe of ONE SM (2 N^3 / 3 flops at 64 FMA/clk) -- see DESIGN.md.
 // ---------------------------------------------------------------------------------------------
+#ifdef EM_TIMING
+// phase timers: thread 0 of block 0 accumulates clock64 deltas in SHARED memory (a global read-modify-write per tick
+// costs ~700 clk on the critical warp and swamps what is being measured)
+__device__ long long g_em_t[16];
+__shared__ long long em_t_s[16];
+#define EM_TICK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); em_t_s[k] += now_ - em_t0_; em_t0_ = clock64(); } } while (0)
+#define EM_TICK_DECL long long em_t0_ = clock64()
+#else
+#define EM_TICK(k) do { } while (0)
+#define EM_TICK_DECL do { } while (0)
+#endif
 constexpr int LU_NB = 8;
-constexpr int LU_PANEL_THREADS = 384;     // SM path: warps 0-5 = one thread per row, warps 6-11 = one per column
+constexpr int LU_SIDE_THREADS = 384;      // phase (2), SM path: warps 0-5 one thread per row, warps 6-11 one per column
 
-__device__ __forceinline__ void panel_barrier(bool sm) {
-    if (sm) asm volatile("bar.sync 1, %0;" ::"n"(LU_PANEL_THREADS) : "memory");
-    else __syncthreads();
+struct LuScratch {
+    double blk[LU_NB][LU_NB];              // factored diagonal block of the current panel (fixed stride: immediate offsets)
+    double rinv[LU_NB];                    // its pivot reciprocals
+    double x[3][LU_NB];                    // solved block of the back substitution
+};
+
+__device__ __forceinline__ void dmma_16x8x8(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
-// SM = true: S is the shared-memory copy (N <= 164, so one thread per row / per column covers a panel step and
-// only the first 12 warps take part in phase A, on a named barrier).  SM = false: S is in the workspace (any N).
+// Warp-wide elimination of the nb x nb diagonal block at (k0, k0), padded to 8 x 8 with the identity.
+// Lane = 8 q + i holds columns 2q, 2q+1 of row i.  Result in place: strictly lower = multipliers, diagonal =
+// pivots, strictly upper = U11' (scaled); rinv[j] = 1 / pivot j.
+__device__ __forceinline__ void diag8(double* __restrict__ S, const int ld, const int k0, const int nb,
+                                      double* __restrict__ rinv, double (*__restrict__ blk)[LU_NB]) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, i = lane & 7, q = lane >> 3;
+    double x[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        const int ci = 2 * q + sl;
+        x[sl] = (i < nb && ci < nb) ? S[(k0 + i) * ld + k0 + ci] : (ci == i ? 1.0 : 0.0);
+    }
+#pragma unroll 1
+    for (int j = 0; j < LU_NB; ++j) {                 // rolled on purpose: the kernel must stay I-cache resident
+        const int pl = 8 * (j >> 1);
+        const double xs = (j & 1) ? x[1] : x[0];
+        const double r = 1.0 / __shfl_sync(FULL, xs, pl + j);
+        const double mult = __shfl_sync(FULL, xs, pl + i);
+        if (lane == j) rinv[j] = r;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            const double u = __shfl_sync(FULL, x[sl], 8 * q + j) * r;
+            if (2 * q + sl > j) {
+                if (i == j) x[sl] = u;
+                else if (i > j) x[sl] = fma(-mult, u, x[sl]);
+            }
+        }
+    }
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        const int ci = 2 * q + sl;
+        if (i < nb && ci < nb) S[(k0 + i) * ld + k0 + ci] = x[sl];
+        blk[i][ci] = x[sl];
+    }
+}
+
+// One 16 x 16 tile of the rank-8 update of panel [k0, k0+8): C -= L21 U12'.
+__device__ __forceinline__ void update_tile(double* __restrict__ S, const int ld, const int N, const int NC, const int k0,
+                                            const int i0, const int c0) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int rg = 4 * (g & 3) + (g >> 2);                   // row permutation: conflict-free for any odd ld
+    const int ia = i0 + rg, ib = ia + 2;
+    const int ra = ((ia < N) ? ia : N - 1) * ld, rb = ((ib < N) ? ib : N - 1) * ld;
+    double a[4];
+    a[0] = -S[ra + k0 + t]; a[1] = -S[rb + k0 + t]; a[2] = -S[ra + k0 + t + 4]; a[3] = -S[rb + k0 + t + 4];
+    const double* __restrict__ u0 = S + (k0 + t) * ld;
+    const double* __restrict__ u1 = u0 + 4 * ld;
+    const int nofs = (g >> 1) + 4 * (g & 1);                 // column permutation inside an 8-column block
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int cb = c0 + 8 * h;
+        if (cb >= NC) break;
+        const int cn = (cb + nofs < NC) ? cb + nofs : NC - 1;
+        const int ca = cb + t, cbb = cb + t + 4;
+        const int la = (ca < NC) ? ca : NC - 1, lb = (cbb < NC) ? cbb : NC - 1;
+        double b[2], c[4];
+        b[0] = u0[cn]; b[1] = u1[cn];
+        c[0] = S[ra + la]; c[1] = S[ra + lb]; c[2] = S[rb + la]; c[3] = S[rb + lb];
+        dmma_16x8x8(c, a, b);
+        if (ia < N) {
+            if (ca < NC) S[ra + ca] = c[0];
+            if (cbb < NC) S[ra + cbb] = c[1];
+        }
+        if (ib < N) {
+            if (ca < NC) S[rb + ca] = c[2];
+            if (cbb < NC) S[rb + cbb] = c[3];
+        }
+    }
+}
+
 template <bool SM>
-__device__ __forceinline__ void lu_solve(double* __restrict__ S, const int N, const int ld, double* __restrict__ sol) {
+__device__ __forceinline__ void lu_solve(double* __restrict__ S, const int N, const int ld, double* __restrict__ sol,
+                                         LuScratch& ls) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int NC = N + 3;
-    const int TA = SM ? LU_PANEL_THREADS / 2 : EM_THREADS;        // stride of the row / column loops of phase A
-    {   // scale row 0
-        const double r = 1.0 / S[0];
-        for (int c = 1 + tid; c < NC; c += EM_THREADS) S[c] *= r;
-    }
-    __syncthreads();
-    for (int k0 = 0; k0 < N; k0 += LU_NB) {
-        const int kend = (k0 + LU_NB < N) ? k0 + LU_NB : N;
-        // ---------------- phase A
-        if (!SM || tid < LU_PANEL_THREADS) {
-            const bool row_role = !SM || tid < TA, col_role = !SM || tid >= TA;
-            const int t = SM ? (tid < TA ? tid : tid - TA) : tid;
-            for (int j = k0; j + 1 < kend; ++j) {
-                double* rowj = S + j * ld;
-                double* rown = rowj + ld;                              // row j + 1: finished (and scaled) by this step
+    const unsigned FULL = 0xffffffffu;
+    const int P = (N + LU_NB - 1) / LU_NB;
+    EM_TICK_DECL;
+    for (int p = -1; p < P; ++p) {                     // p = -1: only the look-ahead factorisation of block 0
+        const int k0 = p * LU_NB;
+        const int nb = (N - k0 < LU_NB) ? N - k0 : LU_NB;
+        const int kend = k0 + nb;
+        if (p >= 0) {
+            // ---------------- (2) L below the panel (thread per row), U' right of it (thread per column)
+            if (!SM || tid < LU_SIDE_THREADS) {
+                const int TA = SM ? LU_SIDE_THREADS / 2 : EM_THREADS;
+                const bool row_role = !SM || tid < TA, col_role = !SM || tid >= TA;
+                const int t = SM ? (tid < TA ? tid : tid - TA) : tid;
+                // the factored diagonal block is read from ls.blk (fixed stride -> immediate offsets, no index math);
+                // rows / columns of a partial last panel are padded with the identity there, so no guards are needed
+                // on the arithmetic, only on the loads / stores of S
                 if (row_role) {
-                    // one thread per row below j: its remaining panel columns (j, kend)
-                    for (int i = j + 1 + t; i < N; i += TA) {
-                        double* row = S + i * ld;
-                        const double l = row[j];
-                        double v[LU_NB - 1];
+                    for (int i = kend + t; i < N; i += TA) {
+                        double* row = S + i * ld + k0;
+                        double a[LU_NB];
 #pragma unroll
-                        for (int q = 0; q < LU_NB - 1; ++q) {
-                            const int c = j + 1 + q;
-                            v[q] = (c < kend) ? fma(-l, rowj[c], row[c]) : 0.0;
+                        for (int c = 0; c < LU_NB; ++c) a[c] = row[c];          // nb == 8 whenever rows exist below
+#pragma unroll
+                        for (int j = 1; j < LU_NB; ++j) {
+#pragma unroll
+                            for (int m = 0; m < j; ++m) a[j] = fma(-a[m], ls.blk[m][j], a[j]);
+                            asm volatile("" ::: "memory");      // 64-register budget: do not hoist all 28 block loads
                         }
-                        if (i == j + 1) {
-                            const double rn = 1.0 / v[0];              // the new pivot; its slot stays stale on purpose
 #pragma unroll
-                            for (int q = 1; q < LU_NB - 1; ++q)
-                                if (j + 1 + q < kend) row[j + 1 + q] = v[q] * rn;
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < LU_NB - 1; ++q)
-                                if (j + 1 + q < kend) row[j + 1 + q] = v[q];
-                        }
+                        for (int j = 1; j < LU_NB; ++j) row[j] = a[j];
                     }
                 }
                 if (col_role) {
-                    // one thread per column right of the panel: the panel rows (j, kend)
                     for (int c = kend + t; c < NC; c += TA) {
-                        const double u = rowj[c];
-                        const double rn = 1.0 / fma(-rown[j], rowj[j + 1], rown[j + 1]);
-                        double v[LU_NB - 1];
+                        double* col = S + k0 * ld + c;
+                        double a[LU_NB];
+                        if (nb == LU_NB) {
 #pragma unroll
-                        for (int q = 0; q < LU_NB - 1; ++q) {
-                            const int i = j + 1 + q;
-                            v[q] = (i < kend) ? fma(-rowj[(q + 1) * ld + j], u, rowj[(q + 1) * ld + c]) : 0.0;
+                            for (int j = 0; j < LU_NB; ++j) a[j] = col[j * ld];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < LU_NB; ++j) a[j] = (j < nb) ? col[j * ld] : 0.0;
                         }
-                        rown[c] = v[0] * rn;
 #pragma unroll
-                        for (int q = 1; q < LU_NB - 1; ++q)
-                            if (j + 1 + q < kend) rown[q * ld + c] = v[q];
+                        for (int j = 0; j < LU_NB; ++j) {
+#pragma unroll
+                            for (int m = 0; m < j; ++m) a[j] = fma(-ls.blk[j][m], a[m], a[j]);
+                            a[j] *= ls.rinv[j];
+                            asm volatile("" ::: "memory");
+                        }
+                        if (nb == LU_NB) {
+#pragma unroll
+                            for (int j = 0; j < LU_NB; ++j) col[j * ld] = a[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < LU_NB; ++j)
+                                if (j < nb) col[j * ld] = a[j];
+                        }
                     }
                 }
-                panel_barrier(SM);
+            }
+            __syncthreads();
+            EM_TICK(5);
+            if (kend >= N) break;
+        }
+        // ---------------- (3) trailing block -= L21 U12' (16 x 16 tiles); warp 0 looks ahead
+        {
+            const int RT = (N - kend + 15) >> 4, CG = (NC - kend + 15) >> 4;
+            const int items = (p >= 0) ? RT * CG : 0;
+            // Warp 0 takes the tile of the next diagonal block and then factors it.  The other warps of ITS scheduler
+            // (w % 4 == 0) stay out of the tensor-core work: diag8 is a chain of dependent FP64 operations, and behind a
+            // queue of DMMAs on the same FP64 pipe every link costs ~60 clk instead of 8 (measured 3600 vs ~1000 clk).
+            constexpr int WORKERS = EM_WARPS - EM_WARPS / 4;
+            if (w == 0 || (w & 3)) {
+                const int wi = (w == 0) ? 0 : w - (w >> 2);           // warp 0 -> item 0 only; workers 1..WORKERS
+                const int step = (w == 0) ? items : WORKERS;
+                int rt = wi / CG, cg = wi - rt * CG;
+                for (int item = wi; item < items; item += step) {
+                    update_tile(S, ld, N, NC, k0, kend + 16 * rt, kend + 16 * cg);
+                    cg += step;
+                    while (cg >= CG) { cg -= CG; ++rt; }
+                }
+            }
+            if (w == 0) {
+                __syncwarp();
+                EM_TICK(11);
+                const int nk = (p >= 0) ? kend : 0;
+                diag8(S, ld, nk, (N - nk < LU_NB) ? N - nk : LU_NB, ls.rinv, ls.blk);
+                EM_TICK(12);
             }
         }
-        if (kend >= N) break;
-        if (SM) __syncthreads();
-        // ---------------- phase B: S[i][c] -= sum_j S[i][j] S[j][c], i >= kend, c >= kend  (4 x 2 register tiles)
-        {
-            const int nb = kend - k0;
-            const int rows = N - kend, cols = NC - kend;
-            const int rblocks = (rows + 3) >> 2, cstrips = (cols + 63) >> 6;
-            const int items = rblocks * cstrips;
-            int rb = w / cstrips, cs = w - rb * cstrips;                 // item = w, advanced incrementally
-            for (int item = w; item < items; item += EM_WARPS) {
-                const int i0 = kend + 4 * rb;
-                const int c0 = kend + 64 * cs + lane;
-                const bool v0 = c0 < NC, v1 = c0 + 32 < NC;
-                const int cc0 = v0 ? c0 : kend, cc1 = v1 ? c0 + 32 : kend;     // clamped (reads only)
-                int ro[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) ro[a] = ((i0 + a < N) ? i0 + a : N - 1) * ld;
-                double acc[4][2];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) { acc[a][0] = S[ro[a] + cc0]; acc[a][1] = S[ro[a] + cc1]; }
-                const double* __restrict__ up = S + k0 * ld;
-                const double* __restrict__ lp = S + k0;
-                if (nb == LU_NB) {
-#pragma unroll
-                    for (int j = 0; j < LU_NB; ++j) {
-                        const double u0 = up[j * ld + cc0], u1 = up[j * ld + cc1];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            const double l = lp[ro[a] + j];
-                            acc[a][0] = fma(-l, u0, acc[a][0]);
-                            acc[a][1] = fma(-l, u1, acc[a][1]);
-                        }
-                    }
-                } else {
-                    for (int j = 0; j < nb; ++j) {
-                        const double u0 = up[j * ld + cc0], u1 = up[j * ld + cc1];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            const double l = lp[ro[a] + j];
-                            acc[a][0] = fma(-l, u0, acc[a][0]);
-                            acc[a][1] = fma(-l, u1, acc[a][1]);
-                        }
-                    }
-                }
-                if (rb == 0) {
-                    // row kend is final: scale it by its pivot (recomputed from entries nobody writes)
-                    const double* __restrict__ rk = S + kend * ld;
-                    double piv = rk[kend];
-                    for (int j = 0; j < nb; ++j) piv = fma(-rk[k0 + j], up[j * ld + kend], piv);
-                    const double rn = 1.0 / piv;
-                    acc[0][0] *= rn;
-                    acc[0][1] *= rn;
-                }
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    if (i0 + a < N) {
-                        // the (kend, kend) pivot entry stays stale on purpose (see above)
-                        if (v0 && !(a == 0 && rb == 0 && c0 == kend)) S[ro[a] + c0] = acc[a][0];
-                        if (v1) S[ro[a] + c0 + 32] = acc[a][1];
-                    }
-                }
-                cs += EM_WARPS;
-                while (cs >= cstrips) { cs -= cstrips; ++rb; }
+        __syncthreads();
+        EM_TICK(10);
+    }
+    // ---------------- back substitution with the unit upper factor, blocked like the panels.
+    // warp d (< 3) solves the 8 x 8 block of right-hand side d in registers; threads (i, d) then update rows above.
+    for (int k0 = (P - 1) * LU_NB; k0 >= 0; k0 -= LU_NB) {
+        const int nb = (N - k0 < LU_NB) ? N - k0 : LU_NB;
+        if (w < 3) {
+            const int li = lane & 7;
+            const double* __restrict__ urow = S + (k0 + (li < nb ? li : 0)) * ld + k0;
+            double y = (li < nb) ? urow[N - k0 + w] : 0.0;
+#pragma unroll 1
+            for (int j = nb - 1; j > 0; --j) {
+                const double uj = urow[j];                       // off the critical chain
+                const double xj = __shfl_sync(FULL, y, j);
+                if (li < j) y = fma(-uj, xj, y);
             }
+            if (lane < nb) {
+                ls.x[w][lane] = y;
+                sol[3 * (k0 + lane) + w] = y;
+            }
+        }
+        if (k0 == 0) break;
+        __syncthreads();
+        for (int e = tid; e < 3 * k0; e += EM_THREADS) {
+            const int i = e / 3, dd = e - 3 * i;
+            const double* __restrict__ urow = S + i * ld + k0;
+            double y = S[i * ld + N + dd];
+#pragma unroll
+            for (int c = 0; c < LU_NB; ++c)
+                if (c < nb) y = fma(-urow[c], ls.x[dd][c], y);
+            S[i * ld + N + dd] = y;
         }
         __syncthreads();
     }
     __syncthreads();
-    // ---------------- back substitution with the unit upper factor: warp d solves right-hand side d
-    if (w < 3) {
-        double* __restrict__ col = S + N + w;
-        for (int k = N - 1; k > 0; --k) {
-            const double x = col[k * ld];
-            for (int i = lane; i < k; i += 32) col[i * ld] = fma(-S[i * ld + k], x, col[i * ld]);
-            __syncwarp();
-        }
-        for (int i = lane; i < N; i += 32) sol[3 * i + w] = col[i * ld];
-    }
-    __syncthreads();
+    EM_TICK(6);
 }
 
 // Shared-memory plan of one CTA (dynamic): the per-point vectors (7 N doubles) first, then the N x ld augmented
 // system when it fits.  EM_SMEM_BUDGET leaves room for the static Scratch.
-constexpr size_t EM_SMEM_BUDGET = 232448 - 1024;
+constexpr size_t EM_STATIC_SMEM = 3584;                    // allowance for the static Scratch + LuScratch
+constexpr size_t EM_SMEM_BUDGET = 232448 - EM_STATIC_SMEM;  // 227 KiB opt-in limit minus the static part
+static_assert(sizeof(Scratch) + sizeof(LuScratch) + 64 <= EM_STATIC_SMEM, "static shared memory allowance too small");
 __host__ __device__ inline int sys_ld(int N) { return (N + 3) | 1; }
 __host__ __device__ inline bool vec_fits(int N) { return (size_t)56 * N <= EM_SMEM_BUDGET; }
 __host__ __device__ inline bool sys_fits(int N) { return (size_t)56 * N + (size_t)8 * N * sys_ld(N) <= EM_SMEM_BUDGET; }
@@ -366,6 +456,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1)
 prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
     extern __shared__ double dyn_smem[];
     __shared__ Scratch s;
+    __shared__ LuScratch lus;
     const DevProblem d = probs[blockIdx.x];
     const int N = d.p.n_ref, M = d.p.n_tgt, L = d.p.n_tracked;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -418,10 +509,17 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
     const double PI = 3.141592653589793;
     int iterations = 0;
 
+#ifdef EM_TIMING
+    if (tid < 16) em_t_s[tid] = 0;
+    __syncthreads();
+#endif
+    EM_TICK_DECL;
+    EM_TICK(0);
     for (int it = 1; it < prm.max_iteration; ++it) {
         iterations = it;
+        EM_TICK(9);
         // ---------------- E-step (track.py:81-88 / trackerlite.py:375-382): one warp per target row
-        const double two_s2 = 2.0 * sigma2;
+        const double neg_inv_two_s2 = -1.0 / (2.0 * sigma2);
         const double norm15 = pow(2.0 * PI * sigma2, 1.5);
         const double outlier = lite ? gamma / prm.vol : gamma * norm15 / ((1.0 - gamma) * prm.vol);
         const double one_m_g = 1.0 - gamma;
@@ -431,7 +529,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             for (int n = lane; n < N; n += 32) {
                 const double dx = cur[3 * n] - y0, dy = cur[3 * n + 1] - y1, dz = cur[3 * n + 2] - y2;
                 const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                const double like = exp(-d2 / two_s2);
+                const double like = exp(d2 * neg_inv_two_s2);
                 const double pr = d.prior[(size_t)m * N + n];
                 // NumPy dtype rule kept: a float32 prior times the scalar (1 - gamma) is a float32 product
                 // (trackerlite.py:377-378 with prior from simple_match on the float32 FFN output)
@@ -441,10 +539,11 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
                 rs += v;
             }
             rs = warp_sum(rs);
-            const double den = rs + outlier;
-            for (int n = lane; n < N; n += 32) P[(size_t)m * N + n] /= den;
+            const double rden = 1.0 / (rs + outlier);
+            for (int n = lane; n < N; n += 32) P[(size_t)m * N + n] *= rden;
         }
         __syncthreads();
+        EM_TICK(1);
         // ---------------- column moments: p_n = sum_m P[m,n], ytp_n = sum_m P[m,n] Y[m]
         // R = 1024/N row groups work in parallel; partials are combined in a fixed order (deterministic).
         {
@@ -473,6 +572,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             }
         }
         __syncthreads();
+        EM_TICK(2);
         // ---------------- M-step assembly (track.py:91-96 / trackerlite.py:411-415)
         //   S = a^T:  S[i][j] = p_i G[i][j] + lambda sigma^2 [i==j]     (G symmetric)
         //   rhs[i]  = ytp_i - p_i * base_i,  base = X (TRACK) or the current prediction (LITE)
@@ -492,7 +592,9 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             S[(size_t)i * ld + N + (e - 3 * i)] = ytp[e] - (lite ? cur[e] : X[e]) * colsum[i];
         }
         __syncthreads();
-        lu_solve<SM>(S, N, ld, rhs);        // rhs now holds W = C^T (N,3)
+        EM_TICK(3);
+        lu_solve<SM>(S, N, ld, rhs, lus);   // rhs now holds W = C^T (N,3)
+        EM_TICK(9);
         // ---------------- apply: move = G W   (track.py:100 / trackerlite.py:337-341)
         double move2 = 0.0;
         for (int i = w; i < N; i += EM_WARPS) {
@@ -522,6 +624,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
             }
         }
         if (lite) move2 = block_sum(move2, s); else __syncthreads();
+        EM_TICK(7);
         // ---------------- gamma, sigma^2 (track.py:103-112 / trackerlite.py:342-350)
         double cs = 0.0;
         for (int n = tid; n < N; n += EM_THREADS) cs += colsum[n];
@@ -539,6 +642,7 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
         }
         sigma2 = block_sum(q, s) / (3.0 * sumP);
         if (!lite && sigma2 < 1.0) sigma2 = 1.0;
+        EM_TICK(8);
         if (lite && sqrt(move2) < 1e-3) break;
     }
 
@@ -550,6 +654,14 @@ prgls_kernel(const DevProblem* __restrict__ probs, CtPrglsParams prm) {
     if (lite && d.p.tracked_out)
         for (int e = tid; e < 3 * L; e += EM_THREADS) d.p.tracked_out[e] = d.cur_l[e];
     if (tid == 0 && d.p.iterations) *d.p.iterations = iterations;
+#ifdef EM_TIMING
+    __syncthreads();
+    if (tid < 16 && blockIdx.x == 0) g_em_t[tid] = em_t_s[tid];
+    __syncthreads();
+    if (tid == 0 && blockIdx.x == 0)
+        printf("EMT setup %lld estep %lld moments %lld assemble %lld luPre %lld lu2 %lld lu3wait %lld back %lld apply %lld sigma %lld other %lld tile0 %lld diag %lld\n",
+               g_em_t[0], g_em_t[1], g_em_t[2], g_em_t[3], g_em_t[4], g_em_t[5], g_em_t[10], g_em_t[6], g_em_t[7], g_em_t[8], g_em_t[9], g_em_t[11], g_em_t[12]);
+#endif
 }
 
 __global__ void __launch_bounds__(EM_THREADS, 1)
