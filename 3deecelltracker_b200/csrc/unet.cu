@@ -398,9 +398,9 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) 
             if (net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s);
             if (rc == 1) return 1;
             if (rc == 2) {
-                CT_REQUIRE(net->engine != 2 || net->layers[op.layer].cin == 1,
-                           "unet: tcgen05 engine forced but layer %d (cin %d, cout %d) is unsupported",
-                           op.layer, net->layers[op.layer].cin, net->layers[op.layer].cout);
+                CT_REQUIRE(net->engine != 2,
+                           "unet: tcgen05 engine forced but layer %d (cin %d, cout %d, z %d) is unsupported",
+                           op.layer, net->layers[op.layer].cin, net->layers[op.layer].cout, op.sz);
                 if (launch_conv_direct(net, op, slab0, stride, tiles, s)) return 1;
             }
         } else {

@@ -47,6 +47,20 @@ def mod(name):
     return importlib.import_module("3deecelltracker_b200." + name)
 
 
+def measured_traffic(tiles_per_batch):
+    """dram bytes per conv launch from the newest committed `ncu --set full` capture (profiles/*_traffic.json); None
+    when the capture was taken at a different batch size."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        t = json.load(f)
+    if t.get("tiles_per_batch") != tiles_per_batch:
+        return None
+    return t["dram_bytes_per_launch_avg"]
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -245,7 +259,7 @@ def gpu_main(args):
             "metric": "voxels/s", "value": voxels * world * args.steps / (dev_ms * 1e-3), "unit": "voxels/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (U-Net/FFN, reference arithmetic) + f64 (PR-GLS EM)", "data": "synthetic",
+            "dtype": "tf32 hi/lo split, fp32 accumulate (U-Net conv); f32 (LCN, FFN); f64 (PR-GLS EM)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "unet_tiles": n_tiles,
                        "unet_engine": args.engine, "tiles_per_batch": args.tiles_per_batch,
                        "l2": "flushed between timed iterations (256 MiB write)",
@@ -261,7 +275,11 @@ def gpu_main(args):
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": pk["source"] + ", bf16 dense sustained",
                          "launches": int(conv_n), "avg_launch_ms": conv_ms / max(conv_n, 1),
-                         "share_of_step": conv_ms / dev_ms if dev_ms else None, "traffic": None},
+                         "share_of_step": conv_ms / dev_ms if dev_ms else None,
+                         "algorithmic_flop_per_launch": conv_flops / max(conv_n, 1),
+                         "traffic": measured_traffic(args.tiles_per_batch), "traffic_unit": "bytes/launch (ncu dram read+write)",
+                         "note": "split-TF32 tcgen05 implicit GEMM: bound by the tensor core's shared-memory operand "
+                                 "reads (ncu: tc smem wavefronts ~80% of peak), see DESIGN.md 3.2"},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "clocks": clocks,
         }

@@ -94,11 +94,65 @@ def test_unet_predict_matches_oracle(mods, variant, batch):
     tiles = rng.normal(0, 1.0, (batch, x, y, z, 1)).astype(np.float32)
     want = oracle.predict(tiles)
     want64 = oracle64(variant, ws, tiles)
-    for engine in ("direct", "auto"):
+    engines = ("direct", "auto", "tcgen05") if variant in ("a", "c") else ("direct", "auto")
+    for engine in engines:
         model.set_engine(engine)
         got = model.predict(tiles)
         assert got.shape == want.shape and got.dtype == np.float32
         assert_prob_close(got, want, want64, f"variant={variant} engine={engine}")
+
+
+def _block_reference(ws, li, x_bxyzc, alpha=0.3):
+    """fp64 Conv3D(3,'same') + LeakyReLU + BatchNorm(eval) of conv block `li` (unet3d.py:101-120)."""
+    w = torch.from_numpy(ws[6 * li]).double().permute(4, 3, 0, 1, 2)
+    bias, gamma, beta, mean, var = (torch.from_numpy(ws[6 * li + k]).double() for k in range(1, 6))
+    y = torch.nn.functional.conv3d(torch.from_numpy(x_bxyzc).double().permute(0, 4, 1, 2, 3), w, bias, padding=1)
+    y = torch.nn.functional.leaky_relu(y, alpha)
+    sh = (1, -1, 1, 1, 1)
+    y = (y - mean.view(sh)) / torch.sqrt(var.view(sh) + 1e-3) * gamma.view(sh) + beta.view(sh)
+    return y.permute(0, 2, 3, 4, 1).numpy()
+
+
+@pytest.mark.parametrize("layer", list(range(14)))
+def test_conv_block_tcgen05_and_direct_match_fp64(mods, layer):
+    """Every conv block of unet3_a through the C ABI (ct_unet_conv_block), both engines, against fp64 torch.
+    Shapes cover partial M tiles in x and y (x not a multiple of the block, y not a multiple of 16), z = 8 and 16,
+    batch > 1.  Tolerance: 2e-5 of the output scale (fp32 arithmetic over K = 27 * Cin <= 3456 terms; the
+    split-TF32 tensor-core path measures <= 1e-6, the fp32 CUDA-core path <= 3e-6)."""
+    _, u, _ = mods
+    ws = ounet.random_weights("a", seed=3)
+    model = u.UNet3("a", weights=ws, tiles_per_batch=2)
+    cin, cout = u._conv_layers(u._SPECS["a"])[layer]
+    rng = np.random.default_rng(100 + layer)
+    for b, (x, y, z) in [(1, (8, 16, 8)), (2, (11, 21, 16)), (1, (20, 40, 16))]:
+        xin = rng.normal(0, 1, (b, x, y, z, cin)).astype(np.float32)
+        ref = _block_reference(ws, layer, xin)
+        scale = np.abs(ref).max()
+        dev = torch.from_numpy(xin).cuda()
+        for engine in ("direct", "tcgen05"):
+            got = model.conv_block_device(layer, dev, engine).cpu().numpy().astype(np.float64)
+            assert got.shape == ref.shape
+            err = np.abs(got - ref).max() / scale
+            assert err < 2e-5, f"layer {layer} {cin}->{cout} {engine} {x}x{y}x{z}: {err:.2e}"
+
+
+def test_tcgen05_engine_is_what_auto_runs(mods):
+    """`auto` must take the tensor-core engine for every block of unet3_a (no silent CUDA-core fallback)."""
+    _, u, _ = mods
+    ws = ounet.random_weights("a", seed=5)
+    model = u.UNet3("a", weights=ws, tiles_per_batch=2)
+    rng = np.random.default_rng(3)
+    tiles = torch.from_numpy(rng.normal(0, 1, (2, 160, 160, 16)).astype(np.float32)).cuda()
+    model.set_engine("auto")
+    a = model.predict_device(tiles)
+    model.set_engine("tcgen05")
+    b = model.predict_device(tiles)
+    assert torch.equal(a, b)
+    model.set_engine("direct")
+    c = model.predict_device(tiles)
+    assert not torch.equal(a, c)            # different arithmetic (split TF32 vs fp32 FMA), same answer to ~1e-4
+    rel = ((a - c).abs() / c.abs().clamp_min(1e-30)).max().item()
+    assert rel < 5e-4
 
 
 @pytest.mark.parametrize("shape,shrink", [((64, 64, 16), (24, 24, 2)), ((130, 120, 20), (24, 24, 2)),
