@@ -32,8 +32,9 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
 __global__ void __launch_bounds__(256)
 gather_tiles(const float* __restrict__ src, float4* __restrict__ slab, size_t slab_stride4, size_t in_off4,
              int mode, int tile_first, int X, int Y, int Z, int TX, int TY, int TZ,
-             int ny, int nz, int cx, int cy, int cz, int bx, int by, int bz) {
+             int ny, int nz, int cx, int cy, int cz, int bx, int by, int bz, int in_slot) {
     const int t = blockIdx.y;
+    float amax = 0.f;
     const size_t tile_vox = (size_t)TX * TY * TZ;
     float4* out = slab + (size_t)t * slab_stride4 + in_off4;
     int gi = tile_first + t;
@@ -55,15 +56,22 @@ gather_tiles(const float* __restrict__ src, float4* __restrict__ slab, size_t sl
             val = src[(size_t)(tile_first + t) * tile_vox + v];
         }
         out[v] = make_float4(val, 0.f, 0.f, 0.f);
+        amax = fmaxf(amax, fabsf(val));
     }
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0) amax_update(reinterpret_cast<float*>(slab + (size_t)t * slab_stride4) + in_slot, amax);
 }
 
 // MaxPooling3D(pool) on c4-blocked buffers (unet3d.py:168).
 __global__ void __launch_bounds__(256)
 pool_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, size_t slab_stride4,
             size_t src_off4, size_t dst_off4, int src_c4off, int c4, int SXs, int SYs, int SZs,
-            int DX, int DY, int DZ, int px, int py, int pz) {
+            int DX, int DY, int DZ, int px, int py, int pz, int src_slot, int dst_slot) {
     const int t = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {          // max over a subset <= max of the source buffer
+        float* hdr = reinterpret_cast<float*>(slab_dst + (size_t)t * slab_stride4);
+        amax_update(hdr + dst_slot, hdr[src_slot]);
+    }
     const size_t dvol = (size_t)DX * DY * DZ, svol = (size_t)SXs * SYs * SZs;
     const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4 + (size_t)src_c4off * svol;
     float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4;
@@ -88,8 +96,12 @@ pool_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, 
 __global__ void __launch_bounds__(256)
 upsample_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, size_t slab_stride4,
                 size_t src_off4, size_t dst_off4, int dst_c4off, int c4, int SXs, int SYs, int SZs,
-                int DX, int DY, int DZ, int px, int py, int pz) {
+                int DX, int DY, int DZ, int px, int py, int pz, int src_slot, int dst_slot) {
     const int t = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float* hdr = reinterpret_cast<float*>(slab_dst + (size_t)t * slab_stride4);
+        amax_update(hdr + dst_slot, hdr[src_slot]);
+    }
     const size_t dvol = (size_t)DX * DY * DZ, svol = (size_t)SXs * SYs * SZs;
     const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4;
     float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4 + (size_t)dst_c4off * dvol;
@@ -147,7 +159,9 @@ head_scatter(const float4* __restrict__ slab, size_t slab_stride4, size_t last_o
 // Keras channels-last (B, X, Y, Z, C) <-> c4-blocked [B][C/4][X][Y][Z][4] (channel pad = 0); used by the
 // single-block operator ct_unet_conv_block.
 __global__ void __launch_bounds__(256)
-ndhwc_to_c4(const float* __restrict__ src, float4* __restrict__ dst, size_t vol, int c, int c4, size_t total) {
+ndhwc_to_c4(const float* __restrict__ src, float4* __restrict__ dst, size_t vol, int c, int c4, size_t total,
+            float* __restrict__ amax_slot) {
+    float amax = 0.f;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t v = idx % vol;
         const size_t r = idx / vol;
@@ -158,7 +172,10 @@ ndhwc_to_c4(const float* __restrict__ src, float4* __restrict__ dst, size_t vol,
 #pragma unroll
         for (int j = 0; j < 4; ++j) q[j] = (ck * 4 + j < c) ? s[j] : 0.f;
         dst[idx] = make_float4(q[0], q[1], q[2], q[3]);
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(q[0]), fabsf(q[1]))), fmaxf(fabsf(q[2]), fabsf(q[3])));
     }
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0) amax_update(amax_slot, amax);
 }
 __global__ void __launch_bounds__(256)
 c4_to_ndhwc(const float4* __restrict__ src, float* __restrict__ dst, size_t vol, int c, int c4, size_t total) {
@@ -246,6 +263,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
     std::vector<float> host;
     struct Offs { size_t wd, wt, b, sc, sh; };
     std::vector<Offs> offs;
+    std::vector<float> inv_scales;
     const float* p = w;
     const float eps = 1e-3f;                    // keras BatchNormalization default epsilon
     for (auto& c : convs) {
@@ -261,7 +279,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
                         p[((size_t)tap * cin + ci) * cout + co];
         const size_t tcn = tc_weight_floats(cin_pad, cout);
         o.wt = take(tcn);
-        if (tcn) tc_pack_weights(p, cin, cin_pad, cout, &host[o.wt]);
+        inv_scales.push_back(tcn ? tc_pack_weights(p, cin, cin_pad, cout, &host[o.wt]) : 1.f);
         p += (size_t)27 * cin * cout;
         o.b = take(cout); o.sc = take(cout); o.sh = take(cout);
         const float *bias = p, *gamma = p + cout, *beta = p + 2 * cout, *mean = p + 3 * cout, *var = p + 4 * cout;
@@ -291,6 +309,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         L.cin = convs[i].first; L.cout = convs[i].second; L.cin_pad = (L.cin + 3) / 4 * 4;
         L.w_direct = net->all_dev + offs[i].wd;
         L.w_tc = tc_weight_floats(L.cin_pad, L.cout) ? net->all_dev + offs[i].wt : nullptr;
+        L.w_tc_inv_scale = inv_scales[i];
         L.bias = net->all_dev + offs[i].b; L.scale = net->all_dev + offs[i].sc; L.shift = net->all_dev + offs[i].sh;
         net->layers.push_back(L);
     }
@@ -300,13 +319,21 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
     int lx[CT_UNET_MAX_LEVELS + 1], ly[CT_UNET_MAX_LEVELS + 1], lz[CT_UNET_MAX_LEVELS + 1];
     lx[0] = sp->in_x; ly[0] = sp->in_y; lz[0] = sp->in_z;
     for (int l = 1; l <= sp->levels; ++l) { lx[l] = lx[l - 1] / sp->pool_x; ly[l] = ly[l - 1] / sp->pool_y; lz[l] = lz[l - 1] / sp->pool_z; }
-    size_t off = 0;
-    auto buf = [&](int c, int l) { size_t at = off; off += (size_t)c * lx[l] * ly[l] * lz[l]; off = (off + 63) / 64 * 64; return at; };
+    size_t off = AMAX_SLOTS;                       // slab header: one max|value| slot per buffer
+    int n_slots = 0;
+    std::vector<std::pair<size_t, int>> slot_of;  // buffer offset -> slot
+    auto buf = [&](int c, int l) {
+        size_t at = off; off += (size_t)c * lx[l] * ly[l] * lz[l]; off = (off + 63) / 64 * 64;
+        slot_of.push_back({at, n_slots++});
+        return at;
+    };
+    auto slot = [&](size_t at) { for (auto& q : slot_of) if (q.first == at) return q.second; return -1; };
     double flops = 0;
     int li = 0;
     auto conv = [&](size_t s_off, int s_c, size_t d_off, int d_c, int d_coff, int l) {
         Op o{}; o.kind = OP_CONV; o.layer = li; o.src_off = s_off; o.dst_off = d_off; o.src_c = s_c; o.dst_c = d_c;
         o.src_coff = 0; o.dst_coff = d_coff; o.c = net->layers[li].cout;
+        o.src_slot = slot(s_off); o.dst_slot = slot(d_off);
         o.sx = o.dx = lx[l]; o.sy = o.dy = ly[l]; o.sz = o.dz = lz[l];
         flops += 2.0 * 27 * net->layers[li].cin * net->layers[li].cout * (double)lx[l] * ly[l] * lz[l];
         net->ops.push_back(o); ++li;
@@ -324,6 +351,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         size_t pl = buf(f2, l + 1);
         Op o{}; o.kind = OP_POOL; o.src_off = cat_off[l]; o.dst_off = pl; o.src_c = cat_c[l]; o.dst_c = f2;
         o.src_coff = upc; o.dst_coff = 0; o.c = f2;
+        o.src_slot = slot(cat_off[l]); o.dst_slot = slot(pl);
         o.sx = lx[l]; o.sy = ly[l]; o.sz = lz[l]; o.dx = lx[l + 1]; o.dy = ly[l + 1]; o.dz = lz[l + 1];
         net->ops.push_back(o);
         x_off = pl; x_c = f2;
@@ -336,6 +364,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         conv(t1, f1, t2, f2, 0, l + 1);
         Op o{}; o.kind = OP_UPSAMPLE; o.src_off = t2; o.dst_off = cat_off[l]; o.src_c = f2; o.dst_c = cat_c[l];
         o.src_coff = 0; o.dst_coff = 0; o.c = f2;
+        o.src_slot = slot(t2); o.dst_slot = slot(cat_off[l]);
         o.sx = lx[l + 1]; o.sy = ly[l + 1]; o.sz = lz[l + 1]; o.dx = lx[l]; o.dy = ly[l]; o.dz = lz[l];
         net->ops.push_back(o);
         x_off = cat_off[l]; x_c = cat_c[l];
@@ -347,6 +376,8 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
     net->last_off = o2;
     net->slab_floats = off;
     net->flops_per_tile = flops;
+    net->in_slot = slot(net->in_off);
+    if (n_slots > AMAX_SLOTS) { set_error("unet: %d buffers exceed the %d header slots", n_slots, AMAX_SLOTS); delete net; return 1; }
     *out = net;
     return 0;
 }
@@ -411,12 +442,12 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) 
             if (op.kind == OP_POOL) {
                 pool_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.src_coff / 4,
                                                  op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
-                                                 net->spec.pool_x, net->spec.pool_y, net->spec.pool_z);
+                                                 net->spec.pool_x, net->spec.pool_y, net->spec.pool_z, op.src_slot, op.dst_slot);
                 CT_LAUNCHED("pool_kernel");
             } else {
                 upsample_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.dst_coff / 4,
                                                      op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
-                                                     net->spec.pool_x, net->spec.pool_y, net->spec.pool_z);
+                                                     net->spec.pool_x, net->spec.pool_y, net->spec.pool_z, op.src_slot, op.dst_slot);
                 CT_LAUNCHED("upsample_kernel");
             }
         }
@@ -437,9 +468,10 @@ static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode,
     for (int t0 = first; t0 < last; t0 += tiles_per_batch) {
         const int nt = (last - t0 < tiles_per_batch) ? last - t0 : tiles_per_batch;
         dim3 g(grid_for(tile_vox), nt);
+        CT_CUDA(cudaMemset2DAsync(slab0, net->slab_floats * sizeof(float), 0, AMAX_SLOTS * sizeof(float), nt, s));
         gather_tiles<<<g, 256, 0, s>>>(src, reinterpret_cast<float4*>(slab0), net->slab_floats / 4, net->in_off / 4, mode, t0,
                                        X, Y, Z, TX, TY, TZ, num[1], num[2], centre[0], centre[1], centre[2],
-                                       shrink[0], shrink[1], shrink[2]);
+                                       shrink[0], shrink[1], shrink[2], net->in_slot);
         CT_LAUNCHED("gather_tiles");
         if (run_plan(net, slab0, nt, s)) return 1;
         head_scatter<<<g, 256, 0, s>>>(reinterpret_cast<const float4*>(slab0), net->slab_floats / 4, net->last_off / 4,
@@ -454,7 +486,7 @@ extern "C" size_t ct_unet_conv_block_workspace_bytes(const CtUNet* net, int laye
     if (!net || layer < 0 || layer >= (int)net->layers.size() || batch < 1) return 0;
     const ConvLayer& L = net->layers[layer];
     const size_t vol = (size_t)x * y * z;
-    return ((size_t)L.cin_pad + (size_t)L.cout) * vol * sizeof(float) * (size_t)batch + 512;
+    return (((size_t)L.cin_pad + (size_t)L.cout) * vol + AMAX_SLOTS) * sizeof(float) * (size_t)batch + 512;
 }
 
 extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, const float* in, float* out, int batch,
@@ -469,17 +501,20 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
     const ConvLayer& L = net->layers[layer];
     const size_t vol = (size_t)x * y * z;
     // one "slab" per batch entry: [cin_pad planes | cout planes]
-    const size_t stride = ((size_t)L.cin_pad + L.cout) * vol;
+    const size_t stride = ((size_t)L.cin_pad + L.cout) * vol + AMAX_SLOTS;
     float* slab0 = static_cast<float*>(ws);
+    CT_CUDA(cudaMemset2DAsync(slab0, stride * sizeof(float), 0, AMAX_SLOTS * sizeof(float), batch, s));
     Op op{};
-    op.kind = OP_CONV; op.layer = layer; op.src_off = 0; op.dst_off = (size_t)L.cin_pad * vol;
+    op.kind = OP_CONV; op.layer = layer; op.src_off = AMAX_SLOTS; op.dst_off = AMAX_SLOTS + (size_t)L.cin_pad * vol;
+    op.src_slot = 0; op.dst_slot = 1;
     op.src_c = L.cin_pad; op.dst_c = L.cout; op.src_coff = 0; op.dst_coff = 0; op.c = L.cout;
     op.sx = op.dx = x; op.sy = op.dy = y; op.sz = op.dz = z;
     const int cin4 = L.cin_pad / 4, cout4 = L.cout / 4;
     for (int b = 0; b < batch; ++b) {
         const size_t total = vol * cin4;
-        ndhwc_to_c4<<<grid_for(total), 256, 0, s>>>(in + (size_t)b * vol * L.cin, reinterpret_cast<float4*>(slab0 + b * stride),
-                                                     vol, L.cin, cin4, total);
+        ndhwc_to_c4<<<grid_for(total), 256, 0, s>>>(in + (size_t)b * vol * L.cin,
+                                                     reinterpret_cast<float4*>(slab0 + b * stride + op.src_off),
+                                                     vol, L.cin, cin4, total, slab0 + b * stride + op.src_slot);
         CT_LAUNCHED("ndhwc_to_c4");
     }
     if (engine == 2) {

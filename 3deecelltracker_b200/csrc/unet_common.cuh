@@ -16,6 +16,7 @@ struct ConvLayer {
     int cin_pad;              // multiple of 4
     float* w_direct;          // device: [cin_pad/4][27][cout][4]   (CUDA-core kernel)
     float* w_tc;              // device: tcgen05 layout (see unet_tc.cu), may be null
+    float w_tc_inv_scale;     // 1 / (power-of-two scale applied to the fp16 weight images)
     float* bias;              // device [cout]
     float* scale;             // device [cout]  gamma / sqrt(var + eps)
     float* shift;             // device [cout]  beta - mean * scale
@@ -32,7 +33,13 @@ struct Op {
     int c;                    // channels moved (pool / upsample) or cout (conv)
     int sx, sy, sz;           // spatial size of src
     int dx, dy, dz;           // spatial size of dst
+    int src_slot, dst_slot;   // index of the buffers' max|value| slots in the per-tile slab header
 };
+
+// Every tile slab starts with a header of AMAX_SLOTS floats: slot b holds an upper bound of max|value| of buffer b
+// of that tile (zeroed per batch; producers atomicMax the bit pattern, which orders like the value for floats >= 0).
+// The tensor-core convolution scales its fp16 operand images by a power of two derived from it.
+constexpr int AMAX_SLOTS = 64;
 
 }  // namespace ct
 
@@ -42,6 +49,7 @@ struct CtUNet {
     std::vector<ct::Op> ops;
     size_t slab_floats;       // workspace floats per tile
     size_t in_off, last_off;  // offsets of the padded input buffer and of the last conv output
+    int in_slot;              // header slot of the input buffer
     int last_c;
     float* head_w;            // device [last_c]
     float head_b;
@@ -59,5 +67,15 @@ int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t sla
 int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
                    cudaStream_t s);
 size_t tc_weight_floats(int cin_pad, int cout);
-void tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
+// returns 1 / scale
+float tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
+
+__device__ __forceinline__ void amax_update(float* slot, float v) {
+    atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 }  // namespace ct

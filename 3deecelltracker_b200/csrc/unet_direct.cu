@@ -23,7 +23,8 @@ conv3_direct_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                     const float* __restrict__ bias, const float* __restrict__ scale,
                     const float* __restrict__ shift, float alpha,
                     int cin4, int cout, int X, int Y, int Z, int nbx, int nby,
-                    size_t src_tile_stride4, size_t dst_tile_stride4, int dst_c4off) {
+                    size_t src_tile_stride4, size_t dst_tile_stride4, int dst_c4off, float* __restrict__ amax_hdr,
+                    int dst_slot) {
     __shared__ float4 in_s[SX][SY][SZ];
     __shared__ float4 w_s[27][CO];
 
@@ -92,6 +93,7 @@ conv3_direct_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
 
     // epilogue: bias -> activation -> BN affine, written as 16-byte channel chunks
     const int gy = y0 + ty, gz = z0 + tz;
+    float amax = 0.f;
     if (gy < Y && gz < Z) {
         float4* d_tile = dst + (size_t)tile * dst_tile_stride4;
 #pragma unroll
@@ -115,10 +117,14 @@ conv3_direct_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                         o[j] = fmaf(t, sc[j], sh[j]);
                     }
                     d_ck[((size_t)gx * Y + gy) * Z + gz] = make_float4(o[0], o[1], o[2], o[3]);
+                    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o[0]), fabsf(o[1]))), fmaxf(fabsf(o[2]), fabsf(o[3])));
                 }
             }
         }
     }
+    // keep the per-tile max|value| bound of the destination buffer current (read by the tensor-core engine)
+    amax = warp_max(amax);
+    if ((tid & 31) == 0) amax_update(amax_hdr + (size_t)tile * dst_tile_stride4 * 4 + dst_slot, amax);
 }
 
 int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
@@ -136,13 +142,13 @@ int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t sla
         grid.y = L.cout / 16;
         conv3_direct_kernel<16><<<grid, 256, 0, s>>>(src, dst, reinterpret_cast<const float4*>(L.w_direct), L.bias,
                                                     L.scale, L.shift, net->alpha, L.cin_pad / 4, L.cout, X, Y, Z,
-                                                    nbx, nby, slab_stride / 4, slab_stride / 4, op.dst_coff / 4);
+                                                    nbx, nby, slab_stride / 4, slab_stride / 4, op.dst_coff / 4, slab0, op.dst_slot);
     } else {
         CT_REQUIRE(L.cout % 8 == 0, "conv: cout %d must be a multiple of 8", L.cout);
         grid.y = L.cout / 8;
         conv3_direct_kernel<8><<<grid, 256, 0, s>>>(src, dst, reinterpret_cast<const float4*>(L.w_direct), L.bias,
                                                    L.scale, L.shift, net->alpha, L.cin_pad / 4, L.cout, X, Y, Z,
-                                                   nbx, nby, slab_stride / 4, slab_stride / 4, op.dst_coff / 4);
+                                                   nbx, nby, slab_stride / 4, slab_stride / 4, op.dst_coff / 4, slab0, op.dst_slot);
     }
     CT_LAUNCHED("conv3_direct_kernel");
     return 0;

@@ -16,25 +16,37 @@
 // halves of one K = 8 MMA are two different taps (LBO = address distance between the taps).
 //
 // Precision.  The reference computes in fp32 (TF-CPU); parity target 1e-4 on probabilities after 15 stacked
-// convolutions.  kind::tf32 alone (10-bit mantissa) cannot meet it, so both operands are split
-// x = hi + lo (hi = RN_tf32(x), lo = x - hi, exact) and the product uses every cross term:
-//   D[:, 0:N)  += (A_hi + A_lo) * B_hi,     D[:, N:2N) += (A_hi + A_lo) * B_lo
-// i.e. two MMAs per K step (A_hi, A_lo) against one B tile [B_hi | B_lo] of 2N columns; the epilogue adds the
-// two column halves.  Activations stay single fp32 tensors in HBM: four converter warps split the TMA-landed
-// block in place inside shared memory (hi overwrites the raw plane, lo goes to a second plane).
+// convolutions.  One pass of any 16/19-bit tensor-core format cannot meet it, so both operands are split into two
+// fp16 images x * s = hi + lo' * 2^-11  (hi = RN_fp16(x s), lo' = RN_fp16((x s - hi) * 2^11); 22 significant bits),
+// with s a power of two chosen per tile from the running max|x| bound of the source buffer (slab header, see
+// unet_common.cuh) so that max|x s| lies in [2^13, 2^14): no overflow, and fp16's subnormal threshold sits 2^27 below
+// the largest element.  Weights are split the same way on the host with one power-of-two scale per layer.  The cross
+// terms are kept in separate accumulator column groups because they carry different weights:
+//     MMA1 = A_hi  x [B_hi | B_lo']  -> columns [0,N) (x1) and [N,2N) (x 2^-11)
+//     MMA2 = A_lo' x [B_hi (| B_lo')] -> columns [N,2N) (x 2^-11)  (and [2N,3N) (x 2^-22) when Cout = 8)
+// K = 16 per MMA: one K step covers two taps x EIGHT input channels, so the shared-memory operand traffic -- the
+// measured bound of this kernel, see DESIGN.md -- is half that of a TF32 split (K = 8).  Activations stay single fp32
+// tensors in HBM: worker warps convert the TMA-landed fp32 block in place (two 4-channel fp32 planes become the
+// 8-channel fp16 hi plane and lo plane).
 //
-// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one lane),
-// warps 2-5 = hi/lo converters during the main loop, then epilogue (tcgen05.ld -> bias/activation/BN ->
-// 16-byte channel-chunk stores).  Stage ring: full (TMA landed) -> conv (split done) -> empty (MMAs retired).
+// The tensor core adds with truncation, so accumulation chains in tensor memory are kept short: every stage (28 MMAs
+// per accumulator) goes into a FRESH accumulator set (ping-pong) that the worker warps drain into fp32 registers
+// (round-to-nearest) while the next stage's MMAs run.
+//
+// Warp roles (320 threads, persistent CTA): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer (one elected
+// lane), warps 2-9 = operand conversion, accumulator drain, epilogue (scale back, bias/activation/BN, 16-byte
+// channel-chunk stores, max|value| bound of the output).  Stage ring: full (TMA landed) -> conv (converted) -> empty.
 #include "unet_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
 namespace ct {
 
 constexpr int TC_SYH = 18, TC_SZH = 10;          // haloed block extent in y and z (16 + 2, 8 + 2)
-constexpr int TC_PAIRS = 14;                     // 27 taps -> 14 K=8 steps (tap 0 is paired with a zero column)
+constexpr int TC_PAIRS = 14;                     // 27 taps -> 14 K=16 steps (tap 0 is paired with a zero column)
 
 // voxel offset of tap t = (dx*3 + dy)*3 + dz inside the haloed block (x stride 180, y stride 10)
 __host__ __device__ constexpr int tap_off(int t) { return ((t / 9) * TC_SYH + (t / 3) % 3) * TC_SZH + t % 3; }
@@ -44,12 +56,18 @@ __host__ __device__ constexpr int pair_second(int p) { return p == 0 ? 1 : 2 * p
 
 template <int N, int BX, int STAGES>
 struct TcCfg {
-    static constexpr int NP = 2 * N;                                   // accumulator columns per M tile
+    static constexpr bool N8 = (N == 8);
+    // B rows per K half: [hi | lo'] -- plus a second copy of hi when Cout = 8, so that the 16-wide MMA2 can read
+    // [lo' | hi] from row 8 and land in columns of its own (one accumulate flag covers a whole MMA)
+    static constexpr int NPR = N8 ? 24 : 2 * N;
+    static constexpr int N1 = 2 * N;                                   // width of MMA1 = A_hi  x [B_hi | B_lo']
+    static constexpr int N2 = N8 ? 16 : N;                             // width of MMA2 = A_lo' x [B_lo' | B_hi] or B_hi
+    static constexpr int NPD = N8 ? 32 : 2 * N;                        // accumulator columns per M tile
     static constexpr int SXH = BX + 2;
-    static constexpr int PLANE = SXH * TC_SYH * TC_SZH * 16;           // bytes of one (hi or lo) plane
-    static constexpr int B_BYTES = TC_PAIRS * NP * 32;                 // [pair][k half][2N rows][16 B]
+    static constexpr int PLANE = SXH * TC_SYH * TC_SZH * 16;           // bytes of one plane (fp32 x4 in, fp16 x8 out)
+    static constexpr int B_BYTES = TC_PAIRS * NPR * 32;                // [pair][k half][NPR rows][8 fp16]
     static constexpr int STAGE = 2 * PLANE + B_BYTES;
-    static constexpr int SET_COLS = BX * NP;                           // one accumulator set
+    static constexpr int SET_COLS = BX * NPD;                          // one accumulator set
     static constexpr int COLS_NEEDED = 2 * SET_COLS;                   // ping-pong sets
     static constexpr int TMEM_COLS = COLS_NEEDED <= 32 ? 32 : COLS_NEEDED <= 64 ? 64 : COLS_NEEDED <= 128 ? 128
                                      : COLS_NEEDED <= 256 ? 256 : 512;
@@ -58,7 +76,7 @@ struct TcCfg {
     static_assert(BX % 2 == 0, "BX must be even (two worker halves)");
     static_assert(COLS_NEEDED <= 512, "accumulators exceed tensor memory");
     static_assert(PLANE % 128 == 0 && B_BYTES % 128 == 0, "stage parts must stay 128-byte aligned");
-    static_assert(NP % 16 == 0 && NP <= 256, "UMMA N out of range for M = 128");
+    static_assert(N1 % 16 == 0 && N1 <= 256 && N2 % 16 == 0, "UMMA N out of range for M = 128");
     static_assert(SMEM <= 232448, "shared memory ring too large");
 };
 
@@ -134,13 +152,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread for the CTA
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), issued by one thread for the CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -159,12 +177,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float rn_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-
 // shared-memory matrix descriptor, no swizzle, K-major: ((8, m), 2) : ((16 B, SBO), LBO)   [units of 16 B]
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr_bytes, uint32_t lbo16, uint32_t sbo16) {
     const uint32_t lo = ((addr_bytes >> 4) & 0x3FFFu) | ((lbo16 & 0x3FFFu) << 16);
@@ -179,9 +191,13 @@ constexpr int TC_WORKERS = 256;                  // 8 worker warps: two per TMEM
 constexpr int TC_THREADS = 64 + TC_WORKERS;
 
 struct TcGeom {
-    int cin4, X, Y, Z, nbx, nby, nbz, units;     // units = nbx * nby * nbz * tiles
+    int cin8, X, Y, Z, nbx, nby, nbz, units;     // cin8 = K stages (8 input channels each); units = blocks * tiles
     int dst_c4off;
     size_t dst_tile_stride4;
+    const float* amax_src;                       // slab header slot of the source buffer (tile stride = slab stride)
+    float* amax_dst;                             // ... of the destination buffer
+    size_t slab_stride;                          // floats
+    float w_inv_scale;                           // 1 / weight scale of the layer
 };
 
 struct TcUnit { int x0, y0, z0, tile; };
@@ -195,11 +211,11 @@ __device__ __forceinline__ TcUnit tc_unit(int u, const TcGeom& g, int bx) {
 }
 
 // Persistent CTA (one per SM).  Work unit = BX x 16 x 8 output voxels x all Cout of one tile; units are taken
-// round-robin.  `g` counts K stages (4-channel input chunks) across all units of the CTA: ring slot g % STAGES,
+// round-robin.  `g` counts K stages (8-channel input chunks) across all units of the CTA: ring slot g % STAGES,
 // accumulator set g & 1.  Every stage accumulates into a FRESH tensor-memory set (28 MMAs per accumulator) that
 // the worker warps drain into fp32 registers while the next stage's MMAs run: the tensor core adds with
-// truncation, so long in-TMEM accumulation chains would bias the result by ~K/8 * 2^-25 (measured 2e-5 at
-// K = 3456); register accumulation rounds to nearest.
+// truncation, so long in-TMEM accumulation chains would bias the result by ~(number of MMAs) * 2^-25 (measured 2e-5
+// of scale at K = 3456 with a TF32 split); register accumulation rounds to nearest.
 template <int N, int BX, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
@@ -213,9 +229,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int cin4 = geo.cin4;
+    const int cin8 = geo.cin8;
     const int n_units = ((int)blockIdx.x < geo.units) ? (geo.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int n_stages = n_units * cin4;
+    const int n_stages = n_units * cin8;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -247,12 +263,13 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             int g = 0;
             for (int k = 0; k < n_units; ++k) {
                 const TcUnit un = tc_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
-                for (int c = 0; c < cin4; ++c, ++g) {
+                for (int c = 0; c < cin8; ++c, ++g) {
                     const int s = g % STAGES, use = g / STAGES;
                     if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1);
                     uint8_t* st = ring + (size_t)s * Cfg::STAGE;
-                    mbar_expect_tx(&bar_full[s], Cfg::PLANE + Cfg::B_BYTES);
-                    tma_load_5d(st, &tmap, &bar_full[s], (un.z0 - 1) * 4, un.y0 - 1, un.x0 - 1, c, un.tile);
+                    mbar_expect_tx(&bar_full[s], 2 * Cfg::PLANE + Cfg::B_BYTES);
+                    // two 4-channel fp32 planes (a missing second plane of a 4-channel input is zero filled)
+                    tma_load_5d(st, &tmap, &bar_full[s], (un.z0 - 1) * 4, un.y0 - 1, un.x0 - 1, 2 * c, un.tile);
                     bulk_load(st + 2 * Cfg::PLANE, wpack + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &bar_full[s]);
                 }
             }
@@ -261,8 +278,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
     } else if (warp == 1) {
         // ---------------- MMA issuer
         if (elect_one()) {
-            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 2N, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Cfg::NP >> 3) << 17) | (8u << 24);
+            // instruction descriptors: D = f32, A = B = f16 (format 0), both K-major, M = 128, N = 2N / N2
+            constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(Cfg::N1 >> 3) << 17) | (8u << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(Cfg::N2 >> 3) << 17) | (8u << 24);
             // descriptor high words: SBO | version 1.  A: 16 y rows 160 B apart; B: 8-row groups 128 B apart
             constexpr uint64_t a_hi_word = (uint64_t)((uint32_t)TC_SZH | (1u << 14)) << 32;
             constexpr uint64_t b_hi_word = (uint64_t)(8u | (1u << 14)) << 32;
@@ -280,13 +298,19 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
                     const uint32_t lbo = (uint32_t)(tap_off(pair_second(p)) - tap_off(pair_first(p))) << 16;
                     const uint32_t ah = (a_hi + (uint32_t)tap_off(pair_first(p))) | lbo;
                     const uint32_t al = (a_lo + (uint32_t)tap_off(pair_first(p))) | lbo;
-                    const uint64_t bdesc = b_hi_word | (uint64_t)((b_base + (uint32_t)p * (Cfg::NP * 2)) | ((uint32_t)Cfg::NP << 16));
+                    // B: rows 16 B apart, 8-row groups 128 B apart, K halves NPR rows apart
+                    const uint32_t b_lo32 = (b_base + (uint32_t)p * (Cfg::NPR * 2)) | ((uint32_t)Cfg::NPR << 16);
+                    const uint64_t bdesc1 = b_hi_word | (uint64_t)b_lo32;
+                    const uint64_t bdesc2 = b_hi_word | (uint64_t)(b_lo32 + (Cfg::N8 ? 8u : 0u));
 #pragma unroll
                     for (int i = 0; i < BX; ++i) {
                         const uint32_t xo = (uint32_t)i * (TC_SYH * TC_SZH);
-                        const uint32_t d = d_set + (uint32_t)i * Cfg::NP;
-                        umma_tf32(d, a_hi_word | (uint64_t)(ah + xo), bdesc, idesc, p != 0);
-                        umma_tf32(d, a_hi_word | (uint64_t)(al + xo), bdesc, idesc, 1u);
+                        const uint32_t d = d_set + (uint32_t)i * Cfg::NPD;
+                        // columns [0, 2N) = A_hi x [B_hi | B_lo'].  A_lo' x B_hi joins columns [N, 2N) (same weight
+                        // 2^-11); for Cout = 8 MMA2 is A_lo' x [B_lo' | B_hi] into columns [16, 32) of its own
+                        umma_f16(d, a_hi_word | (uint64_t)(ah + xo), bdesc1, idesc1, p != 0);
+                        umma_f16(d + (Cfg::N8 ? 16 : N), a_hi_word | (uint64_t)(al + xo), bdesc2, idesc2,
+                                 Cfg::N8 ? (uint32_t)(p != 0) : 1u);
                     }
                 }
                 umma_commit(&bar_empty[s]);
@@ -295,32 +319,45 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         }
         __syncwarp();
     } else {
-        // ---------------- workers: tf32 hi/lo split of the landed block, accumulator drain, epilogue
+        // ---------------- workers: fp16 hi/lo images of the landed block, accumulator drain, epilogue
         const int wt = threadIdx.x - 64;
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;              // which BX/2 M tiles this thread drains
         const int row = q * 32 + lane;
         const size_t vol = (size_t)geo.X * geo.Y * geo.Z;
         float acc[Cfg::TILES_PER_HALF][N];
+        constexpr float W2 = 1.f / 2048.f, W3 = W2 * W2;      // weights of the lo' cross terms
 
         auto drain = [&](int g, bool first) {
             const int set = g & 1, use_a = g >> 1;
             mbar_wait(&bar_acc_full[set], use_a & 1);
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * Cfg::SET_COLS +
-                                (uint32_t)(half * Cfg::TILES_PER_HALF) * Cfg::NP;
+                                (uint32_t)(half * Cfg::TILES_PER_HALF) * Cfg::NPD;
 #pragma unroll
             for (int i = 0; i < Cfg::TILES_PER_HALF; ++i) {
 #pragma unroll
                 for (int n8 = 0; n8 < N / 8; ++n8) {
                     float a[8], b2[8];
-                    tmem_ld8(t0 + i * Cfg::NP + n8 * 8, a);
-                    tmem_ld8(t0 + i * Cfg::NP + N + n8 * 8, b2);
-                    tmem_ld_wait();
+                    tmem_ld8(t0 + i * Cfg::NPD + n8 * 8, a);
+                    tmem_ld8(t0 + i * Cfg::NPD + N + n8 * 8, b2);
+                    if (Cfg::N8) {
+                        float c3[8], c4[8];
+                        tmem_ld8(t0 + i * Cfg::NPD + 16, c3);
+                        tmem_ld8(t0 + i * Cfg::NPD + 24, c4);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float v = a[k] + b2[k];
-                        acc[i][n8 * 8 + k] = first ? v : acc[i][n8 * 8 + k] + v;
+                        for (int k = 0; k < 8; ++k) {
+                            const float v = fmaf(c3[k], W3, fmaf(b2[k] + c4[k], W2, a[k]));
+                            acc[i][k] = first ? v : acc[i][k] + v;
+                        }
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float v = fmaf(b2[k], W2, a[k]);
+                            acc[i][n8 * 8 + k] = first ? v : acc[i][n8 * 8 + k] + v;
+                        }
                     }
                 }
             }
@@ -328,47 +365,73 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_acc_empty[set]);
         };
-        auto store_unit = [&](const TcUnit& un) {
+        auto store_unit = [&](const TcUnit& un, float inv_scale) {
             const int y = un.y0 + (row >> 3), z = un.z0 + (row & 7);
-            if (y >= geo.Y) return;
-            float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)geo.dst_c4off * vol;
+            float amax = 0.f;
+            if (y < geo.Y) {
+                float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)geo.dst_c4off * vol;
 #pragma unroll
-            for (int i = 0; i < Cfg::TILES_PER_HALF; ++i) {
-                const int x = un.x0 + half * Cfg::TILES_PER_HALF + i;
-                if (x >= geo.X) break;
-                const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
+                for (int i = 0; i < Cfg::TILES_PER_HALF; ++i) {
+                    const int x = un.x0 + half * Cfg::TILES_PER_HALF + i;
+                    if (x >= geo.X) break;
+                    const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
 #pragma unroll
-                for (int c4 = 0; c4 < N / 4; ++c4) {
-                    float o[4];
+                    for (int c4 = 0; c4 < N / 4; ++c4) {
+                        float o[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float t = acc[i][c4 * 4 + k] + ep_s[0][c4 * 4 + k];
-                        t = t > 0.f ? t : alpha * t;
-                        o[k] = fmaf(t, ep_s[1][c4 * 4 + k], ep_s[2][c4 * 4 + k]);
+                        for (int k = 0; k < 4; ++k) {
+                            float t = fmaf(acc[i][c4 * 4 + k], inv_scale, ep_s[0][c4 * 4 + k]);
+                            t = t > 0.f ? t : alpha * t;
+                            o[k] = fmaf(t, ep_s[1][c4 * 4 + k], ep_s[2][c4 * 4 + k]);
+                            amax = fmaxf(amax, fabsf(o[k]));
+                        }
+                        d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                    d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
+            amax = warp_max(amax);
+            if (lane == 0) amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
+        };
+        // power-of-two operand scale of a tile: max|x s| in [2^13, 2^14)
+        auto tile_scale = [&](int tile) {
+            const float am = geo.amax_src[(size_t)tile * geo.slab_stride];
+            const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);          // biased exponent, 0 for zero / subnormal
+            const int se = (267 - e > 254) ? 254 : 267 - e;                    // 2^(13 - floor(log2 am)), clamped finite
+            return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
         };
 
-        // flattened stage loop: stage g is split, then stage g - 1 is drained while the MMAs of stage g run
+        // flattened stage loop: stage g is converted, then stage g - 1 is drained while the MMAs of stage g run
         int c = 0, k = 0;                              // chunk / unit ordinal of stage g
         int pc = 0;                                    // chunk of stage g - 1
-        TcUnit prev{};
+        TcUnit prev{}, cur{};
+        float s_cur = 1.f, s_prev = 1.f;
         for (int g = 0; g <= n_stages; ++g) {
             if (g < n_stages) {
+                if (c == 0) {
+                    cur = tc_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+                    s_cur = tile_scale(cur.tile);
+                }
                 const int s = g % STAGES, use = g / STAGES;
                 mbar_wait(&bar_full[s], use & 1);
-                float4* hi = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE);
-                float4* lo = reinterpret_cast<float4*>(ring + (size_t)s * Cfg::STAGE + Cfg::PLANE);
-#pragma unroll 4
+                uint4* p0 = reinterpret_cast<uint4*>(ring + (size_t)s * Cfg::STAGE);
+                uint4* p1 = reinterpret_cast<uint4*>(ring + (size_t)s * Cfg::STAGE + Cfg::PLANE);
+#pragma unroll 2
                 for (int i = wt; i < Cfg::PLANE / 16; i += TC_WORKERS) {
-                    const float4 v = hi[i];
-                    float4 h, l;
-                    h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
-                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                    hi[i] = h;
-                    lo[i] = l;
+                    const float4 v0 = *reinterpret_cast<const float4*>(p0 + i);      // channels 0-3 of the voxel
+                    const float4 v1 = *reinterpret_cast<const float4*>(p1 + i);      // channels 4-7
+                    const float x[8] = {v0.x * s_cur, v0.y * s_cur, v0.z * s_cur, v0.w * s_cur,
+                                        v1.x * s_cur, v1.y * s_cur, v1.z * s_cur, v1.w * s_cur};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((x[2 * j] - hf.x) * 2048.f, (x[2 * j + 1] - hf.y) * 2048.f);
+                        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    p0[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    p1[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -376,11 +439,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             }
             if (g > 0) {
                 drain(g - 1, pc == 0);
-                if (pc == cin4 - 1) store_unit(prev);
+                if (pc == cin8 - 1) store_unit(prev, geo.w_inv_scale / s_prev);
             }
-            if (c == 0) prev = tc_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+            if (c == 0) { prev = cur; s_prev = s_cur; }
             pc = c;
-            if (++c == cin4) { c = 0; ++k; }
+            if (++c == cin8) { c = 0; ++k; }
         }
         tc_fence_before();
     }
@@ -394,44 +457,44 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static float host_rn_tf32(float v) {
-    uint32_t u;
-    std::memcpy(&u, &v, 4);
-    if ((u & 0x7F800000u) == 0x7F800000u) return v;       // inf / nan pass through
-    u += 0x0FFFu + ((u >> 13) & 1u);
-    u &= 0xFFFFE000u;
-    float r;
-    std::memcpy(&r, &u, 4);
-    return r;
-}
-
 static bool tc_shape_ok(int cout) { return cout == 8 || cout == 16 || cout == 32 || cout == 64; }
+static int tc_rows(int cout) { return cout == 8 ? 24 : 2 * cout; }     // TcCfg::NPR
 
 size_t tc_weight_floats(int cin_pad, int cout) {
     if (!tc_shape_ok(cout)) return 0;
-    return (size_t)(cin_pad / 4) * TC_PAIRS * 2 * (2 * cout) * 4;
+    return (size_t)((cin_pad + 7) / 8) * TC_PAIRS * tc_rows(cout) * 8;  // 32 bytes per row per pair
 }
 
-// keras kernel (kx,ky,kz,ci,co) -> [ci/4][pair][k half][row: co (hi) | cout + co (lo)][ci % 4]
-void tc_pack_weights(const float* w, int cin, int cin_pad, int cout, float* dst) {
-    const int np = 2 * cout;
+// keras kernel (kx,ky,kz,ci,co) -> fp16 image [ci/8][pair][k half][row][ci % 8], rows = co (hi) | cout + co (lo')
+// (| 2 cout + co (hi again) when cout = 8); values scaled by a power of two so that max|w| lands in [2^13, 2^14).
+float tc_pack_weights(const float* w, int cin, int cin_pad, int cout, float* dst) {
+    const int npr = tc_rows(cout), c8n = (cin_pad + 7) / 8;
     std::memset(dst, 0, tc_weight_floats(cin_pad, cout) * sizeof(float));
-    for (int c = 0; c < cin_pad / 4; ++c)
+    float wmax = 0.f;
+    for (size_t i = 0; i < (size_t)27 * cin * cout; ++i) wmax = std::fmax(wmax, std::fabs(w[i]));
+    int e = 0;
+    if (wmax > 0.f) std::frexp(wmax, &e);                 // wmax = m * 2^e, m in [0.5, 1)
+    const float scale = std::ldexp(1.f, 14 - e);          // wmax * scale in [2^13, 2^14)
+    __half* img = reinterpret_cast<__half*>(dst);
+    for (int c = 0; c < c8n; ++c)
         for (int p = 0; p < TC_PAIRS; ++p)
             for (int j = 0; j < 2; ++j) {
                 if (p == 0 && j == 1) continue;          // zero column paired with tap 0
                 const int tap = j == 0 ? pair_first(p) : pair_second(p);
-                float* blk = dst + ((((size_t)c * TC_PAIRS + p) * 2 + j) * np) * 4;
+                __half* blk = img + ((((size_t)c * TC_PAIRS + p) * 2 + j) * npr) * 8;
                 for (int co = 0; co < cout; ++co)
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const int ci = c * 4 + qd;
+                    for (int qd = 0; qd < 8; ++qd) {
+                        const int ci = c * 8 + qd;
                         if (ci >= cin) continue;
-                        const float v = w[((size_t)tap * cin + ci) * cout + co];
-                        const float h = host_rn_tf32(v);
-                        blk[(size_t)co * 4 + qd] = h;
-                        blk[(size_t)(cout + co) * 4 + qd] = v - h;
+                        const float v = w[((size_t)tap * cin + ci) * cout + co] * scale;
+                        const __half h = __float2half_rn(v);
+                        const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
+                        blk[(size_t)co * 8 + qd] = h;
+                        blk[(size_t)(cout + co) * 8 + qd] = l;
+                        if (cout == 8) blk[(size_t)(2 * cout + co) * 8 + qd] = h;
                     }
             }
+    return 1.f / scale;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -463,7 +526,7 @@ static int sm_count() {
 
 template <int N, int BX, int STAGES>
 static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, float4* dst, int X, int Y, int Z,
-                     size_t stride4, int dst_c4off, int tiles, cudaStream_t s) {
+                     size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, cudaStream_t s) {
     using Cfg = TcCfg<N, BX, STAGES>;
     static bool attr = false;
     if (!attr) {
@@ -471,7 +534,8 @@ static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, fl
         attr = true;
     }
     TcGeom g;
-    g.cin4 = L.cin_pad / 4; g.X = X; g.Y = Y; g.Z = Z;
+    g.cin8 = (L.cin_pad + 7) / 8; g.X = X; g.Y = Y; g.Z = Z;
+    g.amax_src = amax_src; g.amax_dst = amax_dst; g.slab_stride = stride4 * 4; g.w_inv_scale = L.w_tc_inv_scale;
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
@@ -487,7 +551,7 @@ static int make_map(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, 
     const cuuint64_t dims[5] = {(cuuint64_t)Z * 4, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)c4, (cuuint64_t)tiles};
     const cuuint64_t strides[4] = {(cuuint64_t)Z * 16, (cuuint64_t)Y * Z * 16, (cuuint64_t)X * Y * Z * 16,
                                    (cuuint64_t)slab_stride * 4};
-    const cuuint32_t box[5] = {TC_SZH * 4, TC_SYH, BX + 2, 1, 1};
+    const cuuint32_t box[5] = {TC_SZH * 4, TC_SYH, BX + 2, 2, 1};      // two 4-channel planes per stage
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -509,18 +573,20 @@ int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_st
     const size_t st4 = slab_stride / 4;
     const int co4 = op.dst_coff / 4, c4 = L.cin_pad / 4;
     float* src = slab0 + op.src_off;
+    const float* am_s = slab0 + op.src_slot;
+    float* am_d = slab0 + op.dst_slot;
     if (L.cout == 8) {
         if (make_map<8>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
-        rc = launch_tc<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
+        rc = launch_tc<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     } else if (L.cout == 16) {
         if (make_map<8>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
-        rc = launch_tc<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
+        rc = launch_tc<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     } else if (L.cout == 32) {
         if (make_map<4>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
-        rc = launch_tc<32, 4, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
+        rc = launch_tc<32, 4, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     } else {
         if (make_map<2>(&map, src, X, Y, Z, c4, tiles, slab_stride)) return 1;
-        rc = launch_tc<64, 2, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, s);
+        rc = launch_tc<64, 2, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     }
     if (rc) return 1;
     CT_LAUNCHED("conv3_tc_kernel");
