@@ -43,6 +43,15 @@ SIGNATURES = {
     "ct_normalize_image": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
                                    c_void_p, c_size_t, c_void_p]),
     "ct_median": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ct_select_state_bytes": (c_size_t, []),
+    "ct_select_hist_offset": (c_size_t, []),
+    "ct_select_passes": (c_int, [c_int]),
+    "ct_select_begin": (c_int, [c_void_p, c_longlong, c_void_p]),
+    "ct_select_hist": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_void_p]),
+    "ct_select_scan": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "ct_select_finish": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "ct_normalize_image_with_median": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int,
+                                               c_void_p, c_void_p, c_size_t, c_void_p]),
     "ct_unet_weight_count": (c_size_t, [C.POINTER(CtUNetSpec)]),
     "ct_unet_create": (c_int, [C.POINTER(CtUNetSpec), c_void_p, c_size_t, C.POINTER(c_void_p)]),
     "ct_unet_destroy": (None, [c_void_p]),
@@ -56,6 +65,10 @@ SIGNATURES = {
     "ct_unet_tile_count": (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(c_int * 3), C.POINTER(c_int * 3)]),
     "ct_unet3_prediction": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_int * 3),
                                     c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "ct_unet3_prediction_block": (c_int, [c_void_p, c_void_p, C.POINTER(c_int * 3), C.POINTER(c_int * 3), c_void_p,
+                                          C.POINTER(c_int * 3), C.POINTER(c_int * 3), c_int, c_int, c_int,
+                                          C.POINTER(c_int * 3), C.POINTER(c_int * 3), C.POINTER(c_int * 3),
+                                          c_void_p, c_size_t, c_int, c_void_p]),
     "ct_ffn_weight_count": (c_size_t, []),
     "ct_ffn_create": (c_int, [c_void_p, c_size_t, C.POINTER(c_void_p)]),
     "ct_ffn_destroy": (None, [c_void_p]),

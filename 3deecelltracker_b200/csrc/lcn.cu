@@ -12,6 +12,7 @@
 // merged with __match_any_sync before the shared-memory atomic, because microscopy stacks put most
 // voxels into a handful of background bins.
 #include "common.cuh"
+#include <cstddef>
 
 namespace ct {
 
@@ -227,7 +228,7 @@ __global__ void set_nan(double* p) { *p = __longlong_as_double(0x7ff800000000000
 
 template <typename T>
 static int normalize_impl(const T* raw, float* out, int X, int Y, int Z, float noise, int fx, int fy,
-                          int subtract_median, void* ws, size_t ws_bytes, cudaStream_t s) {
+                          int subtract_median, const double* median_given, void* ws, size_t ws_bytes, cudaStream_t s) {
     const long long n = (long long)X * Y * Z;
     ProfScope prof(PROF_LCN, s);
     Arena a(ws, ws_bytes);
@@ -237,7 +238,9 @@ static int normalize_impl(const T* raw, float* out, int X, int Y, int Z, float n
     float* avg = a.take<float>(n);
     float* t2 = t1;     // t1 is dead after pass 2
     CT_REQUIRE(a.ok(), "ct_normalize_image: workspace too small (%zu < %zu)", ws_bytes, a.off);
-    if (subtract_median) {
+    if (median_given) {
+        med = const_cast<double*>(median_given);
+    } else if (subtract_median) {
         if (median_impl<T>(raw, n, med, st, s)) return 1;
     } else {
         set_nan<<<1, 1, 0, s>>>(med);
@@ -288,12 +291,81 @@ int ct_normalize_image(const void* raw, int dtype, float* out, int x, int y, int
     CT_REQUIRE((filter_x & 1) && (filter_y & 1), "ct_normalize_image: filter sizes must be odd");
     cudaStream_t s = (cudaStream_t)stream;
     switch (dtype) {
-        case 0: return ct::normalize_impl<uint16_t>((const uint16_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, ws, ws_bytes, s);
-        case 1: return ct::normalize_impl<float>((const float*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, ws, ws_bytes, s);
-        case 2: return ct::normalize_impl<uint8_t>((const uint8_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, ws, ws_bytes, s);
+        case 0: return ct::normalize_impl<uint16_t>((const uint16_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, nullptr, ws, ws_bytes, s);
+        case 1: return ct::normalize_impl<float>((const float*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, nullptr, ws, ws_bytes, s);
+        case 2: return ct::normalize_impl<uint8_t>((const uint8_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, subtract_median, nullptr, ws, ws_bytes, s);
     }
     ct::set_error("ct_normalize_image: unsupported dtype %d", dtype);
     return 1;
+}
+
+int ct_normalize_image_with_median(const void* raw, int dtype, float* out, int x, int y, int z, float noise_level,
+                                   int filter_x, int filter_y, const double* median, void* ws, size_t ws_bytes,
+                                   void* stream) {
+    CT_REQUIRE(x > 0 && y > 0 && z > 0, "ct_normalize_image_with_median: empty block");
+    CT_REQUIRE((filter_x & 1) && (filter_y & 1), "ct_normalize_image_with_median: filter sizes must be odd");
+    CT_REQUIRE(median, "ct_normalize_image_with_median: null median");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case 0: return ct::normalize_impl<uint16_t>((const uint16_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, 1, median, ws, ws_bytes, s);
+        case 1: return ct::normalize_impl<float>((const float*)raw, out, x, y, z, noise_level, filter_x, filter_y, 1, median, ws, ws_bytes, s);
+        case 2: return ct::normalize_impl<uint8_t>((const uint8_t*)raw, out, x, y, z, noise_level, filter_x, filter_y, 1, median, ws, ws_bytes, s);
+    }
+    ct::set_error("ct_normalize_image_with_median: unsupported dtype %d", dtype);
+    return 1;
+}
+
+// ---- lock-step radix select for a volume spread over several GPUs (see ct3d.h)
+size_t ct_select_state_bytes(void) { return sizeof(ct::SelectState); }
+size_t ct_select_hist_offset(void) { return offsetof(ct::SelectState, hist); }
+int ct_select_passes(int dtype) { return dtype == 0 ? 2 : dtype == 1 ? 4 : dtype == 2 ? 1 : -1; }
+
+int ct_select_begin(void* state, long long total_count, void* stream) {
+    CT_REQUIRE(state && total_count > 0, "ct_select_begin: bad argument");
+    ct::select_init<<<1, 256, 0, (cudaStream_t)stream>>>((ct::SelectState*)state, total_count);
+    CT_LAUNCHED("select_init");
+    return 0;
+}
+
+int ct_select_hist(const void* raw, int dtype, long long local_count, void* state, int pass, void* stream) {
+    const int passes = ct_select_passes(dtype);
+    CT_REQUIRE(state && passes > 0 && pass >= 0 && pass < passes && local_count >= 0, "ct_select_hist: bad argument");
+    if (local_count == 0) return 0;
+    CT_REQUIRE(raw, "ct_select_hist: null data");
+    const int bits = passes * 8, shift = bits - 8 * (pass + 1);
+    int blocks = (int)((local_count + 256 * 16 - 1) / (256 * 16));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cudaStream_t s = (cudaStream_t)stream;
+    ct::SelectState* st = (ct::SelectState*)state;
+    switch (dtype) {
+        case 0: ct::select_hist<uint16_t><<<blocks, 256, 0, s>>>((const uint16_t*)raw, local_count, st, shift, bits); break;
+        case 1: ct::select_hist<float><<<blocks, 256, 0, s>>>((const float*)raw, local_count, st, shift, bits); break;
+        default: ct::select_hist<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)raw, local_count, st, shift, bits); break;
+    }
+    CT_LAUNCHED("select_hist");
+    return 0;
+}
+
+int ct_select_scan(void* state, int dtype, int pass, void* stream) {
+    const int passes = ct_select_passes(dtype);
+    CT_REQUIRE(state && passes > 0 && pass >= 0 && pass < passes, "ct_select_scan: bad argument");
+    ct::select_scan<<<1, 256, 0, (cudaStream_t)stream>>>((ct::SelectState*)state, passes * 8 - 8 * (pass + 1));
+    CT_LAUNCHED("select_scan");
+    return 0;
+}
+
+int ct_select_finish(const void* state, int dtype, double* median_out, void* stream) {
+    CT_REQUIRE(state && median_out, "ct_select_finish: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const ct::SelectState* st = (const ct::SelectState*)state;
+    switch (dtype) {
+        case 0: ct::select_finish<uint16_t><<<1, 1, 0, s>>>(st, median_out); break;
+        case 1: ct::select_finish<float><<<1, 1, 0, s>>>(st, median_out); break;
+        case 2: ct::select_finish<uint8_t><<<1, 1, 0, s>>>(st, median_out); break;
+        default: ct::set_error("ct_select_finish: unsupported dtype %d", dtype); return 1;
+    }
+    CT_LAUNCHED("select_finish");
+    return 0;
 }
 
 }  // extern "C"

@@ -26,21 +26,37 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
     return j < n ? j : period - j;
 }
 
+// Geometry of a tiled prediction.  The tiles visited are the sub-grid tlo <= (i,j,k) < tlo + tn of the volume's tile
+// grid, enumerated row-major (k fastest); source voxels live in a box `in_lo .. in_lo + in_dim` of the volume
+// (the whole volume on one GPU, the rank's haloed block under spatial decomposition) and results go to a box
+// `out_lo .. out_lo + out_dim`.
+struct TileGeom {
+    int X, Y, Z;                  // whole volume (reflect padding and the final crop refer to it)
+    int TX, TY, TZ;               // model input tile
+    int tlo[3], tn[3];            // tile sub-grid: origin and extent
+    int c[3], b[3];               // centre window size and shrink (= offset of the window inside the tile)
+    int in_lo[3], in_dim[3];
+    int out_lo[3], out_dim[3];
+};
+__device__ __forceinline__ void tile_ijk(const TileGeom& g, int ordinal, int& i, int& j, int& k) {
+    k = g.tlo[2] + ordinal % g.tn[2]; ordinal /= g.tn[2];
+    j = g.tlo[1] + ordinal % g.tn[1]; ordinal /= g.tn[1];
+    i = g.tlo[0] + ordinal;
+}
+
 // Tile gather.  mode 0: tile t of the volume's tile grid, reflect-padded (unet3d.py:235,247-249).
 //               mode 1: tiles are given explicitly as (B, x, y, z) (Keras model.predict).
 // Output: [tile][1 chunk][TX][TY][TZ][4] with channels 1..3 = 0.
 __global__ void __launch_bounds__(256)
 gather_tiles(const float* __restrict__ src, float4* __restrict__ slab, size_t slab_stride4, size_t in_off4,
-             int mode, int tile_first, int X, int Y, int Z, int TX, int TY, int TZ,
-             int ny, int nz, int cx, int cy, int cz, int bx, int by, int bz, int in_slot) {
+             int mode, int tile_first, const TileGeom g, int in_slot) {
     const int t = blockIdx.y;
     float amax = 0.f;
-    const size_t tile_vox = (size_t)TX * TY * TZ;
+    const int TY = g.TY, TZ = g.TZ;
+    const size_t tile_vox = (size_t)g.TX * TY * TZ;
     float4* out = slab + (size_t)t * slab_stride4 + in_off4;
-    int gi = tile_first + t;
-    const int k = gi % nz; gi /= nz;
-    const int j = gi % ny; gi /= ny;
-    const int i = gi;
+    int i, j, k;
+    tile_ijk(g, tile_first + t, i, j, k);
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < tile_vox; v += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(v % TZ);
         size_t r = v / TZ;
@@ -48,10 +64,10 @@ gather_tiles(const float* __restrict__ src, float4* __restrict__ slab, size_t sl
         const int a = (int)(r / TY);
         float val;
         if (mode == 0) {
-            const int sx = reflect_index(i * cx + a - bx, X);
-            const int sy = reflect_index(j * cy + b - by, Y);
-            const int sz = reflect_index(k * cz + c - bz, Z);
-            val = src[((size_t)sx * Y + sy) * Z + sz];
+            const int sx = reflect_index(i * g.c[0] + a - g.b[0], g.X) - g.in_lo[0];
+            const int sy = reflect_index(j * g.c[1] + b - g.b[1], g.Y) - g.in_lo[1];
+            const int sz = reflect_index(k * g.c[2] + c - g.b[2], g.Z) - g.in_lo[2];
+            val = src[((size_t)sx * g.in_dim[1] + sy) * g.in_dim[2] + sz];
         } else {
             val = src[(size_t)(tile_first + t) * tile_vox + v];
         }
@@ -121,17 +137,15 @@ upsample_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_d
 __global__ void __launch_bounds__(256)
 head_scatter(const float4* __restrict__ slab, size_t slab_stride4, size_t last_off4, int c4,
              const float* __restrict__ head_w, float head_b, float* __restrict__ prob,
-             int mode, int tile_first, int X, int Y, int Z, int TX, int TY, int TZ,
-             int ny, int nz, int cx, int cy, int cz, int bx, int by, int bz) {
+             int mode, int tile_first, const TileGeom g) {
     const int t = blockIdx.y;
+    const int TX = g.TX, TY = g.TY, TZ = g.TZ;
     const size_t tile_vox = (size_t)TX * TY * TZ;
     const float4* in = slab + (size_t)t * slab_stride4 + last_off4;
-    int gi = tile_first + t;
-    const int k = gi % nz; gi /= nz;
-    const int j = gi % ny; gi /= ny;
-    const int i = gi;
-    const int wx = mode == 0 ? cx : TX, wy = mode == 0 ? cy : TY, wz = mode == 0 ? cz : TZ;
-    const int ox = mode == 0 ? bx : 0, oy = mode == 0 ? by : 0, oz = mode == 0 ? bz : 0;
+    int i, j, k;
+    tile_ijk(g, tile_first + t, i, j, k);
+    const int wx = mode == 0 ? g.c[0] : TX, wy = mode == 0 ? g.c[1] : TY, wz = mode == 0 ? g.c[2] : TZ;
+    const int ox = mode == 0 ? g.b[0] : 0, oy = mode == 0 ? g.b[1] : 0, oz = mode == 0 ? g.b[2] : 0;
     const size_t win = (size_t)wx * wy * wz;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < win; v += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(v % wz);
@@ -148,8 +162,11 @@ head_scatter(const float4* __restrict__ slab, size_t slab_stride4, size_t last_o
         }
         const float p = 1.f / (1.f + expf(-acc));
         if (mode == 0) {
-            const int gx = i * cx + a, gy = j * cy + b, gz = k * cz + c;
-            if (gx < X && gy < Y && gz < Z) prob[((size_t)gx * Y + gy) * Z + gz] = p;
+            const int gx = i * g.c[0] + a, gy = j * g.c[1] + b, gz = k * g.c[2] + c;
+            const int lx = gx - g.out_lo[0], ly = gy - g.out_lo[1], lz = gz - g.out_lo[2];
+            if (gx < g.X && gy < g.Y && gz < g.Z && lx >= 0 && ly >= 0 && lz >= 0 && lx < g.out_dim[0] &&
+                ly < g.out_dim[1] && lz < g.out_dim[2])
+                prob[((size_t)lx * g.out_dim[1] + ly) * g.out_dim[2] + lz] = p;
         } else {
             prob[(size_t)(tile_first + t) * tile_vox + tv] = p;
         }
@@ -420,6 +437,19 @@ extern "C" int ct_unet_tile_count(const CtUNet* net, int x, int y, int z, const 
     return num[0] * num[1] * num[2];
 }
 
+static TileGeom make_geom(const CtUNet* net, int x, int y, int z, const int centre[3], const int shrink[3],
+                          const int tlo[3], const int tn[3], const int in_lo[3], const int in_dim[3],
+                          const int out_lo[3], const int out_dim[3]) {
+    TileGeom g{};
+    g.X = x; g.Y = y; g.Z = z;
+    g.TX = net->spec.in_x; g.TY = net->spec.in_y; g.TZ = net->spec.in_z;
+    for (int a = 0; a < 3; ++a) {
+        g.tlo[a] = tlo[a]; g.tn[a] = tn[a]; g.c[a] = centre[a]; g.b[a] = shrink[a];
+        g.in_lo[a] = in_lo[a]; g.in_dim[a] = in_dim[a]; g.out_lo[a] = out_lo[a]; g.out_dim[a] = out_dim[a];
+    }
+    return g;
+}
+
 // Runs the op plan on `tiles` slabs that already hold their padded input.
 static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) {
     const size_t stride = net->slab_floats;
@@ -456,8 +486,7 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) 
 }
 
 static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode, int first, int last,
-                     int X, int Y, int Z, const int centre[3], const int num[3], const int shrink[3],
-                     void* ws, size_t ws_bytes, int tiles_per_batch, cudaStream_t s) {
+                     const TileGeom& geo, void* ws, size_t ws_bytes, int tiles_per_batch, cudaStream_t s) {
     CT_REQUIRE(tiles_per_batch >= 1, "unet: tiles_per_batch must be >= 1");
     CT_REQUIRE(ws_bytes >= ct_unet_workspace_bytes(net, tiles_per_batch), "unet: workspace too small (%zu < %zu)",
                ws_bytes, ct_unet_workspace_bytes(net, tiles_per_batch));
@@ -470,13 +499,11 @@ static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode,
         dim3 g(grid_for(tile_vox), nt);
         CT_CUDA(cudaMemset2DAsync(slab0, net->slab_floats * sizeof(float), 0, AMAX_SLOTS * sizeof(float), nt, s));
         gather_tiles<<<g, 256, 0, s>>>(src, reinterpret_cast<float4*>(slab0), net->slab_floats / 4, net->in_off / 4, mode, t0,
-                                       X, Y, Z, TX, TY, TZ, num[1], num[2], centre[0], centre[1], centre[2],
-                                       shrink[0], shrink[1], shrink[2], net->in_slot);
+                                       geo, net->in_slot);
         CT_LAUNCHED("gather_tiles");
         if (run_plan(net, slab0, nt, s)) return 1;
         head_scatter<<<g, 256, 0, s>>>(reinterpret_cast<const float4*>(slab0), net->slab_floats / 4, net->last_off / 4,
-                                       net->last_c / 4, net->head_w, net->head_b, prob, mode, t0, X, Y, Z, TX, TY, TZ,
-                                       num[1], num[2], centre[0], centre[1], centre[2], shrink[0], shrink[1], shrink[2]);
+                                       net->last_c / 4, net->head_w, net->head_b, prob, mode, t0, geo);
         CT_LAUNCHED("head_scatter");
     }
     return 0;
@@ -537,10 +564,11 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
 extern "C" int ct_unet_predict_tiles(const CtUNet* net, const float* tiles, float* prob, int batch,
                                      void* ws, size_t ws_bytes, int tiles_per_batch, void* stream) {
     CT_REQUIRE(net && tiles && prob && batch >= 0, "ct_unet_predict_tiles: bad argument");
-    const int one[3] = {1, 1, 1}, zero[3] = {0, 0, 0};
-    const int num[3] = {batch, 1, 1};
-    return run_tiles(net, tiles, prob, 1, 0, batch, 0, 0, 0, one, num, zero, ws, ws_bytes, tiles_per_batch,
-                     (cudaStream_t)stream);
+    TileGeom g{};
+    g.TX = net->spec.in_x; g.TY = net->spec.in_y; g.TZ = net->spec.in_z;
+    g.tn[0] = batch; g.tn[1] = g.tn[2] = 1;
+    for (int a = 0; a < 3; ++a) g.c[a] = 1;
+    return run_tiles(net, tiles, prob, 1, 0, batch, g, ws, ws_bytes, tiles_per_batch, (cudaStream_t)stream);
 }
 
 extern "C" int ct_unet3_prediction(const CtUNet* net, const float* vol_norm, float* prob, int x, int y, int z,
@@ -552,6 +580,46 @@ extern "C" int ct_unet3_prediction(const CtUNet* net, const float* vol_norm, flo
     const int total = num[0] * num[1] * num[2];
     CT_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= total,
                "ct_unet3_prediction: tile range [%d,%d) outside [0,%d)", tile_begin, tile_end, total);
-    return run_tiles(net, vol_norm, prob, 0, tile_begin, tile_end, x, y, z, centre, num, shrink, ws, ws_bytes,
-                     tiles_per_batch, (cudaStream_t)stream);
+    const int zero[3] = {0, 0, 0}, dim[3] = {x, y, z};
+    const TileGeom g = make_geom(net, x, y, z, centre, shrink, zero, num, zero, dim, zero, dim);
+    return run_tiles(net, vol_norm, prob, 0, tile_begin, tile_end, g, ws, ws_bytes, tiles_per_batch, (cudaStream_t)stream);
+}
+
+// numpy.pad(mode='reflect') index on the host (same triangle wave as the device function)
+static int reflect_host(int j, int n) {
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    j %= period;
+    if (j < 0) j += period;
+    return j < n ? j : period - j;
+}
+
+extern "C" int ct_unet3_prediction_block(const CtUNet* net, const float* vol_block, const int in_lo[3], const int in_dim[3],
+                                         float* prob_block, const int out_lo[3], const int out_dim[3], int x, int y, int z,
+                                         const int shrink[3], const int tile_lo[3], const int tile_hi[3],
+                                         void* ws, size_t ws_bytes, int tiles_per_batch, void* stream) {
+    CT_REQUIRE(net && vol_block && prob_block && in_lo && in_dim && out_lo && out_dim && shrink && tile_lo && tile_hi,
+               "ct_unet3_prediction_block: null argument");
+    int centre[3], num[3], tn[3];
+    if (tile_geometry(net, x, y, z, shrink, centre, num)) return 1;
+    const int in[3] = {net->spec.in_x, net->spec.in_y, net->spec.in_z};
+    const int vol[3] = {x, y, z};
+    for (int a = 0; a < 3; ++a) {
+        CT_REQUIRE(tile_lo[a] >= 0 && tile_lo[a] <= tile_hi[a] && tile_hi[a] <= num[a],
+                   "ct_unet3_prediction_block: tile range [%d,%d) outside [0,%d) on axis %d", tile_lo[a], tile_hi[a], num[a], a);
+        tn[a] = tile_hi[a] - tile_lo[a];
+        CT_REQUIRE(in_dim[a] > 0 && out_dim[a] > 0 && in_lo[a] >= 0 && in_lo[a] + in_dim[a] <= vol[a],
+                   "ct_unet3_prediction_block: input box [%d,%d) outside the volume on axis %d", in_lo[a], in_lo[a] + in_dim[a], a);
+        // every coordinate the tiles read on this axis, after reflection, must be inside the input box
+        for (int j = tile_lo[a] * centre[a] - shrink[a]; j < (tile_hi[a] - 1) * centre[a] - shrink[a] + in[a] && tn[a] > 0; ++j) {
+            const int r = reflect_host(j, vol[a]);
+            CT_REQUIRE(r >= in_lo[a] && r < in_lo[a] + in_dim[a],
+                       "ct_unet3_prediction_block: tiles read voxel %d on axis %d, outside the input box [%d,%d)", r, a,
+                       in_lo[a], in_lo[a] + in_dim[a]);
+        }
+    }
+    const int total = tn[0] * tn[1] * tn[2];
+    if (total == 0) return 0;
+    const TileGeom g = make_geom(net, x, y, z, centre, shrink, tile_lo, tn, in_lo, in_dim, out_lo, out_dim);
+    return run_tiles(net, vol_block, prob_block, 0, 0, total, g, ws, ws_bytes, tiles_per_batch, (cudaStream_t)stream);
 }

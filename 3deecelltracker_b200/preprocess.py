@@ -46,6 +46,26 @@ def normalize_image_device(raw_dev, noise_level, filter_size=(27, 27, 1), out=No
     return out
 
 
+def normalize_block_device(raw_block_dev, noise_level, median_dev, filter_size=(27, 27, 1), out=None):
+    """LCN of a block of a larger volume with the volume's median supplied (1-element float64 CUDA tensor): the
+    per-rank step of the spatially decomposed `_normalize_image` (spatial.py).  Output voxels within filter/2 of a
+    block face that is not a face of the volume are not meaningful (ct3d.h)."""
+    if raw_block_dev.dim() != 3 or filter_size[2] != 1:
+        raise ValueError("expected a 3D block and a filter of z-extent 1")
+    lib = _lib.lib()
+    raw_block_dev = raw_block_dev.contiguous()
+    x, y, z = (int(s) for s in raw_block_dev.shape)
+    if out is None:
+        out = torch.empty((x, y, z), dtype=torch.float32, device=raw_block_dev.device)
+    ws = WORKSPACE.get("lcn", lib.ct_normalize_workspace_bytes(x, y, z))
+    wp = aligned_ptr(ws)
+    _lib.check(lib.ct_normalize_image_with_median(raw_block_dev.data_ptr(), _DTYPES[raw_block_dev.dtype], out.data_ptr(),
+                                                  x, y, z, float(noise_level), int(filter_size[0]), int(filter_size[1]),
+                                                  median_dev.data_ptr(), wp, ws.numel() - (wp - ws.data_ptr()),
+                                                  stream_ptr()))
+    return out
+
+
 def median_device(raw_dev):
     """np.median of a CUDA tensor (uint16 / uint8 / float32), returned as a 1-element float64 CUDA tensor."""
     lib = _lib.lib()

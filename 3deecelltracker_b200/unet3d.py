@@ -210,6 +210,26 @@ class UNet3:
         return out
 
 
+    def prediction_block_device(self, block_dev, block_lo, volume_shape, shrink, tile_lo, tile_hi, out_lo, out_dim,
+                                out=None):
+        """One rank's share of unet3_prediction under spatial decomposition (spatial.py): block_dev holds the
+        normalised voxels of the box starting at block_lo; tiles tile_lo <= (i,j,k) < tile_hi of the volume's tile
+        grid are run and their centre windows written into a block starting at out_lo of extent out_dim."""
+        block_dev = block_dev.contiguous()
+        x, y, z = (int(s) for s in volume_shape)
+        if out is None:
+            out = torch.zeros(tuple(int(s) for s in out_dim), dtype=torch.float32, device=block_dev.device)
+        n = max(1, math.prod(int(h) - int(l) for l, h in zip(tile_lo, tile_hi)))
+        tpb = max(1, min(self.tiles_per_batch, n))
+        wp, wn = self._workspace(tpb)
+        i3 = lambda v: (C.c_int * 3)(*[int(q) for q in v])
+        _lib.check(_lib.lib().ct_unet3_prediction_block(
+            self._handle, block_dev.data_ptr(), C.byref(i3(block_lo)), C.byref(i3(block_dev.shape)), out.data_ptr(),
+            C.byref(i3(out_lo)), C.byref(i3(out.shape)), x, y, z, C.byref(i3(shrink)), C.byref(i3(tile_lo)),
+            C.byref(i3(tile_hi)), wp, wn, tpb, stream_ptr()))
+        return out
+
+
 def unet3_a(**kw):
     """unet3d.py:26-37."""
     return UNet3("a", **kw)

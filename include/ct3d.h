@@ -54,6 +54,31 @@ int ct_normalize_image(const void* raw, int dtype, float* out, int x, int y, int
 int ct_median(const void* raw, int dtype, long long count, double* median_out, void* ws, size_t ws_bytes,
               void* stream);
 
+/* The same median when the voxels of one volume are spread over several GPUs (config 3: a 1024x1024x96 stack cut
+ * 2x2x2).  np.median (preprocess.py:181) is a GLOBAL order statistic, so the radix select runs in
+ * lock-step on every rank: per pass each rank histograms one 8-bit digit of ITS voxels into `state`, the caller
+ * sums the 512 histogram words at byte offset ct_select_hist_offset() of `state` over the ranks (ncclAllReduce on
+ * uint32), and the scan narrows the key prefix identically everywhere.  passes: uint8 1, uint16 2, float32 4.
+ *     ct_select_begin(state, total_count); for pass in 0 .. ct_select_passes(dtype)-1:
+ *         ct_select_hist(...); <all-reduce the histogram>; ct_select_scan(...);
+ *     ct_select_finish(state, dtype, median_out)
+ * With one rank (no all-reduce) the sequence is exactly ct_median. */
+size_t ct_select_state_bytes(void);
+size_t ct_select_hist_offset(void);
+int ct_select_passes(int dtype);
+int ct_select_begin(void* state, long long total_count, void* stream);
+int ct_select_hist(const void* raw, int dtype, long long local_count, void* state, int pass, void* stream);
+int ct_select_scan(void* state, int dtype, int pass, void* stream);
+int ct_select_finish(const void* state, int dtype, double* median_out, void* stream);
+/* ct_normalize_image with the median supplied by the caller (1 double, device): LCN of a BLOCK of a larger
+ * volume.  Zero padding applies at the block's own faces, so output voxels closer than filter/2 to a face that is
+ * not a face of the whole volume are not the volume's values -- the caller passes a block with that margin
+ * (halo exchange) and discards it.  Voxels whose whole window lies inside the block are bit-identical to the
+ * single-call result (per-voxel windows are summed in a fixed order, not by running sums). */
+int ct_normalize_image_with_median(const void* raw, int dtype, float* out, int x, int y, int z, float noise_level,
+                                   int filter_x, int filter_y, const double* median, void* ws, size_t ws_bytes,
+                                   void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3D U-Net.  Replaces the Keras graphs of unet3d.py:26-98 (unet3_a/b/c), the blocks :101-200 and the
  * tiled prediction unet3_prediction (unet3d.py:203-256).
@@ -99,6 +124,16 @@ int ct_unet_tile_count(const CtUNet* net, int x, int y, int z, const int shrink[
 int ct_unet3_prediction(const CtUNet* net, const float* vol_norm, float* prob, int x, int y, int z,
                         const int shrink[3], int tile_begin, int tile_end,
                         void* ws, size_t ws_bytes, int tiles_per_batch, void* stream);
+/* unet3_prediction for one rank of a spatially decomposed volume (config 3).  The rank holds the normalised voxels
+ * of the box in_lo .. in_lo+in_dim (global coordinates) and runs the tiles tile_lo <= (i,j,k) < tile_hi of the
+ * volume's tile grid; every voxel those tiles read after reflect padding against the WHOLE volume (x,y,z) must lie
+ * inside the box (checked, error otherwise).  Centre windows are written into prob_block, which covers the box
+ * out_lo .. out_lo+out_dim; voxels outside it are dropped.  Same tiles, same kernels: the union over ranks is
+ * bit-identical to ct_unet3_prediction on one GPU. */
+int ct_unet3_prediction_block(const CtUNet* net, const float* vol_block, const int in_lo[3], const int in_dim[3],
+                              float* prob_block, const int out_lo[3], const int out_dim[3], int x, int y, int z,
+                              const int shrink[3], const int tile_lo[3], const int tile_hi[3],
+                              void* ws, size_t ws_bytes, int tiles_per_batch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FFN match.  Replaces ffn.py:225-265 (FFN.call), ffn.py:268-327 (initial_matching_ffn) and
