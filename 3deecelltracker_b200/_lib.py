@@ -37,6 +37,7 @@ SIGNATURES = {
     "ct_abi_version": (c_int, []),
     "ct_last_error": (C.c_char_p, []),
     "ct_launch_count": (C.c_ulonglong, []),
+    "ct_set_reserved_sms": (c_int, [c_int]),
     "ct_profile_enable": (c_int, [c_int]),
     "ct_profile_read": (c_int, [c_int, C.POINTER(c_double), C.POINTER(C.c_ulonglong), c_int]),
     "ct_normalize_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -6,6 +6,7 @@
 namespace ct {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_reserved_sms{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -72,6 +73,12 @@ int ct_profile_read(int tag, double* total_ms, unsigned long long* count, int re
         ct::g_prof.swap(keep);
     }
     return 0;
+}
+
+int ct_set_reserved_sms(int n) {
+    if (n < 0) n = 0;
+    if (n > 64) n = 64;
+    return ct::g_reserved_sms.exchange(n);
 }
 
 int ct_abi_version(void) { return CT3D_ABI_VERSION; }

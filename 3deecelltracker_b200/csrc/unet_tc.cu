@@ -539,7 +539,8 @@ static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, fl
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
-    const int grid = g.units < sm_count() ? g.units : sm_count();
+    const int sms = sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
+    const int grid = g.units < sms ? g.units : sms;
     conv3_tc_kernel<N, BX, STAGES><<<grid, TC_THREADS, Cfg::SMEM, s>>>(map, L.w_tc, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
 }

@@ -48,7 +48,7 @@ def normalize_image_device(raw_dev, noise_level, filter_size=(27, 27, 1), out=No
 
 def normalize_block_device(raw_block_dev, noise_level, median_dev, filter_size=(27, 27, 1), out=None):
     """LCN of a block of a larger volume with the volume's median supplied (1-element float64 CUDA tensor): the
-    per-rank step of the spatially decomposed `_normalize_image` (spatial.py).  Output voxels within filter/2 of a
+    per-rank step of the spatially decomposed `_normalize_image` (spatial.py).  Output voxels within 2 * (filter // 2) of a
     block face that is not a face of the volume are not meaningful (ct3d.h)."""
     if raw_block_dev.dim() != 3 or filter_size[2] != 1:
         raise ValueError("expected a 3D block and a filter of z-extent 1")

@@ -7,8 +7,8 @@ contiguous block of the RAW stack and a contiguous sub-grid of the U-Net tile gr
   * 2 (uint16) or 4 (float32) all-reduces of a 512-word histogram: `np.median` is a global order statistic
     (`ct_select_*` in ct3d.h), and
   * one round of send/recv of raw halo boxes: the voxels a rank's tiles read (reflect padding resolved against the
-    whole volume, unet3d.py:235) plus the 13-voxel reach of the 27 x 27 x 1 LCN window (preprocess.py:163-166)
-    that other ranks own.
+    whole volume, unet3d.py:235) plus the 26-voxel reach of the two chained 27 x 27 x 1 LCN windows
+    (preprocess.py:163-166: the std window reads avg, which reads its own window) that other ranks own.
 
 Nothing else moves: tiles are independent given the normalised input, so each rank writes the centre windows of its
 own tiles.  The union over ranks is bit-identical to the single-GPU result (same tiles, same kernels, window sums
@@ -21,7 +21,9 @@ import math
 import torch
 import torch.distributed as dist
 
-LCN_RADIUS = (13, 13, 0)          # (27, 27, 1) window, preprocess.py:185
+# Reach of the LCN with its (27, 27, 1) window (preprocess.py:163-166,185): std[p] sums (v - avg)^2 over the window
+# of p, and avg[q] sums v over the window of q, so one output voxel reads raw voxels up to 2 * 13 away in x and y.
+LCN_RADIUS = (26, 26, 0)
 
 
 def _reflect(j, n):

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 from scipy import ndimage as ndm
 
+from . import _lib
 from ._device import to_device
 from .ffn import FFN
 from .preprocess import normalize_image_device, _raw_to_device
@@ -106,6 +107,7 @@ class Tracker:
         self.cells_on_boundary = None
         self.keep_prob_on_device = False
         self._unet_cache = {}
+        self._seg_stream = None
 
     # ------------------------------------------------------------------ models
     def load_unet(self, model=None):
@@ -156,12 +158,34 @@ class Tracker:
         prob_dev = self.unet_model.prediction_device(norm_dev, self.shrink)
         return prob_dev
 
+    def _enqueue_segmentation(self, image_raw, vol):
+        """LCN + U-Net of `vol` on the segmentation stream (all segmentation work is serialised there: it shares
+        one set of workspaces); returns immediately."""
+        if self._seg_stream is None:
+            self._seg_stream = torch.cuda.Stream()
+        self._seg_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._seg_stream):
+            prob_dev = self._save_unet_regions(image_raw, vol)
+            ready = torch.cuda.Event()
+            ready.record(self._seg_stream)
+        self._unet_cache[vol] = (prob_dev, ready)
+
     def _predict_cellregions(self, image_raw, vol):
-        """tracker.py:652-660 (first-pass fp32 result; the reference's fp16 disk cache is not reproduced)."""
+        """tracker.py:652-660 (first-pass fp32 result; the reference's fp16 disk cache is not reproduced).  A result
+        prefetched by `prefetch_segmentation` is picked up here."""
         if vol not in self._unet_cache:
-            self._unet_cache = {vol: self._save_unet_regions(image_raw, vol)}
-        prob_dev = self._unet_cache[vol]
+            self._enqueue_segmentation(image_raw, vol)
+        prob_dev, ready = self._unet_cache[vol]
+        torch.cuda.current_stream().wait_event(ready)
+        self._unet_cache = {v: e for v, e in self._unet_cache.items() if v >= vol}
         return prob_dev.cpu().numpy()[None, ..., None]
+
+    def prefetch_segmentation(self, vol):
+        """Enqueue LCN + U-Net of volume `vol` so that it overlaps the match + track stage of the volume before it
+        (pipeline.py explains why the two stages pair well).  Used by `track`."""
+        if vol > self.volume_num or vol in self.miss_frame or vol in self._unet_cache:
+            return
+        self._enqueue_segmentation(self._read_raw(vol), vol)
 
     def _watershed(self, image_cell_bg, method):
         """Stand-in for tracker.py:671-684 / watershed.py (see module docstring): connected components."""
@@ -323,8 +347,14 @@ class Tracker:
     def track(self, fig=None, ax=None, from_volume=2):
         """tracker.py:1415-1431."""
         self._reset_tracking_state(from_volume)
-        for vol in range(from_volume, self.volume_num + 1):
-            self.track_one_vol(vol, fig, ax)
+        lib = _lib.lib()
+        old = lib.ct_set_reserved_sms(1)          # the EM's single CTA keeps an SM while the next volume is segmented
+        try:
+            for vol in range(from_volume, self.volume_num + 1):
+                self.prefetch_segmentation(vol + 1)
+                self.track_one_vol(vol, fig, ax)
+        finally:
+            lib.ct_set_reserved_sms(old)
         return None
 
     def save_coordinates(self, path=None):

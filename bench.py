@@ -132,26 +132,17 @@ def make_inputs(frame):
 
 
 class Step:
-    """Device pipeline of one frame; mirrors Tracker.track_one_vol's hot-path calls."""
+    """One frame through the product's FramePipeline (pipeline.py; mirrors Tracker.track_one_vol's hot-path calls):
+    segmentation of the step's volume on the current stream while the match + track stage of the previous volume
+    runs on the side stream; the streams join inside the step, so every step performs one full frame of each stage.
+    With overlap=False the two stages run back to back on one stream."""
 
-    def __init__(self, unet, ffn):
-        self.unet, self.ffn = unet, ffn
-        self.pre, self.track = mod("preprocess"), mod("track")
+    def __init__(self, unet, ffn, overlap=True):
+        self.pipe = mod("pipeline").FramePipeline(unet, ffn, NOISE_LEVEL, BETA_TK, LAMBDA_TK, MAXITER_TK, SHRINK,
+                                                  overlap=overlap)
 
     def run(self, raw_dev, ref_dev, tgt_dev, tracked_dev):
-        import torch
-        norm = self.pre.normalize_image_device(raw_dev, NOISE_LEVEL)
-        prob = self.unet.prediction_device(norm, SHRINK)
-        tr = self.track
-        inter, pred = ref_dev, tracked_dev
-        for i in range(REP_NUM_PRGLS):
-            beta = BETA_TK * (0.8 ** i)
-            corr = self.ffn.match_device(inter, tgt_dev, 20)
-            p = tr.run_em([tr.EmProblem(inter, tgt_dev, corr)], tr.MODE_TRACK, beta, LAMBDA_TK, MAXITER_TK, 1e8, 0.5)[0]
-            pred = tr.predict_one_rep_device(pred, inter, beta, p.coef)
-            inter = p.ref_out
-        out = tr.trim_mean_device(pred[None], 0.1)
-        return prob, out
+        return self.pipe.step(raw_dev, (ref_dev, tgt_dev, tracked_dev))
 
 
 def gpu_main(args):
@@ -172,7 +163,8 @@ def gpu_main(args):
     unet = mod("unet3d").UNet3("a", weights=synth.unet_weights("a", 0), tiles_per_batch=args.tiles_per_batch,
                                engine=args.engine)
     ffn = mod("ffn").FFN(synth.ffn_weights(0))
-    step = Step(unet, ffn)
+    step = Step(unet, ffn, overlap=not args.no_overlap)
+    serial = Step(unet, ffn, overlap=False)
     n_tiles, _ = unet.tile_count(SHAPE, SHRINK)
 
     raw, real0, real_t = make_inputs(frame=1 + rank)
@@ -219,6 +211,22 @@ def gpu_main(args):
         lib.ct_profile_read(tag, C.byref(ms), C.byref(cnt), 1)
         prof[name] = (ms.value, cnt.value)
 
+    # ---- the same frame with the two stages back to back on one stream (frame latency; explains the overlap gain)
+    serial_ms = None
+    if not args.no_overlap:
+        serial.run(raw_dev, ref_dev, tgt_dev, tracked_dev)
+        barrier()
+        ts = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            serial.run(raw_dev, ref_dev, tgt_dev, tracked_dev)
+            e1.record()
+            ts.append((e0, e1))
+        barrier()
+        serial_ms = sum(a.elapsed_time(b) for a, b in ts) / args.steps
+
     # ---- end-to-end arm: host buffers in, host results out, every step
     prob_host = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
     out_host = torch.empty((N_CELLS, 3), dtype=torch.float64).pin_memory()
@@ -259,11 +267,14 @@ def gpu_main(args):
             "metric": "voxels/s", "value": voxels * world * args.steps / (dev_ms * 1e-3), "unit": "voxels/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 hi/lo split, fp32 accumulate (U-Net conv); f32 (LCN, FFN); f64 (PR-GLS EM)", "data": "synthetic",
+            "dtype": "fp16 hi/lo split (22-bit operands), fp32 accumulate (U-Net conv); f32 (LCN, FFN); f64 (PR-GLS EM)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "unet_tiles": n_tiles,
                        "unet_engine": args.engine, "tiles_per_batch": args.tiles_per_batch,
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "sharding": "frames, one per GPU" if world > 1 else "single GPU",
+                       "pipeline": ("serial: segmentation then tracking on one stream" if args.no_overlap else
+                                    "2 streams: segmentation of volume t+1 overlaps match+track of volume t "
+                                    "(1 SM kept out of the persistent conv grid), joined inside every step"),
                        "host_watershed": "excluded (SURVEY 8f-1)"},
             "frames_per_s": world * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": voxels * world * args.steps / (e2e_ms * 1e-3), "unit": "voxels/s",
@@ -278,14 +289,148 @@ def gpu_main(args):
                          "share_of_step": conv_ms / dev_ms if dev_ms else None,
                          "algorithmic_flop_per_launch": conv_flops / max(conv_n, 1),
                          "traffic": measured_traffic(args.tiles_per_batch), "traffic_unit": "bytes/launch (ncu dram read+write)",
-                         "note": "split-TF32 tcgen05 implicit GEMM: bound by the tensor core's shared-memory operand "
-                                 "reads (ncu: tc smem wavefronts ~80% of peak), see DESIGN.md 3.2"},
+                         "note": "split-fp16 tcgen05 implicit GEMM, 3 MMA terms per fp32 product: bound by the tensor "
+                                 "core's shared-memory operand reads (ncu: tc smem wavefronts 55-83% of peak), see DESIGN.md 3.2"},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "serial_ms_per_step": serial_ms,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(sample_tiles=2, threads=None)
         print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# config 3: ONE 1024 x 1024 x 96 volume cut 2 x 2 x 2 over the GPUs (strong scaling of the segmentation half)
+# --------------------------------------------------------------------------------------------------
+C3_SHAPE, C3_CELLS = (1024, 1024, 96), 2048
+_GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def gpu_spatial_main(args):
+    """`--workload c3`: LCN + tiled U-Net of one zebrafish-heart-sized stack, spatially decomposed (spatial.py):
+    histogram all-reduces for the global median, one round of halo send/recv, 800 tiles split over the ranks.
+    With --verify every rank also runs the whole volume alone and checks its block bit for bit."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world not in _GRIDS:
+        raise SystemExit("--workload c3 runs on 1, 2, 4 or 8 GPUs")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = mod("_lib").lib()
+    synth, sp, pre = mod("synth"), mod("spatial"), mod("preprocess")
+    shape = tuple(args.shape) if args.shape else C3_SHAPE
+    unet = mod("unet3d").UNet3("a", weights=synth.unet_weights("a", 0), tiles_per_batch=args.tiles_per_batch,
+                               engine=args.engine)
+    plan = sp.SpatialPlan(shape, _GRIDS[world], unet.input_shape[1:4], SHRINK)
+    cells = max(8, int(C3_CELLS * (shape[0] * shape[1] * shape[2]) / (1024 * 1024 * 96)))
+    raw = synth.blob_stack(shape, synth.blob_centres(shape, cells, 4321), 4321)       # same volume on every rank
+    lo, hi = plan.owned_box(rank)
+    own_pinned = torch.from_numpy(np.ascontiguousarray(raw[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]).view(np.int16)).pin_memory()
+    owned_dev = own_pinned.to(dev).view(torch.uint16)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(block):
+        return sp.segment_block(block, plan, rank, unet, NOISE_LEVEL)
+
+    if args.verify:
+        prob, out = step(owned_dev)
+        whole = pre._raw_to_device(raw)
+        want = unet.prediction_device(pre.normalize_image_device(whole, NOISE_LEVEL), SHRINK)
+        ok = prob is None or torch.equal(prob, want[out[0][0]:out[1][0], out[0][1]:out[1][1], out[0][2]:out[1][2]])
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag[0]) != 1:
+            raise SystemExit(f"rank {rank}: decomposed result differs from the single-GPU result")
+        del whole, want
+    for _ in range(args.warmup):
+        step(owned_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.ct_profile_enable(1)
+    launches0 = lib.ct_launch_count()
+    times = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(owned_dev)
+        e1.record()
+        times.append((e0, e1))
+    barrier()
+    launches = lib.ct_launch_count() - launches0
+    lib.ct_profile_enable(0)
+    dev_ms = sum(a.elapsed_time(b) for a, b in times)
+    import ctypes as C
+    ms, cnt = C.c_double(), C.c_ulonglong()
+    lib.ct_profile_read(1, C.byref(ms), C.byref(cnt), 1)
+    conv_ms, conv_n = ms.value, cnt.value
+
+    out_box = plan.out_box(rank)
+    prob_host = None if out_box is None else torch.empty(tuple(h - l for l, h in zip(*out_box)), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        block = own_pinned.to(dev, non_blocking=True).view(torch.uint16)
+        prob, _ = step(block)
+        if prob is not None:
+            prob_host.copy_(prob, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    my_tiles = int(np.prod([h - l for l, h in zip(*plan.tile_box(rank))]))
+    t = torch.tensor([dev_ms, e2e_s * 1e3, conv_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, conv_ms = float(t[0]), float(t[1]), float(t[2])
+    if rank == 0:
+        voxels = shape[0] * shape[1] * shape[2]
+        n_tiles = int(np.prod(plan.num_tiles))
+        pk = peaks()
+        achieved = n_tiles * FLOP_PER_TILE * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        print(json.dumps({
+            "metric": "voxels/s", "value": voxels * args.steps / (dev_ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp16 hi/lo split, fp32 accumulate (U-Net conv); f32 (LCN)", "data": "synthetic",
+            "config": {"workload": "zebrafish-heart %dx%dx%d stack, LCN + unet3_a seg (%d tiles), spatial %dx%dx%d "
+                                   "decomposition + halo" % (shape + (n_tiles,) + plan.grid),
+                       "tiles_rank0": my_tiles, "tiles_per_batch": args.tiles_per_batch,
+                       "halo_bytes_rank0": plan.halo_bytes(0), "collectives": "2 x all-reduce(512 x u32) + 1 round send/recv",
+                       "verified_bit_identical": bool(args.verify),
+                       "l2": "flushed between timed iterations (256 MiB write)"},
+            "e2e": {"value": voxels * args.steps / (e2e_ms * 1e-3), "unit": "voxels/s",
+                    "h2d_bytes_per_step": int(own_pinned.numel() * 2),
+                    "d2h_bytes_per_step": 0 if prob_host is None else int(prob_host.numel() * 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "unet 3x3x3 conv", "achieved": achieved * world,
+                         "peak": pk["bf16_sustained"] * world, "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16_sustained"], "launches": int(conv_n),
+                         "share_of_step": conv_ms / dev_ms if dev_ms else None, "traffic": None},
+            "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -377,13 +522,22 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05"])
     ap.add_argument("--tiles-per-batch", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run segmentation and tracking back to back on one stream")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c3"],
+                    help="c1 (default, the contract's line): one worm1 frame per step; c3: one 1024x1024x96 volume "
+                         "spatially decomposed over the GPUs")
+    ap.add_argument("--shape", type=int, nargs=3, default=None, help="c3 only: override the volume shape")
+    ap.add_argument("--verify", action="store_true", help="c3 only: check every rank's block against a single-GPU run")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)
     else:
         if args.warmup < 3:
             args.warmup = 3
-        gpu_main(args)
+        if args.workload == "c3":
+            gpu_spatial_main(args)
+        else:
+            gpu_main(args)
 
 
 if __name__ == "__main__":

@@ -35,6 +35,10 @@ unsigned long long ct_launch_count(void);
 /* Opt-in profiler used by bench.py: CUDA events are recorded on the launching stream around every launch of a
  * kernel family.  tag: 1 = U-Net convolutions, 2 = PR-GLS EM, 3 = FFN match, 4 = LCN, 5 = U-Net pool/upsample/
  * gather/head.  ct_profile_read synchronises on the recorded events and returns their summed duration. */
+/* Persistent kernels of this library (the tcgen05 convolution: one CTA per SM) leave `n` SMs unclaimed, so that a
+ * single-CTA kernel running concurrently on another stream (the PR-GLS EM of the previous frame, tracker.py's frame
+ * pipeline) finds a free SM instead of delaying one CTA of every convolution.  Default 0; returns the old value. */
+int ct_set_reserved_sms(int n);
 int ct_profile_enable(int on);
 int ct_profile_read(int tag, double* total_ms, unsigned long long* count, int reset);
 
@@ -71,9 +75,10 @@ int ct_select_hist(const void* raw, int dtype, long long local_count, void* stat
 int ct_select_scan(void* state, int dtype, int pass, void* stream);
 int ct_select_finish(const void* state, int dtype, double* median_out, void* stream);
 /* ct_normalize_image with the median supplied by the caller (1 double, device): LCN of a BLOCK of a larger
- * volume.  Zero padding applies at the block's own faces, so output voxels closer than filter/2 to a face that is
- * not a face of the whole volume are not the volume's values -- the caller passes a block with that margin
- * (halo exchange) and discards it.  Voxels whose whole window lies inside the block are bit-identical to the
+ * volume.  Zero padding applies at the block's own faces, so output voxels closer than 2 * (filter/2) to a face
+ * that is not a face of the whole volume (the std window reads avg, which reads its own window) are not the
+ * volume's values -- the caller passes a block with that margin
+ * (halo exchange) and discards it.  Voxels whose whole two-level window lies inside the block are bit-identical to the
  * single-call result (per-voxel windows are summed in a fixed order, not by running sums). */
 int ct_normalize_image_with_median(const void* raw, int dtype, float* out, int x, int y, int z, float noise_level,
                                    int filter_x, int filter_y, const double* median, void* ws, size_t ws_bytes,

@@ -1,0 +1,126 @@
+"""GPU: the two-stream frame pipeline (pipeline.py) and the Tracker loop end to end (tracker.py:1415-1536).
+
+* FramePipeline.step with overlap must return exactly what the serial order returns (same kernels, same inputs; the
+  streams only change WHEN things run).
+* Tracker.track over a short synthetic time-lapse: with the next volume's segmentation prefetched on a second
+  stream the history equals a plain track_one_vol loop bit for bit; the fitted transforms equal the CPU oracle chain
+  (oracle FFN match + pr_gls_quick + predict_one_rep on the same segmented points, rtol 1e-6 -- looser than the 1e-8
+  of a single EM call because five repetitions are chained).  (The FFN weights are random-init, so the matches --
+  identical on both sides -- are not meaningful and no ground-truth accuracy is asserted.)
+The U-Net weights are a hand-built "pass-through" network (centre taps of channel 0 along the skip path), so that
+probabilities are a monotone function of the normalised intensity and the scipy stand-in watershed finds the blobs."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg
+from oracle import ffn as offn
+from oracle import prgls as oprgls
+
+pytestmark = pytest.mark.gpu
+SHAPE = (224, 224, 24)
+
+
+@pytest.fixture(scope="module")
+def m():
+    load_pkg()
+    names = ("unet3d", "ffn", "synth", "tracker", "pipeline", "preprocess", "_lib")
+    return {n: importlib.import_module("3deecelltracker_b200." + n) for n in names}
+
+
+def passthrough_unet_weights(u, gain=6.0, bias=-3.0):
+    """unet3_a weights whose output is sigmoid(gain * g(x) + bias) with g monotone: channel 0 is carried by centre
+    taps through d0a, d0b, the level-0 skip connection, o_m2 and o_m1; every other kernel is zero."""
+    layers = u._conv_layers(u._SPECS["a"])
+    src_channel = {0: 0, 1: 0, len(layers) - 2: 16, len(layers) - 1: 0}       # o_m2 reads concat [up(16), skip(16)]
+    ws = []
+    for i, (cin, cout) in enumerate(layers):
+        k = np.zeros((3, 3, 3, cin, cout), np.float32)
+        if i in src_channel:
+            k[1, 1, 1, src_channel[i], 0] = 1.0
+        ws += [k, np.zeros(cout, np.float32), np.ones(cout, np.float32), np.zeros(cout, np.float32),
+               np.zeros(cout, np.float32), np.ones(cout, np.float32)]
+    head = np.zeros((1, 1, 1, 8, 1), np.float32)
+    head[0, 0, 0, 0, 0] = gain
+    return ws + [head, np.array([bias], np.float32)]
+
+
+def spaced_centres(n, seed, shape=SHAPE, min_dist=22.0, margin=14):
+    rng = np.random.default_rng(seed)
+    pts = []
+    while len(pts) < n:
+        p = rng.uniform([margin, margin, 5], [shape[0] - margin, shape[1] - margin, shape[2] - 5])
+        if all(np.linalg.norm((p - q) * [1, 1, 3]) > min_dist for q in pts):
+            pts.append(p)
+    return np.array(pts)
+
+
+def moved(centres, t):
+    c = centres.mean(axis=0)
+    a = np.eye(3) + t * np.array([[0.004, 0.006, 0.0], [-0.006, 0.003, 0.0], [0.0, 0.0, 0.0]])
+    return (centres - c) @ a + c + t * np.array([0.8, -0.5, 0.0])
+
+
+def test_overlapped_step_equals_serial_step(m):
+    synth, u = m["synth"], m["unet3d"]
+    unet = u.UNet3("a", weights=synth.unet_weights("a", 0), tiles_per_batch=4)
+    ffn = m["ffn"].FFN(synth.ffn_weights(0))
+    raw = synth.blob_stack(SHAPE, synth.blob_centres(SHAPE, 40, 3), 3)
+    raw_dev = m["preprocess"]._raw_to_device(raw)
+    ref = synth.random_points(64, 1)
+    tgt = synth.move_points(ref, 2)
+    ref_dev, tgt_dev = torch.from_numpy(ref).cuda(), torch.from_numpy(tgt).cuda()
+    P = m["pipeline"].FramePipeline
+    lib = m["_lib"].lib()
+    serial = P(unet, ffn, 20, 300, 0.1, 20, overlap=False).step(raw_dev, (ref_dev, tgt_dev, ref_dev))
+    pipe = P(unet, ffn, 20, 300, 0.1, 20, overlap=True)
+    for _ in range(3):                                     # repeated: stream hazards show up as run-to-run changes
+        prob, tracked = pipe.step(raw_dev, (ref_dev, tgt_dev, ref_dev))
+        torch.cuda.synchronize()
+        assert torch.equal(prob, serial[0]) and torch.equal(tracked, serial[1])
+    assert lib.ct_set_reserved_sms(0) == 0                 # the reservation is scoped to the step
+
+
+def test_tracker_track_prefetch_and_oracle_chain(m):
+    T, u, synth = m["tracker"], m["unet3d"], m["synth"]
+    centres = spaced_centres(36, 11)
+    stacks = {v: synth.blob_stack(SHAPE, moved(centres, v - 1), 100 + v, z_xy_ratio=3.0, sigma_xy=3.0) for v in (1, 2, 3)}
+    unet = u.UNet3("a", weights=passthrough_unet_weights(u), tiles_per_batch=8)
+    fw = offn.random_weights(0)
+    ffn = m["ffn"].FFN(fw)
+
+    def make():
+        t = T.Tracker(volume_num=3, siz_xyz=SHAPE, z_xy_ratio=1.0, z_scaling=1, noise_level=20, min_size=20, beta_tk=300,
+                      lambda_tk=0.1, maxiter_tk=20, image_source=lambda v: stacks[v])
+        t.load_unet(unet)
+        t.load_ffn(ffn)
+        t.segment_vol1()
+        t.initiate_tracking()
+        return t
+
+    a = make()
+    assert a.cell_num == 36                               # every blob found by the pass-through U-Net + stand-in watershed
+    a.track()                                             # prefetches volume t+1 while volume t is tracked
+    b = make()
+    for vol in (2, 3):                                    # plain loop, no prefetch
+        b.track_one_vol(vol)
+    for x, y in zip(a.history.r_tracked_coordinates, b.history.r_tracked_coordinates):
+        assert np.array_equal(x, y)
+    for x, y in zip(a.history.r_segmented_coordinates, b.history.r_segmented_coordinates):
+        assert np.array_equal(x, y)
+
+    # oracle chain on the same segmented point sets (tracker.py:1224-1289)
+    oracle = offn.FFNOracle(fw)
+    for vol in (2, 3):
+        inter = a.history.r_segmented_coordinates[vol - 2]
+        tgt = a.history.r_segmented_coordinates[vol - 1]
+        pred = a.history.r_tracked_coordinates[vol - 2]
+        for i in range(5):
+            beta = 300 * 0.8 ** i
+            corr = offn.initial_matching_quick(oracle, inter, tgt, 20)
+            _, tx, c = oprgls.pr_gls_quick(inter, tgt, corr, BETA=beta, max_iteration=20, LAMBDA=0.1)
+            pred = oprgls.predict_one_rep(pred, inter, beta, c)
+            inter = tx
+        np.testing.assert_allclose(a.history.r_tracked_coordinates[vol - 1], pred, rtol=1e-6, atol=1e-6)

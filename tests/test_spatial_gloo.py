@@ -1,7 +1,7 @@
 """CPU: the spatial decomposition plan (config 3) and its halo exchange over gloo.
 
 The plan is checked against a brute-force restatement of what unet3_prediction reads (unet3d.py:235-249: reflect
-pre-pad, tiles at a stride of the centre size) and what the 27 x 27 x 1 LCN window reaches (preprocess.py:163-166);
+pre-pad, tiles at a stride of the centre size) and what the two chained 27 x 27 x 1 LCN windows reach (preprocess.py:163-166: 26 voxels);
 the exchange is run for real with 2 and 8 gloo ranks and compared with slices of the whole volume."""
 import importlib
 import os
@@ -84,11 +84,11 @@ def test_config3_numbers():
         tlo, thi = plan.tile_box(r)
         assert np.prod([h - l for l, h in zip(tlo, thi)]) == 100
     assert plan.owned_box(0) == ((0, 0, 0), (512, 512, 48))
-    assert plan.norm_box(0) == ((0, 0, 0), (584, 584, 50)) and plan.raw_box(0) == ((0, 0, 0), (597, 597, 50))
-    assert plan.norm_box(7) == ((536, 536, 46), (1024, 1024, 96)) and plan.raw_box(7) == ((523, 523, 46), (1024, 1024, 96))
+    assert plan.norm_box(0) == ((0, 0, 0), (584, 584, 50)) and plan.raw_box(0) == ((0, 0, 0), (610, 610, 50))
+    assert plan.norm_box(7) == ((536, 536, 46), (1024, 1024, 96)) and plan.raw_box(7) == ((510, 510, 46), (1024, 1024, 96))
     own_bytes = 512 * 512 * 48 * 2
     assert 0 < plan.halo_bytes(0) < 0.5 * own_bytes
-    assert plan.halo_bytes(7) == (501 * 501 * 50 - 501 * 501 * 48) * 2      # only the 2-voxel z halo
+    assert plan.halo_bytes(7) == (514 * 514 * 50 - 512 * 512 * 48) * 2      # 2 voxels in x, y and z
 
 
 def _free_port():
