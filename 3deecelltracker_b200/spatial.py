@@ -143,8 +143,8 @@ def _slices(box, origin):
 
 
 def _wire(t):
-    """NCCL / gloo have no uint16: ship the same bytes as int16."""
-    return t.view(torch.int16) if t.dtype == torch.uint16 else t
+    """The NCCL process group takes neither uint16 nor int16: ship the bytes (buffers are contiguous)."""
+    return t.view(torch.uint8) if t.dtype in (torch.uint16, torch.int16) else t
 
 
 def exchange_halo(owned, plan, rank, group=None):

@@ -16,6 +16,14 @@ N > 1   frames shard one per GPU (weak scaling, no data-path collective); timing
 `--impl reference` times the CPU oracle (torch/oneDNN fp32 restatement of the Keras graphs + NumPy EM; TensorFlow is
 not installable in this image) on a bounded sample of the same workload with all host threads.
 """
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (set before NumPy / torch load)
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import argparse
 import importlib
 import json
@@ -426,9 +434,10 @@ def gpu_spatial_main(args):
                     "h2d_bytes_per_step": int(own_pinned.numel() * 2),
                     "d2h_bytes_per_step": 0 if prob_host is None else int(prob_host.numel() * 4)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "unet 3x3x3 conv", "achieved": achieved * world,
+            "roofline": {"bound": "tensor", "kernel": "unet 3x3x3 conv", "achieved": achieved,
                          "peak": pk["bf16_sustained"] * world, "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_sustained"], "launches": int(conv_n),
+                         "frac": achieved / (pk["bf16_sustained"] * world), "launches": int(conv_n),
+                         "note": "whole job: all tiles / slowest rank's conv time, against N x the per-GPU peak",
                          "share_of_step": conv_ms / dev_ms if dev_ms else None, "traffic": None},
             "clocks": clocks}))
     if world > 1:
