@@ -278,7 +278,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
 
     // ---- pack weights on the host into one staging vector, then one device allocation
     std::vector<float> host;
-    struct Offs { size_t wd, wt, b, sc, sh; };
+    struct Offs { size_t wd, wt, wx, b, sc, sh; };
     std::vector<Offs> offs;
     std::vector<float> inv_scales;
     const float* p = w;
@@ -297,6 +297,9 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         const size_t tcn = tc_weight_floats(cin_pad, cout);
         o.wt = take(tcn);
         inv_scales.push_back(tcn ? tc_pack_weights(p, cin, cin_pad, cout, &host[o.wt]) : 1.f);
+        const size_t txn = tcx_weight_floats(cin_pad, cout);
+        o.wx = take(txn);
+        if (txn) tcx_pack_weights(p, cin, cin_pad, cout, &host[o.wx]);       // same scale as the classic image
         p += (size_t)27 * cin * cout;
         o.b = take(cout); o.sc = take(cout); o.sh = take(cout);
         const float *bias = p, *gamma = p + cout, *beta = p + 2 * cout, *mean = p + 3 * cout, *var = p + 4 * cout;
@@ -326,6 +329,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         L.cin = convs[i].first; L.cout = convs[i].second; L.cin_pad = (L.cin + 3) / 4 * 4;
         L.w_direct = net->all_dev + offs[i].wd;
         L.w_tc = tc_weight_floats(L.cin_pad, L.cout) ? net->all_dev + offs[i].wt : nullptr;
+        L.w_tcx = tcx_weight_floats(L.cin_pad, L.cout) ? net->all_dev + offs[i].wx : nullptr;
         L.w_tc_inv_scale = inv_scales[i];
         L.bias = net->all_dev + offs[i].b; L.scale = net->all_dev + offs[i].sc; L.shift = net->all_dev + offs[i].sh;
         net->layers.push_back(L);
@@ -406,7 +410,7 @@ extern "C" void ct_unet_destroy(CtUNet* net) {
 }
 
 extern "C" int ct_unet_set_engine(CtUNet* net, int engine) {
-    CT_REQUIRE(net && engine >= 0 && engine <= 2, "ct_unet_set_engine: bad argument");
+    CT_REQUIRE(net && engine >= 0 && engine <= 4, "ct_unet_set_engine: bad argument");
     net->engine = engine;
     return 0;
 }
@@ -450,20 +454,27 @@ static TileGeom make_geom(const CtUNet* net, int x, int y, int z, const int cent
     return g;
 }
 
+// One convolution block on the engine the network is set to (see CtUNet::engine).
+static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t stride, int tiles, cudaStream_t s) {
+    int rc = 2;
+    if (net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s);
+    if (rc == 2 && net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s);
+    if (rc == 1) return 1;
+    if (rc == 2) {
+        CT_REQUIRE(net->engine == 0 || net->engine == 1,
+                   "unet: tcgen05 engine forced but layer %d (cin %d, cout %d, z %d) is unsupported",
+                   op.layer, net->layers[op.layer].cin, net->layers[op.layer].cout, op.sz);
+        if (launch_conv_direct(net, op, slab0, stride, tiles, s)) return 1;
+    }
+    return 0;
+}
+
 // Runs the op plan on `tiles` slabs that already hold their padded input.
 static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) {
     const size_t stride = net->slab_floats;
     for (const Op& op : net->ops) {
         if (op.kind == OP_CONV) {
-            int rc = 2;
-            if (net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s);
-            if (rc == 1) return 1;
-            if (rc == 2) {
-                CT_REQUIRE(net->engine != 2,
-                           "unet: tcgen05 engine forced but layer %d (cin %d, cout %d, z %d) is unsupported",
-                           op.layer, net->layers[op.layer].cin, net->layers[op.layer].cout, op.sz);
-                if (launch_conv_direct(net, op, slab0, stride, tiles, s)) return 1;
-            }
+            if (launch_conv(net, op, slab0, stride, tiles, s)) return 1;
         } else {
             const float4* src = reinterpret_cast<const float4*>(slab0);
             float4* dst = reinterpret_cast<float4*>(slab0);
@@ -521,7 +532,7 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
     CT_REQUIRE(net && in && out && ws, "ct_unet_conv_block: null argument");
     CT_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "ct_unet_conv_block: layer %d out of range", layer);
     CT_REQUIRE(batch >= 1 && x > 0 && y > 0 && z > 0, "ct_unet_conv_block: bad shape");
-    CT_REQUIRE(engine == 1 || engine == 2, "ct_unet_conv_block: engine must be 1 (direct) or 2 (tcgen05)");
+    CT_REQUIRE(engine >= 1 && engine <= 4, "ct_unet_conv_block: engine must be 1 (direct), 2 (tcgen05), 3 (tcgen05 classic) or 4 (tcgen05 x-stacked)");
     CT_REQUIRE(ws_bytes >= ct_unet_conv_block_workspace_bytes(net, layer, batch, x, y, z), "ct_unet_conv_block: workspace too small");
     CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_unet_conv_block: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
@@ -544,13 +555,10 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
                                                      vol, L.cin, cin4, total, slab0 + b * stride + op.src_slot);
         CT_LAUNCHED("ndhwc_to_c4");
     }
-    if (engine == 2) {
-        const int rc = launch_conv_tc(net, op, slab0, stride, batch, s);
-        CT_REQUIRE(rc != 2, "ct_unet_conv_block: layer %d (cin %d, cout %d, z %d) is not supported by the tcgen05 engine",
-                   layer, L.cin, L.cout, z);
-        if (rc) return 1;
-    } else if (launch_conv_direct(net, op, slab0, stride, batch, s)) {
-        return 1;
+    {
+        CtUNet view = *net;                     // shallow copy: same device arrays, engine chosen for this call
+        view.engine = engine;
+        if (launch_conv(&view, op, slab0, stride, batch, s)) return 1;
     }
     for (int b = 0; b < batch; ++b) {
         const size_t total = vol * cout4;

@@ -16,6 +16,7 @@ struct ConvLayer {
     int cin_pad;              // multiple of 4
     float* w_direct;          // device: [cin_pad/4][27][cout][4]   (CUDA-core kernel)
     float* w_tc;              // device: tcgen05 layout (see unet_tc.cu), may be null
+    float* w_tcx;             // device: x-stacked tcgen05 layout (see unet_tcx.cu), may be null
     float w_tc_inv_scale;     // 1 / (power-of-two scale applied to the fp16 weight images)
     float* bias;              // device [cout]
     float* scale;             // device [cout]  gamma / sqrt(var + eps)
@@ -54,7 +55,8 @@ struct CtUNet {
     float* head_w;            // device [last_c]
     float head_b;
     float alpha;              // 0.3 (LeakyReLU) or 0 (ReLU)
-    int engine;               // 1 direct, 2 tcgen05
+    int engine;               // 0 auto, 1 direct, 2 tcgen05 (stacked where it pays, else classic), 3 classic only,
+                              // 4 stacked wherever the shape allows
     double flops_per_tile;
     float* all_dev;           // one allocation holding every device array
 };
@@ -66,6 +68,11 @@ int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t sla
 // implemented in unet_tc.cu (returns 2 when the layer shape is not supported by the tensor-core path)
 int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
                    cudaStream_t s);
+// implemented in unet_tcx.cu: x-stacked variant for Cout 8/16/32 (returns 2 when it does not take the layer)
+int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
+                    cudaStream_t s);
+size_t tcx_weight_floats(int cin_pad, int cout);
+float tcx_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
 size_t tc_weight_floats(int cin_pad, int cout);
 // returns 1 / scale
 float tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);

@@ -1,0 +1,430 @@
+// tcgen05 implicit-GEMM 3x3x3 convolution, "x-stacked" variant for layers with few output channels (Cout 8 / 16).
+//
+// Same operator, operand precision and memory layout as unet_tc.cu (Conv3D 3x3x3 'same' + bias -> LeakyReLU/ReLU ->
+// BatchNorm(eval), unet3d.py:117-119 / :139-140; fp16 hi/lo operand images, fp32 accumulation drained into registers),
+// but a different GEMM decomposition.  unet_tc.cu issues one MMA per (tap, output plane) with N = 2 Cout: with
+// Cout <= 32 every MMA is bound by the 4 KB shared-memory read of its A tile (128 voxels x 16 K), not by math.  Here
+// the three x-taps of the kernel are stacked in the N dimension instead:
+//
+//     D_j[voxel (y,z), (dx, co)] = sum over (dy, dz, ci) of  in[plane j][y+dy, z+dz, ci] * W[dx, dy, dz, ci, co]
+//     out[plane i] = D_i[dx = 0] + D_(i+1)[dx = 1] + D_(i+2)[dx = 2]          (input planes j are haloed by one)
+//
+// so one A tile (one of 9 (dy,dz) taps of one INPUT plane) feeds N = 3 x 2 Cout accumulator columns: a third of the
+// shared-memory operand reads per output voxel, at the price of (BX+2)/BX more MMAs (halo planes) and of the shift-add
+// over dx, which the worker warps do in registers while they drain tensor memory (each thread owns one voxel row of
+// every plane, so the three contributions of an output voxel meet in the same thread).
+//
+// B rows per K half: [hi dx0 | hi dx1 | hi dx2 | lo' dx0 | lo' dx1 | lo' dx2] (+ [hi dx0..2] again when Cout = 8):
+//     MMA1 = A_hi  x rows [0, 6N)            -> columns [0, 3N) = hi.hi, [3N, 6N) = hi.lo'
+//     MMA2 = A_lo' x rows [0, 3N)            -> accumulated onto columns [3N, 6N)          (same weight 2^-11)
+//     Cout = 8: MMA2 = A_lo' x rows [3N, 9N) -> columns [6N, 9N) = lo'.lo', [9N, 12N) = lo'.hi  (N must be >= 16 wide)
+// K = 16 per MMA = two (dy,dz) taps x 8 input channels; 9 taps -> 5 K steps (tap 7 appears twice, once with zero
+// weights).  One accumulator set = one input plane x one 8-channel chunk = 5 MMAs per column group, drained into fp32
+// registers (round-to-nearest) while the next plane's MMAs run into the other set.
+#include "unet_common.cuh"
+#include "tc_ptx.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace ct {
+
+int tc_sm_count();
+int tc_make_map(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, int tiles, size_t slab_stride, int bx);
+
+constexpr int TX_SYH = 18, TX_SZH = 10;          // haloed block extent in y and z (16 + 2, 8 + 2)
+constexpr int TX_PLANE_VOX = TX_SYH * TX_SZH;    // voxels (16-byte units) per haloed x plane
+constexpr int TX_PAIRS = 5;
+
+// (dy,dz) tap t2 = dy*3 + dz sits t2/3 rows and t2%3 voxels into the haloed plane
+__host__ __device__ constexpr int tx_off(int t2) { return (t2 / 3) * TX_SZH + t2 % 3; }
+// K step p covers taps (first, second); step 4 is (tap 7 with zero weights, tap 8)
+__host__ __device__ constexpr int tx_first(int p) { return p < 4 ? 2 * p : 7; }
+__host__ __device__ constexpr int tx_second(int p) { return p < 4 ? 2 * p + 1 : 8; }
+
+constexpr int TX_CONV_WARPS = 4;                // operand conversion (fp32 -> fp16 hi / lo' images, in place)
+constexpr int TX_DRAIN_WARPS = 8;                // accumulator drain + x shift-add + epilogue: two per lane quarter
+constexpr int TX_THREADS = 64 + 32 * (TX_CONV_WARPS + TX_DRAIN_WARPS);
+
+template <int N, int BX, int STAGES>
+struct TxCfg {
+    static constexpr bool N8 = (N == 8);
+    static constexpr int NPR = N8 ? 9 * N : 6 * N;                     // B rows per K half
+    static constexpr int N1 = 6 * N;
+    static constexpr int N2 = N8 ? 6 * N : 3 * N;
+    static constexpr int B2_ROW = N8 ? 3 * N : 0;                      // first B row of MMA2
+    static constexpr int D2_COL = N8 ? 6 * N : 3 * N;                  // first accumulator column of MMA2
+    static constexpr int NPD = N8 ? 12 * N : 6 * N;                    // accumulator columns of one set
+    static constexpr int NSETS = 512 / NPD >= 4 ? 4 : 2;               // accumulator sets in flight
+    static constexpr int SXH = BX + 2;
+    static constexpr int PLANE = SXH * TX_PLANE_VOX * 16;              // bytes of one operand image of the block
+    static constexpr int B_BYTES = TX_PAIRS * 2 * NPR * 16;
+    static constexpr int STAGE = 2 * PLANE + B_BYTES;
+    static constexpr int TMEM_COLS = NSETS * NPD <= 256 ? 256 : 512;
+    static constexpr int SMEM = STAGES * STAGE + 1024;
+    static constexpr int CH = N / (TX_DRAIN_WARPS / 4);                // output channels per drain thread
+    static_assert(NSETS * NPD <= 512, "accumulators exceed tensor memory");
+    static_assert(N1 % 16 == 0 && N1 <= 256 && N2 % 16 == 0, "UMMA N out of range for M = 128");
+    static_assert(PLANE % 128 == 0 && B_BYTES % 128 == 0, "stage parts must stay 128-byte aligned");
+    static_assert(CH == 4 || CH == 8, "a drain thread owns 4 or 8 channels");
+    static_assert(SMEM <= 232448, "shared memory ring too large");
+};
+
+struct TxGeom {
+    int cin8, X, Y, Z, nbx, nby, nbz, units;
+    int dst_c4off;
+    size_t dst_tile_stride4;
+    const float* amax_src;
+    float* amax_dst;
+    size_t slab_stride;
+    float w_inv_scale;
+};
+
+struct TxUnit { int x0, y0, z0, tile; };
+__device__ __forceinline__ TxUnit tx_unit(int u, const TxGeom& g, int bx) {
+    TxUnit r;
+    r.x0 = (u % g.nbx) * bx; u /= g.nbx;
+    r.y0 = (u % g.nby) * 16; u /= g.nby;
+    r.z0 = (u % g.nbz) * 8;
+    r.tile = u / g.nbz;
+    return r;
+}
+
+// issue only: the caller batches several loads in front of one tcgen05.wait::ld
+template <int CH>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[CH]) {
+    if constexpr (CH == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+    }
+}
+
+// Persistent CTA.  Work unit = BX x 16 x 8 output voxels x all Cout of one tile.  Stage g = one 8-channel chunk of one
+// unit (ring slot g % STAGES); accumulator step a = g * (BX+2) + j = input plane j of stage g (tensor-memory set
+// a % NSETS).  Warp roles: 0 TMA producer (+ tensor-memory allocator), 1 MMA issuer, 2-5 operand conversion,
+// 6-13 accumulator drain / x shift-add / epilogue.
+template <int N, int BX, int STAGES>
+__global__ void __launch_bounds__(TX_THREADS, 1)
+conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
+                 const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                 float alpha, float4* __restrict__ dst, const TxGeom geo) {
+    using Cfg = TxCfg<N, BX, STAGES>;
+    constexpr int SXH = Cfg::SXH, CH = Cfg::CH, NSETS = Cfg::NSETS;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc_full[NSETS], bar_acc_empty[NSETS];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float ep_s[3][N];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int cin8 = geo.cin8;
+    const int n_units = ((int)blockIdx.x < geo.units) ? (geo.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_stages = n_units * cin8;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_conv[s], TX_CONV_WARPS);
+            mbar_init(&bar_empty[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < NSETS; ++a) {
+            mbar_init(&bar_acc_full[a], 1);
+            mbar_init(&bar_acc_empty[a], TX_DRAIN_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+    if (threadIdx.x >= 64) {
+        for (int i = threadIdx.x - 64; i < 3 * N; i += TX_THREADS - 64)
+            ep_s[i / N][i % N] = (i < N) ? bias[i] : (i < 2 * N ? scale[i - N] : shift[i - 2 * N]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    // power-of-two operand scale of a tile: max|x s| in [2^13, 2^14) (see unet_tc.cu)
+    auto tile_scale = [&](int tile) {
+        const float am = geo.amax_src[(size_t)tile * geo.slab_stride];
+        const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);
+        const int se = (267 - e > 254) ? 254 : 267 - e;
+        return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
+    };
+
+    if (warp == 0) {
+        // ---------------- TMA producer
+        if (elect_one()) {
+            int g = 0;
+            for (int k = 0; k < n_units; ++k) {
+                const TxUnit un = tx_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+                for (int c = 0; c < cin8; ++c, ++g) {
+                    const int s = g % STAGES, use = g / STAGES;
+                    if (use > 0) mbar_wait(&bar_empty[s], (use - 1) & 1);
+                    uint8_t* st = ring + (size_t)s * Cfg::STAGE;
+                    mbar_expect_tx(&bar_full[s], 2 * Cfg::PLANE + Cfg::B_BYTES);
+                    tma_load_5d(st, &tmap, &bar_full[s], (un.z0 - 1) * 4, un.y0 - 1, un.x0 - 1, 2 * c, un.tile);
+                    bulk_load(st + 2 * Cfg::PLANE, wpack + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &bar_full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(Cfg::N1 >> 3) << 17) | (8u << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(Cfg::N2 >> 3) << 17) | (8u << 24);
+            constexpr uint64_t a_hi_word = (uint64_t)((uint32_t)TX_SZH | (1u << 14)) << 32;   // SBO: y rows 160 B apart
+            constexpr uint64_t b_hi_word = (uint64_t)(8u | (1u << 14)) << 32;                 // SBO: 8-row groups 128 B apart
+            const uint32_t ring16 = smem_u32(ring) >> 4;
+            int a = 0;
+            for (int g = 0; g < n_stages; ++g) {
+                const int s = g % STAGES, use = g / STAGES;
+                mbar_wait(&bar_conv[s], use & 1);
+                const uint32_t a_hi = ring16 + (uint32_t)s * (Cfg::STAGE / 16), a_lo = a_hi + Cfg::PLANE / 16;
+                const uint32_t b_base = a_hi + 2 * (Cfg::PLANE / 16);
+#pragma unroll 1
+                for (int j = 0; j < SXH; ++j, ++a) {
+                    const int set = a % NSETS, use_a = a / NSETS;
+                    if (use_a > 0) mbar_wait(&bar_acc_empty[set], (use_a - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)set * Cfg::NPD;
+                    const uint32_t pl = (uint32_t)j * TX_PLANE_VOX;
+#pragma unroll
+                    for (int p = 0; p < TX_PAIRS; ++p) {
+                        const uint32_t lbo = (uint32_t)(tx_off(tx_second(p)) - tx_off(tx_first(p))) << 16;
+                        const uint32_t ah = (a_hi + pl + (uint32_t)tx_off(tx_first(p))) | lbo;
+                        const uint32_t al = (a_lo + pl + (uint32_t)tx_off(tx_first(p))) | lbo;
+                        const uint32_t b32 = (b_base + (uint32_t)p * (Cfg::NPR * 2)) | ((uint32_t)Cfg::NPR << 16);
+                        umma_f16(d, a_hi_word | (uint64_t)ah, b_hi_word | (uint64_t)b32, idesc1, p != 0);
+                        umma_f16(d + Cfg::D2_COL, a_hi_word | (uint64_t)al, b_hi_word | (uint64_t)(b32 + Cfg::B2_ROW),
+                                 idesc2, Cfg::N8 ? (uint32_t)(p != 0) : 1u);
+                    }
+                    umma_commit(&bar_acc_full[set]);
+                }
+                umma_commit(&bar_empty[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 2 + TX_CONV_WARPS) {
+        // ---------------- converters: fp32 -> fp16 hi / lo' images of every landed stage, in place
+        const int ct = threadIdx.x - 64;
+        int g = 0;
+        for (int k = 0; k < n_units; ++k) {
+            const TxUnit un = tx_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+            const float sc = tile_scale(un.tile);
+            for (int c = 0; c < cin8; ++c, ++g) {
+                const int s = g % STAGES, use = g / STAGES;
+                mbar_wait(&bar_full[s], use & 1);
+                uint4* p0 = reinterpret_cast<uint4*>(ring + (size_t)s * Cfg::STAGE);
+                uint4* p1 = p0 + Cfg::PLANE / 16;
+#pragma unroll 2
+                for (int i = ct; i < Cfg::PLANE / 16; i += 32 * TX_CONV_WARPS) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(p0 + i);      // channels 0-3 of the voxel
+                    const float4 v1 = *reinterpret_cast<const float4*>(p1 + i);      // channels 4-7
+                    const float x[8] = {v0.x * sc, v0.y * sc, v0.z * sc, v0.w * sc, v1.x * sc, v1.y * sc, v1.z * sc, v1.w * sc};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int q2 = 0; q2 < 4; ++q2) {
+                        const __half2 h = __floats2half2_rn(x[2 * q2], x[2 * q2 + 1]);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((x[2 * q2] - hf.x) * 2048.f, (x[2 * q2 + 1] - hf.y) * 2048.f);
+                        hi[q2] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[q2] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    p0[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    p1[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_conv[s]);
+            }
+        }
+    } else {
+        // ---------------- drain warps: tensor memory -> registers with the x shift-add, epilogue
+        const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
+        const int part = (warp - 2 - TX_CONV_WARPS) >> 2;          // which CH channels this thread owns
+        const int ch0 = part * CH;
+        const int row = q * 32 + lane;
+        const size_t vol = (size_t)geo.X * geo.Y * geo.Z;
+        float acc[BX][CH];
+        constexpr float W2 = 1.f / 2048.f, W3 = W2 * W2;
+        constexpr int TERMS = Cfg::N8 ? 4 : 2;                     // column groups per x-tap: hh, hl (, ll, lh)
+
+        int a = 0;
+        for (int k = 0; k < n_units; ++k) {
+            const TxUnit un = tx_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+#pragma unroll
+            for (int i = 0; i < BX; ++i)
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) acc[i][ch] = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < cin8; ++c) {
+#pragma unroll
+                for (int j = 0; j < SXH; ++j, ++a) {
+                    const int set = a % NSETS, use_a = a / NSETS;
+                    mbar_wait(&bar_acc_full[set], use_a & 1);
+                    tc_fence_after();
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * Cfg::NPD + (uint32_t)ch0;
+                    uint32_t v[3][TERMS][CH];
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (j - dx < 0 || j - dx >= BX) continue;  // output plane j - dx is fed through x-tap dx
+#pragma unroll
+                        for (int t = 0; t < TERMS; ++t) tmem_ld_issue<CH>(t0 + t * 3 * N + dx * N, v[dx][t]);
+                    }
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_acc_empty[set]);          // values are in registers: set is free
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int i = j - dx;
+                        if (i < 0 || i >= BX) continue;
+#pragma unroll
+                        for (int ch = 0; ch < CH; ++ch) {
+                            const float hh = __uint_as_float(v[dx][0][ch]), hl = __uint_as_float(v[dx][1][ch]);
+                            if (Cfg::N8) {
+                                const float ll = __uint_as_float(v[dx][2][ch]), lh = __uint_as_float(v[dx][3][ch]);
+                                acc[i][ch] += fmaf(ll, W3, fmaf(hl + lh, W2, hh));
+                            } else {
+                                acc[i][ch] += fmaf(hl, W2, hh);
+                            }
+                        }
+                    }
+                }
+            }
+            // epilogue: scale back, bias -> activation -> BatchNorm, 16-byte channel-chunk stores, max|value| bound
+            const float inv_scale = geo.w_inv_scale / tile_scale(un.tile);
+            const int y = un.y0 + (row >> 3), z = un.z0 + (row & 7);
+            float amax = 0.f;
+            if (y < geo.Y) {
+                float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)(geo.dst_c4off + ch0 / 4) * vol;
+#pragma unroll
+                for (int i = 0; i < BX; ++i) {
+                    const int x = un.x0 + i;
+                    if (x >= geo.X) break;
+                    const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
+#pragma unroll
+                    for (int c4 = 0; c4 < CH / 4; ++c4) {
+                        float o[4];
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int ch = ch0 + c4 * 4 + kk;
+                            float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch]);
+                            t = t > 0.f ? t : alpha * t;
+                            o[kk] = fmaf(t, ep_s[1][ch], ep_s[2][ch]);
+                            amax = fmaxf(amax, fabsf(o[kk]));
+                        }
+                        d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            amax = warp_max(amax);
+            if (lane == 0) amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int tx_rows(int cout) { return cout == 8 ? 72 : 6 * cout; }
+
+size_t tcx_weight_floats(int cin_pad, int cout) {
+    if (cout != 8 && cout != 16) return 0;
+    return (size_t)((cin_pad + 7) / 8) * TX_PAIRS * 2 * tx_rows(cout) * 4;      // 16 bytes per row per K half
+}
+
+// keras kernel (kx,ky,kz,ci,co) -> fp16 image [ci/8][K step][K half][row][ci % 8] with rows
+// dx*cout + co (hi) | 3 cout + dx*cout + co (lo') (| 6 cout + dx*cout + co (hi again) when cout = 8); same power-of-two
+// scale as the classic packing (max|w| in [2^13, 2^14)).  Returns 1 / scale.
+float tcx_pack_weights(const float* w, int cin, int cin_pad, int cout, float* dst) {
+    const int npr = tx_rows(cout), c8n = (cin_pad + 7) / 8;
+    std::memset(dst, 0, tcx_weight_floats(cin_pad, cout) * sizeof(float));
+    float wmax = 0.f;
+    for (size_t i = 0; i < (size_t)27 * cin * cout; ++i) wmax = std::fmax(wmax, std::fabs(w[i]));
+    int e = 0;
+    if (wmax > 0.f) std::frexp(wmax, &e);
+    const float scale = std::ldexp(1.f, 14 - e);
+    __half* img = reinterpret_cast<__half*>(dst);
+    for (int c = 0; c < c8n; ++c)
+        for (int p = 0; p < TX_PAIRS; ++p)
+            for (int j = 0; j < 2; ++j) {
+                if (p == 4 && j == 0) continue;          // tap 7's second appearance carries zero weights
+                const int t2 = j == 0 ? tx_first(p) : tx_second(p);
+                __half* blk = img + ((((size_t)c * TX_PAIRS + p) * 2 + j) * npr) * 8;
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int co = 0; co < cout; ++co)
+                        for (int qd = 0; qd < 8; ++qd) {
+                            const int ci = c * 8 + qd;
+                            if (ci >= cin) continue;
+                            const int tap = dx * 9 + t2;
+                            const float v = w[((size_t)tap * cin + ci) * cout + co] * scale;
+                            const __half h = __float2half_rn(v);
+                            const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
+                            blk[(size_t)(dx * cout + co) * 8 + qd] = h;
+                            blk[(size_t)(3 * cout + dx * cout + co) * 8 + qd] = l;
+                            if (cout == 8) blk[(size_t)(6 * cout + dx * cout + co) * 8 + qd] = h;
+                        }
+            }
+    return 1.f / scale;
+}
+
+template <int N, int BX, int STAGES>
+static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, float alpha, float4* dst, int X, int Y, int Z,
+                      size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, cudaStream_t s) {
+    using Cfg = TxCfg<N, BX, STAGES>;
+    static bool attr = false;
+    if (!attr) {
+        CT_CUDA(cudaFuncSetAttribute(conv3_tcx_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr = true;
+    }
+    TxGeom g;
+    g.cin8 = (L.cin_pad + 7) / 8; g.X = X; g.Y = Y; g.Z = Z;
+    g.amax_src = amax_src; g.amax_dst = amax_dst; g.slab_stride = stride4 * 4; g.w_inv_scale = L.w_tc_inv_scale;
+    g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
+    g.units = g.nbx * g.nby * g.nbz * tiles;
+    g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
+    const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
+    const int grid = g.units < sms ? g.units : sms;
+    conv3_tcx_kernel<N, BX, STAGES><<<grid, TX_THREADS, Cfg::SMEM, s>>>(map, L.w_tcx, L.bias, L.scale, L.shift, alpha, dst, g);
+    return 0;
+}
+
+// returns 2 when the layer is not handled by the stacked kernel (the caller falls back to unet_tc.cu's kernel)
+int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
+    const ConvLayer& L = net->layers[op.layer];
+    const int X = op.sx, Y = op.sy, Z = op.sz;
+    if (!L.w_tcx || Z % 8 != 0) return 2;
+    CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
+    CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
+    float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
+    CUtensorMap map;
+    ProfScope prof(PROF_CONV, s);
+    const size_t st4 = slab_stride / 4;
+    const int co4 = op.dst_coff / 4, c4 = L.cin_pad / 4;
+    float* src = slab0 + op.src_off;
+    const float* am_s = slab0 + op.src_slot;
+    float* am_d = slab0 + op.dst_slot;
+    if (tc_make_map(&map, src, X, Y, Z, c4, tiles, slab_stride, 8)) return 1;
+    int rc;
+    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+    else rc = launch_tcx<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+    if (rc) return 1;
+    CT_LAUNCHED("conv3_tcx_kernel");
+    return 0;
+}
+
+}  // namespace ct

@@ -24,7 +24,7 @@ _SPECS = {
               up=[(64, 64), (32, 32), (16, 16)], out=(8, 8)),          # unet3d.py:70-81
 }
 
-ENGINES = {"auto": 0, "direct": 1, "tcgen05": 2}
+ENGINES = {"auto": 0, "direct": 1, "tcgen05": 2, "tcgen05_classic": 3, "tcgen05_stacked": 4}
 
 
 def _conv_layers(spec):

@@ -528,7 +528,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05", "tcgen05_classic", "tcgen05_stacked"])
     ap.add_argument("--tiles-per-batch", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run segmentation and tracking back to back on one stream")

@@ -106,7 +106,9 @@ typedef struct CtUNet CtUNet;
 size_t ct_unet_weight_count(const CtUNetSpec* spec);
 int ct_unet_create(const CtUNetSpec* spec, const float* weights_host, size_t n_floats, CtUNet** out);
 void ct_unet_destroy(CtUNet* net);
-/* engine: 0 = auto, 1 = CUDA-core fp32 direct convolution, 2 = tcgen05 implicit GEMM (split TF32: hi/lo operands, all cross terms). */
+/* engine: 0 = auto, 1 = CUDA-core fp32 direct convolution, 2 = tcgen05 implicit GEMM (fp16 hi/lo operand split, fp32
+ * accumulate; the x-stacked kernel where it pays, the 27-tap kernel elsewhere), 3 = tcgen05 27-tap kernel only,
+ * 4 = tcgen05 x-stacked kernel for every layer with Cout <= 32. */
 int ct_unet_set_engine(CtUNet* net, int engine);
 double ct_unet_flops_per_tile(const CtUNet* net);
 
@@ -116,7 +118,7 @@ int ct_unet_predict_tiles(const CtUNet* net, const float* tiles, float* prob, in
                           void* ws, size_t ws_bytes, int tiles_per_batch, void* stream);
 /* One Conv3D(3, 'same') + LeakyReLU/ReLU + BatchNormalization block (unet3d.py:101-141) of the network, on
  * Keras channels-last tensors: in (B, x, y, z, Cin) float32 -> out (B, x, y, z, Cout) float32.  `layer` indexes the
- * network's conv blocks in graph order; engine 1 = CUDA-core fp32, 2 = tcgen05 (split-TF32).  Any x, y; the tcgen05
+ * network's conv blocks in graph order; engine 1..4 as in ct_unet_set_engine.  Any x, y; the tcgen05
  * engine needs z % 8 == 0. */
 size_t ct_unet_conv_block_workspace_bytes(const CtUNet* net, int layer, int batch, int x, int y, int z);
 int ct_unet_conv_block(const CtUNet* net, int layer, int engine, const float* in, float* out, int batch,

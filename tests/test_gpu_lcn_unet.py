@@ -94,7 +94,7 @@ def test_unet_predict_matches_oracle(mods, variant, batch):
     tiles = rng.normal(0, 1.0, (batch, x, y, z, 1)).astype(np.float32)
     want = oracle.predict(tiles)
     want64 = oracle64(variant, ws, tiles)
-    engines = ("direct", "auto", "tcgen05") if variant in ("a", "c") else ("direct", "auto")
+    engines = ("direct", "auto", "tcgen05", "tcgen05_classic", "tcgen05_stacked") if variant in ("a", "c") else ("direct", "auto")
     for engine in engines:
         model.set_engine(engine)
         got = model.predict(tiles)
@@ -115,7 +115,8 @@ def _block_reference(ws, li, x_bxyzc, alpha=0.3):
 
 @pytest.mark.parametrize("layer", list(range(14)))
 def test_conv_block_tcgen05_and_direct_match_fp64(mods, layer):
-    """Every conv block of unet3_a through the C ABI (ct_unet_conv_block), both engines, against fp64 torch.
+    """Every conv block of unet3_a through the C ABI (ct_unet_conv_block), every engine (CUDA-core fp32, tcgen05
+    default mix, tcgen05 27-tap kernel only, tcgen05 x-stacked kernel for every Cout <= 32), against fp64 torch.
     Shapes cover partial M tiles in x and y (x not a multiple of the block, y not a multiple of 16), z = 8 and 16,
     batch > 1.  Tolerance: 2e-5 of the output scale (fp32 arithmetic over K = 27 * Cin <= 3456 terms; the
     split-TF32 tensor-core path measures <= 1e-6, the fp32 CUDA-core path <= 3e-6)."""
@@ -129,7 +130,8 @@ def test_conv_block_tcgen05_and_direct_match_fp64(mods, layer):
         ref = _block_reference(ws, layer, xin)
         scale = np.abs(ref).max()
         dev = torch.from_numpy(xin).cuda()
-        for engine in ("direct", "tcgen05"):
+        engines = ["direct", "tcgen05", "tcgen05_classic"] + (["tcgen05_stacked"] if cout <= 32 else [])
+        for engine in engines:
             got = model.conv_block_device(layer, dev, engine).cpu().numpy().astype(np.float64)
             assert got.shape == ref.shape
             err = np.abs(got - ref).max() / scale
