@@ -33,14 +33,15 @@ def ptr(t):
 
 
 class Workspace:
-    """Grow-only cache of device scratch buffers, keyed by name (caller-owned workspaces of the C ABI)."""
+    """Grow-only cache of device scratch buffers, keyed by name AND by the stream they are used on (caller-owned
+    workspaces of the C ABI): work enqueued on different streams may run concurrently and must not share scratch."""
 
     def __init__(self):
         self._bufs = {}
 
     def get(self, name, nbytes):
         dev = require_cuda()
-        key = (name, dev.index)
+        key = (name, dev.index, torch.cuda.current_stream().cuda_stream)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)

@@ -50,35 +50,39 @@ __device__ __forceinline__ void tile_ijk(const TileGeom& g, int ordinal, int& i,
 __global__ void __launch_bounds__(256)
 gather_tiles(const float* __restrict__ src, float4* __restrict__ slab, size_t slab_stride4, size_t in_off4,
              int mode, int tile_first, const TileGeom g, int in_slot) {
-    const int t = blockIdx.y;
+    // grid (TX, tiles): one x plane of one tile per block, threads over the (y, z) plane -- no 64-bit div / mod
+    const int t = blockIdx.y, a = blockIdx.x;
     float amax = 0.f;
-    const int TY = g.TY, TZ = g.TZ;
-    const size_t tile_vox = (size_t)g.TX * TY * TZ;
-    float4* out = slab + (size_t)t * slab_stride4 + in_off4;
+    const int TY = g.TY, TZ = g.TZ, plane = TY * TZ;
+    const size_t tile_vox = (size_t)g.TX * plane;
+    float4* out = slab + (size_t)t * slab_stride4 + in_off4 + (size_t)a * plane;
     int i, j, k;
     tile_ijk(g, tile_first + t, i, j, k);
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < tile_vox; v += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(v % TZ);
-        size_t r = v / TZ;
-        const int b = (int)(r % TY);
-        const int a = (int)(r / TY);
-        float val;
-        if (mode == 0) {
-            const int sx = reflect_index(i * g.c[0] + a - g.b[0], g.X) - g.in_lo[0];
+    if (mode == 0) {
+        const int sx = reflect_index(i * g.c[0] + a - g.b[0], g.X) - g.in_lo[0];
+        const float* row0 = src + (size_t)sx * g.in_dim[1] * g.in_dim[2];
+        for (int f = threadIdx.x; f < plane; f += blockDim.x) {
+            const int b = f / TZ, c = f - b * TZ;
             const int sy = reflect_index(j * g.c[1] + b - g.b[1], g.Y) - g.in_lo[1];
             const int sz = reflect_index(k * g.c[2] + c - g.b[2], g.Z) - g.in_lo[2];
-            val = src[((size_t)sx * g.in_dim[1] + sy) * g.in_dim[2] + sz];
-        } else {
-            val = src[(size_t)(tile_first + t) * tile_vox + v];
+            const float val = row0[(size_t)sy * g.in_dim[2] + sz];
+            out[f] = make_float4(val, 0.f, 0.f, 0.f);
+            amax = fmaxf(amax, fabsf(val));
         }
-        out[v] = make_float4(val, 0.f, 0.f, 0.f);
-        amax = fmaxf(amax, fabsf(val));
+    } else {
+        const float* row0 = src + (size_t)(tile_first + t) * tile_vox + (size_t)a * plane;
+        for (int f = threadIdx.x; f < plane; f += blockDim.x) {
+            const float val = row0[f];
+            out[f] = make_float4(val, 0.f, 0.f, 0.f);
+            amax = fmaxf(amax, fabsf(val));
+        }
     }
     amax = warp_max(amax);
     if ((threadIdx.x & 31) == 0) amax_update(reinterpret_cast<float*>(slab + (size_t)t * slab_stride4) + in_slot, amax);
 }
 
-// MaxPooling3D(pool) on c4-blocked buffers (unet3d.py:168).
+// MaxPooling3D(pool) on c4-blocked buffers (unet3d.py:168).  grid (c4 * DX, tiles): one destination x plane of one
+// channel chunk per block, threads over the destination (y, z) plane.
 __global__ void __launch_bounds__(256)
 pool_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, size_t slab_stride4,
             size_t src_off4, size_t dst_off4, int src_c4off, int c4, int SXs, int SYs, int SZs,
@@ -88,27 +92,25 @@ pool_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, 
         float* hdr = reinterpret_cast<float*>(slab_dst + (size_t)t * slab_stride4);
         amax_update(hdr + dst_slot, hdr[src_slot]);
     }
+    const int ck = blockIdx.x / DX, x = blockIdx.x - ck * DX;
     const size_t dvol = (size_t)DX * DY * DZ, svol = (size_t)SXs * SYs * SZs;
-    const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4 + (size_t)src_c4off * svol;
-    float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4;
-    const size_t total = dvol * c4;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t ck = idx / dvol, v = idx % dvol;
-        const int z = (int)(v % DZ);
-        const size_t r = v / DZ;
-        const int y = (int)(r % DY), x = (int)(r / DY);
+    const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4 + (size_t)(src_c4off + ck) * svol;
+    float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4 + (size_t)ck * dvol + (size_t)x * DY * DZ;
+    for (int f = threadIdx.x; f < DY * DZ; f += blockDim.x) {
+        const int y = f / DZ, z = f - y * DZ;
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         for (int a = 0; a < px; ++a)
             for (int b = 0; b < py; ++b)
                 for (int c = 0; c < pz; ++c) {
-                    const float4 q = src[ck * svol + ((size_t)(x * px + a) * SYs + (y * py + b)) * SZs + (z * pz + c)];
+                    const float4 q = src[((size_t)(x * px + a) * SYs + (y * py + b)) * SZs + (z * pz + c)];
                     m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y); m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
                 }
-        dst[idx] = m;
+        dst[f] = m;
     }
 }
 
-// UpSampling3D(size) nearest, written into the first channels of the concat buffer (unet3d.py:199).
+// UpSampling3D(size) nearest, written into the first channels of the concat buffer (unet3d.py:199).  grid (c4 * SX,
+// tiles): one SOURCE x plane of one channel chunk per block; every source voxel is read once and stored px*py*pz times.
 __global__ void __launch_bounds__(256)
 upsample_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, size_t slab_stride4,
                 size_t src_off4, size_t dst_off4, int dst_c4off, int c4, int SXs, int SYs, int SZs,
@@ -118,16 +120,17 @@ upsample_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_d
         float* hdr = reinterpret_cast<float*>(slab_dst + (size_t)t * slab_stride4);
         amax_update(hdr + dst_slot, hdr[src_slot]);
     }
+    const int ck = blockIdx.x / SXs, x = blockIdx.x - ck * SXs;
     const size_t dvol = (size_t)DX * DY * DZ, svol = (size_t)SXs * SYs * SZs;
-    const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4;
-    float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4 + (size_t)dst_c4off * dvol;
-    const size_t total = dvol * c4;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t ck = idx / dvol, v = idx % dvol;
-        const int z = (int)(v % DZ);
-        const size_t r = v / DZ;
-        const int y = (int)(r % DY), x = (int)(r / DY);
-        dst[idx] = src[ck * svol + ((size_t)(x / px) * SYs + (y / py)) * SZs + (z / pz)];
+    const float4* src = slab_src + (size_t)t * slab_stride4 + src_off4 + (size_t)ck * svol + (size_t)x * SYs * SZs;
+    float4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4 + (size_t)(dst_c4off + ck) * dvol;
+    for (int f = threadIdx.x; f < SYs * SZs; f += blockDim.x) {
+        const int y = f / SZs, z = f - y * SZs;
+        const float4 q = src[f];
+        for (int a = 0; a < px; ++a)
+            for (int b = 0; b < py; ++b)
+                for (int c = 0; c < pz; ++c)
+                    dst[((size_t)(x * px + a) * DY + (y * py + b)) * DZ + (z * pz + c)] = q;
     }
 }
 
@@ -138,19 +141,19 @@ __global__ void __launch_bounds__(256)
 head_scatter(const float4* __restrict__ slab, size_t slab_stride4, size_t last_off4, int c4,
              const float* __restrict__ head_w, float head_b, float* __restrict__ prob,
              int mode, int tile_first, const TileGeom g) {
-    const int t = blockIdx.y;
+    // grid (window x extent, tiles): one x plane of the written window per block, threads over its (y, z) plane
+    const int t = blockIdx.y, a = blockIdx.x;
     const int TX = g.TX, TY = g.TY, TZ = g.TZ;
     const size_t tile_vox = (size_t)TX * TY * TZ;
     const float4* in = slab + (size_t)t * slab_stride4 + last_off4;
     int i, j, k;
     tile_ijk(g, tile_first + t, i, j, k);
-    const int wx = mode == 0 ? g.c[0] : TX, wy = mode == 0 ? g.c[1] : TY, wz = mode == 0 ? g.c[2] : TZ;
+    const int wy = mode == 0 ? g.c[1] : TY, wz = mode == 0 ? g.c[2] : TZ;
     const int ox = mode == 0 ? g.b[0] : 0, oy = mode == 0 ? g.b[1] : 0, oz = mode == 0 ? g.b[2] : 0;
-    const size_t win = (size_t)wx * wy * wz;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < win; v += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(v % wz);
-        const size_t r = v / wz;
-        const int b = (int)(r % wy), a = (int)(r / wy);
+    const int gx = i * g.c[0] + a, lx = gx - g.out_lo[0];
+    if (mode == 0 && (gx >= g.X || lx < 0 || lx >= g.out_dim[0])) return;
+    for (int f = threadIdx.x; f < wy * wz; f += blockDim.x) {
+        const int b = f / wz, c = f - b * wz;
         const size_t tv = ((size_t)(a + ox) * TY + (b + oy)) * TZ + (c + oz);
         float acc = head_b;
         for (int ck = 0; ck < c4; ++ck) {
@@ -162,10 +165,9 @@ head_scatter(const float4* __restrict__ slab, size_t slab_stride4, size_t last_o
         }
         const float p = 1.f / (1.f + expf(-acc));
         if (mode == 0) {
-            const int gx = i * g.c[0] + a, gy = j * g.c[1] + b, gz = k * g.c[2] + c;
-            const int lx = gx - g.out_lo[0], ly = gy - g.out_lo[1], lz = gz - g.out_lo[2];
-            if (gx < g.X && gy < g.Y && gz < g.Z && lx >= 0 && ly >= 0 && lz >= 0 && lx < g.out_dim[0] &&
-                ly < g.out_dim[1] && lz < g.out_dim[2])
+            const int gy = j * g.c[1] + b, gz = k * g.c[2] + c;
+            const int ly = gy - g.out_lo[1], lz = gz - g.out_lo[2];
+            if (gy < g.Y && gz < g.Z && ly >= 0 && lz >= 0 && ly < g.out_dim[1] && lz < g.out_dim[2])
                 prob[((size_t)lx * g.out_dim[1] + ly) * g.out_dim[2] + lz] = p;
         } else {
             prob[(size_t)(tile_first + t) * tile_vox + tv] = p;
@@ -478,14 +480,14 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) 
         } else {
             const float4* src = reinterpret_cast<const float4*>(slab0);
             float4* dst = reinterpret_cast<float4*>(slab0);
-            const size_t work = (size_t)op.dx * op.dy * op.dz * (op.c / 4);
-            dim3 grid(grid_for(work), tiles);
             if (op.kind == OP_POOL) {
+                dim3 grid((op.c / 4) * op.dx, tiles);
                 pool_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.src_coff / 4,
                                                  op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
                                                  net->spec.pool_x, net->spec.pool_y, net->spec.pool_z, op.src_slot, op.dst_slot);
                 CT_LAUNCHED("pool_kernel");
             } else {
+                dim3 grid((op.c / 4) * op.sx, tiles);
                 upsample_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.dst_coff / 4,
                                                      op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
                                                      net->spec.pool_x, net->spec.pool_y, net->spec.pool_z, op.src_slot, op.dst_slot);
@@ -504,16 +506,15 @@ static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode,
     CT_REQUIRE(((uintptr_t)ws & 255) == 0, "unet: workspace must be 256-byte aligned");
     float* slab0 = static_cast<float*>(ws);
     const int TX = net->spec.in_x, TY = net->spec.in_y, TZ = net->spec.in_z;
-    const size_t tile_vox = (size_t)TX * TY * TZ;
     for (int t0 = first; t0 < last; t0 += tiles_per_batch) {
         const int nt = (last - t0 < tiles_per_batch) ? last - t0 : tiles_per_batch;
-        dim3 g(grid_for(tile_vox), nt);
+        dim3 g(TX, nt), gh(mode == 0 ? geo.c[0] : TX, nt);
         CT_CUDA(cudaMemset2DAsync(slab0, net->slab_floats * sizeof(float), 0, AMAX_SLOTS * sizeof(float), nt, s));
         gather_tiles<<<g, 256, 0, s>>>(src, reinterpret_cast<float4*>(slab0), net->slab_floats / 4, net->in_off / 4, mode, t0,
                                        geo, net->in_slot);
         CT_LAUNCHED("gather_tiles");
         if (run_plan(net, slab0, nt, s)) return 1;
-        head_scatter<<<g, 256, 0, s>>>(reinterpret_cast<const float4*>(slab0), net->slab_floats / 4, net->last_off / 4,
+        head_scatter<<<gh, 256, 0, s>>>(reinterpret_cast<const float4*>(slab0), net->slab_floats / 4, net->last_off / 4,
                                        net->last_c / 4, net->head_w, net->head_b, prob, mode, t0, geo);
         CT_LAUNCHED("head_scatter");
     }

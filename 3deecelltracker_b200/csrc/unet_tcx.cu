@@ -14,10 +14,11 @@
 // over dx, which the worker warps do in registers while they drain tensor memory (each thread owns one voxel row of
 // every plane, so the three contributions of an output voxel meet in the same thread).
 //
-// B rows per K half: [hi dx0 | hi dx1 | hi dx2 | lo' dx0 | lo' dx1 | lo' dx2] (+ [hi dx0..2] again when Cout = 8):
+// B rows per K half: [hi dx0 | hi dx1 | hi dx2 | lo' dx0 | lo' dx1 | lo' dx2]:
 //     MMA1 = A_hi  x rows [0, 6N)            -> columns [0, 3N) = hi.hi, [3N, 6N) = hi.lo'
 //     MMA2 = A_lo' x rows [0, 3N)            -> accumulated onto columns [3N, 6N)          (same weight 2^-11)
-//     Cout = 8: MMA2 = A_lo' x rows [3N, 9N) -> columns [6N, 9N) = lo'.lo', [9N, 12N) = lo'.hi  (N must be >= 16 wide)
+//     Cout = 8 (3N = 24 is not a legal MMA width): MMA2 = A_lo' x rows [0, 6N) at column 3N -- lo'.hi still lands on
+//     columns [3N, 6N); columns [6N, 9N) receive lo'.lo' (weight 2^-22), which is never read, like in the wider layers.
 // K = 16 per MMA = two (dy,dz) taps x 8 input channels; 9 taps -> 5 K steps (tap 7 appears twice, once with zero
 // weights).  One accumulator set = one input plane x one 8-channel chunk = 5 MMAs per column group, drained into fp32
 // registers (round-to-nearest) while the next plane's MMAs run into the other set.
@@ -41,31 +42,40 @@ __host__ __device__ constexpr int tx_off(int t2) { return (t2 / 3) * TX_SZH + t2
 __host__ __device__ constexpr int tx_first(int p) { return p < 4 ? 2 * p : 7; }
 __host__ __device__ constexpr int tx_second(int p) { return p < 4 ? 2 * p + 1 : 8; }
 
-constexpr int TX_CONV_WARPS = 4;                // operand conversion (fp32 -> fp16 hi / lo' images, in place)
-constexpr int TX_DRAIN_WARPS = 8;                // accumulator drain + x shift-add + epilogue: two per lane quarter
-constexpr int TX_THREADS = 64 + 32 * (TX_CONV_WARPS + TX_DRAIN_WARPS);
+#ifdef TX_TIMING
+// debug build only: cycles block 0's role warps spend waiting (see scripts/tcx_timing.py)
+__device__ unsigned long long g_tx_timers[16];
+#define TX_T0() const long long _t0 = clock64()
+#define TX_ACC(var) var += clock64() - _t0
+#else
+#define TX_T0()
+#define TX_ACC(var)
+#endif
+
+constexpr int TX_CONV_WARPS = 2;                // operand conversion (fp32 -> fp16 hi / lo' images, in place)
+// + 8 warps (two per tensor-memory lane quarter, half the channels each) for accumulator drain, x shift-add, epilogue
 
 template <int N, int BX, int STAGES>
 struct TxCfg {
     static constexpr bool N8 = (N == 8);
-    static constexpr int NPR = N8 ? 9 * N : 6 * N;                     // B rows per K half
+    static constexpr int NPR = 6 * N;                                  // B rows per K half
     static constexpr int N1 = 6 * N;
     static constexpr int N2 = N8 ? 6 * N : 3 * N;
-    static constexpr int B2_ROW = N8 ? 3 * N : 0;                      // first B row of MMA2
-    static constexpr int D2_COL = N8 ? 6 * N : 3 * N;                  // first accumulator column of MMA2
-    static constexpr int NPD = N8 ? 12 * N : 6 * N;                    // accumulator columns of one set
-    static constexpr int NSETS = 512 / NPD >= 4 ? 4 : 2;               // accumulator sets in flight
+    static constexpr int D2_COL = 3 * N;                               // first accumulator column of MMA2
+    static constexpr int NPD = N8 ? 9 * N : 6 * N;                     // accumulator columns of one set
+    static constexpr int NSETS = 4;                                    // accumulator sets in flight
     static constexpr int SXH = BX + 2;
     static constexpr int PLANE = SXH * TX_PLANE_VOX * 16;              // bytes of one operand image of the block
     static constexpr int B_BYTES = TX_PAIRS * 2 * NPR * 16;
     static constexpr int STAGE = 2 * PLANE + B_BYTES;
     static constexpr int TMEM_COLS = NSETS * NPD <= 256 ? 256 : 512;
     static constexpr int SMEM = STAGES * STAGE + 1024;
-    static constexpr int CH = N / (TX_DRAIN_WARPS / 4);                // output channels per drain thread
+    static constexpr int DRAIN_WARPS = 8;                              // two per tensor-memory lane quarter
+    static constexpr int THREADS = 64 + 32 * (TX_CONV_WARPS + DRAIN_WARPS);
+    static constexpr int CH = N / 2;                                   // output channels per drain thread
     static_assert(NSETS * NPD <= 512, "accumulators exceed tensor memory");
     static_assert(N1 % 16 == 0 && N1 <= 256 && N2 % 16 == 0, "UMMA N out of range for M = 128");
     static_assert(PLANE % 128 == 0 && B_BYTES % 128 == 0, "stage parts must stay 128-byte aligned");
-    static_assert(CH == 4 || CH == 8, "a drain thread owns 4 or 8 channels");
     static_assert(SMEM <= 232448, "shared memory ring too large");
 };
 
@@ -105,10 +115,10 @@ __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[CH])
 
 // Persistent CTA.  Work unit = BX x 16 x 8 output voxels x all Cout of one tile.  Stage g = one 8-channel chunk of one
 // unit (ring slot g % STAGES); accumulator step a = g * (BX+2) + j = input plane j of stage g (tensor-memory set
-// a % NSETS).  Warp roles: 0 TMA producer (+ tensor-memory allocator), 1 MMA issuer, 2-5 operand conversion,
-// 6-13 accumulator drain / x shift-add / epilogue.
+// a % NSETS).  Warp roles: 0 TMA producer (+ tensor-memory allocator), 1 MMA issuer, 2-3 operand conversion,
+// 4-11 accumulator drain / x shift-add / epilogue.
 template <int N, int BX, int STAGES>
-__global__ void __launch_bounds__(TX_THREADS, 1)
+__global__ void __launch_bounds__(TxCfg<N, BX, STAGES>::THREADS, 1)
 conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
                  const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                  float alpha, float4* __restrict__ dst, const TxGeom geo) {
@@ -135,13 +145,13 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
         for (int a = 0; a < NSETS; ++a) {
             mbar_init(&bar_acc_full[a], 1);
-            mbar_init(&bar_acc_empty[a], TX_DRAIN_WARPS);
+            mbar_init(&bar_acc_empty[a], Cfg::DRAIN_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
     if (threadIdx.x >= 64) {
-        for (int i = threadIdx.x - 64; i < 3 * N; i += TX_THREADS - 64)
+        for (int i = threadIdx.x - 64; i < 3 * N; i += Cfg::THREADS - 64)
             ep_s[i / N][i % N] = (i < N) ? bias[i] : (i < 2 * N ? scale[i - N] : shift[i - 2 * N]);
     }
     tc_fence_before();
@@ -150,8 +160,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     const uint32_t tmem_base = tmem_base_s;
 
     // power-of-two operand scale of a tile: max|x s| in [2^13, 2^14) (see unet_tc.cu)
-    auto tile_scale = [&](int tile) {
-        const float am = geo.amax_src[(size_t)tile * geo.slab_stride];
+    auto scale_of = [](float am) {
         const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);
         const int se = (267 - e > 254) ? 254 : 267 - e;
         return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
@@ -183,15 +192,16 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             constexpr uint64_t b_hi_word = (uint64_t)(8u | (1u << 14)) << 32;                 // SBO: 8-row groups 128 B apart
             const uint32_t ring16 = smem_u32(ring) >> 4;
             int a = 0;
+            long long w_conv = 0, w_acc = 0, t_begin = clock64();
             for (int g = 0; g < n_stages; ++g) {
                 const int s = g % STAGES, use = g / STAGES;
-                mbar_wait(&bar_conv[s], use & 1);
+                { TX_T0(); mbar_wait(&bar_conv[s], use & 1); TX_ACC(w_conv); }
                 const uint32_t a_hi = ring16 + (uint32_t)s * (Cfg::STAGE / 16), a_lo = a_hi + Cfg::PLANE / 16;
                 const uint32_t b_base = a_hi + 2 * (Cfg::PLANE / 16);
 #pragma unroll 1
                 for (int j = 0; j < SXH; ++j, ++a) {
                     const int set = a % NSETS, use_a = a / NSETS;
-                    if (use_a > 0) mbar_wait(&bar_acc_empty[set], (use_a - 1) & 1);
+                    if (use_a > 0) { TX_T0(); mbar_wait(&bar_acc_empty[set], (use_a - 1) & 1); TX_ACC(w_acc); }
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)set * Cfg::NPD;
                     const uint32_t pl = (uint32_t)j * TX_PLANE_VOX;
@@ -202,25 +212,30 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         const uint32_t al = (a_lo + pl + (uint32_t)tx_off(tx_first(p))) | lbo;
                         const uint32_t b32 = (b_base + (uint32_t)p * (Cfg::NPR * 2)) | ((uint32_t)Cfg::NPR << 16);
                         umma_f16(d, a_hi_word | (uint64_t)ah, b_hi_word | (uint64_t)b32, idesc1, p != 0);
-                        umma_f16(d + Cfg::D2_COL, a_hi_word | (uint64_t)al, b_hi_word | (uint64_t)(b32 + Cfg::B2_ROW),
-                                 idesc2, Cfg::N8 ? (uint32_t)(p != 0) : 1u);
+                        umma_f16(d + Cfg::D2_COL, a_hi_word | (uint64_t)al, b_hi_word | (uint64_t)b32, idesc2, 1u);
                     }
                     umma_commit(&bar_acc_full[set]);
                 }
                 umma_commit(&bar_empty[s]);
             }
+#ifdef TX_TIMING
+            if (blockIdx.x == 0) { g_tx_timers[0] = w_conv; g_tx_timers[1] = w_acc; g_tx_timers[2] = clock64() - t_begin; }
+#else
+            (void)w_conv; (void)w_acc; (void)t_begin;
+#endif
         }
         __syncwarp();
     } else if (warp < 2 + TX_CONV_WARPS) {
         // ---------------- converters: fp32 -> fp16 hi / lo' images of every landed stage, in place
         const int ct = threadIdx.x - 64;
         int g = 0;
+        long long w_full = 0, t_begin = clock64();
         for (int k = 0; k < n_units; ++k) {
             const TxUnit un = tx_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
-            const float sc = tile_scale(un.tile);
+            const float sc = scale_of(geo.amax_src[(size_t)un.tile * geo.slab_stride]);
             for (int c = 0; c < cin8; ++c, ++g) {
                 const int s = g % STAGES, use = g / STAGES;
-                mbar_wait(&bar_full[s], use & 1);
+                { TX_T0(); mbar_wait(&bar_full[s], use & 1); TX_ACC(w_full); }
                 uint4* p0 = reinterpret_cast<uint4*>(ring + (size_t)s * Cfg::STAGE);
                 uint4* p1 = p0 + Cfg::PLANE / 16;
 #pragma unroll 2
@@ -245,6 +260,11 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 if (lane == 0) mbar_arrive(&bar_conv[s]);
             }
         }
+#ifdef TX_TIMING
+        if (blockIdx.x == 0 && threadIdx.x == 64) { g_tx_timers[3] = w_full; g_tx_timers[4] = clock64() - t_begin; }
+#else
+        (void)w_full; (void)t_begin;
+#endif
     } else {
         // ---------------- drain warps: tensor memory -> registers with the x shift-add, epilogue
         const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
@@ -253,22 +273,56 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         const int row = q * 32 + lane;
         const size_t vol = (size_t)geo.X * geo.Y * geo.Z;
         float acc[BX][CH];
-        constexpr float W2 = 1.f / 2048.f, W3 = W2 * W2;
-        constexpr int TERMS = Cfg::N8 ? 4 : 2;                     // column groups per x-tap: hh, hl (, ll, lh)
+        constexpr float W2 = 1.f / 2048.f;                         // weight of the hi.lo' + lo'.hi column group
+        constexpr int TERMS = 2;                                   // column groups per x-tap
 
         int a = 0;
+        long long w_accf = 0, t_epi = 0, t_begin = clock64();
+        // max|x| of the unit's tile is fetched one unit ahead: the load's latency never sits in front of the epilogue
+        TxUnit un_next = tx_unit((int)blockIdx.x, geo, BX);
+        float am_next = n_units > 0 ? geo.amax_src[(size_t)un_next.tile * geo.slab_stride] : 0.f;
         for (int k = 0; k < n_units; ++k) {
-            const TxUnit un = tx_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
+            const TxUnit un = un_next;
+            const float inv_scale = geo.w_inv_scale / scale_of(am_next);
+            if (k + 1 < n_units) {
+                un_next = tx_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
+                am_next = geo.amax_src[(size_t)un_next.tile * geo.slab_stride];
+            }
+            const int y = un.y0 + (row >> 3), z = un.z0 + (row & 7);
+            float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)(geo.dst_c4off + ch0 / 4) * vol;
+            float amax = 0.f;
+            // epilogue of ONE output plane: scale back, bias -> activation -> BatchNorm, 16-byte channel-chunk stores.
+            // Plane i is complete once input plane i + 2 of the last chunk is drained, so its stores are issued there
+            // and trickle out under the remaining drains instead of bursting at the end of the unit.
+            auto store_plane = [&](int i) {
+                const int x = un.x0 + i;
+                if (y >= geo.Y || x >= geo.X) return;
+                const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
+#pragma unroll
+                for (int c4 = 0; c4 < CH / 4; ++c4) {
+                    float o[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int ch = ch0 + c4 * 4 + kk;
+                        float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch]);
+                        t = t > 0.f ? t : alpha * t;
+                        o[kk] = fmaf(t, ep_s[1][ch], ep_s[2][ch]);
+                        amax = fmaxf(amax, fabsf(o[kk]));
+                    }
+                    d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            };
 #pragma unroll
             for (int i = 0; i < BX; ++i)
 #pragma unroll
                 for (int ch = 0; ch < CH; ++ch) acc[i][ch] = 0.f;
 #pragma unroll 1
             for (int c = 0; c < cin8; ++c) {
+                const bool last = (c == cin8 - 1);
 #pragma unroll
                 for (int j = 0; j < SXH; ++j, ++a) {
                     const int set = a % NSETS, use_a = a / NSETS;
-                    mbar_wait(&bar_acc_full[set], use_a & 1);
+                    { TX_T0(); mbar_wait(&bar_acc_full[set], use_a & 1); TX_ACC(w_accf); }
                     tc_fence_after();
                     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * Cfg::NPD + (uint32_t)ch0;
                     uint32_t v[3][TERMS][CH];
@@ -289,45 +343,22 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                         for (int ch = 0; ch < CH; ++ch) {
                             const float hh = __uint_as_float(v[dx][0][ch]), hl = __uint_as_float(v[dx][1][ch]);
-                            if (Cfg::N8) {
-                                const float ll = __uint_as_float(v[dx][2][ch]), lh = __uint_as_float(v[dx][3][ch]);
-                                acc[i][ch] += fmaf(ll, W3, fmaf(hl + lh, W2, hh));
-                            } else {
-                                acc[i][ch] += fmaf(hl, W2, hh);
-                            }
+                            acc[i][ch] += fmaf(hl, W2, hh);
                         }
                     }
-                }
-            }
-            // epilogue: scale back, bias -> activation -> BatchNorm, 16-byte channel-chunk stores, max|value| bound
-            const float inv_scale = geo.w_inv_scale / tile_scale(un.tile);
-            const int y = un.y0 + (row >> 3), z = un.z0 + (row & 7);
-            float amax = 0.f;
-            if (y < geo.Y) {
-                float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)(geo.dst_c4off + ch0 / 4) * vol;
-#pragma unroll
-                for (int i = 0; i < BX; ++i) {
-                    const int x = un.x0 + i;
-                    if (x >= geo.X) break;
-                    const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
-#pragma unroll
-                    for (int c4 = 0; c4 < CH / 4; ++c4) {
-                        float o[4];
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int ch = ch0 + c4 * 4 + kk;
-                            float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch]);
-                            t = t > 0.f ? t : alpha * t;
-                            o[kk] = fmaf(t, ep_s[1][ch], ep_s[2][ch]);
-                            amax = fmaxf(amax, fabsf(o[kk]));
-                        }
-                        d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
-                    }
+                    if (last && j >= 2) { TX_T0(); store_plane(j - 2); TX_ACC(t_epi); }
                 }
             }
             amax = warp_max(amax);
             if (lane == 0) amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
         }
+#ifdef TX_TIMING
+        if (blockIdx.x == 0 && warp == 2 + TX_CONV_WARPS && lane == 0) {
+            g_tx_timers[5] = w_accf; g_tx_timers[6] = t_epi; g_tx_timers[7] = clock64() - t_begin;
+        }
+#else
+        (void)w_accf; (void)t_epi; (void)t_begin;
+#endif
         tc_fence_before();
     }
     __syncthreads();
@@ -340,7 +371,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int tx_rows(int cout) { return cout == 8 ? 72 : 6 * cout; }
+static int tx_rows(int cout) { return 6 * cout; }
 
 size_t tcx_weight_floats(int cin_pad, int cout) {
     if (cout != 8 && cout != 16) return 0;
@@ -348,7 +379,7 @@ size_t tcx_weight_floats(int cin_pad, int cout) {
 }
 
 // keras kernel (kx,ky,kz,ci,co) -> fp16 image [ci/8][K step][K half][row][ci % 8] with rows
-// dx*cout + co (hi) | 3 cout + dx*cout + co (lo') (| 6 cout + dx*cout + co (hi again) when cout = 8); same power-of-two
+// dx*cout + co (hi) | 3 cout + dx*cout + co (lo'); same power-of-two
 // scale as the classic packing (max|w| in [2^13, 2^14)).  Returns 1 / scale.
 float tcx_pack_weights(const float* w, int cin, int cin_pad, int cout, float* dst) {
     const int npr = tx_rows(cout), c8n = (cin_pad + 7) / 8;
@@ -376,7 +407,6 @@ float tcx_pack_weights(const float* w, int cin, int cin_pad, int cout, float* ds
                             const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
                             blk[(size_t)(dx * cout + co) * 8 + qd] = h;
                             blk[(size_t)(3 * cout + dx * cout + co) * 8 + qd] = l;
-                            if (cout == 8) blk[(size_t)(6 * cout + dx * cout + co) * 8 + qd] = h;
                         }
             }
     return 1.f / scale;
@@ -399,7 +429,7 @@ static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, float alpha, f
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
     const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
     const int grid = g.units < sms ? g.units : sms;
-    conv3_tcx_kernel<N, BX, STAGES><<<grid, TX_THREADS, Cfg::SMEM, s>>>(map, L.w_tcx, L.bias, L.scale, L.shift, alpha, dst, g);
+    conv3_tcx_kernel<N, BX, STAGES><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, L.w_tcx, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
 }
 
@@ -428,3 +458,9 @@ int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
 }
 
 }  // namespace ct
+
+#ifdef TX_TIMING
+extern "C" int ct_debug_tcx_timers(unsigned long long* out16) {
+    return cudaMemcpyFromSymbol(out16, ct::g_tx_timers, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif

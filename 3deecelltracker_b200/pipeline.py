@@ -1,14 +1,24 @@
-"""Frame pipeline of a time-lapse: the two hot paths of `Tracker.track_one_vol` (tracker.py:1473-1536) on two streams.
+"""Frame pipeline of a time-lapse: the two hot paths of `Tracker.track_one_vol` (tracker.py:1473-1536) on separate streams.
 
-Segmentation of volume t+1 (`_normalize_image` + `unet3_prediction`, tracker.py:662-669) does not depend on the
-tracking of volume t (`_fit_ffn_prgls` x REP_NUM_PRGLS + `_predict_one_rep` + `trim_mean`, tracker.py:1224-1289,1507),
-and the two stages want opposite things from the machine: the U-Net is a persistent tensor-core kernel that fills
-every SM, the PR-GLS EM is ONE latency-bound fp64 CTA per problem (5 sequential repetitions x 19 iterations).  Run back
-to back the EM leaves 147 SMs idle for a third of the frame.  `FramePipeline.step` enqueues the tracking stage of the
-previous volume on a high-priority side stream and the segmentation of the next volume on the caller's stream, with
-one SM kept out of the convolution's persistent grid (`ct_set_reserved_sms`) so the EM CTA never waits behind a
-convolution CTA; the streams join before `step` returns, so a step is still one frame of each stage.
+Three facts of the reference make the loop pipelinable without changing a single result:
+  * segmentation of volume t+1 (`_normalize_image` + `unet3_prediction`, tracker.py:662-669) does not depend on the
+    tracking of volume t;
+  * the expensive part of tracking, `_fit_ffn_prgls` (tracker.py:1224-1254: REP_NUM_PRGLS x (FFN match + PR-GLS)), fits
+    transforms between the SEGMENTED point sets of two volumes -- it does not read any tracking result;
+  * only the replay `_predict_one_rep` (tracker.py:1269-1289, five tiny Gaussian-kernel products) carries state from one
+    volume to the next.
+And the two stages want opposite things from the machine: the U-Net is a persistent tensor-core kernel that fills every
+SM, the PR-GLS EM is ONE latency-bound fp64 CTA per problem (5 sequential repetitions x 19 iterations).  Back to back,
+the EM leaves 147 SMs idle for a third of the frame.
+
+`FramePipeline.step` therefore (1) joins the fit submitted `depth` steps ago and replays it on the tracked cells,
+(2) enqueues this step's fit on a high-priority side stream (`depth` of them take turns, so `depth` fits are in
+flight), (3) enqueues the segmentation on the caller's stream, with a few SMs kept out of the convolution's persistent
+grid (`ct_set_reserved_sms`) so the EM CTAs and the small FFN kernels never queue behind a convolution CTA.  Every step
+still performs exactly one segmentation, one fit and one replay; results are those of the serial order.
 """
+import collections
+
 import torch
 
 from . import _lib
@@ -21,57 +31,96 @@ K_POINTS = 20              # tracker.py:1259
 
 class FramePipeline:
     def __init__(self, unet_model, ffn_model, noise_level, beta_tk, lambda_tk, maxiter_tk, shrink=(24, 24, 2),
-                 overlap=True, reserve_sms=1):
+                 overlap=True, reserve_sms=8, depth=2):
         self.unet, self.ffn = unet_model, ffn_model
         self.noise_level, self.shrink = noise_level, tuple(shrink)
         self.beta_tk, self.lambda_tk, self.max_iteration = beta_tk, lambda_tk, maxiter_tk
         self.overlap = bool(overlap)
         self.reserve_sms = int(reserve_sms)
-        self._side = None
+        self.depth = max(1, int(depth))
+        self._streams = None
+        self._pending = collections.deque()          # (stream, fit, tracked_prev or None)
+        self._tracked = None                         # running tracked coordinates when the caller does not pass them
+        self._count = 0
 
-    # ---- the two stages, each on the current stream
+    # ---- the stages, each on the current stream
     def segment(self, raw_dev):
         """tracker.py:662-669: raw (x,y,z) CUDA tensor -> probability map (x,y,z) float32 CUDA tensor."""
         norm = normalize_image_device(raw_dev, self.noise_level, (27, 27, 1))
         return self.unet.prediction_device(norm, self.shrink)
 
-    def fit_predict(self, seg_prev_dev, seg_cur_dev, tracked_prev_dev):
-        """tracker.py:1224-1289 for one source volume: REP_NUM_PRGLS x (FFN match + PR-GLS with beta * 0.8**i), the
-        fitted transforms replayed on the tracked cells.  (N,3), (M,3), (L,3) float64 CUDA -> (L,3)."""
-        inter, pred = seg_prev_dev, tracked_prev_dev
+    def fit(self, seg_prev_dev, seg_cur_dev):
+        """tracker.py:1224-1254 for one source volume: REP_NUM_PRGLS x (FFN match + PR-GLS with beta * 0.8**i).
+        (N,3), (M,3) float64 CUDA -> [(intermediate points, beta, C)] per repetition."""
+        inter, out = seg_prev_dev, []
         for i in range(REP_NUM_PRGLS):
             beta = self.beta_tk * (0.8 ** i)
             corr = self.ffn.match_device(inter, seg_cur_dev, K_POINTS)
             p = run_em([EmProblem(inter, seg_cur_dev, corr)], MODE_TRACK, beta, self.lambda_tk, self.max_iteration,
                        1e8, 0.5)[0]
-            pred = predict_one_rep_device(pred, inter, beta, p.coef)
+            out.append((inter, beta, p.coef))
             inter = p.ref_out
-        return pred
+        return out
+
+    def replay(self, fit, tracked_prev_dev):
+        """tracker.py:1269-1289 + the single-mode trimmed mean of :1503-1507: (L,3) -> (L,3)."""
+        pred = tracked_prev_dev
+        for inter, beta, coef in fit:
+            pred = predict_one_rep_device(pred, inter, beta, coef)
+        return trim_mean_device(pred[None], 0.1)
 
     def track(self, seg_prev_dev, seg_cur_dev, tracked_prev_dev):
-        """Single-mode prediction of tracker.py:1503-1507 (one source volume, trimmed mean over a stack of one)."""
-        return trim_mean_device(self.fit_predict(seg_prev_dev, seg_cur_dev, tracked_prev_dev)[None], 0.1)
+        return self.replay(self.fit(seg_prev_dev, seg_cur_dev), tracked_prev_dev)
+
+    def reset(self, tracked0_dev=None):
+        """Forget fits in flight; `tracked0_dev` seeds the running tracked coordinates."""
+        self.flush()
+        self._tracked = tracked0_dev
 
     # ---- one pipelined step
-    def step(self, raw_next_dev, track_args):
-        """Segment `raw_next_dev` (volume t+1) while volume t is tracked: track_args = (segmented points of t-1,
-        segmented points of t, tracked points of t-1), all float64 CUDA tensors produced before this call on the
-        current stream.  Returns (prob of t+1, predicted coordinates of t); both are safe to use on the current
-        stream when the call returns."""
+    def _join_oldest(self):
+        stream, fit, tracked_prev = self._pending.popleft()
+        main = torch.cuda.current_stream()
+        main.wait_stream(stream)
+        prev = tracked_prev if tracked_prev is not None else self._tracked
+        tracked = self.replay(fit, prev)
+        if tracked_prev is None:
+            self._tracked = tracked
+        return tracked
+
+    def step(self, raw_next_dev, seg_prev_dev, seg_cur_dev, tracked_prev_dev=None):
+        """One frame of each stage.  Segments `raw_next_dev`; submits the fit seg_prev -> seg_cur; returns
+        (probability map, tracked coordinates of the fit submitted `depth` steps ago, or None while the pipeline
+        fills).  tracked_prev_dev = None replays onto the pipeline's running coordinates (see `reset`).  Everything
+        returned is safe to use on the current stream."""
         if not self.overlap:
-            return self.segment(raw_next_dev), self.track(*track_args)
-        if self._side is None:
-            self._side = torch.cuda.Stream(priority=-1)
+            prob = self.segment(raw_next_dev)
+            prev = tracked_prev_dev if tracked_prev_dev is not None else self._tracked
+            tracked = self.track(seg_prev_dev, seg_cur_dev, prev)
+            if tracked_prev_dev is None:
+                self._tracked = tracked
+            return prob, tracked
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(priority=-1) for _ in range(self.depth)]
         lib = _lib.lib()
         main = torch.cuda.current_stream()
-        self._side.wait_stream(main)                          # inputs (and the previous step) are ordered before
+        tracked = self._join_oldest() if len(self._pending) >= self.depth else None
+        side = self._streams[self._count % self.depth]
+        self._count += 1
+        side.wait_stream(main)                                # inputs are ordered before the fit
         old = lib.ct_set_reserved_sms(self.reserve_sms)
         try:
-            with torch.cuda.stream(self._side):
-                tracked = self.track(*track_args)
+            with torch.cuda.stream(side):
+                fit = self.fit(seg_prev_dev, seg_cur_dev)
+            self._pending.append((side, fit, tracked_prev_dev))
             prob = self.segment(raw_next_dev)
         finally:
             lib.ct_set_reserved_sms(old)
-        main.wait_stream(self._side)                          # join
-        tracked.record_stream(main)
         return prob, tracked
+
+    def flush(self):
+        """Join every fit still in flight; returns their tracked coordinates, oldest first."""
+        out = []
+        while self._pending:
+            out.append(self._join_oldest())
+        return out

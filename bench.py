@@ -140,17 +140,21 @@ def make_inputs(frame):
 
 
 class Step:
-    """One frame through the product's FramePipeline (pipeline.py; mirrors Tracker.track_one_vol's hot-path calls):
-    segmentation of the step's volume on the current stream while the match + track stage of the previous volume
-    runs on the side stream; the streams join inside the step, so every step performs one full frame of each stage.
-    With overlap=False the two stages run back to back on one stream."""
+    """One frame through the product's FramePipeline (pipeline.py; mirrors Tracker.track_one_vol's hot-path calls).
+    Every step performs one segmentation (LCN + U-Net), submits one fit (5 x (FFN match + PR-GLS)) to a side stream
+    and joins + replays the fit submitted `depth` steps earlier, so K timed steps contain K full frames of every stage;
+    the fits still in flight after the last step are joined (flush) INSIDE the timed region.
+    With overlap=False the stages run back to back on one stream."""
 
-    def __init__(self, unet, ffn, overlap=True):
+    def __init__(self, unet, ffn, overlap=True, reserve_sms=8, depth=2):
         self.pipe = mod("pipeline").FramePipeline(unet, ffn, NOISE_LEVEL, BETA_TK, LAMBDA_TK, MAXITER_TK, SHRINK,
-                                                  overlap=overlap)
+                                                  overlap=overlap, reserve_sms=reserve_sms, depth=depth)
 
     def run(self, raw_dev, ref_dev, tgt_dev, tracked_dev):
-        return self.pipe.step(raw_dev, (ref_dev, tgt_dev, tracked_dev))
+        return self.pipe.step(raw_dev, ref_dev, tgt_dev, tracked_dev)
+
+    def flush(self):
+        return self.pipe.flush()
 
 
 def gpu_main(args):
@@ -171,7 +175,7 @@ def gpu_main(args):
     unet = mod("unet3d").UNet3("a", weights=synth.unet_weights("a", 0), tiles_per_batch=args.tiles_per_batch,
                                engine=args.engine)
     ffn = mod("ffn").FFN(synth.ffn_weights(0))
-    step = Step(unet, ffn, overlap=not args.no_overlap)
+    step = Step(unet, ffn, overlap=not args.no_overlap, reserve_sms=args.reserve_sms, depth=args.depth)
     serial = Step(unet, ffn, overlap=False)
     n_tiles, _ = unet.tile_count(SHAPE, SHRINK)
 
@@ -191,24 +195,29 @@ def gpu_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm
+    # ---- device-resident arm.  The timed region is ONE interval around K steps plus the drain of the pipeline (the
+    # fits still in flight are joined inside it), so it contains K full frames of every stage and nothing else; the
+    # warm-up's own in-flight fits are drained before it starts.
     for _ in range(args.warmup):
         step.run(raw_dev, ref_dev, tgt_dev, tracked_dev)
+    step.flush()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     lib.ct_profile_enable(1)
     launches0 = lib.ct_launch_count()
-    times = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_tracked = 0
     for _ in range(args.steps):
-        flush.zero_()                                            # flush L2 between timed iterations
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step.run(raw_dev, ref_dev, tgt_dev, tracked_dev)
-        e1.record()
-        times.append((e0, e1))
+        flush.zero_()                                            # flush L2 between timed iterations (inside the region)
+        n_tracked += step.run(raw_dev, ref_dev, tgt_dev, tracked_dev)[1] is not None
+    n_tracked += len(step.flush())
+    e1.record()
     barrier()
+    assert n_tracked == args.steps, f"{n_tracked} tracking results for {args.steps} steps"
+    times = [(e0, e1)]
     launches = lib.ct_launch_count() - launches0
     lib.ct_profile_enable(0)
     dev_ms = sum(a.elapsed_time(b) for a, b in times)
@@ -239,23 +248,30 @@ def gpu_main(args):
     prob_host = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
     out_host = torch.empty((N_CELLS, 3), dtype=torch.float64).pin_memory()
 
-    def e2e_step():
+    def e2e_step(last=False):
         r = raw_pinned.to(dev, non_blocking=True).view(torch.uint16)
         a = ref_pinned.to(dev, non_blocking=True)
         b = tgt_pinned.to(dev, non_blocking=True)
         prob, out = step.run(r, a, b, a)
         prob_host.copy_(prob, non_blocking=True)
-        out_host.copy_(out, non_blocking=True)
-        torch.cuda.synchronize()
+        outs = ([] if out is None else [out]) + (step.flush() if last else [])
+        for o in outs:
+            out_host.copy_(o, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        done.synchronize()            # this step's results are on the host; fits in flight keep running
+        return len(outs)
 
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
+    for i in range(max(1, args.warmup // 2)):
+        e2e_step(last=(i == max(1, args.warmup // 2) - 1))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    got = 0
+    for i in range(args.steps):
+        got += e2e_step(last=(i == args.steps - 1))
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert got == args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks
@@ -281,8 +297,10 @@ def gpu_main(args):
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "sharding": "frames, one per GPU" if world > 1 else "single GPU",
                        "pipeline": ("serial: segmentation then tracking on one stream" if args.no_overlap else
-                                    "2 streams: segmentation of volume t+1 overlaps match+track of volume t "
-                                    "(1 SM kept out of the persistent conv grid), joined inside every step"),
+                                    "segmentation on the main stream; %d fits (5x FFN+PR-GLS) in flight on side "
+                                    "streams, each joined + replayed %d steps after submission; %d SMs kept out of the "
+                                    "persistent conv grid; pipeline drained inside the timed region"
+                                    % (args.depth, args.depth, args.reserve_sms)),
                        "host_watershed": "excluded (SURVEY 8f-1)"},
             "frames_per_s": world * args.steps / (dev_ms * 1e-3),
             "e2e": {"value": voxels * world * args.steps / (e2e_ms * 1e-3), "unit": "voxels/s",
@@ -531,6 +549,8 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05", "tcgen05_classic", "tcgen05_stacked"])
     ap.add_argument("--tiles-per-batch", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=2, help="fits (FFN + PR-GLS chains) in flight on side streams")
+    ap.add_argument("--reserve-sms", type=int, default=8, help="SMs kept out of the persistent conv grid while overlapping")
     ap.add_argument("--no-overlap", action="store_true", help="run segmentation and tracking back to back on one stream")
     ap.add_argument("--workload", default="c1", choices=["c1", "c3"],
                     help="c1 (default, the contract's line): one worm1 frame per step; c3: one 1024x1024x96 volume "

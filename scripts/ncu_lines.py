@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attribute the stall samples / executed instructions of an ncu report to CUDA source lines.
 
-usage: ncu_lines.py <report.ncu-rep> <source.cu> <kernel-substring> [top]
+usage: ncu_lines.py <report.ncu-rep> <source.cu> <mangled-kernel-substring> [top] [demangled-substring] [nth launch]
 
 ncu's CSV source page is SASS-only, so the SASS offsets are joined with `nvdisasm -g` line annotations of a cubin
 built from the same source with the library's flags.
@@ -16,6 +16,8 @@ import collections
 
 rep, src, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+kern_ncu = sys.argv[5] if len(sys.argv) > 5 else kern          # demangled-name substring for the ncu side
+nth = int(sys.argv[6]) if len(sys.argv) > 6 else -1            # which matching launch (-1: all)
 cub = "/tmp/_ncu_lines.cubin"
 subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
                 "--expt-relaxed-constexpr", "-cubin", "-o", cub, src], check=True, stderr=subprocess.DEVNULL)
@@ -41,7 +43,11 @@ stalls = collections.defaultdict(lambda: collections.Counter())
 h, base, use = None, None, False
 for r in rows:
     if r and r[0] == "Kernel Name":
-        use = kern in r[1]
+        use = kern_ncu in r[1]
+        if use:
+            seen = globals().get("seen", -1) + 1
+            globals()["seen"] = seen
+            use = nth < 0 or seen == nth
         base = None
         continue
     if r and r[0] == "Address":

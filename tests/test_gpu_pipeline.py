@@ -74,13 +74,31 @@ def test_overlapped_step_equals_serial_step(m):
     ref_dev, tgt_dev = torch.from_numpy(ref).cuda(), torch.from_numpy(tgt).cuda()
     P = m["pipeline"].FramePipeline
     lib = m["_lib"].lib()
-    serial = P(unet, ffn, 20, 300, 0.1, 20, overlap=False).step(raw_dev, (ref_dev, tgt_dev, ref_dev))
-    pipe = P(unet, ffn, 20, 300, 0.1, 20, overlap=True)
-    for _ in range(3):                                     # repeated: stream hazards show up as run-to-run changes
-        prob, tracked = pipe.step(raw_dev, (ref_dev, tgt_dev, ref_dev))
+    serial = P(unet, ffn, 20, 300, 0.1, 20, overlap=False).step(raw_dev, ref_dev, tgt_dev, ref_dev)
+    for depth in (1, 2, 3):
+        pipe = P(unet, ffn, 20, 300, 0.1, 20, overlap=True, depth=depth)
+        results = []
+        for _ in range(5):                                 # repeated: stream hazards show up as run-to-run changes
+            prob, tracked = pipe.step(raw_dev, ref_dev, tgt_dev, ref_dev)
+            assert torch.equal(prob, serial[0])
+            results.append(tracked)
+        assert [r is None for r in results] == [i < depth for i in range(5)]      # the pipeline fills for `depth` steps
+        results = [r for r in results if r is not None] + pipe.flush()
         torch.cuda.synchronize()
-        assert torch.equal(prob, serial[0]) and torch.equal(tracked, serial[1])
+        assert len(results) == 5 and all(torch.equal(r, serial[1]) for r in results)
     assert lib.ct_set_reserved_sms(0) == 0                 # the reservation is scoped to the step
+
+    # running state: without tracked_prev the replays chain, exactly like the serial chain
+    chain_serial = P(unet, ffn, 20, 300, 0.1, 20, overlap=False)
+    chain_serial.reset(ref_dev)
+    want = [chain_serial.step(raw_dev, ref_dev, tgt_dev)[1] for _ in range(4)]
+    chain = P(unet, ffn, 20, 300, 0.1, 20, overlap=True, depth=2)
+    chain.reset(ref_dev)
+    got = [chain.step(raw_dev, ref_dev, tgt_dev)[1] for _ in range(4)]
+    got = [g for g in got if g is not None] + chain.flush()
+    torch.cuda.synchronize()
+    assert len(got) == 4 and all(torch.equal(g, w) for g, w in zip(got, want))
+    assert not torch.equal(want[0], want[1])               # the chain really moves
 
 
 def test_tracker_track_prefetch_and_oracle_chain(m):
