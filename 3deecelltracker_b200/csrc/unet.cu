@@ -17,33 +17,6 @@ namespace ct {
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int reflect_index(int j, int n) {
-    // numpy.pad(mode='reflect') for arbitrarily wide pads: triangle wave of period 2(n-1)
-    if (n == 1) return 0;
-    const int period = 2 * (n - 1);
-    j %= period;
-    if (j < 0) j += period;
-    return j < n ? j : period - j;
-}
-
-// Geometry of a tiled prediction.  The tiles visited are the sub-grid tlo <= (i,j,k) < tlo + tn of the volume's tile
-// grid, enumerated row-major (k fastest); source voxels live in a box `in_lo .. in_lo + in_dim` of the volume
-// (the whole volume on one GPU, the rank's haloed block under spatial decomposition) and results go to a box
-// `out_lo .. out_lo + out_dim`.
-struct TileGeom {
-    int X, Y, Z;                  // whole volume (reflect padding and the final crop refer to it)
-    int TX, TY, TZ;               // model input tile
-    int tlo[3], tn[3];            // tile sub-grid: origin and extent
-    int c[3], b[3];               // centre window size and shrink (= offset of the window inside the tile)
-    int in_lo[3], in_dim[3];
-    int out_lo[3], out_dim[3];
-};
-__device__ __forceinline__ void tile_ijk(const TileGeom& g, int ordinal, int& i, int& j, int& k) {
-    k = g.tlo[2] + ordinal % g.tn[2]; ordinal /= g.tn[2];
-    j = g.tlo[1] + ordinal % g.tn[1]; ordinal /= g.tn[1];
-    i = g.tlo[0] + ordinal;
-}
-
 // Tile gather.  mode 0: tile t of the volume's tile grid, reflect-padded (unet3d.py:235,247-249).
 //               mode 1: tiles are given explicitly as (B, x, y, z) (Keras model.predict).
 // Output: [tile][1 chunk][TX][TY][TZ][4] with channels 1..3 = 0.
@@ -471,10 +444,14 @@ static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t str
     return 0;
 }
 
-// Runs the op plan on `tiles` slabs that already hold their padded input.
-static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s) {
+// Runs the op plan on `tiles` slabs that already hold their padded input (or, with skip_first, the output of the
+// first convolution block).
+static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s, bool skip_first = false) {
     const size_t stride = net->slab_floats;
+    bool first = true;
     for (const Op& op : net->ops) {
+        if (first && skip_first) { first = false; continue; }
+        first = false;
         if (op.kind == OP_CONV) {
             if (launch_conv(net, op, slab0, stride, tiles, s)) return 1;
         } else {
@@ -510,10 +487,17 @@ static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode,
         const int nt = (last - t0 < tiles_per_batch) ? last - t0 : tiles_per_batch;
         dim3 g(TX, nt), gh(mode == 0 ? geo.c[0] : TX, nt);
         CT_CUDA(cudaMemset2DAsync(slab0, net->slab_floats * sizeof(float), 0, AMAX_SLOTS * sizeof(float), nt, s));
-        gather_tiles<<<g, 256, 0, s>>>(src, reinterpret_cast<float4*>(slab0), net->slab_floats / 4, net->in_off / 4, mode, t0,
-                                       geo, net->in_slot);
-        CT_LAUNCHED("gather_tiles");
-        if (run_plan(net, slab0, nt, s)) return 1;
+        // engines 0 / 2 / 4: the first block (Cin = 1) reads the volume itself; otherwise gather, then the generic engines
+        int fused = 2;
+        if (net->engine != 1 && net->engine != 3)
+            fused = launch_first_conv_fused(net, net->ops[0], src, mode, t0, geo, slab0, net->slab_floats, nt, s);
+        if (fused == 1) return 1;
+        if (fused == 2) {
+            gather_tiles<<<g, 256, 0, s>>>(src, reinterpret_cast<float4*>(slab0), net->slab_floats / 4, net->in_off / 4, mode, t0,
+                                           geo, net->in_slot);
+            CT_LAUNCHED("gather_tiles");
+        }
+        if (run_plan(net, slab0, nt, s, fused == 0)) return 1;
         head_scatter<<<gh, 256, 0, s>>>(reinterpret_cast<const float4*>(slab0), net->slab_floats / 4, net->last_off / 4,
                                        net->last_c / 4, net->head_w, net->head_b, prob, mode, t0, geo);
         CT_LAUNCHED("head_scatter");

@@ -62,7 +62,13 @@ struct CtUNet {
 };
 
 namespace ct {
+struct TileGeom;
 // implemented in unet_direct.cu
+// First block of the network (Cin = 1, Cout = 8) fused with the tile gather: reads the normalised volume (mode 0,
+// reflect padding) or explicit tiles (mode 1) and writes the block's output.  Returns 2 when the layer shape is not
+// the fused kernel's (the caller then runs gather_tiles + a generic convolution).
+int launch_first_conv_fused(const CtUNet* net, const Op& op, const float* src, int mode, int tile_first,
+                            const TileGeom& geo, float* slab0, size_t slab_stride, int tiles, cudaStream_t s);
 int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
                        cudaStream_t s);
 // implemented in unet_tc.cu (returns 2 when the layer shape is not supported by the tensor-core path)
@@ -76,6 +82,33 @@ float tcx_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout
 size_t tc_weight_floats(int cin_pad, int cout);
 // returns 1 / scale
 float tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
+
+__device__ __forceinline__ int reflect_index(int j, int n) {
+    // numpy.pad(mode='reflect') for arbitrarily wide pads: triangle wave of period 2(n-1)
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    j %= period;
+    if (j < 0) j += period;
+    return j < n ? j : period - j;
+}
+
+// Geometry of a tiled prediction.  The tiles visited are the sub-grid tlo <= (i,j,k) < tlo + tn of the volume's tile
+// grid, enumerated row-major (k fastest); source voxels live in a box `in_lo .. in_lo + in_dim` of the volume
+// (the whole volume on one GPU, the rank's haloed block under spatial decomposition) and results go to a box
+// `out_lo .. out_lo + out_dim`.
+struct TileGeom {
+    int X, Y, Z;                  // whole volume (reflect padding and the final crop refer to it)
+    int TX, TY, TZ;               // model input tile
+    int tlo[3], tn[3];            // tile sub-grid: origin and extent
+    int c[3], b[3];               // centre window size and shrink (= offset of the window inside the tile)
+    int in_lo[3], in_dim[3];
+    int out_lo[3], out_dim[3];
+};
+__device__ __forceinline__ void tile_ijk(const TileGeom& g, int ordinal, int& i, int& j, int& k) {
+    k = g.tlo[2] + ordinal % g.tn[2]; ordinal /= g.tn[2];
+    j = g.tlo[1] + ordinal % g.tn[1]; ordinal /= g.tn[1];
+    i = g.tlo[0] + ordinal;
+}
 
 __device__ __forceinline__ void amax_update(float* slot, float v) {
     atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));

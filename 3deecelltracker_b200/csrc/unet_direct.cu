@@ -154,4 +154,138 @@ int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t sla
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// First block of the network: Cin = 1 -> Cout = 8, fused with the tile gather.
+//
+// With one input channel the tensor-core path wastes 7/8 of its K (channels are chunked by 8) and the generic
+// CUDA-core kernel 3/4 of its FMAs (chunks of 4); and the padded 4-channel tile copy that gather_tiles writes exists
+// only to feed them.  Here a CTA stages the haloed 10 x 18 x 18 single-channel block straight from the normalised
+// volume (reflect padding of unet3d.py:235 resolved per voxel; zero outside the TILE = the Keras 'same' padding) and
+// each thread computes 8 consecutive-x voxels x 8 output channels for its (y, z): one shared-memory read of an input
+// value feeds 24 FMAs.  Exact fp32.
+// ---------------------------------------------------------------------------------------------
+constexpr int FX = 8, FY = 16, FZ = 16;
+
+__global__ void __launch_bounds__(256, 2)
+first_conv_kernel(const float* __restrict__ src, int mode, int tile_first, const TileGeom g,
+                  float4* __restrict__ dst, const float4* __restrict__ wts,      // [27][8] float4, .x = the one input channel
+                  const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                  float alpha, int nbx, int nby, size_t dst_tile_stride4, int dst_c4off, float* __restrict__ amax_hdr,
+                  int dst_slot) {
+    __shared__ float in_s[FX + 2][FY + 2][FZ + 2];
+    __shared__ float4 w_s[27][2];
+
+    const int tid = threadIdx.x;
+    const int tz = tid & 15, ty = tid >> 4;
+    int b = blockIdx.x;
+    const int bxi = b % nbx; b /= nbx;
+    const int byi = b % nby; b /= nby;
+    const int x0 = bxi * FX, y0 = byi * FY, z0 = b * FZ;
+    const int tile = blockIdx.z;
+    const int TX = g.TX, TY = g.TY, TZ = g.TZ;
+    const size_t vol = (size_t)TX * TY * TZ;
+    int ti, tj, tk;
+    tile_ijk(g, tile_first + tile, ti, tj, tk);
+
+    // source index of every haloed x / y / z coordinate of the block (reflect padding is separable), -1 = outside
+    // the tile: 46 reflections per CTA instead of 3 per voxel
+    __shared__ int ix_s[FX + 2], iy_s[FY + 2], iz_s[FZ + 2];
+    if (tid < FX + 2) {
+        const int l = x0 + tid - 1;
+        ix_s[tid] = (l < 0 || l >= TX) ? -1 : (mode == 0 ? reflect_index(ti * g.c[0] + l - g.b[0], g.X) - g.in_lo[0] : l);
+    } else if (tid >= 32 && tid < 32 + FY + 2) {
+        const int l = y0 + tid - 32 - 1;
+        iy_s[tid - 32] = (l < 0 || l >= TY) ? -1 : (mode == 0 ? reflect_index(tj * g.c[1] + l - g.b[1], g.Y) - g.in_lo[1] : l);
+    } else if (tid >= 64 && tid < 64 + FZ + 2) {
+        const int l = z0 + tid - 64 - 1;
+        iz_s[tid - 64] = (l < 0 || l >= TZ) ? -1 : (mode == 0 ? reflect_index(tk * g.c[2] + l - g.b[2], g.Z) - g.in_lo[2] : l);
+    }
+    __syncthreads();
+    const int d1 = mode == 0 ? g.in_dim[1] : TY, d2 = mode == 0 ? g.in_dim[2] : TZ;
+    const float* base = mode == 0 ? src : src + (size_t)(tile_first + tile) * vol;
+    for (int i = tid; i < (FX + 2) * (FY + 2) * (FZ + 2); i += 256) {
+        const int sz = i % (FZ + 2), r = i / (FZ + 2);
+        const int sy = r % (FY + 2), sx = r / (FY + 2);
+        const int gx = ix_s[sx], gy = iy_s[sy], gz = iz_s[sz];
+        in_s[sx][sy][sz] = (gx | gy | gz) < 0 ? 0.f : base[((size_t)gx * d1 + gy) * d2 + gz];
+    }
+    for (int i = tid; i < 27 * 8; i += 256) reinterpret_cast<float*>(&w_s[0][0])[i] = wts[i].x;
+    __syncthreads();
+
+    float acc[FX][8];
+#pragma unroll
+    for (int v = 0; v < FX; ++v)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[v][c] = 0.f;
+#pragma unroll 1
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+        for (int dz = 0; dz < 3; ++dz) {
+            float w[3][8];
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 w0 = w_s[(dx * 3 + dy) * 3 + dz][0], w1 = w_s[(dx * 3 + dy) * 3 + dz][1];
+                w[dx][0] = w0.x; w[dx][1] = w0.y; w[dx][2] = w0.z; w[dx][3] = w0.w;
+                w[dx][4] = w1.x; w[dx][5] = w1.y; w[dx][6] = w1.z; w[dx][7] = w1.w;
+            }
+#pragma unroll
+            for (int xx = 0; xx < FX + 2; ++xx) {
+                const float a = in_s[xx][ty + dy][tz + dz];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int v = xx - dx;
+                    if (v < 0 || v >= FX) continue;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[v][c] = fmaf(a, w[dx][c], acc[v][c]);
+                }
+            }
+        }
+    }
+
+    const int ly = y0 + ty, lz = z0 + tz;
+    float amax = 0.f;
+    if (ly < TY && lz < TZ) {
+        float4* d_tile = dst + (size_t)tile * dst_tile_stride4;
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+            float bs[4], sc[4], sh[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { bs[j] = bias[c4 * 4 + j]; sc[j] = scale[c4 * 4 + j]; sh[j] = shift[c4 * 4 + j]; }
+            float4* d_ck = d_tile + (size_t)(dst_c4off + c4) * vol;
+#pragma unroll
+            for (int v = 0; v < FX; ++v) {
+                const int lx = x0 + v;
+                if (lx < TX) {
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = acc[v][c4 * 4 + j] + bs[j];
+                        t = t > 0.f ? t : alpha * t;
+                        o[j] = fmaf(t, sc[j], sh[j]);
+                    }
+                    d_ck[((size_t)lx * TY + ly) * TZ + lz] = make_float4(o[0], o[1], o[2], o[3]);
+                    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o[0]), fabsf(o[1]))), fmaxf(fabsf(o[2]), fabsf(o[3])));
+                }
+            }
+        }
+    }
+    amax = warp_max(amax);
+    if ((tid & 31) == 0) amax_update(amax_hdr + (size_t)tile * dst_tile_stride4 * 4 + dst_slot, amax);
+}
+
+int launch_first_conv_fused(const CtUNet* net, const Op& op, const float* src, int mode, int tile_first,
+                            const TileGeom& geo, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
+    const ConvLayer& L = net->layers[op.layer];
+    if (L.cin != 1 || L.cout != 8 || L.cin_pad != 4) return 2;
+    CT_REQUIRE(slab_stride % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
+    const int nbx = cdiv(op.sx, FX), nby = cdiv(op.sy, FY), nbz = cdiv(op.sz, FZ);
+    dim3 grid(nbx * nby * nbz, 1, tiles);
+    ProfScope prof(PROF_CONV, s);
+    first_conv_kernel<<<grid, 256, 0, s>>>(src, mode, tile_first, geo, reinterpret_cast<float4*>(slab0 + op.dst_off),
+                                           reinterpret_cast<const float4*>(L.w_direct), L.bias, L.scale, L.shift, net->alpha,
+                                           nbx, nby, slab_stride / 4, op.dst_coff / 4, slab0, op.dst_slot);
+    CT_LAUNCHED("first_conv_kernel");
+    return 0;
+}
+
 }  // namespace ct

@@ -288,8 +288,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             if (lane == 0) amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
         };
         // power-of-two operand scale of a tile: max|x s| in [2^13, 2^14)
-        auto tile_scale = [&](int tile) {
-            const float am = geo.amax_src[(size_t)tile * geo.slab_stride];
+        auto scale_of = [](float am) {
             const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);          // biased exponent, 0 for zero / subnormal
             const int se = (267 - e > 254) ? 254 : 267 - e;                    // 2^(13 - floor(log2 am)), clamped finite
             return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
@@ -300,11 +299,18 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         int pc = 0;                                    // chunk of stage g - 1
         TcUnit prev{}, cur{};
         float s_cur = 1.f, s_prev = 1.f;
+        // max|x| of a unit's tile is fetched one unit ahead, so the load's latency is never in front of a conversion
+        TcUnit nxt = tc_unit((int)blockIdx.x, geo, BX);
+        float am_nxt = n_units > 0 ? geo.amax_src[(size_t)nxt.tile * geo.slab_stride] : 0.f;
         for (int g = 0; g <= n_stages; ++g) {
             if (g < n_stages) {
                 if (c == 0) {
-                    cur = tc_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
-                    s_cur = tile_scale(cur.tile);
+                    cur = nxt;
+                    s_cur = scale_of(am_nxt);
+                    if (k + 1 < n_units) {
+                        nxt = tc_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
+                        am_nxt = geo.amax_src[(size_t)nxt.tile * geo.slab_stride];
+                    }
                 }
                 const int s = g % STAGES, use = g / STAGES;
                 mbar_wait(&bar_full[s], use & 1);

@@ -547,7 +547,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05", "tcgen05_classic", "tcgen05_stacked"])
-    ap.add_argument("--tiles-per-batch", type=int, default=15)
+    ap.add_argument("--tiles-per-batch", type=int, default=38)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="fits (FFN + PR-GLS chains) in flight on side streams")
     ap.add_argument("--reserve-sms", type=int, default=8, help="SMs kept out of the persistent conv grid while overlapping")
