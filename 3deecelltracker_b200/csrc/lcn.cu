@@ -152,34 +152,61 @@ __device__ __forceinline__ float clamped(const T* __restrict__ raw, long long id
     return v > 0.0 ? (float)v : 0.0f;       // keras casts the float64 array to float32 (exact here)
 }
 
+// Every box-filter thread produces LCN_R consecutive outputs along the filtered axis from ONE pass over the
+// LCN_R + 2r inputs they share (register window), instead of 2r + 1 loads per output.  Each output still sums ITS OWN
+// window in ascending order with its own accumulator, so a value does not depend on where the block / volume starts:
+// this is what keeps the spatially decomposed LCN (spatial.py) bit-identical to the single-GPU one.
+constexpr int LCN_R = 8;
+
 // pass 1: T1 = sum over dy of v   (float32; exact for integer-valued input)
 template <typename T>
 __global__ void __launch_bounds__(256) box_y_v(const T* __restrict__ raw, const double* __restrict__ med_p,
                                                float* __restrict__ t1, int X, int Y, int Z, int ry) {
+    // thread = (y group of LCN_R, z); grid.y = x
+    const int groups = (Y + LCN_R - 1) / LCN_R;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= groups * Z) return;
+    const int z = f % Z, yb = (f / Z) * LCN_R;
     const long long plane = (long long)Y * Z;
-    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // index inside the (y,z) plane
-    if (f >= plane) return;
-    const int x = blockIdx.y;
-    const int y = (int)(f / Z);
+    const T* base = raw + (long long)blockIdx.y * plane + z;
+    float* out = t1 + (long long)blockIdx.y * plane + z;
     const double med = *med_p;
-    const T* base = raw + (long long)x * plane;
-    const int y0 = max(y - ry, 0), y1 = min(y + ry, Y - 1);
-    float acc = 0.f;
-    for (int yy = y0; yy <= y1; ++yy) acc += clamped(base, f + (long long)(yy - y) * Z, med);
-    t1[(long long)x * plane + f] = acc;
+    float acc[LCN_R];
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) acc[k] = 0.f;
+    const int lo = max(yb - ry, 0), hi = min(yb + LCN_R - 1 + ry, Y - 1);
+    for (int yy = lo; yy <= hi; ++yy) {
+        const float v = clamped(base, (long long)yy * Z, med);
+#pragma unroll
+        for (int k = 0; k < LCN_R; ++k)
+            if (yy >= yb + k - ry && yy <= yb + k + ry) acc[k] += v;
+    }
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k)
+        if (yb + k < Y) out[(long long)(yb + k) * Z] = acc[k];
 }
 
 // pass 2: avg = float32(sum over dx of T1) / volume
 __global__ void __launch_bounds__(256) box_x_avg(const float* __restrict__ t1, float* __restrict__ avg,
                                                  int X, int Y, int Z, int rx, float volume) {
+    // thread = one (y, z) column position; grid.y = x group of LCN_R
     const long long plane = (long long)Y * Z;
-    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= plane) return;
-    const int x = blockIdx.y;
-    const int x0 = max(x - rx, 0), x1 = min(x + rx, X - 1);
-    double acc = 0.0;
-    for (int xx = x0; xx <= x1; ++xx) acc += (double)t1[(long long)xx * plane + f];
-    avg[(long long)x * plane + f] = (float)acc / volume;
+    const int xb = blockIdx.y * LCN_R;
+    double acc[LCN_R];
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) acc[k] = 0.0;
+    const int lo = max(xb - rx, 0), hi = min(xb + LCN_R - 1 + rx, X - 1);
+    for (int xx = lo; xx <= hi; ++xx) {
+        const double v = (double)t1[(long long)xx * plane + f];
+#pragma unroll
+        for (int k = 0; k < LCN_R; ++k)
+            if (xx >= xb + k - rx && xx <= xb + k + rx) acc[k] += v;
+    }
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k)
+        if (xb + k < X) avg[(long long)(xb + k) * plane + f] = (float)acc[k] / volume;
 }
 
 // pass 3: T2 = sum over dy of float32((v-avg)^2)
@@ -187,21 +214,28 @@ template <typename T>
 __global__ void __launch_bounds__(256) box_y_sq(const T* __restrict__ raw, const double* __restrict__ med_p,
                                                 const float* __restrict__ avg, float* __restrict__ t2,
                                                 int X, int Y, int Z, int ry) {
+    const int groups = (Y + LCN_R - 1) / LCN_R;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= groups * Z) return;
+    const int z = f % Z, yb = (f / Z) * LCN_R;
     const long long plane = (long long)Y * Z;
-    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= plane) return;
-    const int x = blockIdx.y;
-    const int y = (int)(f / Z);
+    const long long off = (long long)blockIdx.y * plane + z;
     const double med = *med_p;
-    const long long off = (long long)x * plane;
-    const int y0 = max(y - ry, 0), y1 = min(y + ry, Y - 1);
-    double acc = 0.0;
-    for (int yy = y0; yy <= y1; ++yy) {
-        long long i = off + f + (long long)(yy - y) * Z;
-        double d = (double)clamped(raw, i, med) - (double)avg[i];
-        acc += (double)(float)(d * d);
+    double acc[LCN_R];
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) acc[k] = 0.0;
+    const int lo = max(yb - ry, 0), hi = min(yb + LCN_R - 1 + ry, Y - 1);
+    for (int yy = lo; yy <= hi; ++yy) {
+        const long long i = off + (long long)yy * Z;
+        const double d = (double)clamped(raw, i, med) - (double)avg[i];
+        const double sq = (double)(float)(d * d);
+#pragma unroll
+        for (int k = 0; k < LCN_R; ++k)
+            if (yy >= yb + k - ry && yy <= yb + k + ry) acc[k] += sq;
     }
-    t2[off + f] = (float)acc;
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k)
+        if (yb + k < Y) t2[off + (long long)(yb + k) * Z] = (float)acc[k];
 }
 
 // pass 4: std, normalise
@@ -211,17 +245,29 @@ __global__ void __launch_bounds__(256) box_x_norm(const T* __restrict__ raw, con
                                                   float* __restrict__ out, int X, int Y, int Z, int rx,
                                                   float volume, float noise) {
     const long long plane = (long long)Y * Z;
-    long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= plane) return;
-    const int x = blockIdx.y;
-    const int x0 = max(x - rx, 0), x1 = min(x + rx, X - 1);
-    double acc = 0.0;
-    for (int xx = x0; xx <= x1; ++xx) acc += (double)t2[(long long)xx * plane + f];
-    const long long i = (long long)x * plane + f;
-    const float sd = sqrtf((float)acc / volume);
-    const float den = sd + noise;
-    const double d = (double)clamped(raw, i, *med_p) - (double)avg[i];
-    out[i] = (float)(d / (double)den);
+    const int xb = blockIdx.y * LCN_R;
+    double acc[LCN_R];
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) acc[k] = 0.0;
+    const int lo = max(xb - rx, 0), hi = min(xb + LCN_R - 1 + rx, X - 1);
+    for (int xx = lo; xx <= hi; ++xx) {
+        const double v = (double)t2[(long long)xx * plane + f];
+#pragma unroll
+        for (int k = 0; k < LCN_R; ++k)
+            if (xx >= xb + k - rx && xx <= xb + k + rx) acc[k] += v;
+    }
+    const double med = *med_p;
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) {
+        if (xb + k >= X) break;
+        const long long i = (long long)(xb + k) * plane + f;
+        const float sd = sqrtf((float)acc[k] / volume);
+        const float den = sd + noise;
+        const double d = (double)clamped(raw, i, med) - (double)avg[i];
+        out[i] = (float)(d / (double)den);
+    }
 }
 
 __global__ void set_nan(double* p) { *p = __longlong_as_double(0x7ff8000000000000LL); }
@@ -247,15 +293,17 @@ static int normalize_impl(const T* raw, float* out, int X, int Y, int Z, float n
         CT_LAUNCHED("set_nan");
     }
     const long long plane = (long long)Y * Z;
-    dim3 grid((unsigned)((plane + 255) / 256), X);
+    const int ygroups = (Y + LCN_R - 1) / LCN_R, xgroups = (X + LCN_R - 1) / LCN_R;
+    dim3 grid_y((unsigned)(((long long)ygroups * Z + 255) / 256), X);       // y filters: thread = (y group, z), per x
+    dim3 grid_x((unsigned)((plane + 255) / 256), xgroups);                  // x filters: thread = (y, z), per x group
     const float volume = (float)(fx * fy);
-    box_y_v<T><<<grid, 256, 0, s>>>(raw, med, t1, X, Y, Z, fy / 2);
+    box_y_v<T><<<grid_y, 256, 0, s>>>(raw, med, t1, X, Y, Z, fy / 2);
     CT_LAUNCHED("box_y_v");
-    box_x_avg<<<grid, 256, 0, s>>>(t1, avg, X, Y, Z, fx / 2, volume);
+    box_x_avg<<<grid_x, 256, 0, s>>>(t1, avg, X, Y, Z, fx / 2, volume);
     CT_LAUNCHED("box_x_avg");
-    box_y_sq<T><<<grid, 256, 0, s>>>(raw, med, avg, t2, X, Y, Z, fy / 2);
+    box_y_sq<T><<<grid_y, 256, 0, s>>>(raw, med, avg, t2, X, Y, Z, fy / 2);
     CT_LAUNCHED("box_y_sq");
-    box_x_norm<T><<<grid, 256, 0, s>>>(raw, med, avg, t2, out, X, Y, Z, fx / 2, volume, noise);
+    box_x_norm<T><<<grid_x, 256, 0, s>>>(raw, med, avg, t2, out, X, Y, Z, fx / 2, volume, noise);
     CT_LAUNCHED("box_x_norm");
     return 0;
 }

@@ -244,31 +244,44 @@ def gpu_main(args):
         barrier()
         serial_ms = sum(a.elapsed_time(b) for a, b in ts) / args.steps
 
-    # ---- end-to-end arm: host buffers in, host results out, every step
-    prob_host = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    # ---- end-to-end arm: host buffers in, host results out, every step.  Inputs go up on the compute stream; the
+    # results of step i (36.7 MB probability map + tracked coordinates) come down on a copy stream into one of two
+    # pinned buffers while step i+1 computes; the host waits for step i's download before it submits step i+2, and for
+    # everything at the end of the timed region.
+    prob_host = [torch.empty(SHAPE, dtype=torch.float32).pin_memory() for _ in range(2)]
     out_host = torch.empty((N_CELLS, 3), dtype=torch.float64).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    downloads = []
 
-    def e2e_step(last=False):
+    def e2e_step(i, last=False):
         r = raw_pinned.to(dev, non_blocking=True).view(torch.uint16)
         a = ref_pinned.to(dev, non_blocking=True)
         b = tgt_pinned.to(dev, non_blocking=True)
         prob, out = step.run(r, a, b, a)
-        prob_host.copy_(prob, non_blocking=True)
         outs = ([] if out is None else [out]) + (step.flush() if last else [])
-        for o in outs:
-            out_host.copy_(o, non_blocking=True)
-        done = torch.cuda.Event()
-        done.record()
-        done.synchronize()            # this step's results are on the host; fits in flight keep running
+        ready = torch.cuda.Event()
+        ready.record()
+        copy_stream.wait_event(ready)
+        with torch.cuda.stream(copy_stream):
+            prob_host[i % 2].copy_(prob, non_blocking=True)
+            for o in outs:
+                out_host.copy_(o, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        for t_ in [prob] + outs:
+            t_.record_stream(copy_stream)
+        downloads.append(done)
+        while len(downloads) > (0 if last else 1):
+            downloads.pop(0).synchronize()
         return len(outs)
 
     for i in range(max(1, args.warmup // 2)):
-        e2e_step(last=(i == max(1, args.warmup // 2) - 1))
+        e2e_step(i, last=(i == max(1, args.warmup // 2) - 1))
     barrier()
     t0 = time.perf_counter()
     got = 0
     for i in range(args.steps):
-        got += e2e_step(last=(i == args.steps - 1))
+        got += e2e_step(i, last=(i == args.steps - 1))
     barrier()
     e2e_s = time.perf_counter() - t0
     assert got == args.steps
@@ -306,7 +319,7 @@ def gpu_main(args):
             "e2e": {"value": voxels * world * args.steps / (e2e_ms * 1e-3), "unit": "voxels/s",
                     "frames_per_s": world * args.steps / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": int(raw.nbytes + real0.nbytes + real_t.nbytes),
-                    "d2h_bytes_per_step": int(prob_host.numel() * 4 + out_host.numel() * 8)},
+                    "d2h_bytes_per_step": int(prob_host[0].numel() * 4 + out_host.numel() * 8)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "unet 3x3x3 conv (%s engine)" % args.engine,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
