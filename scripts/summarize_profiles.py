@@ -19,6 +19,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+TILES = int(sys.argv[2]) if len(sys.argv) > 2 else 38          # tiles of the captured U-Net batch (bench --tiles-per-batch)
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
@@ -28,7 +29,8 @@ GFLOP = [0.088, 1.416, 0.708, 1.416, 0.708, 1.416, 0.708, 0.708, 2.831, 0.708, 2
 
 
 def family(name):
-    for key, fam in (("conv3_tc", "conv (tcgen05)"), ("conv3_direct", "conv (CUDA core)"), ("prgls", "PR-GLS EM"),
+    for key, fam in (("conv3_tc", "conv (tcgen05)"), ("first_conv", "conv (CUDA core, fused gather)"),
+                     ("conv3_direct", "conv (CUDA core)"), ("prgls", "PR-GLS EM"),
                      ("greedy", "PR-GLS EM"), ("predict_one_rep", "PR-GLS EM"), ("trim_mean", "PR-GLS EM"),
                      ("pool_kernel", "unet aux"), ("upsample", "unet aux"), ("gather_tiles", "unet aux"),
                      ("head_scatter", "unet aux"), ("sgemm_bn", "FFN"), ("knn_features", "FFN"), ("ffn_pair", "FFN"),
@@ -52,7 +54,7 @@ def launches():
         per_k[name][0] += 1; per_k[name][1] += v
         f = family(r[ki]); per_f[f][0] += 1; per_f[f][1] += v
     tot = sum(v[1] for v in per_k.values())
-    out = [f"# {tag}: every launch of bench.py (3 warm-up + 1 timed step), ncu gpu__time_duration.sum", "",
+    out = [f"# {tag}: every launch of one bench.py run (--steps 1 --warmup 3: device, serial-comparison and e2e arms, 8 frames in all), ncu gpu__time_duration.sum", "",
            "Source: `ncu --metrics gpu__time_duration.sum --clock-control none` around `python bench.py --steps 1 --warmup 3`.",
            "Per-launch times under ncu are cold-cache and serialised: compare SHARES with the bench line, not absolutes.", "",
            "| kernel family | launches | total ms | share |", "|---|---:|---:|---:|"]
@@ -64,7 +66,11 @@ def launches():
         b = json.loads(line)
         st = b["stage_ms_per_step"]
         out += ["", f"Un-profiled bench line of the same build: {b['ms_per_step']:.2f} ms/step; CUDA-event stage times per step: "
-                + ", ".join(f"{k} {v:.2f} ms ({v / b['ms_per_step']:.3f})" for k, v in st.items()) + "."]
+                + ", ".join(f"{k} {v:.2f} ms ({v / b['ms_per_step']:.3f})" for k, v in st.items()) + ".  "
+                "(em / ffn run on the side streams of the frame pipeline, concurrently with conv / lcn of the next volumes, "
+                "and their event times include waiting for a free SM, so the stage shares do not add up to 1; under ncu "
+                "everything is serialised, which is why the EM's share of the launch list is larger than its share of "
+                "the step.)"]
     out += ["", "| kernel | launches | total ms | share |", "|---|---:|---:|---:|"]
     for k, (n, us) in sorted(per_k.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k[:70]}` | {n} | {us / 1e3:.3f} | {us / tot:.3f} |")
@@ -112,8 +118,10 @@ def conv():
         v = float(v.replace(",", ""))
         return {"Mbyte": v, "Gbyte": v * 1e3, "Kbyte": v / 1e3, "byte": v / 1e6}.get(u, v)
 
-    md = [f"# {tag}: tcgen05 convolution blocks of one U-Net batch (15 tiles of 160x160x16), ncu --set full", "",
-          "One row per conv block in graph order (`conv3_tc_kernel<Cout, BX, STAGES>`); full metric table in "
+    md = [f"# {tag}: convolution blocks of one U-Net batch ({TILES} tiles of 160x160x16), ncu --set full", "",
+          "One row per conv block in graph order (`first_conv_kernel` = CUDA-core Cin=1 block fused with the tile gather, "
+          "`conv3_tcx_kernel<Cout, BX, STAGES>` = x-stacked tcgen05 kernel, `conv3_tc_kernel<...>` = 27-tap tcgen05 kernel; "
+          "see the csv for which kernel ran a block); full metric table in "
           f"`{tag}_conv_tc.csv`.  `tc pipe busy` = sm__pipe_tc_cycles_active (tensor-core pipe incl. operand fetch), "
           "`tensor math` = sm__pipe_tensor_cycles_active, `tc smem` = l1tex__data_pipe_tc_wavefronts_mem_shared "
           "(shared-memory wavefronts read by the tensor core, % of peak).", "",
@@ -127,20 +135,21 @@ def conv():
     for n, r, gm, ci, co, vx in zip(CONV_NAMES, rows, GFLOP, cin, cout, vox):
         ms = to_ms(r[t], units[t]); tot_ms += ms
         mb = to_mb(r[dr], units[dr]) + to_mb(r[dw], units[dw])
-        alg = 15 * vx * 4 * (max(ci, 4) + co) / 1e6
-        md.append(f"| {n} | {ms:.3f} | {15 * gm * 2 / ms:.1f} | "
+        alg = TILES * vx * 4 * ((1 if ci == 1 else ci) + co) / 1e6
+        md.append(f"| {n} | {ms:.3f} | {TILES * gm * 2 / ms:.1f} | "
                   f"{float(r[g('sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed')]):.1f} | "
                   f"{float(r[g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')]):.1f} | "
                   f"{float(r[g('l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed')]):.1f} | "
                   f"{mb:.0f} | {alg:.0f} |")
-    md += ["", f"Sum of the 14 blocks: {tot_ms:.3f} ms per 15 tiles -> {15 * 35.573 / tot_ms:.1f} TFLOP/s algorithmic "
-           "(35.573 GFLOP/tile).  Reading: the blocks are bound by the tensor core's shared-memory operand path "
-           "(A tile of an M=128, K=8 tf32 MMA = 4 KB = 32 wavefronts, read twice per K step for the hi/lo split), not by "
-           "MMA math and not by HBM."]
+    md += ["", f"Sum of the 14 blocks: {tot_ms:.3f} ms per {TILES} tiles -> {TILES * 35.573 / tot_ms:.1f} TFLOP/s algorithmic "
+           "(35.573 GFLOP/tile; per-launch times under ncu are cold-cache and serialised).  Reading: the tcgen05 blocks are "
+           "bound by the tensor core's shared-memory operand path (`tc pipe busy` >> `tensor math`: an M=128, K=16 fp16 MMA "
+           "reads a 4 KB A tile plus its B rows from shared memory at 128 B/clk, which takes longer than its math for "
+           "N <= 96), not by MMA math and not by HBM; DESIGN.md 3.2 has the arithmetic."]
     open(os.path.join(P, f"{tag}_conv_tc.md"), "w").write("\n".join(md) + "\n")
     total_bytes = sum(to_mb(r[dr], units[dr]) + to_mb(r[dw], units[dw]) for r in rows[:14]) * 1e6
-    json.dump({"kernel": "conv3_tc_kernel (14 conv blocks of one 15-tile U-Net batch)", "launches": 14,
-               "dram_bytes_per_launch_avg": total_bytes / 14, "tiles_per_batch": 15,
+    json.dump({"kernel": f"14 conv blocks of one {TILES}-tile U-Net batch (first_conv + conv3_tcx + conv3_tc)", "launches": 14,
+               "dram_bytes_per_launch_avg": total_bytes / 14, "tiles_per_batch": TILES,
                "source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/{tag}_conv_tc.csv"},
               open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
 
