@@ -4,4 +4,3 @@ for E in tcgen05_classic tcgen05; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$E.csv python scripts/tc_prof.py $E 15 2 > gpurun_out/tcprof_$E.log 2>&1
 done
 python scripts/launch_table.py gpurun_out/launches_tcgen05_classic.csv gpurun_out/launches_tcgen05.csv 2>&1 | tail -17
-timeout 600 python scripts/tcx_timing.py 2>&1 | tail -8
