@@ -430,9 +430,11 @@ static TileGeom make_geom(const CtUNet* net, int x, int y, int z, const int cent
 }
 
 // One convolution block on the engine the network is set to (see CtUNet::engine).
-static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t stride, int tiles, cudaStream_t s) {
+static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t stride, int tiles, cudaStream_t s,
+                       const Op* next = nullptr, bool* next_fused = nullptr) {
     int rc = 2;
-    if (net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s);
+    if (next_fused) *next_fused = false;
+    if (net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s, next, next_fused);
     if (rc == 2 && net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s);
     if (rc == 1) return 1;
     if (rc == 2) {
@@ -448,12 +450,13 @@ static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t str
 // first convolution block).
 static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s, bool skip_first = false) {
     const size_t stride = net->slab_floats;
-    bool first = true;
-    for (const Op& op : net->ops) {
-        if (first && skip_first) { first = false; continue; }
-        first = false;
+    for (size_t idx = skip_first ? 1 : 0; idx < net->ops.size(); ++idx) {
+        const Op& op = net->ops[idx];
         if (op.kind == OP_CONV) {
-            if (launch_conv(net, op, slab0, stride, tiles, s)) return 1;
+            bool fused = false;
+            const Op* next = idx + 1 < net->ops.size() ? &net->ops[idx + 1] : nullptr;
+            if (launch_conv(net, op, slab0, stride, tiles, s, next, &fused)) return 1;
+            if (fused) ++idx;                      // the pooling that followed was written by the block's epilogue
         } else {
             const float4* src = reinterpret_cast<const float4*>(slab0);
             float4* dst = reinterpret_cast<float4*>(slab0);

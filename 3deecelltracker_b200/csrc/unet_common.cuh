@@ -75,8 +75,10 @@ int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t sla
 int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
                    cudaStream_t s);
 // implemented in unet_tcx.cu: x-stacked variant for Cout 8/16/32 (returns 2 when it does not take the layer)
+// `pool` = the op that follows in the plan; when it is the (2,2,1) max-pool of this block's output the kernel writes
+// the pooled copy itself and sets *pool_fused (the caller then skips that op).
 int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
-                    cudaStream_t s);
+                    cudaStream_t s, const Op* pool = nullptr, bool* pool_fused = nullptr);
 size_t tcx_weight_floats(int cin_pad, int cout);
 float tcx_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
 size_t tc_weight_floats(int cin_pad, int cout);

@@ -87,6 +87,9 @@ struct TxGeom {
     float* amax_dst;
     size_t slab_stride;
     float w_inv_scale;
+    // optional fused MaxPooling3D((2,2,1)) of the output (unet3d.py:168): pooled copy written by the epilogue
+    float4* pool_dst;                            // null = no pooling; c4-blocked [Cout/4][X/2][Y/2][Z][4] per tile
+    float* amax_pool;                            // slab header slot of the pooled buffer
 };
 
 struct TxUnit { int x0, y0, z0, tile; };
@@ -294,9 +297,12 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             // epilogue of ONE output plane: scale back, bias -> activation -> BatchNorm, 16-byte channel-chunk stores.
             // Plane i is complete once input plane i + 2 of the last chunk is drained, so its stores are issued there
             // and trickle out under the remaining drains instead of bursting at the end of the unit.
+            // With pooling fused, the pair of x planes (2p, 2p+1) meets in this thread and the pair of y rows sits 8
+            // lanes apart (row = 8 y + z), so a 2 x 2 x 1 window is one register max and one shuffle.
+            float keep[CH];
             auto store_plane = [&](int i) {
                 const int x = un.x0 + i;
-                if (y >= geo.Y || x >= geo.X) return;
+                const bool ok = (y < geo.Y && x < geo.X);
                 const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
 #pragma unroll
                 for (int c4 = 0; c4 < CH / 4; ++c4) {
@@ -307,9 +313,28 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch]);
                         t = t > 0.f ? t : alpha * t;
                         o[kk] = fmaf(t, ep_s[1][ch], ep_s[2][ch]);
-                        amax = fmaxf(amax, fabsf(o[kk]));
+                        if (ok) amax = fmaxf(amax, fabsf(o[kk]));
                     }
-                    d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
+                    if (ok) d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
+                    if (geo.pool_dst != nullptr) {                     // uniform over the CTA
+                        if ((i & 1) == 0) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) keep[c4 * 4 + kk] = o[kk];
+                        } else {
+                            float m[4];
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                m[kk] = fmaxf(keep[c4 * 4 + kk], o[kk]);
+                                m[kk] = fmaxf(m[kk], __shfl_xor_sync(0xffffffffu, m[kk], 8));
+                            }
+                            if (ok && ((row >> 3) & 1) == 0) {
+                                const int PX = geo.X >> 1, PY = geo.Y >> 1;
+                                float4* p_tile = geo.pool_dst + (size_t)un.tile * geo.dst_tile_stride4 +
+                                                 (size_t)(ch0 / 4 + c4) * ((size_t)PX * PY * geo.Z);
+                                p_tile[((size_t)(x >> 1) * PY + (y >> 1)) * geo.Z + z] = make_float4(m[0], m[1], m[2], m[3]);
+                            }
+                        }
+                    }
                 }
             };
 #pragma unroll
@@ -350,7 +375,10 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 }
             }
             amax = warp_max(amax);
-            if (lane == 0) amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
+            if (lane == 0) {
+                amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
+                if (geo.pool_dst != nullptr) amax_update(geo.amax_pool + (size_t)un.tile * geo.slab_stride, amax);
+            }
         }
 #ifdef TX_TIMING
         if (blockIdx.x == 0 && warp == 2 + TX_CONV_WARPS && lane == 0) {
@@ -414,7 +442,8 @@ float tcx_pack_weights(const float* w, int cin, int cin_pad, int cout, float* ds
 
 template <int N, int BX, int STAGES>
 static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, float alpha, float4* dst, int X, int Y, int Z,
-                      size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, cudaStream_t s) {
+                      size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst,
+                      float4* pool_dst, float* amax_pool, cudaStream_t s) {
     using Cfg = TxCfg<N, BX, STAGES>;
     static bool attr = false;
     if (!attr) {
@@ -427,6 +456,7 @@ static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, float alpha, f
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
+    g.pool_dst = pool_dst; g.amax_pool = amax_pool;
     const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
     const int grid = g.units < sms ? g.units : sms;
     conv3_tcx_kernel<N, BX, STAGES><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, L.w_tcx, L.bias, L.scale, L.shift, alpha, dst, g);
@@ -434,7 +464,8 @@ static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, float alpha, f
 }
 
 // returns 2 when the layer is not handled by the stacked kernel (the caller falls back to unet_tc.cu's kernel)
-int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
+int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
+                    const Op* pool, bool* pool_fused) {
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;
     if (!L.w_tcx || Z % 8 != 0) return 2;
@@ -449,9 +480,21 @@ int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
     const float* am_s = slab0 + op.src_slot;
     float* am_d = slab0 + op.dst_slot;
     if (tc_make_map(&map, src, X, Y, Z, c4, tiles, slab_stride, 8)) return 1;
+    // the MaxPooling3D that follows this block in the plan, when it is the (2,2,1) pool of exactly this output
+    float4* pool_dst = nullptr;
+    float* am_p = nullptr;
+    if (pool_fused) *pool_fused = false;
+    if (pool && pool_fused && pool->kind == OP_POOL && pool->src_off == op.dst_off && pool->src_coff == op.dst_coff &&
+        pool->c == L.cout && pool->dst_coff == 0 && pool->dst_c == L.cout && net->spec.pool_x == 2 && net->spec.pool_y == 2 &&
+        net->spec.pool_z == 1 && X % 2 == 0 && Y % 2 == 0 && pool->dx == X / 2 && pool->dy == Y / 2 && pool->dz == Z &&
+        pool->dst_off % 4 == 0) {
+        pool_dst = reinterpret_cast<float4*>(slab0 + pool->dst_off);
+        am_p = slab0 + pool->dst_slot;
+        *pool_fused = true;
+    }
     int rc;
-    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
-    else rc = launch_tcx<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
+    else rc = launch_tcx<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
     if (rc) return 1;
     CT_LAUNCHED("conv3_tcx_kernel");
     return 0;

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_lcn_unet.py tests/test_gpu_spatial.py tests/test_gpu_pipeline.py -m gpu -x -q -k "median or normalize or spatial or decomposed or pipeline or config2 or overlapped or tracker" 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_gpu_lcn_unet.py tests/test_gpu_spatial.py -m gpu -x -q 2>&1 | tail -4
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_quick.json'))
