@@ -55,8 +55,8 @@ struct CtUNet {
     float* head_w;            // device [last_c]
     float head_b;
     float alpha;              // 0.3 (LeakyReLU) or 0 (ReLU)
-    int engine;               // 0 auto, 1 direct, 2 tcgen05 (stacked where it pays, else classic), 3 classic only,
-                              // 4 stacked wherever the shape allows
+    int engine;               // 0 auto, 1 direct, 2 tcgen05 (stacked for Cout 8/16, else 27-tap), 3 27-tap only,
+                              // 4 stacked wherever the shape allows (= 2 today)
     double flops_per_tile;
     float* all_dev;           // one allocation holding every device array
 };

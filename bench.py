@@ -244,8 +244,8 @@ def gpu_main(args):
         barrier()
         serial_ms = sum(a.elapsed_time(b) for a, b in ts) / args.steps
 
-    # ---- end-to-end arm: host buffers in, host results out, every step.  Inputs go up on the compute stream; the
-    # results of step i (36.7 MB probability map + tracked coordinates) come down on a copy stream into one of two
+    # ---- end-to-end arm: host buffers in, host results out, every step.  The inputs of step i+1 go up on a copy stream
+    # while step i computes (the first step's upload is exposed); the results of step i (36.7 MB probability map + tracked coordinates) come down on a copy stream into one of two
     # pinned buffers while step i+1 computes; the host waits for step i's download before it submits step i+2, and for
     # everything at the end of the timed region.
     prob_host = [torch.empty(SHAPE, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -253,10 +253,25 @@ def gpu_main(args):
     copy_stream = torch.cuda.Stream()
     downloads = []
 
+    uploads = []
+
+    def upload():
+        """One step's inputs, pinned host -> HBM on the copy stream."""
+        with torch.cuda.stream(copy_stream):
+            ts = (raw_pinned.to(dev, non_blocking=True).view(torch.uint16), ref_pinned.to(dev, non_blocking=True),
+                  tgt_pinned.to(dev, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record()
+        return ts, ev
+
     def e2e_step(i, last=False):
-        r = raw_pinned.to(dev, non_blocking=True).view(torch.uint16)
-        a = ref_pinned.to(dev, non_blocking=True)
-        b = tgt_pinned.to(dev, non_blocking=True)
+        (r, a, b), up = uploads.pop(0) if uploads else upload()
+        main = torch.cuda.current_stream()
+        main.wait_event(up)
+        for t_ in (r, a, b):
+            t_.record_stream(main)
+        if not last:
+            uploads.append(upload())                  # the next step's inputs go up while this one computes
         prob, out = step.run(r, a, b, a)
         outs = ([] if out is None else [out]) + (step.flush() if last else [])
         ready = torch.cuda.Event()

@@ -107,8 +107,9 @@ size_t ct_unet_weight_count(const CtUNetSpec* spec);
 int ct_unet_create(const CtUNetSpec* spec, const float* weights_host, size_t n_floats, CtUNet** out);
 void ct_unet_destroy(CtUNet* net);
 /* engine: 0 = auto, 1 = CUDA-core fp32 direct convolution, 2 = tcgen05 implicit GEMM (fp16 hi/lo operand split, fp32
- * accumulate; the x-stacked kernel where it pays, the 27-tap kernel elsewhere), 3 = tcgen05 27-tap kernel only,
- * 4 = tcgen05 x-stacked kernel for every layer with Cout <= 32. */
+ * accumulate; the x-stacked kernel for Cout 8/16, the 27-tap kernel for Cout 32/64; first block Cin = 1 on CUDA cores
+ * fused with the tile gather), 3 = tcgen05 27-tap kernel only (no stacked kernel, no fused first block),
+ * 4 = x-stacked kernel wherever it supports the layer (today identical to 2). */
 int ct_unet_set_engine(CtUNet* net, int engine);
 double ct_unet_flops_per_tile(const CtUNet* net);
 
