@@ -110,18 +110,27 @@ class TrackerLite:
                            interpolation_factor=self.proofed_coords_vol1.interpolation_factor,
                            voxel_size=self.proofed_coords_vol1.voxel_size, dtype="raw")
 
+    def _predict_device_batch(self, members, seg_t2_real, beta, lambda_):
+        """The device pipeline of predict_cell_positions for several reference volumes at once: per member
+        (segmented points of t1, confirmed points of t1) an FFN match, then ONE batched EM launch (simple_match +
+        prgls_with_two_ref, one persistent CTA per member) with no host round trip in between.
+        Returns [(EmProblem with outputs on the device, mean_t1, scale_t1)]."""
+        probs, paras = [], []
+        for seg_t1_real, confirmed_t1_real in members:
+            conf_norm, (mean_t1, scale_t1) = normalize_points(confirmed_t1_real, return_para=True)
+            seg2_norm = (seg_t2_real - mean_t1) / scale_t1
+            seg1_norm = (seg_t1_real - mean_t1) / scale_t1
+            ref_dev = to_device(seg1_norm.astype(np.float64), torch.float64)
+            tgt_dev = to_device(seg2_norm.astype(np.float64), torch.float64)
+            corr = self.ffn_model.match_device(ref_dev, tgt_dev, K_POINTS)
+            probs.append(EmProblem(ref_dev, tgt_dev, corr, tracked=conf_norm.astype(np.float64), prior_given=False))
+            paras.append((mean_t1, scale_t1))
+        run_em(probs, MODE_LITE, beta, lambda_, MAX_ITERATION, 1.0, 0.1)
+        return [(p, m, sc) for p, (m, sc) in zip(probs, paras)]
+
     def _predict_device(self, seg_t1_real, seg_t2_real, confirmed_t1_real, beta, lambda_):
-        """The device pipeline of predict_cell_positions: FFN match -> simple_match -> prgls_with_two_ref,
-        with no host round trip in between.  Returns the EmProblem (outputs still on the device)."""
-        conf_norm, (mean_t1, scale_t1) = normalize_points(confirmed_t1_real, return_para=True)
-        seg2_norm = (seg_t2_real - mean_t1) / scale_t1
-        seg1_norm = (seg_t1_real - mean_t1) / scale_t1
-        ref_dev = to_device(seg1_norm.astype(np.float64), torch.float64)
-        tgt_dev = to_device(seg2_norm.astype(np.float64), torch.float64)
-        corr = self.ffn_model.match_device(ref_dev, tgt_dev, K_POINTS)
-        prob = EmProblem(ref_dev, tgt_dev, corr, tracked=conf_norm.astype(np.float64), prior_given=False)
-        run_em([prob], MODE_LITE, beta, lambda_, MAX_ITERATION, 1.0, 0.1)
-        return prob, mean_t1, scale_t1
+        """One member of `_predict_device_batch`: FFN match -> simple_match -> prgls_with_two_ref."""
+        return self._predict_device_batch([(seg_t1_real, confirmed_t1_real)], seg_t2_real, beta, lambda_)[0]
 
     def predict_cell_positions(self, t1, t2, confirmed_coord_t1=None, beta=BETA, lambda_=LAMBDA, draw_fig=False):
         """Positions of the confirmed cells of t1 at t2 (trackerlite.py:70-109)."""
@@ -138,18 +147,25 @@ class TrackerLite:
 
     def predict_cell_positions_ensemble(self, skipped_volumes, t2, coord_t1, beta, lambda_, sampling_number=20,
                                         adjacent=False, t_start=1):
-        """trackerlite.py:111-125: one prediction per reference volume, 10 %-trimmed mean."""
-        coord_prgls = []
+        """trackerlite.py:111-125: one prediction per reference volume, 10 %-trimmed mean.  The reference calls
+        predict_cell_positions once per volume; here all members share one batched EM launch (results are those of
+        the per-member calls bit for bit, see tests)."""
+        assert t2 not in self.miss_frame
+        factor, voxel = self.proofed_coords_vol1.interpolation_factor, self.proofed_coords_vol1.voxel_size
+        segmented_pos_t2 = self._get_segmented_pos(t2)
+        members = []
         for t1 in get_volumes_list(current_vol=t2, skip_volumes=skipped_volumes, sampling_number=sampling_number,
                                    adjacent=adjacent, start_vol=t_start):
             loaded = np.load(str(self.results_dir / TRACK_RESULTS / COORDS_REAL / f"coords{str(t1).zfill(6)}.npy"))
             loaded_ = Coordinates(loaded, coord_t1.interpolation_factor, coord_t1.voxel_size, dtype="real")
-            coord_prgls.append(self.predict_cell_positions(t1=t1, t2=t2, confirmed_coord_t1=loaded_, beta=beta,
-                                                           lambda_=lambda_).real)
+            members.append((self._get_segmented_pos(t1).real, loaded_.real))
+        coord_prgls = []
+        for prob, mean_t1, scale_t1 in self._predict_device_batch(members, segmented_pos_t2.real, beta, lambda_):
+            tracked = prob.tracked_out.cpu().numpy() * scale_t1 + mean_t1
+            coord_prgls.append(Coordinates(tracked, factor, voxel, dtype="real").real)      # float32 round trip of :109
         stack = to_device(np.asarray(coord_prgls, dtype=np.float64), torch.float64)
         mean = trim_mean_device(stack, 0.1).cpu().numpy()
-        return Coordinates(mean, interpolation_factor=self.proofed_coords_vol1.interpolation_factor,
-                           voxel_size=self.proofed_coords_vol1.voxel_size, dtype="real")
+        return Coordinates(mean, interpolation_factor=factor, voxel_size=voxel, dtype="real")
 
     def match_by_ffn(self, t1, t2, confirmed_coord_t1=None):
         """trackerlite.py:127-142 without the plot: returns (matching_matrix, pairs_px2)."""

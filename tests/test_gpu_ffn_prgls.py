@@ -202,3 +202,33 @@ def test_trackerlite_predict_cell_positions(m, tmp_path):
         m["trackerlite"].TrackerLite(str(tmp_path), model, proof, miss_frame=[2]).predict_cell_positions(1, 2)
     with pytest.raises(TypeError):
         m["trackerlite"].TrackerLite(str(tmp_path), model, proof, miss_frame=(2,))
+
+
+def test_trackerlite_ensemble_batched_equals_member_calls(m, tmp_path):
+    """predict_cell_positions_ensemble (trackerlite.py:111-125) runs its reference volumes as ONE batched EM launch;
+    the result must be what the reference's loop of predict_cell_positions calls + trim_mean gives."""
+    g = golden("trackerlite_em.npz")
+    Coordinates = m["coord_image_transformer"].Coordinates
+    voxel = np.array([0.4, 0.4, 1.5])
+    base = g["points"].astype(np.float64)
+    (tmp_path / "seg").mkdir()
+    (tmp_path / "track_results" / "coords_real").mkdir(parents=True)
+    rng = np.random.default_rng(5)
+    for t in range(1, 7):
+        seg = m["synth"].move_points(base, 20 + t, affine_level=0.01 * t, noise=0.001, drop=0.04, add=0.04)
+        np.save(tmp_path / "seg" / f"coords{t:06d}.npy", seg)
+        if t < 6:
+            np.save(tmp_path / "track_results" / "coords_real" / f"coords{t:06d}.npy",
+                    (base + rng.normal(0, 0.3, base.shape) * t) * voxel)
+    model = m["ffn"].FFN(offn.random_weights(3))
+    proof = Coordinates(base, 1, voxel, dtype="raw")
+    lite = m["trackerlite"].TrackerLite(str(tmp_path), model, proof, miss_frame=[3])
+    got = lite.predict_cell_positions_ensemble(skipped_volumes=[3], t2=6, coord_t1=proof, beta=3.0, lambda_=3.0)
+    members = []
+    for t1 in (1, 2, 4, 5):                                                     # get_volumes_list(6, [3]) with < 20 volumes
+        loaded = Coordinates(np.load(tmp_path / "track_results" / "coords_real" / f"coords{t1:06d}.npy"), 1, voxel, "real")
+        members.append(lite.predict_cell_positions(t1=t1, t2=6, confirmed_coord_t1=loaded, beta=3.0, lambda_=3.0).real)
+    want = scipy.stats.trim_mean(np.asarray(members, dtype=np.float64), 0.1, axis=0)
+    np.testing.assert_allclose(got.real, Coordinates(want, 1, voxel, "real").real, rtol=1e-6, atol=1e-6)
+    with pytest.raises(AssertionError):
+        lite.predict_cell_positions_ensemble(skipped_volumes=[], t2=3, coord_t1=proof, beta=3.0, lambda_=3.0)
