@@ -83,6 +83,8 @@ class FramePipeline:
         main = torch.cuda.current_stream()
         main.wait_stream(stream)
         prev = tracked_prev if tracked_prev is not None else self._tracked
+        if prev is None:
+            raise ValueError("no tracked coordinates to replay onto: pass tracked_prev_dev or call reset(tracked0_dev)")
         tracked = self.replay(fit, prev)
         if tracked_prev is None:
             self._tracked = tracked
@@ -96,6 +98,8 @@ class FramePipeline:
         if not self.overlap:
             prob = self.segment(raw_next_dev)
             prev = tracked_prev_dev if tracked_prev_dev is not None else self._tracked
+            if prev is None:
+                raise ValueError("no tracked coordinates to replay onto: pass tracked_prev_dev or call reset(tracked0_dev)")
             tracked = self.track(seg_prev_dev, seg_cur_dev, prev)
             if tracked_prev_dev is None:
                 self._tracked = tracked
