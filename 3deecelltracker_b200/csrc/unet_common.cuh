@@ -112,6 +112,14 @@ __device__ __forceinline__ void tile_ijk(const TileGeom& g, int ordinal, int& i,
     i = g.tlo[0] + ordinal;
 }
 
+// Power-of-two operand scale of a tile for the fp16 hi/lo split of the tensor-core kernels: max|x s| lands in
+// [2^13, 2^14), so nothing overflows fp16 and its subnormal threshold sits 2^27 below the largest element.
+// `am` = the tile's max|x| bound from the slab header (0 or subnormal -> scale 1).
+__device__ __forceinline__ float tc_operand_scale(float am) {
+    const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);          // biased exponent, 0 for zero / subnormal
+    const int se = (267 - e > 254) ? 254 : 267 - e;                    // 2^(13 - floor(log2 am)), clamped finite
+    return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
+}
 __device__ __forceinline__ void amax_update(float* slot, float v) {
     atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));
 }

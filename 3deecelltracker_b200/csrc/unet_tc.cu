@@ -287,12 +287,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             amax = warp_max(amax);
             if (lane == 0) amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
         };
-        // power-of-two operand scale of a tile: max|x s| in [2^13, 2^14)
-        auto scale_of = [](float am) {
-            const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);          // biased exponent, 0 for zero / subnormal
-            const int se = (267 - e > 254) ? 254 : 267 - e;                    // 2^(13 - floor(log2 am)), clamped finite
-            return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
-        };
 
         // flattened stage loop: stage g is converted, then stage g - 1 is drained while the MMAs of stage g run
         int c = 0, k = 0;                              // chunk / unit ordinal of stage g
@@ -306,7 +300,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             if (g < n_stages) {
                 if (c == 0) {
                     cur = nxt;
-                    s_cur = scale_of(am_nxt);
+                    s_cur = tc_operand_scale(am_nxt);
                     if (k + 1 < n_units) {
                         nxt = tc_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
                         am_nxt = geo.amax_src[(size_t)nxt.tile * geo.slab_stride];

@@ -162,12 +162,6 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    // power-of-two operand scale of a tile: max|x s| in [2^13, 2^14) (see unet_tc.cu)
-    auto scale_of = [](float am) {
-        const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);
-        const int se = (267 - e > 254) ? 254 : 267 - e;
-        return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
-    };
 
     if (warp == 0) {
         // ---------------- TMA producer
@@ -235,7 +229,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         long long w_full = 0, t_begin = clock64();
         for (int k = 0; k < n_units; ++k) {
             const TxUnit un = tx_unit((int)blockIdx.x + k * (int)gridDim.x, geo, BX);
-            const float sc = scale_of(geo.amax_src[(size_t)un.tile * geo.slab_stride]);
+            const float sc = tc_operand_scale(geo.amax_src[(size_t)un.tile * geo.slab_stride]);
             for (int c = 0; c < cin8; ++c, ++g) {
                 const int s = g % STAGES, use = g / STAGES;
                 { TX_T0(); mbar_wait(&bar_full[s], use & 1); TX_ACC(w_full); }
@@ -286,7 +280,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         float am_next = n_units > 0 ? geo.amax_src[(size_t)un_next.tile * geo.slab_stride] : 0.f;
         for (int k = 0; k < n_units; ++k) {
             const TxUnit un = un_next;
-            const float inv_scale = geo.w_inv_scale / scale_of(am_next);
+            const float inv_scale = geo.w_inv_scale / tc_operand_scale(am_next);
             if (k + 1 < n_units) {
                 un_next = tx_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
                 am_next = geo.amax_src[(size_t)un_next.tile * geo.slab_stride];
