@@ -183,8 +183,10 @@ def test_config2_ensemble_mode_matches_oracle(m):
             inter = tx
         want.append(pred)
     want = np.asarray(want)
-    # lambda = 1e-5 leaves the M-step system nearly singular (cond ~1e9): coefficients agree to ~1e-4 relative, the
-    # displacements they generate -- what the reference consumes -- to the tolerance of north_star (1e-4 relative)
+    # north_star asks for CPD displacements within 1e-4 relative; measured on B200: max |gpu - oracle| = 1.1e-11 for
+    # displacements of up to 33 voxels (lambda = 1e-5 leaves the M-step system badly conditioned, which is why the bar
+    # below is 1e-8 of the displacement scale and not the 1e-8 relative of the well-conditioned single-mode cases)
     disp_scale = np.abs(want - np.asarray([tracked[v] for v in sources])).max()
-    assert np.abs(stack - want).max() <= 1e-4 * max(disp_scale, 1.0)
-    np.testing.assert_allclose(got_mean, oprgls.trim_mean(want, 0.1), rtol=0, atol=1e-4 * max(disp_scale, 1.0))
+    print(f"config 2: max |gpu - oracle| = {np.abs(stack - want).max():.3e}, displacement scale {disp_scale:.3e}")
+    assert np.abs(stack - want).max() <= 1e-8 * max(disp_scale, 1.0)
+    np.testing.assert_allclose(got_mean, oprgls.trim_mean(want, 0.1), rtol=0, atol=1e-8 * max(disp_scale, 1.0))
