@@ -80,3 +80,13 @@ def test_host_logic_schedules():
     norm, (mean, scale) = ffn.normalize_points(e["points"], return_para=True)
     np.testing.assert_allclose(norm, e["ref_norm"], rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(scale, e["scale"], rtol=1e-11)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/ct3d.h is the C-ABI contract: it must compile as C99 (no C++ or torch types in the signatures)."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "ct3d.h"\nint main(void) { return ct_abi_version() == CT3D_ABI_VERSION ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
