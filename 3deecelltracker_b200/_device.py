@@ -23,8 +23,11 @@ def to_device(a, dtype, pinned_stage=None):
     arr = np.ascontiguousarray(a)
     if arr.dtype == np.uint16:
         # torch has limited uint16 support on older builds: ship the bytes
+        if dtype != torch.uint16:
+            # convert on the host: a device-side cast of the int16 view would turn values >= 32768 negative
+            return torch.from_numpy(arr.astype(np.int64)).to(device=dev, dtype=dtype)
         t = torch.from_numpy(arr.view(np.int16)).to(dev, non_blocking=False)
-        return t.view(torch.uint16) if dtype == torch.uint16 else t.to(dtype)
+        return t.view(torch.uint16)
     return torch.from_numpy(arr).to(device=dev, dtype=dtype)
 
 

@@ -1,6 +1,7 @@
 // Error reporting, ABI version and launch accounting for libct3d.
 #include "common.cuh"
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace ct {
@@ -24,8 +25,10 @@ struct ProfRec { int tag; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_pool;
+static std::mutex g_prof_mu;                 // launches may come from several host threads (one stream each)
 
 static cudaEvent_t prof_event() {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -41,6 +44,7 @@ ProfScope::~ProfScope() {
     if (!on_) return;
     cudaEvent_t b = prof_event();
     cudaEventRecord(b, s_);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof.push_back({tag_, a_, b});
 }
 }  // namespace ct
@@ -54,6 +58,7 @@ int ct_profile_enable(int on) {
 int ct_profile_read(int tag, double* total_ms, unsigned long long* count, int reset) {
     double ms = 0.0;
     unsigned long long n = 0;
+    std::lock_guard<std::mutex> lock(ct::g_prof_mu);
     for (auto& r : ct::g_prof) {
         if (r.tag != tag) continue;
         if (cudaEventSynchronize(r.b) != cudaSuccess) { ct::set_error("ct_profile_read: event sync failed"); return 1; }

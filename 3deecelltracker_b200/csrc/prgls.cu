@@ -9,8 +9,10 @@
 // iterations with the convergence test -- runs inside one 1024-thread CTA with no host round trip;
 // a batch (ensemble members x repetitions) is one launch with one CTA per problem.  The N x N system
 //      (G diag(p) + lambda sigma^2 I)^T C^T = (Y^T P - X^T diag(p))^T
-// is non-symmetric, so it is solved like LAPACK gesv does: LU with partial pivoting (first maximum),
-// reciprocal-scaled multipliers, then back substitution.  The system matrix and the five per-point vectors
+// is non-symmetric; the reference solves it with LAPACK gesv (track.py:97).  Here it is eliminated WITHOUT row
+// exchanges (blocked right-looking LU, see lu_solve below: S^T is a positive row scaling of an SPD matrix, so the
+// unpivoted elimination is backward stable while lambda sigma^2 > 0 -- ct_prgls rejects lambda <= 0 and the kernel
+// raises an error flag on a non-finite solution).  The system matrix and the five per-point vectors
 // live in shared memory when they fit (N <= 164: 8 N (N|1) + 88 N bytes <= 226 KiB), otherwise the matrix
 // moves to the L2-resident workspace (vectors stay in shared memory up to N ~ 2600).
 #include "common.cuh"
@@ -31,7 +33,6 @@ struct DevProblem {
     double* ytp;        // (N,3)   sum_m P[m,n] Y[m]
     double* colpart;    // (R*N,4) partial column moments, R*N <= max(N, 1024)
     double* rhs;        // (N,3)   right-hand side, overwritten by the solution W = C^T
-    double* mult;       // (N)     multipliers of the current LU column
     double* cur;        // (N,3)   T_X / predicted ref
     double* cur_l;      // (L,3)   predicted tracked
     double* rowmax;     // (M)     greedy scratch
@@ -705,7 +706,7 @@ trim_mean_kernel(const double* __restrict__ stack, int E, int count, int cut, do
 }
 
 struct Layout {
-    size_t gram, gram_nl, sys, prior, colsum, ytp, colpart, rhs, mult, cur, cur_l, rowmax, rowarg, match, col_dead, pairs, n_pairs, total;
+    size_t gram, gram_nl, sys, prior, colsum, ytp, colpart, rhs, cur, cur_l, rowmax, rowarg, match, col_dead, pairs, n_pairs, total;
 };
 
 static Layout layout_for(int N, int M, int L) {
@@ -720,7 +721,6 @@ static Layout layout_for(int N, int M, int L) {
     o.ytp = take((size_t)N * 24);
     o.colpart = take((size_t)(N > EM_THREADS ? N : EM_THREADS) * 32);
     o.rhs = take((size_t)N * 24);
-    o.mult = take((size_t)N * 8);
     o.cur = take((size_t)N * 24);
     o.cur_l = take((size_t)(L > 0 ? L : 1) * 24);
     o.rowmax = take((size_t)M * 8);
@@ -736,7 +736,7 @@ static Layout layout_for(int N, int M, int L) {
 static void bind(DevProblem& d, char* base, const Layout& o) {
     d.gram = (double*)(base + o.gram); d.gram_nl = (double*)(base + o.gram_nl); d.sys = (double*)(base + o.sys);
     d.prior = (double*)(base + o.prior); d.colsum = (double*)(base + o.colsum); d.ytp = (double*)(base + o.ytp); d.colpart = (double*)(base + o.colpart);
-    d.rhs = (double*)(base + o.rhs); d.mult = (double*)(base + o.mult); d.cur = (double*)(base + o.cur);
+    d.rhs = (double*)(base + o.rhs); d.cur = (double*)(base + o.cur);
     d.cur_l = (double*)(base + o.cur_l); d.rowmax = (double*)(base + o.rowmax); d.rowarg = (int*)(base + o.rowarg);
     d.match = (int*)(base + o.match); d.col_dead = (unsigned char*)(base + o.col_dead);
     d.pairs = (int*)(base + o.pairs); d.n_pairs = (int*)(base + o.n_pairs);
@@ -756,6 +756,9 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
                         void* ws, size_t ws_bytes, void* stream) {
     CT_REQUIRE(prm && problems && ws, "ct_prgls: null argument");
     CT_REQUIRE(prm->mode == CT_PRGLS_TRACK || prm->mode == CT_PRGLS_LITE, "ct_prgls: unknown mode %d", prm->mode);
+    // the unpivoted elimination needs the regularised system (lambda sigma^2 > 0 keeps every pivot positive); with
+    // lambda = 0 and duplicate points G is singular and LAPACK gesv (track.py:97) would raise LinAlgError
+    CT_REQUIRE(prm->lambda > 0.0, "ct_prgls: lambda must be > 0 (singular M-step system), got %g", prm->lambda);
     if (batch == 0) return 0;
     CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_prgls: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
@@ -787,12 +790,9 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
     }
     bool all_sm = true;
     for (int b = 0; b < batch; ++b) all_sm = all_sm && sys_fits(problems[b].n_ref);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CT_CUDA(cudaFuncSetAttribute(prgls_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
-        CT_CUDA(cudaFuncSetAttribute(prgls_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
-        attr_set = true;
-    }
+    // per device / context attribute: set on every call (cheap) so a process that drives several GPUs is correct
+    CT_CUDA(cudaFuncSetAttribute(prgls_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
+    CT_CUDA(cudaFuncSetAttribute(prgls_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM_BUDGET));
     ProfScope prof(PROF_EM, s);
     if (all_sm) {
         prgls_kernel<true><<<batch, EM_THREADS, smem, s>>>(static_cast<const DevProblem*>(ws), *prm);

@@ -439,11 +439,8 @@ static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, float alpha, f
                       size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst,
                       float4* pool_dst, float* amax_pool, cudaStream_t s) {
     using Cfg = TxCfg<N, BX, STAGES>;
-    static bool attr = false;
-    if (!attr) {
-        CT_CUDA(cudaFuncSetAttribute(conv3_tcx_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr = true;
-    }
+    // per device / context attribute: set on every launch (cheap) so several GPUs in one process are correct
+    CT_CUDA(cudaFuncSetAttribute(conv3_tcx_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     TxGeom g;
     g.cin8 = (L.cin_pad + 7) / 8; g.X = X; g.Y = Y; g.Z = Z;
     g.amax_src = amax_src; g.amax_dst = amax_dst; g.slab_stride = stride4 * 4; g.w_inv_scale = L.w_tc_inv_scale;

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._device import WORKSPACE, aligned_ptr, require_cuda, stream_ptr, to_device
 
-_DTYPES = {torch.uint16: 0, torch.int16: 0, torch.float32: 1, torch.uint8: 2}
+_DTYPES = {torch.uint16: 0, torch.float32: 1, torch.uint8: 2}     # kernel dtype codes (ct3d.h); anything else -> float32
 
 
 def _raw_to_device(image):

@@ -70,6 +70,38 @@ def unet_weights(variant="a", seed=0):
     return ws
 
 
+def detector_unet_weights(seed=0, gain=8.0, bias=-4.0, mix=0.05):
+    """unet3_a weights that DETECT bright blobs, for end-to-end runs without trained weights (the reference's
+    unet3_pretrained.h5 is a download, README.md:67-69): output channel 0 of d0a, d0b, o_m2 (reading the level-0 skip
+    half of its concat input) and o_m1 carries the normalised intensity (3x3x3 box means in d0a and d0b, which
+    suppress the single-voxel background noise, then centre taps) with identity
+    BatchNorm, every other kernel keeps its seeded random-init value, and the 1x1x1 head is
+    sigmoid(gain * ch0 + mix * (random combination of the other 7 channels) + bias).  The probability map is therefore
+    a steep monotone function of the LCN-normalised intensity, perturbed by the full random network -- every layer
+    contributes to every output value, and the cell / background decision is the blob detector's."""
+    from .unet3d import _SPECS, _conv_layers
+    ws = unet_weights("a", seed)
+    layers = _conv_layers(_SPECS["a"])
+    src_channel = {0: 0, 1: 0, len(layers) - 2: 16, len(layers) - 1: 0}
+    for i, src in src_channel.items():
+        k = ws[6 * i]
+        k[..., 0] = 0.0
+        if i <= 1:
+            k[:, :, :, src, 0] = 1.0 / 27.0
+        else:
+            k[1, 1, 1, src, 0] = 1.0
+        ws[6 * i + 1][0] = 0.0                       # conv bias
+        ws[6 * i + 2][0] = 1.0                       # gamma
+        ws[6 * i + 3][0] = 0.0                       # beta
+        ws[6 * i + 4][0] = 0.0                       # moving mean
+        ws[6 * i + 5][0] = 1.0                       # moving variance
+    head = ws[-2]
+    head[0, 0, 0, 1:, 0] *= mix
+    head[0, 0, 0, 0, 0] = gain
+    ws[-1][0] = bias
+    return ws
+
+
 def ffn_weights(seed=0):
     """Seeded random-init FFN weights in Keras order (Glorot-uniform kernels, non-trivial BatchNorm statistics)."""
     import math

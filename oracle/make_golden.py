@@ -87,8 +87,42 @@ def synth_corr(ref, tgt, rng, width):
     return np.clip(np.exp(-d2 / (2 * width ** 2)) * 0.95 + rng.random(d2.shape) * 0.3, 0, 1)
 
 
+def adversarial():
+    """tests/golden/pr_gls_adversarial.npz: pr_gls_quick (track.py:11-114, unmodified) on M-step systems that stress
+    an elimination WITHOUT row exchanges (the GPU kernel's solver): reference points far from every target so that
+    their posterior column sums are exactly 0 (pivot = lambda sigma^2 alone), near-duplicate reference points (almost
+    equal Gram rows) and lambda = 1e-5.  Own RNG stream: the other golden files do not change."""
+    track, _ = _ref_shim.load()
+    pts = np.loadtxt(CSV)
+    rng = np.random.default_rng(777)
+
+    def corr_of(X, Y):
+        d2 = ((X[None] - Y[:, None]) ** 2).sum(axis=2)
+        return np.clip(np.exp(-d2 / 72.0) * 0.95 + rng.random(d2.shape) * 0.3, 0, 1)
+
+    Xa = pts.copy()
+    Xa[:12] += np.array([4000.0, -3000.0, 2500.0])
+    Ya = pts[12:] + rng.normal(0, 1.5, pts[12:].shape)
+    ca = corr_of(Xa, Ya)
+    Xb = np.concatenate([pts[:100], pts[:20] + rng.normal(0, 1e-6, (20, 3))])
+    Yb = pts[:110] + rng.normal(0, 2.0, (110, 3))
+    cb = corr_of(Xb, Yb)
+    out = {}
+    for name, (X, Y, cr, kw) in {
+        "far_cols": (Xa, Ya, ca, dict(BETA=300, max_iteration=20, LAMBDA=1e-5)),
+        "far_cols_b1000": (Xa, Ya, ca, dict(BETA=1000, max_iteration=10, LAMBDA=1e-5)),
+        "near_dup": (Xb, Yb, cb, dict(BETA=1000, max_iteration=10, LAMBDA=1e-5)),
+    }.items():
+        P, TX, C = track.pr_gls_quick(X.copy(), Y.copy(), cr.copy(), **kw)
+        d = dict(X=X, Y=Y, corr=cr, P=P, T_X=TX, C=C, **{k: np.float64(v) for k, v in kw.items()})
+        out.update({f"{name}__{k}": v for k, v in d.items()})
+    np.savez_compressed(os.path.join(GOLD, "pr_gls_adversarial.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-adversarial" in sys.argv:
+        return adversarial()
     track, lite = _ref_shim.load()
     pts = np.loadtxt(CSV)            # worm3, 180 x 3
     rng = np.random.default_rng(20260101)
@@ -217,6 +251,7 @@ def main():
         tiles[f"{tag}__tin"] = np.array(tin)
         tiles[f"{tag}__shrink"] = np.array(shrink)
     np.savez_compressed(os.path.join(GOLD, "unet_tiling.npz"), **tiles)
+    adversarial()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -182,6 +182,60 @@ def test_unet3_prediction_matches_oracle(mods, shape, shrink):
     assert torch.equal(full, part)
 
 
+NAMED = {"config1": ((512, 512, 35), 75, 164), "config2": ((160, 160, 16), 8, 113)}
+
+
+@pytest.mark.parametrize("config", ["config1", "config2"])
+def test_unet3_prediction_on_named_configs(mods, config):
+    """BASELINE.json configs[1] (512 x 512 x 35, 75 tiles) and configs[2] (160 x 160 x 16, 8 tiles), whole volumes:
+    LCN-normalised synthetic stack -> unet3_prediction (unet3d.py:203-256) vs the fp32 and fp64 oracle, with seeded
+    random weights and at the bench's batch size (38 tiles per launch)."""
+    pre, u, synth = mods
+    shape, n_tiles, cells = NAMED[config]
+    raw = synth.blob_stack(shape, synth.blob_centres(shape, cells, 1234), 1234, z_xy_ratio=9.2)
+    norm = ounet.normalize_image(raw.copy(), 20).astype(np.float32)
+    img = norm[None, ..., None]
+    ws = ounet.random_weights("a", seed=4)
+    model = u.UNet3("a", weights=ws, tiles_per_batch=38)
+    assert model.tile_count(shape, (24, 24, 2))[0] == n_tiles
+    got = u.unet3_prediction(img, model, (24, 24, 2))
+    want = ounet.unet3_prediction(img, ounet.UNetOracle("a", ws), (24, 24, 2))
+    want64 = ounet.unet3_prediction(img, ounet.UNetOracle("a", ws, dtype=torch.float64), (24, 24, 2))
+    assert got.shape == want.shape == img.shape
+    assert_prob_close(got, want, want64.astype(np.float64), config)
+
+
+@pytest.mark.parametrize("config", ["config1", "config2"])
+def test_binarised_maps_identical_on_named_configs(mods, config):
+    """The reduced label-map check of SURVEY section 7-6: the binarised probability map `p > 0.5` that the watershed
+    starts from (watershed.py:38,49) must be IDENTICAL between the GPU path and the oracle.  Weights: the blob detector
+    of synth.detector_unet_weights (every random layer still contributes to every logit).  A voxel whose fp64
+    probability lies within the north_star tolerance (1e-4 relative) of 0.5 is undecidable at that tolerance -- two
+    correct fp32 evaluations may disagree there; such voxels are counted, must be a vanishing fraction, and the masks
+    must agree bit for bit everywhere else AND in total when there are none."""
+    pre, u, synth = mods
+    shape, n_tiles, cells = NAMED[config]
+    raw = synth.blob_stack(shape, synth.blob_centres(shape, cells, 1234), 1234, z_xy_ratio=9.2)
+    got_norm = pre._normalize_image(raw, 20)
+    norm = ounet.normalize_image(raw.copy(), 20).astype(np.float32)
+    np.testing.assert_allclose(got_norm, norm, rtol=RTOL, atol=1e-5)
+    ws = synth.detector_unet_weights(0)
+    model = u.UNet3("a", weights=ws, tiles_per_batch=38)
+    img = norm[None, ..., None]
+    got = u.unet3_prediction(img, model, (24, 24, 2))[0, ..., 0]
+    want = ounet.unet3_prediction(img, ounet.UNetOracle("a", ws), (24, 24, 2))[0, ..., 0]
+    want64 = ounet.unet3_prediction(img, ounet.UNetOracle("a", ws, dtype=torch.float64), (24, 24, 2))[0, ..., 0]
+    band = np.abs(want64.astype(np.float64) - 0.5) <= 0.5e-4
+    frac_cells = float((want64 > 0.5).mean())
+    print(f"{config}: {int(band.sum())} of {band.size} voxels within 1e-4 of the threshold; foreground {frac_cells:.4f}")
+    assert 0.001 < frac_cells < 0.5                       # the detector segments something, not everything
+    assert band.mean() < 5e-5
+    assert np.array_equal((got > 0.5)[~band], (want64 > 0.5)[~band])
+    assert np.array_equal((got > 0.5)[~band], (want > 0.5)[~band])
+    if not band.any():
+        assert np.array_equal(got > 0.5, want > 0.5)
+
+
 def test_unet_errors(mods):
     _, u, _ = mods
     model = u.UNet3("c", weights=ounet.random_weights("c", 0))

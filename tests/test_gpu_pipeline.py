@@ -149,7 +149,7 @@ def test_config2_ensemble_mode_matches_oracle(m):
     maxiter_tk=10 (ensemble_mode_worm4-clear.ipynb:117).  Tracker._fit_predict_batch runs the 20 members as ONE
     batched EM launch per repetition (one CTA per member); checked against the oracle chain member by member
     (tracker.py:1224-1289) and through the 10 %-trimmed mean (tracker.py:1507).  The segmentation half of the config
-    (160 x 160 x 16 stacks, 8 tiles) is covered by test_unet3_prediction_matches_oracle."""
+    (160 x 160 x 16 stacks, 8 tiles) is covered by test_gpu_lcn_unet.py::test_unet3_prediction_on_named_configs[config2]."""
     T, synth = m["tracker"], m["synth"]
     track = importlib.import_module("3deecelltracker_b200.track")
     n_cells, target = 113, 22

@@ -20,6 +20,16 @@ def test_pr_gls_quick_matches_reference(case):
     np.testing.assert_allclose(C, c["C"], rtol=1e-6, atol=1e-9 * np.abs(c["C"]).max())
 
 
+@pytest.mark.parametrize("case", ["far_cols", "far_cols_b1000", "near_dup"])
+def test_pr_gls_quick_adversarial_matches_reference(case):
+    """Ill-conditioned M-step systems (zero posterior columns, near-duplicate points, lambda = 1e-5; cond ~ 1e7)."""
+    c = split_cases(golden("pr_gls_adversarial.npz"))[case]
+    P, TX, C = oprgls.pr_gls_quick(c["X"], c["Y"], c["corr"], BETA=float(c["BETA"]),
+                                   max_iteration=int(c["max_iteration"]), LAMBDA=float(c["LAMBDA"]))
+    np.testing.assert_allclose(TX, c["T_X"], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(P, c["P"], rtol=1e-5, atol=1e-12)
+
+
 def test_predict_one_rep_matches_reference():
     g = golden("predict_one_rep.npz")
     post = oprgls.predict_one_rep(g["pre"], g["inter"], float(g["beta"]), g["C"])
