@@ -1,0 +1,543 @@
+// Watershed + centroid stage (Tracker._watershed, tracker.py:671-684; watershed.py:16-108; centre of mass
+// tracker.py:646-648) as data-parallel passes over the (x, y, z) volume plus one priority flood per connected
+// component of the foreground.
+//
+// Every pass is a functor `void operator()(long long i)` over a flat index range, launched through a Policy:
+// watershed.cu instantiates the pipeline with a CUDA policy (one thread per index, global atomics); the CPU test
+// harness tests/emul/ws_host.cpp instantiates THE SAME pipeline with a sequential policy so that the pass logic can be
+// checked against the oracle on a machine without a GPU.  (The harness is test infrastructure: the product library
+// only contains the CUDA instantiation.)
+//
+// Exactness.  The label map must be bit-identical to the CPU path, so every floating-point value that feeds a
+// comparison is computed with the reference's own arithmetic:
+//   * distance_transform_edt: exact integer squared distances in the plane (two separable passes), the z term added
+//     as (double)(dx^2 + dy^2) + fl(fl(dz r) fl(dz r)) -- SciPy's `dt *= sampling; dt *= dt; add.reduce(axis 0)` -- and
+//     a correctly rounded sqrt.
+//   * gaussian_filter: SciPy's correlate1d for symmetric kernels, centre term first, then
+//     `acc += (in[-j] + in[+j]) * w[j]` for j = radius .. 1, with separately rounded multiply and add (no FMA), zero
+//     padding, axes in order x, y, z.  The weights come from the caller (NumPy's exp, as SciPy computes them).
+//   * maximum filter / peak test / flood order only compare those values.
+// Flood order (value, age, index) and the other choices scikit-image leaves open are stated in oracle/watershed.py.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define WS_HD __host__ __device__ __forceinline__
+#else
+#define WS_HD inline
+#endif
+
+namespace ws {
+
+typedef long long i64;
+constexpr int COL_INF = 30000;              // "no background in this column": 30000^2 + 30000^2 < 2^31
+
+WS_HD int atomic_min_i(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    return atomicMin(p, v);
+#else
+    const int o = *p; if (v < o) *p = v; return o;
+#endif
+}
+WS_HD int atomic_add_i(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    const int o = *p; *p = o + v; return o;
+#endif
+}
+WS_HD void atomic_add_u64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+WS_HD void atomic_min_u64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+WS_HD double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+WS_HD double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+WS_HD unsigned long long dbl_bits(double v) {
+#ifdef __CUDA_ARCH__
+    return (unsigned long long)__double_as_longlong(v);
+#else
+    unsigned long long u; __builtin_memcpy(&u, &v, 8); return u;
+#endif
+}
+WS_HD double bits_dbl(unsigned long long u) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double v; __builtin_memcpy(&v, &u, 8); return v;
+#endif
+}
+WS_HD int vload(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+struct Dims {
+    int X, Y, Z;
+    WS_HD i64 n() const { return (i64)X * Y * Z; }
+    WS_HD void split(i64 i, int& x, int& y, int& z) const {
+        z = (int)(i % Z); i /= Z; y = (int)(i % Y); x = (int)(i / Y);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- threshold
+struct Threshold {                               // watershed.py:38,49: image_pred > 0.5
+    const float* prob; uint8_t* mask;
+    WS_HD void operator()(i64 i) const { mask[i] = prob[i] > 0.5f ? 1 : 0; }
+};
+
+// ---------------------------------------------------------------------------------------------- in-plane EDT
+// pass 1, one index per (x, z) column: distance along y to the nearest background voxel of the column
+struct ColDist {
+    Dims d; const uint8_t* mask; int* g;
+    WS_HD void operator()(i64 c) const {
+        const int z = (int)(c % d.Z), x = (int)(c / d.Z);
+        const i64 base = (i64)x * d.Y * d.Z + z;
+        int run = COL_INF;
+        for (int y = 0; y < d.Y; ++y) {
+            const i64 i = base + (i64)y * d.Z;
+            run = mask[i] ? (run < COL_INF ? run + 1 : COL_INF) : 0;
+            g[i] = run;
+        }
+        run = COL_INF;
+        for (int y = d.Y - 1; y >= 0; --y) {
+            const i64 i = base + (i64)y * d.Z;
+            run = mask[i] ? (run < COL_INF ? run + 1 : COL_INF) : 0;
+            if (run < g[i]) g[i] = run;
+        }
+    }
+};
+// pass 2, one index per voxel: exact squared in-plane distance min over x' of (x - x')^2 + g(x', y)^2
+struct RowDist {
+    Dims d; const uint8_t* mask; const int* g; int* d2;
+    WS_HD void operator()(i64 i) const {
+        if (!mask[i]) { d2[i] = 0; return; }
+        int x, y, z; d.split(i, x, y, z);
+        const i64 sx = (i64)d.Y * d.Z;
+        int best = g[i] * g[i];
+        for (int o = 1; o * o < best; ++o) {
+            if (x - o >= 0) { const int v = g[i - o * sx]; const int c = o * o + v * v; if (c < best) best = c; }
+            if (x + o < d.X) { const int v = g[i + o * sx]; const int c = o * o + v * v; if (c < best) best = c; }
+            if (x - o < 0 && x + o >= d.X) break;
+        }
+        d2[i] = best;
+    }
+};
+struct SqrtPlane {                               // distance_transform_edt(bn_image, sampling=[1, 1])
+    const int* d2; double* dist;
+    WS_HD void operator()(i64 i) const { dist[i] = sqrt((double)d2[i]); }
+};
+// distance_transform_edt(volume, sampling=[1, 1, r]) from the in-plane squared distances of every slice
+struct DistZ {
+    Dims d; const uint8_t* mask; const int* d2; double r; double* dist;
+    WS_HD void operator()(i64 i) const {
+        if (!mask[i]) { dist[i] = 0.0; return; }
+        int x, y, z; d.split(i, x, y, z);
+        const i64 col = i - z;
+        double best = (double)d2[i];
+        for (int zz = 0; zz < d.Z; ++zz) {
+            if (zz == z) continue;
+            const double dz = mul_rn((double)(zz - z), r);
+            const double c = add_rn((double)d2[col + zz], mul_rn(dz, dz));
+            if (c < best) best = c;
+        }
+        dist[i] = sqrt(best);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- gaussian_filter
+template <int AXIS>
+struct Gauss1D {                                 // scipy.ndimage.correlate1d, symmetric kernel, mode='constant'
+    Dims d; const double* in; double* out; int radius; double w[9];
+    WS_HD void operator()(i64 i) const {
+        int c[3]; d.split(i, c[0], c[1], c[2]);
+        const int len = AXIS == 0 ? d.X : (AXIS == 1 ? d.Y : d.Z);
+        const i64 st = AXIS == 0 ? (i64)d.Y * d.Z : (AXIS == 1 ? (i64)d.Z : 1);
+        const int p = c[AXIS];
+        double acc = mul_rn(in[i], w[0]);
+        for (int j = radius; j >= 1; --j) {
+            const double l = p - j >= 0 ? in[i - j * st] : 0.0;
+            const double h = p + j < len ? in[i + j * st] : 0.0;
+            acc = add_rn(acc, mul_rn(add_rn(l, h), w[j]));
+        }
+        out[i] = acc;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- peak_local_max
+template <int AXIS>
+struct Max1D {                                   // maximum_filter(size = 2 r + 1, mode='constant'): values are >= 0
+    Dims d; const double* in; double* out; int radius;
+    WS_HD void operator()(i64 i) const {
+        int c[3]; d.split(i, c[0], c[1], c[2]);
+        const int len = AXIS == 0 ? d.X : (AXIS == 1 ? d.Y : d.Z);
+        const i64 st = AXIS == 0 ? (i64)d.Y * d.Z : (AXIS == 1 ? (i64)d.Z : 1);
+        const int p = c[AXIS];
+        const int lo = p - radius < 0 ? 0 : p - radius, hi = p + radius >= len ? len - 1 : p + radius;
+        double m = (p - radius < 0 || p + radius >= len) ? 0.0 : in[i];          // zero padding takes part
+        for (int q = lo; q <= hi; ++q) { const double v = in[i + (q - p) * st]; if (v > m) m = v; }
+        out[i] = m;
+    }
+};
+struct MinReduce {                               // image.min(): per slice (2-D stage) or global (3-D stage)
+    Dims d; const double* in; unsigned long long* slot; int per_slice;
+    WS_HD void operator()(i64 i) const {
+        atomic_min_u64(slot + (per_slice ? (int)(i % d.Z) : 0), dbl_bits(in[i]));   // values >= +0: bit order = value order
+    }
+};
+struct Peaks {
+    Dims d; const double* img; const double* imgmax; const unsigned long long* minslot; int per_slice; int border;
+    uint8_t* peak;
+    WS_HD void operator()(i64 i) const {
+        int x, y, z; d.split(i, x, y, z);
+        const double thr = bits_dbl(minslot[per_slice ? z : 0]);
+        bool p = img[i] == imgmax[i] && img[i] > thr;
+        if (border > 0 && (x < border || x >= d.X - border || y < border || y >= d.Y - border)) p = false;
+        peak[i] = p ? 1 : 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- connected components
+// Lock-free union-find on voxel indices (root = smallest index of the set = first voxel in raster order).
+WS_HD int uf_find(const int* L, int a) {
+    int p = vload(L + a);
+    while (p != a) { a = p; p = vload(L + a); }
+    return a;
+}
+WS_HD void uf_union(int* L, int a, int b) {
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { const int old = atomic_min_i(L + b, a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomic_min_i(L + a, b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+struct UfInit {
+    const uint8_t* on; int* L;
+    WS_HD void operator()(i64 i) const { L[i] = on[i] ? (int)i : -1; }
+};
+// FULL = 0: connectivity 1 (4 in the plane / 6 in the volume); FULL = 1: full connectivity (8 / 26).  planar = no z links.
+struct UfLink {
+    Dims d; const uint8_t* on; int* L; int full; int planar;
+    WS_HD void operator()(i64 i) const {
+        if (!on[i]) return;
+        int x, y, z; d.split(i, x, y, z);
+        // the 13 (or 4 in the plane) neighbours that precede voxel i in raster order
+        for (int dx = -1; dx <= 0; ++dx)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dz = -1; dz <= 1; ++dz) {
+                    if (dx == 0 && (dy > 0 || (dy == 0 && dz >= 0))) continue;
+                    if (planar && dz != 0) continue;
+                    if (!full && (dx != 0) + (dy != 0) + (dz != 0) != 1) continue;
+                    const int xx = x + dx, yy = y + dy, zz = z + dz;
+                    if (xx < 0 || yy < 0 || yy >= d.Y || zz < 0 || zz >= d.Z) continue;
+                    const i64 j = ((i64)xx * d.Y + yy) * d.Z + zz;
+                    if (on[j]) uf_union(L, (int)i, (int)j);
+                }
+    }
+};
+struct UfFlatten {
+    const uint8_t* on; int* L;
+    WS_HD void operator()(i64 i) const { if (on[i]) L[i] = uf_find(L, (int)i); }
+};
+
+// ---------------------------------------------------------------------------------------------- flood
+struct HeapE { double v; int age; int idx; };
+WS_HD bool heap_less(const HeapE& a, const HeapE& b) {
+    if (a.v != b.v) return a.v < b.v;
+    if (a.age != b.age) return a.age < b.age;
+    return a.idx < b.idx;
+}
+WS_HD void heap_down(HeapE* h, int n, int k) {
+    const HeapE e = h[k];
+    for (;;) {
+        int c = 2 * k + 1;
+        if (c >= n) break;
+        if (c + 1 < n && heap_less(h[c + 1], h[c])) ++c;
+        if (!heap_less(h[c], e)) break;
+        h[k] = h[c];
+        k = c;
+    }
+    h[k] = e;
+}
+WS_HD void heap_up(HeapE* h, int k) {
+    const HeapE e = h[k];
+    while (k > 0) {
+        const int p = (k - 1) >> 1;
+        if (!heap_less(e, h[p])) break;
+        h[k] = h[p];
+        k = p;
+    }
+    h[k] = e;
+}
+struct CompSize {                                // voxels per foreground component, accumulated at the root
+    const uint8_t* mask; const int* comp; int* csize;
+    WS_HD void operator()(i64 i) const { if (mask[i]) atomic_add_i(csize + comp[i], 1); }
+};
+struct HeapAlloc {                               // every root reserves heap room for its whole component
+    const uint8_t* mask; const int* comp; const int* csize; int* hoff; int* hcnt; int* counter;
+    WS_HD void operator()(i64 i) const {
+        if (mask[i] && comp[i] == (int)i) { hoff[i] = atomic_add_i(counter, csize[i]); hcnt[i] = 0; }
+    }
+};
+struct SeedMarkers {                             // markers = label(local_maxi) * mask; seeds enter with age 0
+    const uint8_t* mask; const uint8_t* peak; const int* mk; const int* comp; const double* img;
+    const int* hoff; int* hcnt; HeapE* heap; int* lab;
+    WS_HD void operator()(i64 i) const {
+        if (mask[i] && peak[i]) {
+            const int r = comp[i];
+            const int slot = atomic_add_i(hcnt + r, 1);
+            HeapE e; e.v = -img[i]; e.age = 0; e.idx = (int)i;
+            heap[hoff[r] + slot] = e;
+            lab[i] = mk[i] + 1;                  // label id = 1 + first voxel of the marker's plateau
+        } else {
+            lab[i] = 0;
+        }
+    }
+};
+struct Flood {                                   // skimage.segmentation.watershed(-img, markers, mask), connectivity 1
+    Dims d; const uint8_t* mask; const int* comp; const double* img; const int* hoff; const int* hcnt;
+    HeapE* heap; int* lab; int planar;
+    WS_HD void operator()(i64 i) const {
+        if (!mask[i] || comp[i] != (int)i) return;
+        int n = hcnt[i];
+        if (n == 0) return;
+        HeapE* h = heap + hoff[i];
+        for (int k = n / 2 - 1; k >= 0; --k) heap_down(h, n, k);
+        const i64 sx = (i64)d.Y * d.Z, sy = d.Z;
+        int age = 0;
+        while (n > 0) {
+            const HeapE top = h[0];
+            --n;
+            if (n > 0) { h[0] = h[n]; heap_down(h, n, 0); }
+            int x, y, z; d.split(top.idx, x, y, z);
+            const int l = lab[top.idx];
+            // C order of the neighbour offsets: x-1, y-1, z-1, z+1, y+1, x+1
+            const i64 nb[6] = {top.idx - sx, top.idx - sy, (i64)top.idx - 1, (i64)top.idx + 1, top.idx + sy, top.idx + sx};
+            const bool ok[6] = {x > 0, y > 0, !planar && z > 0, !planar && z + 1 < d.Z, y + 1 < d.Y, x + 1 < d.X};
+            for (int k = 0; k < 6; ++k) {
+                if (!ok[k]) continue;
+                const i64 j = nb[k];
+                if (!mask[j] || lab[j] != 0) continue;
+                ++age;
+                lab[j] = l;
+                HeapE e; e.v = -img[j]; e.age = age; e.idx = (int)j;
+                h[n] = e;
+                heap_up(h, n);
+                ++n;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- find_boundaries
+struct Boundary2D {                              // find_boundaries(labels, connectivity=2, mode='outer', background=0)
+    Dims d; const uint8_t* mask; const int* lab; uint8_t* out;      // out = mask & ~boundary  (watershed.py:49-50)
+    WS_HD void operator()(i64 i) const {
+        int x, y, z; d.split(i, x, y, z);
+        const int l = lab[i];
+        int mx = l, mn_nz = l ? l : 0x7fffffff;
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int xx = x + dx, yy = y + dy;
+                if (xx < 0 || xx >= d.X || yy < 0 || yy >= d.Y) continue;
+                const int v = lab[((i64)xx * d.Y + yy) * d.Z + z];
+                if (v > mx) mx = v;
+                if (v != 0 && v < mn_nz) mn_nz = v;
+            }
+        // background voxel: boundary iff a label is adjacent; labelled voxel: iff two different labels are adjacent
+        const bool boundary = l == 0 ? mx != 0 : mx != mn_nz;
+        out[i] = (mask[i] && !boundary) ? 1 : 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- sizes, relabel, centres
+struct LabelSize {                               // np.bincount(labels_ws.ravel()): slot 0 = background, 1 + root = label
+    const int* lab; int* lsize; int* bg;
+    WS_HD void operator()(i64 i) const {
+        const int l = lab[i];
+        if (l) atomic_add_i(lsize + (l - 1), 1); else atomic_add_i(bg, 1);
+    }
+};
+struct Scalars {                                 // device-resident scalars of one call
+    int min_size, cell_num, n_labels, n_cells, bg_count, heap_counter, count_ge, pad;
+};
+struct CountGE {                                 // number of marker labels with at least `thr` voxels (roots only)
+    const uint8_t* peak; const int* mk; const int* lsize; const int* thr; int* out;
+    WS_HD void operator()(i64 i) const {
+        if (peak[i] && mk[i] == (int)i && lsize[i] >= *thr) atomic_add_i(out, 1);
+    }
+};
+struct KeepFlag {                                // remove_small_objects: labels with fewer than min_size voxels go
+    const uint8_t* peak; const int* mk; const int* lsize; const Scalars* sc; int* flag;
+    WS_HD void operator()(i64 i) const {
+        flag[i] = (peak[i] && mk[i] == (int)i && lsize[i] > 0 && lsize[i] >= sc->min_size) ? 1 : 0;
+    }
+};
+struct Relabel {                                 // relabel_sequential + centre-of-mass sums (tracker.py:646-648, :682)
+    Dims d; const int* lab; const int* flag; const int* rank; int* out; unsigned long long* sums; int max_cells;
+    WS_HD void operator()(i64 i) const {
+        const int l = lab[i];
+        int id = 0;
+        if (l && flag[l - 1]) id = rank[l - 1] + 1;
+        out[i] = id;
+        if (id && id <= max_cells) {
+            int x, y, z; d.split(i, x, y, z);
+            unsigned long long* s = sums + (i64)(id - 1) * 4;
+            atomic_add_u64(s + 0, (unsigned long long)x);
+            atomic_add_u64(s + 1, (unsigned long long)y);
+            atomic_add_u64(s + 2, (unsigned long long)z);
+            atomic_add_u64(s + 3, 1ull);
+        }
+    }
+};
+struct Centres {
+    const unsigned long long* sums; double* centres; const Scalars* sc; int max_cells;
+    WS_HD void operator()(i64 k) const {
+        if (k >= sc->n_cells || k >= max_cells) return;
+        const double n = (double)sums[k * 4 + 3];
+        centres[k * 3 + 0] = (double)sums[k * 4 + 0] / n;
+        centres[k * 3 + 1] = (double)sums[k * 4 + 1] / n;
+        centres[k * 3 + 2] = (double)sums[k * 4 + 2] / n;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- workspace
+struct Buffers {
+    uint8_t *mask, *mask2, *peak;
+    int *g, *d2, *mk, *comp, *lab, *csize, *hoff, *hcnt, *flag, *rank;
+    double *fa, *fb, *fc;
+    HeapE* heap;
+    unsigned long long* minslot;     // Z + 1 slots
+    unsigned long long* sums;        // max_cells x 4
+    Scalars* sc;
+    int* thr;                        // 2 ints: binary-search threshold, count
+};
+inline size_t a256(size_t v) { return (v + 255) / 256 * 256; }
+inline size_t workspace_bytes(i64 n, int Z, int max_cells) {
+    size_t t = 0;
+    t += 3 * a256((size_t)n);                       // mask, mask2, peak
+    t += 10 * a256((size_t)n * 4);                  // g, d2, mk, comp, lab, csize, hoff, hcnt, flag, rank
+    t += 3 * a256((size_t)n * 8);                   // fa, fb, fc
+    t += a256((size_t)n * sizeof(HeapE));
+    t += a256((size_t)(Z + 1) * 8) + a256((size_t)max_cells * 32) + a256(sizeof(Scalars)) + a256(64);
+    return t + 256;
+}
+inline void carve(Buffers& b, void* ws, i64 n, int Z, int max_cells) {
+    char* p = reinterpret_cast<char*>(((uintptr_t)ws + 255) / 256 * 256);
+    auto take = [&](size_t bytes) { char* r = p; p += a256(bytes); return r; };
+    b.mask = (uint8_t*)take(n); b.mask2 = (uint8_t*)take(n); b.peak = (uint8_t*)take(n);
+    b.g = (int*)take(n * 4); b.d2 = (int*)take(n * 4); b.mk = (int*)take(n * 4); b.comp = (int*)take(n * 4);
+    b.lab = (int*)take(n * 4); b.csize = (int*)take(n * 4); b.hoff = (int*)take(n * 4); b.hcnt = (int*)take(n * 4);
+    b.flag = (int*)take(n * 4); b.rank = (int*)take(n * 4);
+    b.fa = (double*)take(n * 8); b.fb = (double*)take(n * 8); b.fc = (double*)take(n * 8);
+    b.heap = (HeapE*)take(n * sizeof(HeapE));
+    b.minslot = (unsigned long long*)take((size_t)(Z + 1) * 8);
+    b.sums = (unsigned long long*)take((size_t)max_cells * 32);
+    b.sc = (Scalars*)take(sizeof(Scalars));
+    b.thr = (int*)take(64);
+}
+
+struct Params {
+    int X, Y, Z;
+    double z_xy_ratio;
+    int method;                       // 0 = "min_size", 1 = "cell_num" (watershed.py:95-98)
+    int min_size, cell_num;
+    int max_cells;
+    double w_xy[9];                   // gaussian weights sigma = 2, radius 8: w[j] = weight at offset +-j
+    double w_z[2];                    // sigma = 0.3, radius 1
+};
+
+// One flood stage: markers -> labels.  `img` = smoothed distance, `fg` = foreground, planar = per-slice (2-D stage).
+template <class P>
+void flood_stage(P& pol, const Dims& d, const Buffers& b, const uint8_t* fg, const double* img, int planar) {
+    const i64 n = d.n();
+    pol.run(UfInit{b.peak, b.mk}, n);
+    pol.run(UfLink{d, b.peak, b.mk, 1, planar}, n);
+    pol.run(UfFlatten{b.peak, b.mk}, n);
+    pol.run(UfInit{fg, b.comp}, n);
+    pol.run(UfLink{d, fg, b.comp, 0, planar}, n);
+    pol.run(UfFlatten{fg, b.comp}, n);
+    pol.zero(b.csize, (size_t)n * 4);
+    pol.zero(&b.sc->heap_counter, 4);
+    pol.run(CompSize{fg, b.comp, b.csize}, n);
+    pol.run(HeapAlloc{fg, b.comp, b.csize, b.hoff, b.hcnt, &b.sc->heap_counter}, n);
+    pol.run(SeedMarkers{fg, b.peak, b.mk, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab}, n);
+    pol.run_sparse(Flood{d, fg, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab, planar}, n);
+}
+
+// The whole stage.  prob (x,y,z) float32 -> labels (x,y,z) int32, centres (max_cells,3) float64, scalars.
+template <class P>
+void segment(P& pol, const Params& prm, const float* prob, int* labels, double* centres, const Buffers& b) {
+    const Dims d{prm.X, prm.Y, prm.Z};
+    const i64 n = d.n();
+    Gauss1D<0> gx{d, nullptr, nullptr, 8, {}};
+    Gauss1D<1> gy{d, nullptr, nullptr, 8, {}};
+    Gauss1D<2> gz{d, nullptr, nullptr, 1, {}};
+    for (int j = 0; j < 9; ++j) { gx.w[j] = prm.w_xy[j]; gy.w[j] = prm.w_xy[j]; gz.w[j] = j < 2 ? prm.w_z[j] : 0.0; }
+
+    // ---- watershed_2d (watershed.py:16-52), all slices at once
+    pol.run(Threshold{prob, b.mask}, n);
+    pol.run(ColDist{d, b.mask, b.g}, (i64)d.X * d.Z);
+    pol.run(RowDist{d, b.mask, b.g, b.d2}, n);
+    pol.run(SqrtPlane{b.d2, b.fa}, n);
+    gx.in = b.fa; gx.out = b.fb; pol.run(gx, n);
+    gy.in = b.fb; gy.out = b.fa; pol.run(gy, n);                              // fa = dist_smooth
+    pol.fill_u64(b.minslot, 0x7ff0000000000000ull, d.Z + 1);
+    pol.run(MinReduce{d, b.fa, b.minslot, 1}, n);
+    pol.run(Max1D<0>{d, b.fa, b.fb, 7}, n);
+    pol.run(Max1D<1>{d, b.fb, b.fc, 7}, n);
+    pol.run(Peaks{d, b.fa, b.fc, b.minslot, 1, 7, b.peak}, n);
+    flood_stage(pol, d, b, b.mask, b.fa, 1);
+    pol.run(Boundary2D{d, b.mask, b.lab, b.mask2}, n);                         // mask2 = bn_output
+
+    // ---- watershed_3d (watershed.py:55-101)
+    pol.run(ColDist{d, b.mask2, b.g}, (i64)d.X * d.Z);
+    pol.run(RowDist{d, b.mask2, b.g, b.d2}, n);
+    pol.run(DistZ{d, b.mask2, b.d2, prm.z_xy_ratio, b.fa}, n);
+    gx.in = b.fa; gx.out = b.fb; pol.run(gx, n);
+    gy.in = b.fb; gy.out = b.fa; pol.run(gy, n);
+    gz.in = b.fa; gz.out = b.fb; pol.run(gz, n);                              // fb = dist_smooth
+    pol.fill_u64(b.minslot, 0x7ff0000000000000ull, d.Z + 1);
+    pol.run(MinReduce{d, b.fb, b.minslot, 0}, n);
+    pol.run(Max1D<0>{d, b.fb, b.fa, 3}, n);
+    pol.run(Max1D<1>{d, b.fa, b.fc, 3}, n);
+    pol.run(Max1D<2>{d, b.fc, b.fa, 3}, n);
+    pol.run(Peaks{d, b.fb, b.fa, b.minslot, 0, 0, b.peak}, n);
+    flood_stage(pol, d, b, b.mask2, b.fb, 0);
+
+    // ---- sizes, min_size / cell_num, remove_small_objects, relabel_sequential, centres
+    int* lsize = b.csize;                                                      // reuse: voxels per marker label (at its root)
+    pol.zero(lsize, (size_t)n * 4);
+    pol.zero(b.sc, sizeof(Scalars));
+    pol.run(LabelSize{b.lab, lsize, &b.sc->bg_count}, n);
+    pol.select_min_size(prm, b, lsize, n);
+    pol.run(KeepFlag{b.peak, b.mk, lsize, b.sc, b.flag}, n);
+    pol.exclusive_scan(b.flag, b.rank, n, &b.sc->n_cells);
+    pol.zero(b.sums, (size_t)prm.max_cells * 32);
+    pol.run(Relabel{d, b.lab, b.flag, b.rank, labels, b.sums, prm.max_cells}, n);
+    pol.run(Centres{b.sums, centres, b.sc, prm.max_cells}, prm.max_cells);
+}
+
+}  // namespace ws
