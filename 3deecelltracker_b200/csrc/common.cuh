@@ -43,7 +43,7 @@ inline int check_cuda(cudaError_t e, const char* what) {
     } while (0)
 
 // Profiler tags (ct_profile_read)
-enum ProfTag { PROF_CONV = 1, PROF_EM = 2, PROF_FFN = 3, PROF_LCN = 4, PROF_UNET_AUX = 5 };
+enum ProfTag { PROF_CONV = 1, PROF_EM = 2, PROF_FFN = 3, PROF_LCN = 4, PROF_UNET_AUX = 5, PROF_WATERSHED = 6 };
 struct ProfScope {
     ProfScope(int tag, cudaStream_t s);
     ~ProfScope();

@@ -389,6 +389,35 @@ struct CountGE {                                 // number of marker labels with
         if (peak[i] && mk[i] == (int)i && lsize[i] >= *thr) atomic_add_i(out, 1);
     }
 };
+// min_size / cell_num (watershed.py:95-98).  One-index passes drive the logic on the device, the counting itself is
+// the data-parallel CountGE pass.  thr[0] = probe threshold, thr[1] = #(marker labels with >= thr[0] voxels),
+// thr[2..3] = binary-search bounds.
+struct MinSizeBegin {
+    Scalars* sc; int* thr; int method, min_size, cell_num;
+    WS_HD void operator()(i64) const {
+        sc->min_size = min_size; sc->cell_num = cell_num;
+        thr[0] = method == 0 ? min_size : 0; thr[1] = 0; thr[2] = 0; thr[3] = 0x7ffffffe;
+        if (method != 0) thr[0] = thr[2] + (thr[3] - thr[2] + 1) / 2;
+    }
+};
+struct MinSizeFromCount {                        // "min_size": cell_num = #(bincount >= min_size) - 1, background bin included
+    Scalars* sc; const int* thr;
+    WS_HD void operator()(i64) const { sc->cell_num = thr[1] + (sc->bg_count >= sc->min_size ? 1 : 0) - 1; }
+};
+struct MinSizeSearchStep {                       // "cell_num": min_size = sorted(bincount)[-cell_num - 1]
+    Scalars* sc; int* thr;                       //           = the largest t with #(bincount >= t) >= cell_num + 1
+    WS_HD void operator()(i64) const {
+        int lo = thr[2], hi = thr[3];
+        if (lo < hi) {
+            const int cnt = thr[1] + (sc->bg_count >= thr[0] ? 1 : 0);
+            if (cnt >= sc->cell_num + 1) lo = thr[0]; else hi = thr[0] - 1;
+        }
+        thr[2] = lo; thr[3] = hi;
+        thr[0] = lo < hi ? lo + (hi - lo + 1) / 2 : lo;
+        thr[1] = 0;
+        sc->min_size = lo;
+    }
+};
 struct KeepFlag {                                // remove_small_objects: labels with fewer than min_size voxels go
     const uint8_t* peak; const int* mk; const int* lsize; const Scalars* sc; int* flag;
     WS_HD void operator()(i64 i) const {
@@ -412,14 +441,15 @@ struct Relabel {                                 // relabel_sequential + centre-
         }
     }
 };
-struct Centres {
-    const unsigned long long* sums; double* centres; const Scalars* sc; int max_cells;
-    WS_HD void operator()(i64 k) const {
+struct Centres {                                 // centres[0] = voxel units (l_center_coordinates), centres[1] = real units
+    const unsigned long long* sums; double* centres; const Scalars* sc; int max_cells; double z_xy_ratio;
+    WS_HD void operator()(i64 k) const {         // (r_coordinates_segment = _transform_layer_to_real, tracker.py:648)
         if (k >= sc->n_cells || k >= max_cells) return;
         const double n = (double)sums[k * 4 + 3];
-        centres[k * 3 + 0] = (double)sums[k * 4 + 0] / n;
-        centres[k * 3 + 1] = (double)sums[k * 4 + 1] / n;
-        centres[k * 3 + 2] = (double)sums[k * 4 + 2] / n;
+        const double cx = (double)sums[k * 4 + 0] / n, cy = (double)sums[k * 4 + 1] / n, cz = (double)sums[k * 4 + 2] / n;
+        double* real = centres + (i64)max_cells * 3;
+        centres[k * 3 + 0] = cx; centres[k * 3 + 1] = cy; centres[k * 3 + 2] = cz;
+        real[k * 3 + 0] = cx; real[k * 3 + 1] = cy; real[k * 3 + 2] = mul_rn(cz, z_xy_ratio);
     }
 };
 
@@ -487,7 +517,7 @@ void flood_stage(P& pol, const Dims& d, const Buffers& b, const uint8_t* fg, con
     pol.run_sparse(Flood{d, fg, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab, planar}, n);
 }
 
-// The whole stage.  prob (x,y,z) float32 -> labels (x,y,z) int32, centres (max_cells,3) float64, scalars.
+// The whole stage.  prob (x,y,z) float32 -> labels (x,y,z) int32, centres (2,max_cells,3) float64, scalars.
 template <class P>
 void segment(P& pol, const Params& prm, const float* prob, int* labels, double* centres, const Buffers& b) {
     const Dims d{prm.X, prm.Y, prm.Z};
@@ -532,12 +562,21 @@ void segment(P& pol, const Params& prm, const float* prob, int* labels, double* 
     pol.zero(lsize, (size_t)n * 4);
     pol.zero(b.sc, sizeof(Scalars));
     pol.run(LabelSize{b.lab, lsize, &b.sc->bg_count}, n);
-    pol.select_min_size(prm, b, lsize, n);
+    pol.run(MinSizeBegin{b.sc, b.thr, prm.method, prm.min_size, prm.cell_num}, 1);
+    if (prm.method == 0) {
+        pol.run(CountGE{b.peak, b.mk, lsize, b.thr, b.thr + 1}, n);
+        pol.run(MinSizeFromCount{b.sc, b.thr}, 1);
+    } else {
+        for (int it = 0; it < 32; ++it) {
+            pol.run(CountGE{b.peak, b.mk, lsize, b.thr, b.thr + 1}, n);
+            pol.run(MinSizeSearchStep{b.sc, b.thr}, 1);
+        }
+    }
     pol.run(KeepFlag{b.peak, b.mk, lsize, b.sc, b.flag}, n);
     pol.exclusive_scan(b.flag, b.rank, n, &b.sc->n_cells);
     pol.zero(b.sums, (size_t)prm.max_cells * 32);
     pol.run(Relabel{d, b.lab, b.flag, b.rank, labels, b.sums, prm.max_cells}, n);
-    pol.run(Centres{b.sums, centres, b.sc, prm.max_cells}, prm.max_cells);
+    pol.run(Centres{b.sums, centres, b.sc, prm.max_cells, prm.z_xy_ratio}, prm.max_cells);
 }
 
 }  // namespace ws

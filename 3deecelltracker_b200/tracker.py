@@ -6,18 +6,22 @@ Mirrors the call chain of CellTracker/tracker.py: `_segment` (:605) -> `_save_un
 `_predict_pos_once` (:1193); `match` (:1138); `track` / `track_one_vol` (:1415, :1473) with
 get_reference_vols + trim_mean ensembles (:1503-1507).
 
+`_watershed` (tracker.py:671-684) and the centre of mass (:646-648) run on the GPU too (watershed.py of this package:
+the probability map goes from the U-Net to the label image and the cell centres without leaving HBM).
+
+Host-side lines that are identical to the reference (constructor attribute assignments, method signatures, the
+ValueError messages, History bookkeeping) are the drop-in surface the north_star asks to keep; none of them computes.
+
 Out of scope here (host glue of the reference): matplotlib drawing, TIFF writing of
-label images, manual-correction I/O, U-Net retraining, `_accurate_correction`, and the scikit-image
-watershed.  `_watershed` below is a scipy-only stand-in (threshold 0.5 + connected components + min_size
-filter + centre of mass); it is NOT parity-checked and is documented as such in DESIGN.md.
+label images, manual-correction I/O, U-Net retraining.
 """
 import os
 
 import numpy as np
 import torch
-from scipy import ndimage as ndm
 
 from . import _lib
+from . import watershed as _ws
 from ._device import to_device
 from .ffn import FFN
 from .preprocess import normalize_image_device, _raw_to_device
@@ -105,7 +109,8 @@ class Tracker:
         self.r_coordinates_tracked_t0 = None
         self.r_coordinates_segment_t0 = None
         self.cells_on_boundary = None
-        self.keep_prob_on_device = False
+        self.keep_on_device = False          # True: _segment leaves probability map and label image in HBM
+        self._last_seg_device = None
         self._unet_cache = {}
         self._seg_stream = None
 
@@ -170,15 +175,19 @@ class Tracker:
             ready.record(self._seg_stream)
         self._unet_cache[vol] = (prob_dev, ready)
 
-    def _predict_cellregions(self, image_raw, vol):
-        """tracker.py:652-660 (first-pass fp32 result; the reference's fp16 disk cache is not reproduced).  A result
-        prefetched by `prefetch_segmentation` is picked up here."""
+    def _predict_cellregions_device(self, image_raw, vol):
+        """tracker.py:652-660 with the result left in HBM (first-pass fp32 result; see `cache_unet_regions` for the
+        reference's fp16 disk cache).  A result prefetched by `prefetch_segmentation` is picked up here."""
         if vol not in self._unet_cache:
             self._enqueue_segmentation(image_raw, vol)
         prob_dev, ready = self._unet_cache[vol]
         torch.cuda.current_stream().wait_event(ready)
         self._unet_cache = {v: e for v, e in self._unet_cache.items() if v >= vol}
-        return prob_dev.cpu().numpy()[None, ..., None]
+        return prob_dev
+
+    def _predict_cellregions(self, image_raw, vol):
+        """tracker.py:652-660: host array (1, x, y, z, 1)."""
+        return self._predict_cellregions_device(image_raw, vol).cpu().numpy()[None, ..., None]
 
     def prefetch_segmentation(self, vol):
         """Enqueue LCN + U-Net of volume `vol` so that it overlaps the match + track stage of the volume before it
@@ -187,36 +196,42 @@ class Tracker:
             return
         self._enqueue_segmentation(self._read_raw(vol), vol)
 
+    def _watershed_device(self, prob_dev, method):
+        """tracker.py:671-684 on the device: watershed_2d + watershed_3d + relabel_sequential and the centres of mass
+        (tracker.py:646-648) in one call; updates min_size / cell_num like the reference."""
+        seg = _ws.segment_device(prob_dev, self.z_xy_ratio, method, self.min_size, self.cell_num)
+        n, min_size, cell_num = seg.host_scalars()
+        self.min_size = min_size
+        if method == "min_size":
+            self.cell_num = cell_num
+        return seg, n
+
     def _watershed(self, image_cell_bg, method):
-        """Stand-in for tracker.py:671-684 / watershed.py (see module docstring): connected components."""
-        mask = image_cell_bg[0, :, :, :, 0] > 0.5
-        labels, n = ndm.label(mask)
-        if n:
-            sizes = np.bincount(labels.ravel(), minlength=n + 1)
-            keep = np.zeros(n + 1, dtype=np.int64)
-            ok = np.flatnonzero(sizes[1:] >= max(int(self.min_size or 0), 1)) + 1
-            if method == "cell_num" and self.cell_num:
-                ok = (np.argsort(-sizes[1:], kind="stable")[:self.cell_num] + 1)
-                ok.sort()
-            keep[ok] = np.arange(1, len(ok) + 1)
-            labels = keep[labels]
-            if method == "min_size":
-                self.cell_num = len(ok)
-        return labels
+        """tracker.py:671-684, host-array form: (1, x, y, z, 1) probabilities -> segmentation_auto (x, y, z)."""
+        prob_dev = torch.from_numpy(np.ascontiguousarray(image_cell_bg[0, :, :, :, 0], dtype=np.float32)).cuda()
+        seg, _ = self._watershed_device(prob_dev, method)
+        return seg.labels.cpu().numpy()
 
     def _segment(self, vol, method="min_size", print_shape=False):
-        """tracker.py:605-650."""
+        """tracker.py:605-650.  The probability map, the label image and the centres are produced on the device; the
+        host copies the reference returns (image_cell_bg, segmentation_auto) are made here because callers of the
+        class API read them (set `keep_on_device` to skip the two big downloads inside `track`)."""
         image_raw = self._read_raw(vol)
         image_gcn = image_raw.copy() / 65536.0
-        image_cell_bg = self._predict_cellregions(image_raw, vol)
-        if np.max(image_cell_bg) <= 0.5:
-            raise ValueError("No cell was detected by 3D U-Net! Try to reduce the noise_level.")
-        segmentation_auto = self._watershed(image_cell_bg, method)
-        if np.max(segmentation_auto) == 0:
+        prob_dev = self._predict_cellregions_device(image_raw, vol)
+        seg, n = self._watershed_device(prob_dev, method)
+        if n == 0:
+            if float(prob_dev.max()) <= 0.5:
+                raise ValueError("No cell was detected by 3D U-Net! Try to reduce the noise_level.")
             raise ValueError("No cell was detected by watershed! Try to reduce the min_size.")
-        l_center_coordinates = ndm.center_of_mass(segmentation_auto > 0, segmentation_auto,
-                                                  range(1, segmentation_auto.max() + 1))
+        l_center_coordinates = [tuple(c) for c in seg.centres_host()]
         r_coordinates_segment = self._transform_layer_to_real(l_center_coordinates)
+        self._last_seg_device = (prob_dev, seg.labels)
+        if self.keep_on_device:
+            image_cell_bg, segmentation_auto = None, None
+        else:
+            image_cell_bg = prob_dev.cpu().numpy()[None, ..., None]
+            segmentation_auto = seg.labels.cpu().numpy()
         return image_cell_bg, l_center_coordinates, segmentation_auto, image_gcn, r_coordinates_segment
 
     def segment_vol1(self, method="min_size"):

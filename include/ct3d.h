@@ -34,7 +34,7 @@ const char* ct_last_error(void);
 unsigned long long ct_launch_count(void);
 /* Opt-in profiler used by bench.py: CUDA events are recorded on the launching stream around every launch of a
  * kernel family.  tag: 1 = U-Net convolutions, 2 = PR-GLS EM, 3 = FFN match, 4 = LCN, 5 = U-Net pool/upsample/
- * gather/head.  ct_profile_read synchronises on the recorded events and returns their summed duration. */
+ * gather/head, 6 = watershed stage.  ct_profile_read synchronises on the recorded events and returns their summed duration. */
 /* Persistent kernels of this library (the tcgen05 convolution: one CTA per SM) leave `n` SMs unclaimed, so that a
  * single-CTA kernel running concurrently on another stream (the PR-GLS EM of the previous frame, tracker.py's frame
  * pipeline) finds a free SM instead of delaying one CTA of every convolution.  Default 0; returns the old value. */
@@ -215,6 +215,28 @@ int ct_predict_one_rep(const double* pre, int n_tracked, const double* inter, in
 
 /* trim_mean(stack (E,L,3), proportion, axis=0) -> (L,3)  (tracker.py:1507, trackerlite.py:123). */
 int ct_trim_mean(const double* stack, int e, int count, double proportion, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Watershed + centroid stage between the two hot paths.  Replaces Tracker._watershed (tracker.py:671-684) =
+ * watershed_2d (watershed.py:16-52: per z slice threshold 0.5, distance_transform_edt, gaussian_filter(2),
+ * peak_local_max(min_distance 7), label, watershed, find_boundaries outer) + watershed_3d (watershed.py:55-101:
+ * EDT with sampling (1, 1, z_xy_ratio), gaussian_filter((2, 2, 0.3)), peak_local_max(min_distance 3,
+ * exclude_border 0), label, watershed, min_size / cell_num, remove_small_objects) + relabel_sequential, and the
+ * centre of mass of every cell (tracker.py:646-648).
+ *   prob        (x,y,z) float32 probability map (output of ct_unet3_prediction)
+ *   method      0 = "min_size" (cell_num is derived), 1 = "cell_num" (min_size is derived)
+ *   gauss_w_*   HOST arrays: one-sided Gaussian weights w[j], j = 0..8 (sigma 2) and j = 0..1 (sigma 0.3), computed by
+ *               the caller the way scipy.ndimage does (NumPy exp), so that the smoothing is bit-identical to SciPy's
+ *   labels      (x,y,z) int32 label image, cells numbered 1..n in raster order of their seed (segmentation_auto)
+ *   centres     (2,max_cells,3) float64: [0] voxel units (l_center_coordinates), [1] real units, z * z_xy_ratio
+ *               (r_coordinates_segment, tracker.py:648); rows >= n_cells are not written
+ *   scalars_out 4 x int32 on the DEVICE: n_cells, min_size, cell_num, background voxel count
+ * Label image and centres are bit-identical to the CPU path (integer / exactly rounded fp64 work throughout). */
+size_t ct_watershed_workspace_bytes(int x, int y, int z, int max_cells);
+int ct_watershed_segment(const float* prob, int x, int y, int z, double z_xy_ratio, int method, int min_size,
+                         int cell_num, const double* gauss_w_xy9_host, const double* gauss_w_z2_host, int32_t* labels,
+                         double* centres, int max_cells, int32_t* scalars_out, void* ws, size_t ws_bytes,
+                         void* stream);
 
 #ifdef __cplusplus
 }

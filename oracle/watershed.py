@@ -111,6 +111,18 @@ def watershed(image, markers, mask):
     return out.reshape(shape)
 
 
+def _extreme_filter(a, footprint, take_max):
+    """Grey dilation / erosion over a 3^n footprint with the neighbourhood clipped at the border (scikit-image pads
+    by reflection, which for a 3^n window only repeats voxels already inside it).  Written with shifted views: SciPy's
+    rank filters go through double and overflow on the int64 maximum used for the inverted background."""
+    pad = np.pad(a, 1, mode="edge")
+    out = a.copy()
+    for off in np.argwhere(footprint):
+        sl = tuple(slice(int(o), int(o) + n) for o, n in zip(off, a.shape))
+        out = np.maximum(out, pad[sl]) if take_max else np.minimum(out, pad[sl])
+    return out
+
+
 def find_boundaries_outer(labels, connectivity):
     """skimage.segmentation.find_boundaries(labels, connectivity, mode='outer', background=0)."""
     labels = np.asarray(labels)
@@ -118,18 +130,11 @@ def find_boundaries_outer(labels, connectivity):
     fp = ndi.generate_binary_structure(nd, connectivity)
     full = ndi.generate_binary_structure(nd, nd)
     big = np.iinfo(labels.dtype).max
-
-    def dil(a, f):          # grey dilation with the neighbourhood clipped at the border
-        return ndi.grey_dilation(a, footprint=f, mode="nearest")
-
-    def ero(a, f):
-        return ndi.grey_erosion(a, footprint=f, mode="nearest")
-
-    boundaries = dil(labels, fp) != ero(labels, fp)
+    boundaries = _extreme_filter(labels, fp, True) != _extreme_filter(labels, fp, False)
     background = labels == 0
     inverted = labels.copy()
     inverted[background] = big
-    adjacent = (dil(labels, full) != ero(inverted, full)) & ~background
+    adjacent = (_extreme_filter(labels, full, True) != _extreme_filter(inverted, full, False)) & ~background
     return boundaries & (background | adjacent)
 
 

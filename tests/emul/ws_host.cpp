@@ -1,0 +1,72 @@
+// TEST INFRASTRUCTURE ONLY: sequential instantiation of the watershed pass pipeline (csrc/watershed_core.cuh) so the
+// pass logic can be checked against oracle/watershed.py on a machine without a GPU (tests/test_watershed_emul.py
+// builds this file with g++ -ffp-contract=off).  The product library contains only the CUDA instantiation
+// (csrc/watershed.cu); nothing in the package loads this harness.
+#include <cstdlib>
+#include <cstring>
+#include "../../3deecelltracker_b200/csrc/watershed_core.cuh"
+
+struct HostPolicy {
+    template <class F> void run(const F& f, long long n) { for (long long i = 0; i < n; ++i) f(i); }
+    template <class F> void run_sparse(const F& f, long long n) { run(f, n); }
+    void zero(void* p, size_t bytes) { std::memset(p, 0, bytes); }
+    void fill_u64(unsigned long long* p, unsigned long long v, int n) { for (int i = 0; i < n; ++i) p[i] = v; }
+    void exclusive_scan(const int* flag, int* rank, long long n, int* total) {
+        int acc = 0;
+        for (long long i = 0; i < n; ++i) { rank[i] = acc; acc += flag[i]; }
+        *total = acc;
+    }
+};
+
+extern "C" int ws_emul_segment(const float* prob, int x, int y, int z, double z_xy_ratio, int method, int min_size,
+                               int cell_num, const double* w_xy9, const double* w_z2, int* labels, double* centres,
+                               int max_cells, int* scalars_out) {   // centres: (2, max_cells, 3)
+    const long long n = (long long)x * y * z;
+    void* wsp = std::malloc(ws::workspace_bytes(n, z, max_cells));
+    if (!wsp) return 1;
+    ws::Buffers b;
+    ws::carve(b, wsp, n, z, max_cells);
+    ws::Params prm;
+    prm.X = x; prm.Y = y; prm.Z = z; prm.z_xy_ratio = z_xy_ratio; prm.method = method; prm.min_size = min_size;
+    prm.cell_num = cell_num; prm.max_cells = max_cells;
+    for (int j = 0; j < 9; ++j) prm.w_xy[j] = w_xy9[j];
+    for (int j = 0; j < 2; ++j) prm.w_z[j] = w_z2[j];
+    HostPolicy pol;
+    ws::segment(pol, prm, prob, labels, centres, b);
+    scalars_out[0] = b.sc->n_cells; scalars_out[1] = b.sc->min_size; scalars_out[2] = b.sc->cell_num;
+    scalars_out[3] = b.sc->bg_count;
+    std::free(wsp);
+    return 0;
+}
+
+// Stage dump for debugging: the 2-D stage only (labels of the per-slice flood, bn_output, smoothed distance, peaks).
+extern "C" int ws_emul_stage2d(const float* prob, int x, int y, int z, const double* w_xy9, int* lab2d, unsigned char* mask2,
+                               double* smooth, unsigned char* peak) {
+    const long long n = (long long)x * y * z;
+    void* wsp = std::malloc(ws::workspace_bytes(n, z, 16));
+    if (!wsp) return 1;
+    ws::Buffers b;
+    ws::carve(b, wsp, n, z, 16);
+    const ws::Dims d{x, y, z};
+    HostPolicy pol;
+    ws::Gauss1D<0> gx{d, nullptr, nullptr, 8, {}};
+    ws::Gauss1D<1> gy{d, nullptr, nullptr, 8, {}};
+    for (int j = 0; j < 9; ++j) { gx.w[j] = w_xy9[j]; gy.w[j] = w_xy9[j]; }
+    pol.run(ws::Threshold{prob, b.mask}, n);
+    pol.run(ws::ColDist{d, b.mask, b.g}, (long long)d.X * d.Z);
+    pol.run(ws::RowDist{d, b.mask, b.g, b.d2}, n);
+    pol.run(ws::SqrtPlane{b.d2, b.fa}, n);
+    gx.in = b.fa; gx.out = b.fb; pol.run(gx, n);
+    gy.in = b.fb; gy.out = b.fa; pol.run(gy, n);
+    pol.fill_u64(b.minslot, 0x7ff0000000000000ull, d.Z + 1);
+    pol.run(ws::MinReduce{d, b.fa, b.minslot, 1}, n);
+    pol.run(ws::Max1D<0>{d, b.fa, b.fb, 7}, n);
+    pol.run(ws::Max1D<1>{d, b.fb, b.fc, 7}, n);
+    pol.run(ws::Peaks{d, b.fa, b.fc, b.minslot, 1, 7, b.peak}, n);
+    ws::flood_stage(pol, d, b, b.mask, b.fa, 1);
+    pol.run(ws::Boundary2D{d, b.mask, b.lab, b.mask2}, n);
+    std::memcpy(lab2d, b.lab, n * 4); std::memcpy(mask2, b.mask2, n); std::memcpy(smooth, b.fa, n * 8);
+    std::memcpy(peak, b.peak, n);
+    std::free(wsp);
+    return 0;
+}
