@@ -53,7 +53,8 @@ __device__ unsigned long long g_tx_timers[16];
 #endif
 
 constexpr int TX_CONV_WARPS = 2;                // operand conversion (fp32 -> fp16 hi / lo' images, in place)
-// + 8 warps (two per tensor-memory lane quarter, half the channels each) for accumulator drain, x shift-add, epilogue
+// + 8 warps (two per tensor-memory lane quarter, half the channels each) for accumulator drain, x shift-add, epilogue;
+// Cout = 32: 16 drain warps (four per lane quarter, 8 channels each) and two accumulator sets of 192 columns
 
 template <int N, int BX, int STAGES>
 struct TxCfg {
@@ -63,16 +64,23 @@ struct TxCfg {
     static constexpr int N2 = N8 ? 6 * N : 3 * N;
     static constexpr int D2_COL = 3 * N;                               // first accumulator column of MMA2
     static constexpr int NPD = N8 ? 9 * N : 6 * N;                     // accumulator columns of one set
-    static constexpr int NSETS = 4;                                    // accumulator sets in flight
+    static constexpr int NSETS = (4 * NPD <= 512) ? 4 : 2;             // accumulator sets in flight
     static constexpr int SXH = BX + 2;
     static constexpr int PLANE = SXH * TX_PLANE_VOX * 16;              // bytes of one operand image of the block
     static constexpr int B_BYTES = TX_PAIRS * 2 * NPR * 16;
     static constexpr int STAGE = 2 * PLANE + B_BYTES;
     static constexpr int TMEM_COLS = NSETS * NPD <= 256 ? 256 : 512;
     static constexpr int SMEM = STAGES * STAGE + 1024;
-    static constexpr int DRAIN_WARPS = 8;                              // two per tensor-memory lane quarter
+    static constexpr int DRAIN_WARPS = (N == 32) ? 16 : 8;             // two / four per tensor-memory lane quarter
     static constexpr int THREADS = 64 + 32 * (TX_CONV_WARPS + DRAIN_WARPS);
-    static constexpr int CH = N / 2;                                   // output channels per drain thread
+    static constexpr int CH = N / (DRAIN_WARPS / 4);                   // output channels per drain thread
+    // Cout = 32: the three x-taps of a set are loaded one at a time (16 live registers instead of 48) so that
+    // acc[BX][CH] + loads fit the 96 registers a 640-thread CTA leaves per thread
+    static constexpr bool SPLIT_LD = (N == 32);
+    // ... and the drain warps take registers from the producer / MMA / converter warpgroup (setmaxnreg):
+    // 128 x 56 + 512 x 112 = 64512 <= 65536
+    static constexpr bool REBALANCE = (N == 32);
+    static constexpr bool POOL = (N == 16);                            // fused (2,2,1) max-pool epilogue (d0b only)
     static_assert(NSETS * NPD <= 512, "accumulators exceed tensor memory");
     static_assert(N1 % 16 == 0 && N1 <= 256 && N2 % 16 == 0, "UMMA N out of range for M = 128");
     static_assert(PLANE % 128 == 0 && B_BYTES % 128 == 0, "stage parts must stay 128-byte aligned");
@@ -162,7 +170,9 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-
+    if (warp < 2 + TX_CONV_WARPS) {
+    // warpgroup 0 (producer, MMA issuer, converters) gives registers to the drain warpgroups
+    if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ---------------- TMA producer
         if (elect_one()) {
@@ -222,7 +232,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #endif
         }
         __syncwarp();
-    } else if (warp < 2 + TX_CONV_WARPS) {
+    } else {
         // ---------------- converters: fp32 -> fp16 hi / lo' images of every landed stage, in place
         const int ct = threadIdx.x - 64;
         int g = 0;
@@ -262,8 +272,10 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #else
         (void)w_full; (void)t_begin;
 #endif
+    }
     } else {
         // ---------------- drain warps: tensor memory -> registers with the x shift-add, epilogue
+        if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
         const int part = (warp - 2 - TX_CONV_WARPS) >> 2;          // which CH channels this thread owns
         const int ch0 = part * CH;
@@ -310,7 +322,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         if (ok) amax = fmaxf(amax, fabsf(o[kk]));
                     }
                     if (ok) d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
-                    if (geo.pool_dst != nullptr) {                     // uniform over the CTA
+                    if (Cfg::POOL && geo.pool_dst != nullptr) {        // uniform over the CTA
                         if ((i & 1) == 0) {
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) keep[c4 * 4 + kk] = o[kk];
@@ -344,25 +356,43 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                     { TX_T0(); mbar_wait(&bar_acc_full[set], use_a & 1); TX_ACC(w_accf); }
                     tc_fence_after();
                     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * Cfg::NPD + (uint32_t)ch0;
-                    uint32_t v[3][TERMS][CH];
+                    if constexpr (Cfg::SPLIT_LD) {
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        if (j - dx < 0 || j - dx >= BX) continue;  // output plane j - dx is fed through x-tap dx
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int i = j - dx;
+                            if (i < 0 || i >= BX) continue;        // output plane j - dx is fed through x-tap dx
+                            uint32_t v[TERMS][CH];
 #pragma unroll
-                        for (int t = 0; t < TERMS; ++t) tmem_ld_issue<CH>(t0 + t * 3 * N + dx * N, v[dx][t]);
-                    }
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_acc_empty[set]);          // values are in registers: set is free
+                            for (int t = 0; t < TERMS; ++t) tmem_ld_issue<CH>(t0 + t * 3 * N + dx * N, v[t]);
+                            tmem_ld_wait();
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int i = j - dx;
-                        if (i < 0 || i >= BX) continue;
+                            for (int ch = 0; ch < CH; ++ch)
+                                acc[i][ch] += fmaf(__uint_as_float(v[1][ch]), W2, __uint_as_float(v[0][ch]));
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_acc_empty[set]);      // values are in registers: set is free
+                    } else {
+                        uint32_t v[3][TERMS][CH];
 #pragma unroll
-                        for (int ch = 0; ch < CH; ++ch) {
-                            const float hh = __uint_as_float(v[dx][0][ch]), hl = __uint_as_float(v[dx][1][ch]);
-                            acc[i][ch] += fmaf(hl, W2, hh);
+                        for (int dx = 0; dx < 3; ++dx) {
+                            if (j - dx < 0 || j - dx >= BX) continue;  // output plane j - dx is fed through x-tap dx
+#pragma unroll
+                            for (int t = 0; t < TERMS; ++t) tmem_ld_issue<CH>(t0 + t * 3 * N + dx * N, v[dx][t]);
+                        }
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_acc_empty[set]);      // values are in registers: set is free
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int i = j - dx;
+                            if (i < 0 || i >= BX) continue;
+#pragma unroll
+                            for (int ch = 0; ch < CH; ++ch) {
+                                const float hh = __uint_as_float(v[dx][0][ch]), hl = __uint_as_float(v[dx][1][ch]);
+                                acc[i][ch] += fmaf(hl, W2, hh);
+                            }
                         }
                     }
                     if (last && j >= 2) { TX_T0(); store_plane(j - 2); TX_ACC(t_epi); }
@@ -371,7 +401,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             amax = warp_max(amax);
             if (lane == 0) {
                 amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
-                if (geo.pool_dst != nullptr) amax_update(geo.amax_pool + (size_t)un.tile * geo.slab_stride, amax);
+                if (Cfg::POOL && geo.pool_dst != nullptr) amax_update(geo.amax_pool + (size_t)un.tile * geo.slab_stride, amax);
             }
         }
 #ifdef TX_TIMING
@@ -396,7 +426,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 static int tx_rows(int cout) { return 6 * cout; }
 
 size_t tcx_weight_floats(int cin_pad, int cout) {
-    if (cout != 8 && cout != 16) return 0;
+    if (cout != 8 && cout != 16 && cout != 32) return 0;
     return (size_t)((cin_pad + 7) / 8) * TX_PAIRS * 2 * tx_rows(cout) * 4;      // 16 bytes per row per K half
 }
 
@@ -478,14 +508,15 @@ int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
     if (pool && pool_fused && pool->kind == OP_POOL && pool->src_off == op.dst_off && pool->src_coff == op.dst_coff &&
         pool->c == L.cout && pool->dst_coff == 0 && pool->dst_c == L.cout && net->spec.pool_x == 2 && net->spec.pool_y == 2 &&
         net->spec.pool_z == 1 && X % 2 == 0 && Y % 2 == 0 && pool->dx == X / 2 && pool->dy == Y / 2 && pool->dz == Z &&
-        pool->dst_off % 4 == 0) {
+        pool->dst_off % 4 == 0 && L.cout == 16) {
         pool_dst = reinterpret_cast<float4*>(slab0 + pool->dst_off);
         am_p = slab0 + pool->dst_slot;
         *pool_fused = true;
     }
     int rc;
     if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
-    else rc = launch_tcx<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
+    else if (L.cout == 16) rc = launch_tcx<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
+    else rc = launch_tcx<32, 8, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
     if (rc) return 1;
     CT_LAUNCHED("conv3_tcx_kernel");
     return 0;

@@ -22,6 +22,7 @@ import collections
 import torch
 
 from . import _lib
+from . import watershed as _ws
 from .preprocess import normalize_image_device
 from .track import MODE_TRACK, EmProblem, predict_one_rep_device, run_em, trim_mean_device
 
@@ -42,6 +43,14 @@ class FramePipeline:
         self._pending = collections.deque()          # (stream, fit, tracked_prev or None)
         self._tracked = None                         # running tracked coordinates when the caller does not pass them
         self._count = 0
+        # raw-stack mode (step_raw): watershed results whose cell count is still on its way to the host, and the
+        # point set of the last volume whose count is known
+        self._segmented = collections.deque()        # (Segmentation, pinned scalars, event)
+        self._prev_points = None
+        self._first_points = None
+        self.collect_fits = False                    # True: joined fits are kept in `collected` instead of replayed
+        self.collected = []                          # (timelapse.py replays them on the rank that owns the state)
+        self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num = 1.0, "min_size", 0, 0
 
     # ---- the stages, each on the current stream
     def segment(self, raw_dev):
@@ -77,11 +86,23 @@ class FramePipeline:
         self.flush()
         self._tracked = tracked0_dev
 
+    def reset_raw(self):
+        """Raw-stack mode: forget every volume seen so far (the next `step_raw` volume is volume 1 again)."""
+        self.flush_raw()
+        self._prev_points = self._first_points = self._tracked = None
+        self.collected = []
+
     # ---- one pipelined step
     def _join_oldest(self):
         stream, fit, tracked_prev = self._pending.popleft()
         main = torch.cuda.current_stream()
         main.wait_stream(stream)
+        for inter, _, coef in fit:                   # allocated on the side stream, read by the replay on this one
+            inter.record_stream(main)
+            coef.record_stream(main)
+        if self.collect_fits:
+            self.collected.append(fit)
+            return None
         prev = tracked_prev if tracked_prev is not None else self._tracked
         if prev is None:
             raise ValueError("no tracked coordinates to replay onto: pass tracked_prev_dev or call reset(tracked0_dev)")
@@ -128,3 +149,86 @@ class FramePipeline:
         while self._pending:
             out.append(self._join_oldest())
         return out
+
+    # ---- raw-stack mode: segmentation -> watershed -> centres -> fit, the whole Tracker.track_one_vol chain
+    def configure_watershed(self, z_xy_ratio, method="min_size", min_size=0, cell_num=0):
+        """Parameters of Tracker._watershed (tracker.py:671-684) for `step_raw`."""
+        self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num = float(z_xy_ratio), method, min_size, cell_num
+
+    def segment_cells(self, raw_dev):
+        """tracker.py:605-650 on the device: LCN + U-Net + watershed + centres of mass; nothing leaves HBM except the
+        four scalars (cell count ...), which go to pinned memory asynchronously."""
+        prob = self.segment(raw_dev)
+        seg = _ws.segment_device(prob, self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num)
+        pinned = torch.empty(4, dtype=torch.int32).pin_memory()
+        pinned.copy_(seg.scalars, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return prob, seg, pinned, ev
+
+    def _resolve_segmented(self):
+        """Point sets (n,3) of the volumes whose cell count has arrived, oldest first.  Waiting here does not idle
+        the GPU: the caller has already enqueued the next volume's segmentation behind the one waited for."""
+        out = []
+        while self._segmented:
+            seg, pinned, ev = self._segmented.popleft()
+            ev.synchronize()
+            n = int(pinned[0])
+            if n > _ws.MAX_CELLS:
+                raise ValueError(f"watershed found {n} cells; at most {_ws.MAX_CELLS} are supported")
+            if n == 0:
+                raise ValueError("No cell was detected by watershed! Try to reduce the min_size.")   # tracker.py:643
+            out.append((seg.centres_real[:n], ev))
+        return out
+
+    def _submit_fits(self, point_sets):
+        for pts, ev in point_sets:
+            if self._prev_points is not None:
+                if self._streams is None:
+                    self._streams = [torch.cuda.Stream(priority=-1) for _ in range(self.depth)]
+                side = self._streams[self._count % self.depth] if self.overlap else torch.cuda.current_stream()
+                self._count += 1
+                # the fit depends on the two watershed results only (the older one precedes `ev` on the same stream),
+                # NOT on the segmentation of the next volume that is already enqueued behind them
+                side.wait_event(ev)
+                pts.record_stream(side)
+                self._prev_points.record_stream(side)
+                with torch.cuda.stream(side):
+                    fit = self.fit(self._prev_points, pts)
+                self._pending.append((side, fit, None))
+            else:
+                self._first_points = pts
+                if self._tracked is None:
+                    self._tracked = pts.clone()      # initiate_tracking: volume 1's centres are the tracked set
+            self._prev_points = pts
+
+    def step_raw(self, raw_dev):
+        """One volume of the whole chain on a RAW stack: joins + replays the oldest fit when `depth` are in flight,
+        enqueues LCN + U-Net + watershed of `raw_dev`, then -- while that runs -- takes the cell count of the volume
+        before and submits its fit (previous point set -> that volume's point set) to a side stream.
+        Returns (probability map, Segmentation, tracked coordinates or None while the pipeline fills)."""
+        lib = _lib.lib()
+        tracked = self._join_oldest() if len(self._pending) >= self.depth else None
+        old = lib.ct_set_reserved_sms(self.reserve_sms if self.overlap else 0)
+        try:
+            prob, seg, pinned, ev = self.segment_cells(raw_dev)
+            self._segmented.append((seg, pinned, ev))
+            if not self.overlap:
+                self._submit_fits(self._resolve_segmented())      # serial order: count now, fit now
+                while self._pending:
+                    tracked = self._join_oldest()
+            else:
+                ready = [self._segmented.popleft()] if len(self._segmented) > 1 else []
+                keep = list(self._segmented)
+                self._segmented = collections.deque(ready)
+                pts = self._resolve_segmented()
+                self._segmented = collections.deque(keep)
+                self._submit_fits(pts)
+        finally:
+            lib.ct_set_reserved_sms(old)
+        return prob, seg, tracked
+
+    def flush_raw(self):
+        """Resolve the last segmented volume, submit its fit and join everything; tracked coordinates, oldest first."""
+        self._submit_fits(self._resolve_segmented())
+        return self.flush()

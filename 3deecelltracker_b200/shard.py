@@ -1,9 +1,10 @@
 """Host-side sharding rules for N GPUs of one box (one process per GPU, torch.distributed for the plumbing).
 
 Two independent ways the path shards, neither needs a data-path collective:
-  * frames of a time-lapse go round-robin to ranks (config 4: 256 frames over 8 GPUs); segmentation of a frame is
-    independent of every other frame, and the per-frame point sets / tracked coordinates (a few KB) are gathered to
-    the rank that runs the sequential tracking tail (tracker.py:1179-1180 carries state frame to frame);
+  * frames of a time-lapse (config 4: 256 frames over 8 GPUs) go to ranks in contiguous blocks (`block_for_rank`, used
+    by timelapse.py) or round-robin (`frames_for_rank`); segmentation of a frame is independent of every other frame,
+    and the per-frame fitted transforms (a few KB) are gathered to the rank that runs the sequential tracking tail
+    (tracker.py:1179-1180 carries state frame to frame);
   * the tiles of ONE volume split into contiguous ranges of the (i, j, k) row-major tile grid of
     unet3_prediction (unet3d.py:246); `ct_unet3_prediction(tile_begin, tile_end)` writes only its tiles' centre
     windows, so the union over ranks is bit-identical to the single-GPU result.
@@ -17,6 +18,12 @@ def frames_for_rank(n_frames, rank, world, first=0):
     if not (0 <= rank < world):
         raise ValueError(f"rank {rank} outside world of {world}")
     return list(range(first + rank, first + n_frames, world))
+
+
+def block_for_rank(n_frames, rank, world):
+    """Contiguous [lo, hi) block of a time-lapse handled by `rank` (np.array_split boundaries): the streaming pipeline
+    of a rank needs consecutive volumes, so only one fit per rank straddles two blocks (timelapse.py)."""
+    return tile_range_for_rank(n_frames, rank, world)
 
 
 def tile_range_for_rank(n_tiles, rank, world):

@@ -151,6 +151,12 @@ def exchange_halo(owned, plan, rank, group=None):
     """owned: this rank's raw block (tensor shaped like plan.owned_box(rank), any device) -> the block
     plan.raw_box(rank) with the halo filled in from the other ranks (None when the rank runs no tiles; it still
     serves its neighbours).  One batch of point-to-point transfers (ncclSend/ncclRecv grouped on GPUs)."""
+    return finish_halo(*start_halo(owned, plan, rank, group))
+
+
+def start_halo(owned, plan, rank, group=None):
+    """Post the sends / receives of `exchange_halo` and return without waiting, so that the caller can enqueue
+    independent work (the global-median all-reduces run on a different NCCL communicator and stream) behind them."""
     own = plan.owned_box(rank)
     if tuple(owned.shape) != tuple(h - l for l, h in zip(*own)):
         raise ValueError(f"rank {rank} owns box {own}, got a block of shape {tuple(owned.shape)}")
@@ -171,9 +177,13 @@ def exchange_halo(owned, plan, rank, group=None):
             buf = torch.empty(tuple(h - l for l, h in zip(*box)), dtype=owned.dtype, device=owned.device)
             recvs.append((box, buf))
             ops.append(dist.P2POp(dist.irecv, _wire(buf), src, group=group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    return ext, need, recvs, reqs, keep
+
+
+def finish_halo(ext, need, recvs, reqs, keep):
+    for req in reqs:
+        req.wait()
     for box, buf in recvs:
         ext[_slices(box, need[0])] = buf
     return ext
@@ -203,20 +213,35 @@ def distributed_median(owned_dev, total_count, group=None):
     return med
 
 
-def segment_block(owned_dev, plan, rank, model, noise_level, group=None, median=None):
+def segment_block(owned_dev, plan, rank, model, noise_level, group=None, median=None, marks=None):
     """The rank's share of `_normalize_image` + `unet3_prediction` for one volume.
 
     owned_dev: the rank's raw block on its GPU.  Returns (prob_block, out_box): float32 probabilities of
-    plan.out_box(rank), or (None, None) for a rank without tiles."""
+    plan.out_box(rank), or (None, None) for a rank without tiles.  The halo sends / receives are posted first and the
+    lock-step radix select of the global median (histogram all-reduces) runs while they are in flight.
+    `marks`: optional list that receives (name, CUDA event) pairs recorded on the current stream between the phases."""
     from .preprocess import normalize_block_device
+
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
+    halo = start_halo(owned_dev, plan, rank, group)
     if median is None:
         median = distributed_median(owned_dev, math.prod(plan.shape), group)
-    ext = exchange_halo(owned_dev, plan, rank, group)
+    mark("median")
+    ext = finish_halo(*halo)
+    mark("halo")
     if ext is None:
         return None, None
     need, out = plan.raw_box(rank), plan.out_box(rank)
     norm = normalize_block_device(ext, noise_level, median)
     tlo, thi = plan.tile_box(rank)
+    mark("lcn")
     prob = model.prediction_block_device(norm, need[0], plan.shape, plan.shrink, tlo, thi, out[0],
                                          tuple(h - l for l, h in zip(*out)))
+    mark("unet")
     return prob, out

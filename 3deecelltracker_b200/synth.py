@@ -10,11 +10,16 @@ def blob_centres(shape_xyz, k, seed, margin=8):
     return rng.uniform(lo, hi, (k, 3))
 
 
-def blob_stack(shape_xyz, centres, seed, z_xy_ratio=1.0, sigma_xy=4.0):
-    """uint16 (x,y,z): background N(100,10^2) clipped at 0 + Gaussian blobs of amplitude U(300,3000)."""
+def blob_stack(shape_xyz, centres, seed, z_xy_ratio=1.0, sigma_xy=4.0, background=None):
+    """uint16 (x,y,z): background N(100,10^2) clipped at 0 + Gaussian blobs of amplitude U(300,3000).
+    `background`: a ready-made float32 noise field (time-lapses reuse one field instead of drawing 9 M normals per
+    volume); the blob amplitudes then come first from the generator, so they are the same for every volume."""
     rng = np.random.default_rng(seed)
     x, y, z = shape_xyz
-    img = rng.normal(100.0, 10.0, shape_xyz).astype(np.float32)
+    if background is None:
+        img = rng.normal(100.0, 10.0, shape_xyz).astype(np.float32)
+    else:
+        img = np.array(background, dtype=np.float32, copy=True)
     sigma_z = max(1.0, sigma_xy / z_xy_ratio)
     amp = rng.uniform(300, 3000, len(centres))
     rx, rz = int(3 * sigma_xy) + 1, int(3 * sigma_z) + 1

@@ -29,10 +29,26 @@ Explicit choices (where the scikit-image text leaves order to the implementation
     restricted to background voxels and to voxels whose full 3^n neighbourhood holds two different non-zero labels;
     neighbourhoods are clipped at the image border.
 """
+import ctypes
 import heapq
+import os
 
 import numpy as np
 from scipy import ndimage as ndi
+
+_FLOOD_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libws_flood.so")
+_flood_c = None
+
+
+def _load_flood():
+    """The C restatement of the flood (oracle/ws_flood.c, built by __graft_entry__.build()); None when not built."""
+    global _flood_c
+    if _flood_c is None and os.path.isfile(_FLOOD_SO):
+        lib = ctypes.CDLL(_FLOOD_SO)
+        lib.ws_flood.restype = ctypes.c_int
+        lib.ws_flood.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        _flood_c = lib
+    return _flood_c
 
 
 # --------------------------------------------------------------------------------------------------
@@ -78,8 +94,18 @@ def _neighbour_offsets(shape):
     return [(o[1], o[2], o[3]) for o in offs]
 
 
-def watershed(image, markers, mask):
-    """skimage.segmentation.watershed(image, markers, mask=mask) (connectivity 1).  Pure-Python priority flood."""
+def watershed(image, markers, mask, force_python=False):
+    """skimage.segmentation.watershed(image, markers, mask=mask) (connectivity 1): priority flood.  Runs the C
+    restatement (oracle/ws_flood.c, same order) when it has been built, else the pure-Python loop below."""
+    lib = None if force_python else _load_flood()
+    if lib is not None and np.asarray(image).ndim in (2, 3):
+        img = np.ascontiguousarray(image, dtype=np.float64)
+        msk = np.ascontiguousarray(mask, dtype=np.uint8)
+        out = np.ascontiguousarray(np.asarray(markers, dtype=np.int64) * (msk != 0))
+        shp = np.asarray(img.shape, dtype=np.int64)
+        rc = lib.ws_flood(img.ctypes.data, out.ctypes.data, msk.ctypes.data, img.ndim, shp.ctypes.data)
+        assert rc == 0
+        return out
     image = np.asarray(image, dtype=np.float64)
     shape = image.shape
     mask_f = np.asarray(mask, dtype=bool).ravel()
