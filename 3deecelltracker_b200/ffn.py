@@ -62,10 +62,10 @@ class FFN:
         np.savez(path, *self._weights)
 
     def load_weights(self, path):
-        """npz container written by save_weights (Keras .h5 needs h5py, absent in this image)."""
+        """`.npz` (save_weights / io_formats.convert_keras_h5) or a Keras `.h5` file (tracker.py:1121; needs h5py)."""
+        from .io_formats import load_weight_file
         try:
-            with np.load(path) as f:
-                self.set_weights([f[f"arr_{i}"] for i in range(len(f.files))])
+            self.set_weights(load_weight_file(path))
         except (OSError, KeyError) as e:
             raise ValueError(f"Failed to load the FFN model from {path}: {e}") from e
 

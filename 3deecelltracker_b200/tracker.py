@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import io_formats
 from . import watershed as _ws
 from ._device import to_device
 from .ffn import FFN
@@ -100,6 +101,12 @@ class Tracker:
         self.shrink = shrink
         self.miss_frame = [] if not miss_frame else miss_frame
         self.image_source = image_source
+        self.use_8_bit = True if cell_num <= 255 else False                      # tracker.py:881
+        # folder layout + float16 U-Net cache of the reference (tracker.py:652-669,734-752) when a folder is given
+        self.paths = io_formats.Paths(folder_path, image_name, unet_model_file, ffn_model_file)
+        self.cache_unet_regions = folder_path is not None
+        if folder_path is not None:
+            self.paths.make_folders(adjacent, ensemble)
         self.unet_model = None
         self.ffn_model = None
         self.vol = None
@@ -140,6 +147,9 @@ class Tracker:
             self.min_size, changed = min_size, True
         if changed or del_cache:
             self._unet_cache.clear()
+            if self.cache_unet_regions and self.paths.unet_cache:
+                for f in os.listdir(self.paths.unet_cache):                     # tracker.py:543-547
+                    os.remove(os.path.join(self.paths.unet_cache, f))
 
     def set_tracking(self, beta_tk, lambda_tk, maxiter_tk):
         """tracker.py:889-917."""
@@ -178,11 +188,18 @@ class Tracker:
     def _predict_cellregions_device(self, image_raw, vol):
         """tracker.py:652-660 with the result left in HBM (first-pass fp32 result; see `cache_unet_regions` for the
         reference's fp16 disk cache).  A result prefetched by `prefetch_segmentation` is picked up here."""
-        if vol not in self._unet_cache:
+        if vol not in self._unet_cache and self.cache_unet_regions:
+            cached = io_formats.load_unet_cache(self.paths.unet_cache, vol)     # float16 (1, x, y, z, 1), tracker.py:656
+            if cached is not None:
+                return to_device(np.ascontiguousarray(cached[0, :, :, :, 0]).astype(np.float32), torch.float32)
+        fresh = vol not in self._unet_cache
+        if fresh:
             self._enqueue_segmentation(image_raw, vol)
         prob_dev, ready = self._unet_cache[vol]
         torch.cuda.current_stream().wait_event(ready)
         self._unet_cache = {v: e for v, e in self._unet_cache.items() if v >= vol}
+        if self.cache_unet_regions:
+            io_formats.save_unet_cache(self.paths.unet_cache, vol, prob_dev.cpu().numpy()[None, ..., None])
         return prob_dev
 
     def _predict_cellregions(self, image_raw, vol):
@@ -374,7 +391,7 @@ class Tracker:
 
     def save_coordinates(self, path=None):
         """tracker.py:1538-1551: CSV of tracked coordinates (t, cell, x, y, z)."""
-        path = path or os.path.join(self.folder_path, "track_information", "tracked_coordinates.csv")
+        path = path or os.path.join(self.paths.track_information, "tracked_coordinates.csv")
         os.makedirs(os.path.dirname(path), exist_ok=True)
         coord = np.asarray(self.history.r_tracked_coordinates)
         t, cell = np.meshgrid(np.arange(1, coord.shape[0] + 1), np.arange(1, coord.shape[1] + 1), indexing="ij")

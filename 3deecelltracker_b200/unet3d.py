@@ -120,8 +120,10 @@ class UNet3:
         np.savez(path, *self._weights)
 
     def load_weights(self, path):
-        with np.load(path) as f:
-            self.set_weights([f[f"arr_{i}"] for i in range(len(f.files))])
+        """`.npz` (save_weights / io_formats.convert_keras_h5) or a Keras `.h5` model / weights file (tracker.py:579;
+        needs h5py)."""
+        from .io_formats import load_weight_file
+        self.set_weights(load_weight_file(path))
 
     def set_engine(self, engine):
         self._engine = engine

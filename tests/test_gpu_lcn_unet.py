@@ -236,6 +236,27 @@ def test_binarised_maps_identical_on_named_configs(mods, config):
         assert np.array_equal(got > 0.5, want > 0.5)
 
 
+def test_gpu_matches_keras_fixture(mods):
+    """The CUDA path against outputs of the reference's own Keras graphs (tests/golden/keras_fixture.npz, produced by
+    oracle/make_keras_fixture.py on a machine with TensorFlow).  Skips loudly while no fixture is committed."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "keras_fixture.npz")
+    if not os.path.isfile(path):
+        pytest.skip("tests/golden/keras_fixture.npz is absent (needs tensorflow==2.11 to generate): the Keras half of "
+                    "the parity chain is pinned only through the torch restatement")
+    pre, u, _ = mods
+    f = np.load(path)
+    for variant in ("a", "b", "c"):
+        model = u.UNet3(variant, weights=ounet.random_weights(variant, seed=7), tiles_per_batch=1)
+        np.testing.assert_allclose(model.predict(f[f"unet_{variant}__x"]), f[f"unet_{variant}__y"], rtol=3e-4, atol=1e-6)
+    model = u.UNet3("a", weights=ounet.random_weights("a", seed=7), tiles_per_batch=4)
+    np.testing.assert_allclose(u.unet3_prediction(f["prediction_a__img"], model, (24, 24, 2)), f["prediction_a__out"],
+                               rtol=3e-4, atol=1e-6)
+    np.testing.assert_allclose(pre._normalize_image(f["lcn__raw"], 20), f["lcn__normalize_image"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(pre.lcn_gpu(f["lcn__img"], 5), f["lcn__lcn_gpu"], rtol=1e-4, atol=1e-5)
+
+
 def test_unet_errors(mods):
     _, u, _ = mods
     model = u.UNet3("c", weights=ounet.random_weights("c", 0))

@@ -150,3 +150,36 @@ def test_unet_oracle_shapes_and_flops():
     # small smoke of the graph on a crop is impossible (fixed pools) -> run variant c at reduced size
     y = m.predict(x[:, :16, :16, :16])
     assert y.shape == (1, 16, 16, 16, 1) and np.all((y > 0) & (y < 1))
+
+
+# ---------------------------------------------------------------------------------------------- Keras fixture
+KERAS_FIXTURE = __import__("os").path.join(__import__("conftest").GOLDEN, "keras_fixture.npz")
+
+
+def _keras_fixture():
+    import os
+    if not os.path.isfile(KERAS_FIXTURE):
+        pytest.skip("tests/golden/keras_fixture.npz is absent: the Keras half of the oracle is PARITY UNPINNED until "
+                    "someone runs `python -m oracle.make_keras_fixture --reference <checkout>` on a machine with "
+                    "tensorflow==2.11 and commits the file")
+    return np.load(KERAS_FIXTURE)
+
+
+@pytest.mark.parametrize("variant", ["a", "b", "c"])
+def test_keras_fixture_unet_graphs(variant):
+    """The torch restatement of unet3_a/b/c (oracle/unet.py) against outputs of the reference's own Keras models."""
+    f = _keras_fixture()
+    model = ounet.UNetOracle(variant, ounet.random_weights(variant, seed=7))
+    got = model.predict(f[f"unet_{variant}__x"])
+    np.testing.assert_allclose(got, f[f"unet_{variant}__y"], rtol=2e-4, atol=1e-6)
+    if variant == "a":
+        out = ounet.unet3_prediction(f["prediction_a__img"], model, (24, 24, 2))
+        np.testing.assert_allclose(out, f["prediction_a__out"], rtol=2e-4, atol=1e-6)
+
+
+def test_keras_fixture_ffn_and_lcn():
+    f = _keras_fixture()
+    got = offn.FFNOracle(offn.random_weights(7)).predict(f["ffn__x"])
+    np.testing.assert_allclose(got, f["ffn__y"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ounet.normalize_image(f["lcn__raw"].copy(), 20), f["lcn__normalize_image"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(ounet.lcn(f["lcn__img"].astype(np.float64), 5), f["lcn__lcn_gpu"], rtol=1e-4, atol=1e-5)
