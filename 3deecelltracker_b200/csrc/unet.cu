@@ -253,9 +253,14 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
 
     // ---- pack weights on the host into one staging vector, then one device allocation
     std::vector<float> host;
-    struct Offs { size_t wd, wt, wx, b, sc, sh; };
+    struct Offs { size_t wd, wt, wx, b, sc, sh, wu, ws; int c_up; float inv_u, inv_s; };
     std::vector<Offs> offs;
     std::vector<float> inv_scales;
+    // decoder blocks that read concatenate([up, skip]): layer index -> channels of the up-sampled half
+    std::vector<int> c_up_of(convs.size(), 0);
+    if (sp->pool_x == 2 && sp->pool_y == 2 && sp->pool_z == 1)
+        for (int u = 0; u < sp->levels; ++u)
+            c_up_of[2 * sp->levels + 2 * (u + 1)] = sp->up[u][1];          // next up block's first conv, or the output conv
     const float* p = w;
     const float eps = 1e-3f;                    // keras BatchNormalization default epsilon
     for (auto& c : convs) {
@@ -275,6 +280,15 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         const size_t txn = tcx_weight_floats(cin_pad, cout);
         o.wx = take(txn);
         if (txn) tcx_pack_weights(p, cin, cin_pad, cout, &host[o.wx]);       // same scale as the classic image
+        o.c_up = 0; o.wu = o.ws = 0; o.inv_u = o.inv_s = 1.f;
+        const int cu = c_up_of[offs.size()];
+        if (cu > 0 && cu % 8 == 0 && (cin - cu) % 8 == 0 && tcu_weight_floats(cu, cout) && tcx_weight_floats(cin - cu, cout)) {
+            o.c_up = cu;
+            o.wu = take(tcu_weight_floats(cu, cout));
+            o.inv_u = tcu_pack_weights(p, cin, cu, cout, &host[o.wu]);
+            o.ws = take(tcx_weight_floats(cin - cu, cout));
+            o.inv_s = tcx_pack_weights_range(p, cin, cu, cin - cu, cout, &host[o.ws]);
+        }
         p += (size_t)27 * cin * cout;
         o.b = take(cout); o.sc = take(cout); o.sh = take(cout);
         const float *bias = p, *gamma = p + cout, *beta = p + 2 * cout, *mean = p + 3 * cout, *var = p + 4 * cout;
@@ -306,6 +320,10 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         L.w_tc = tc_weight_floats(L.cin_pad, L.cout) ? net->all_dev + offs[i].wt : nullptr;
         L.w_tcx = tcx_weight_floats(L.cin_pad, L.cout) ? net->all_dev + offs[i].wx : nullptr;
         L.w_tc_inv_scale = inv_scales[i];
+        L.c_up = offs[i].c_up;
+        L.w_tcu = offs[i].c_up ? net->all_dev + offs[i].wu : nullptr;
+        L.w_tcx_skip = offs[i].c_up ? net->all_dev + offs[i].ws : nullptr;
+        L.w_tcu_inv_scale = offs[i].inv_u; L.w_tcx_skip_inv_scale = offs[i].inv_s;
         L.bias = net->all_dev + offs[i].b; L.scale = net->all_dev + offs[i].sc; L.shift = net->all_dev + offs[i].sh;
         net->layers.push_back(L);
     }
@@ -467,6 +485,21 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s, 
                                                  net->spec.pool_x, net->spec.pool_y, net->spec.pool_z, op.src_slot, op.dst_slot);
                 CT_LAUNCHED("pool_kernel");
             } else {
+                // UpSampling3D + concatenate + conv block (unet3d.py:96-98) without the up-sampled tensor: the phase
+                // kernel convolves the low-resolution source into partial sums, the x-stacked kernel adds the skip half
+                const Op* nx = idx + 1 < net->ops.size() ? &net->ops[idx + 1] : nullptr;
+                if (nx && nx->kind == OP_CONV && nx->src_off == op.dst_off && (net->engine == 0 || net->engine == 2 || net->engine == 4) &&
+                    net->layers[nx->layer].c_up == op.c && op.dst_coff == 0 && op.dx == 2 * op.sx && op.dy == 2 * op.sy && op.dz == op.sz) {
+                    const int rc = launch_conv_tcu(net, net->layers[nx->layer], slab0, stride, tiles, op.src_off, op.src_slot,
+                                                   op.sx, op.sy, op.sz, nx->dst_off, nx->dst_coff, s);
+                    if (rc == 1) return 1;
+                    if (rc == 0) {
+                        const int rc2 = launch_conv_tcx_skip(net, *nx, slab0, stride, tiles, s);
+                        CT_REQUIRE(rc2 == 0, "unet: skip-half convolution of layer %d failed", nx->layer);
+                        ++idx;
+                        continue;
+                    }
+                }
                 dim3 grid((op.c / 4) * op.sx, tiles);
                 upsample_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.dst_coff / 4,
                                                      op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,

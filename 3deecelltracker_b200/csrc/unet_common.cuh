@@ -18,6 +18,14 @@ struct ConvLayer {
     float* w_tc;              // device: tcgen05 layout (see unet_tc.cu), may be null
     float* w_tcx;             // device: x-stacked tcgen05 layout (see unet_tcx.cu), may be null
     float w_tc_inv_scale;     // 1 / (power-of-two scale applied to the fp16 weight images)
+    // decoder blocks that read concatenate([UpSampling3D(x), skip]) (unet3d.py:96-97): c_up = channels of the up-sampled
+    // half; w_tcu = phase weights of that half on the low-resolution grid (unet_tcu.cu), w_tcx_skip = x-stacked image of
+    // the skip half alone.  c_up = 0 / null pointers for every other block.
+    int c_up;
+    float* w_tcu;
+    float w_tcu_inv_scale;
+    float* w_tcx_skip;
+    float w_tcx_skip_inv_scale;
     float* bias;              // device [cout]
     float* scale;             // device [cout]  gamma / sqrt(var + eps)
     float* shift;             // device [cout]  beta - mean * scale
@@ -81,6 +89,15 @@ int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
                     cudaStream_t s, const Op* pool = nullptr, bool* pool_fused = nullptr);
 size_t tcx_weight_floats(int cin_pad, int cout);
 float tcx_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
+// input channels [c_begin, c_begin + c_count) of the kernel only (the skip half of a decoder block)
+float tcx_pack_weights_range(const float* keras_kernel, int cin, int c_begin, int c_count, int cout, float* dst);
+// x-stacked block over the skip half of a concatenation, adding the partial sums the phase kernel left in dst
+int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s);
+// implemented in unet_tcu.cu: convolution over the up-sampled half, on the low-resolution grid
+size_t tcu_weight_floats(int c_up, int cout);
+float tcu_pack_weights(const float* keras_kernel, int cin, int c_up, int cout, float* dst);
+int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t slab_stride, int tiles, size_t up_off,
+                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s);
 size_t tc_weight_floats(int cin_pad, int cout);
 // returns 1 / scale
 float tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);

@@ -98,6 +98,9 @@ struct TxGeom {
     // optional fused MaxPooling3D((2,2,1)) of the output (unet3d.py:168): pooled copy written by the epilogue
     float4* pool_dst;                            // null = no pooling; c4-blocked [Cout/4][X/2][Y/2][Z][4] per tile
     float* amax_pool;                            // slab header slot of the pooled buffer
+    // 1: dst already holds partial pre-activation sums of this block (the up-sampled half of a decoder block's
+    // concatenated input, convolved on the low-resolution grid by unet_tcu.cu); the epilogue adds them in
+    int add_partial;
 };
 
 struct TxUnit { int x0, y0, z0, tile; };
@@ -313,10 +316,13 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                 for (int c4 = 0; c4 < CH / 4; ++c4) {
                     float o[4];
+                    float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (geo.add_partial && ok) part = d_tile[(size_t)c4 * vol + vox];       // uniform over the CTA
+                    const float pp[4] = {part.x, part.y, part.z, part.w};
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const int ch = ch0 + c4 * 4 + kk;
-                        float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch]);
+                        float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch] + pp[kk]);
                         t = t > 0.f ? t : alpha * t;
                         o[kk] = fmaf(t, ep_s[1][ch], ep_s[2][ch]);
                         if (ok) amax = fmaxf(amax, fabsf(o[kk]));
@@ -434,10 +440,19 @@ size_t tcx_weight_floats(int cin_pad, int cout) {
 // dx*cout + co (hi) | 3 cout + dx*cout + co (lo'); same power-of-two
 // scale as the classic packing (max|w| in [2^13, 2^14)).  Returns 1 / scale.
 float tcx_pack_weights(const float* w, int cin, int cin_pad, int cout, float* dst) {
+    (void)cin_pad;
+    return tcx_pack_weights_range(w, cin, 0, cin, cout, dst);
+}
+
+float tcx_pack_weights_range(const float* w, int cin_total, int c_begin, int cin, int cout, float* dst) {
+    const int cin_pad = (cin + 3) / 4 * 4;
     const int npr = tx_rows(cout), c8n = (cin_pad + 7) / 8;
     std::memset(dst, 0, tcx_weight_floats(cin_pad, cout) * sizeof(float));
     float wmax = 0.f;
-    for (size_t i = 0; i < (size_t)27 * cin * cout; ++i) wmax = std::fmax(wmax, std::fabs(w[i]));
+    for (int tap = 0; tap < 27; ++tap)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int co = 0; co < cout; ++co)
+                wmax = std::fmax(wmax, std::fabs(w[((size_t)tap * cin_total + c_begin + ci) * cout + co]));
     int e = 0;
     if (wmax > 0.f) std::frexp(wmax, &e);
     const float scale = std::ldexp(1.f, 14 - e);
@@ -454,7 +469,7 @@ float tcx_pack_weights(const float* w, int cin, int cin_pad, int cout, float* ds
                             const int ci = c * 8 + qd;
                             if (ci >= cin) continue;
                             const int tap = dx * 9 + t2;
-                            const float v = w[((size_t)tap * cin + ci) * cout + co] * scale;
+                            const float v = w[((size_t)tap * cin_total + c_begin + ci) * cout + co] * scale;
                             const __half h = __float2half_rn(v);
                             const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
                             blk[(size_t)(dx * cout + co) * 8 + qd] = h;
@@ -464,23 +479,25 @@ float tcx_pack_weights(const float* w, int cin, int cin_pad, int cout, float* ds
     return 1.f / scale;
 }
 
+struct TxSource { const float* w; float inv_scale; int cin8; int add_partial; };
+
 template <int N, int BX, int STAGES>
-static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, float alpha, float4* dst, int X, int Y, int Z,
+static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, const TxSource& src, float alpha, float4* dst, int X, int Y, int Z,
                       size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst,
                       float4* pool_dst, float* amax_pool, cudaStream_t s) {
     using Cfg = TxCfg<N, BX, STAGES>;
     // per device / context attribute: set on every launch (cheap) so several GPUs in one process are correct
     CT_CUDA(cudaFuncSetAttribute(conv3_tcx_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     TxGeom g;
-    g.cin8 = (L.cin_pad + 7) / 8; g.X = X; g.Y = Y; g.Z = Z;
-    g.amax_src = amax_src; g.amax_dst = amax_dst; g.slab_stride = stride4 * 4; g.w_inv_scale = L.w_tc_inv_scale;
+    g.cin8 = src.cin8; g.X = X; g.Y = Y; g.Z = Z;
+    g.amax_src = amax_src; g.amax_dst = amax_dst; g.slab_stride = stride4 * 4; g.w_inv_scale = src.inv_scale;
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
-    g.pool_dst = pool_dst; g.amax_pool = amax_pool;
+    g.pool_dst = pool_dst; g.amax_pool = amax_pool; g.add_partial = src.add_partial;
     const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
     const int grid = g.units < sms ? g.units : sms;
-    conv3_tcx_kernel<N, BX, STAGES><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, L.w_tcx, L.bias, L.scale, L.shift, alpha, dst, g);
+    conv3_tcx_kernel<N, BX, STAGES><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
 }
 
@@ -513,10 +530,38 @@ int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
         am_p = slab0 + pool->dst_slot;
         *pool_fused = true;
     }
+    const TxSource whole{L.w_tcx, L.w_tc_inv_scale, (L.cin_pad + 7) / 8, 0};
     int rc;
-    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
-    else if (L.cout == 16) rc = launch_tcx<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
-    else rc = launch_tcx<32, 8, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
+    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, whole, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
+    else if (L.cout == 16) rc = launch_tcx<16, 8, 3>(map, L, whole, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
+    else rc = launch_tcx<32, 8, 2>(map, L, whole, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
+    if (rc) return 1;
+    CT_LAUNCHED("conv3_tcx_kernel");
+    return 0;
+}
+
+// The skip half of a decoder block: input channels [c_up, cin) of the concatenation buffer, partial sums of the
+// up-sampled half (unet_tcu.cu) already in the destination.
+int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
+    const ConvLayer& L = net->layers[op.layer];
+    const int X = op.sx, Y = op.sy, Z = op.sz;
+    if (!L.w_tcx_skip || L.c_up <= 0 || Z % 8 != 0) return 2;
+    const int c_skip = L.cin - L.c_up;
+    CT_REQUIRE(c_skip % 8 == 0 && L.c_up % 4 == 0, "conv: skip half of layer %d has %d channels", op.layer, c_skip);
+    float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
+    CUtensorMap map;
+    ProfScope prof(PROF_CONV, s);
+    const size_t st4 = slab_stride / 4, vol = (size_t)X * Y * Z;
+    float* src = slab0 + op.src_off + (size_t)L.c_up * vol;           // c4-blocked: channel chunk c starts at c * vol * 4
+    if (tc_make_map(&map, src, X, Y, Z, c_skip / 4, tiles, slab_stride, 8)) return 1;
+    const TxSource skip{L.w_tcx_skip, L.w_tcx_skip_inv_scale, c_skip / 8, 1};
+    const float* am_s = slab0 + op.src_slot;
+    float* am_d = slab0 + op.dst_slot;
+    const int co4 = op.dst_coff / 4;
+    int rc;
+    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, skip, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, nullptr, nullptr, s);
+    else if (L.cout == 16) rc = launch_tcx<16, 8, 3>(map, L, skip, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, nullptr, nullptr, s);
+    else rc = launch_tcx<32, 8, 2>(map, L, skip, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, nullptr, nullptr, s);
     if (rc) return 1;
     CT_LAUNCHED("conv3_tcx_kernel");
     return 0;
