@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libct3d.so")
+LIB_PATH = os.environ.get("CT3D_LIB") or os.path.join(_HERE, "libct3d.so")     # CT3D_LIB: debug builds of the same library
 
 c_void_p, c_int, c_size_t, c_double, c_float, c_longlong = C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.c_float, C.c_longlong
 

@@ -54,10 +54,16 @@ struct TuCfg {
     static constexpr int STAGE = 2 * PLANE + B_BYTES;
     static constexpr int TMEM_COLS = NSETS * NPD <= 256 ? 256 : 512;
     static constexpr int SMEM = STAGES * STAGE + 1024;
-    static constexpr int DRAIN_WARPS = (N == 8) ? 8 : 16;
+    static constexpr int DRAIN_WARPS = 8;
     static constexpr int THREADS = 64 + 32 * (TU_CONV_WARPS + DRAIN_WARPS);
-    static constexpr int CH = N / (DRAIN_WARPS / 4);                   // 4 (Cout 8, 16) or 8 (Cout 32)
-    static constexpr bool REBALANCE = (DRAIN_WARPS == 16);             // setmaxnreg: 128 x 56 + 512 x 112 registers
+    static constexpr int CH = N / (DRAIN_WARPS / 4);                   // 4 / 8 / 16 output channels per drain thread
+    // acc[BX][2][2][CH] = 128 registers per drain thread in every configuration (BX = 8 / 4 / 2): the drain warps take
+    // registers from warps 0-3 (setmaxnreg inside the launch-time pool of 384 x 168: 128 x 56 + 256 x 224 = 64512)
+#ifdef CT_NO_REBALANCE
+    static constexpr bool REBALANCE = false;                           // debug build: no setmaxnreg (spills instead)
+#else
+    static constexpr bool REBALANCE = true;
+#endif
     static_assert(N1 % 16 == 0 && N1 <= 256 && N2 % 16 == 0, "UMMA N out of range for M = 128");
     static_assert(NSETS * NPD <= 512, "accumulators exceed tensor memory");
     static_assert(PLANE % 128 == 0 && B_BYTES % 128 == 0, "stage parts must stay 128-byte aligned");
@@ -88,6 +94,11 @@ __device__ __forceinline__ void tu_ld_issue(uint32_t taddr, uint32_t (&r)[CH]) {
     if constexpr (CH == 4) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr));
+    } else if constexpr (CH == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                      : "r"(taddr));
     } else {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -230,7 +241,7 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     }
     } else {
         // ---------------- drain warps: tensor memory -> registers (phase add), partial sums -> destination
-        if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int q = warp & 3;
         const int part = (warp - 2 - TU_CONV_WARPS) >> 2;
         const int ch0 = part * CH;
@@ -401,15 +412,15 @@ int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t 
     CT_REQUIRE(slab_stride % 4 == 0 && up_off % 4 == 0 && dst_off % 4 == 0, "conv: misaligned slab");
     CUtensorMap map;
     ProfScope prof(PROF_CONV, s);
-    if (tc_make_map(&map, slab0 + up_off, X, Y, Z, L.c_up / 4, tiles, slab_stride, 4)) return 1;
+    if (tc_make_map(&map, slab0 + up_off, X, Y, Z, L.c_up / 4, tiles, slab_stride, L.cout == 8 ? 8 : (L.cout == 16 ? 4 : 2))) return 1;
     float4* dst = reinterpret_cast<float4*>(slab0 + dst_off);
     const float* am = slab0 + up_slot;
     const size_t st4 = slab_stride / 4;
     const int cin8 = L.c_up / 8, co4 = dst_coff / 4;
     int rc;
-    if (L.cout == 8) rc = launch_tcu<8, 4, 3>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+    if (L.cout == 8) rc = launch_tcu<8, 8, 3>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
     else if (L.cout == 16) rc = launch_tcu<16, 4, 3>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
-    else rc = launch_tcu<32, 2, 2>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+    else rc = launch_tcu<32, 2, 3>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
     if (rc) return 1;
     CT_LAUNCHED("conv3_tcu_kernel");
     (void)net;

@@ -54,7 +54,7 @@ __device__ unsigned long long g_tx_timers[16];
 
 constexpr int TX_CONV_WARPS = 2;                // operand conversion (fp32 -> fp16 hi / lo' images, in place)
 // + 8 warps (two per tensor-memory lane quarter, half the channels each) for accumulator drain, x shift-add, epilogue;
-// Cout = 32: 16 drain warps (four per lane quarter, 8 channels each) and two accumulator sets of 192 columns
+// Cout = 32: two accumulator sets of 192 columns, and the drain warps take registers from warps 0-3 (setmaxnreg)
 
 template <int N, int BX, int STAGES>
 struct TxCfg {
@@ -71,15 +71,18 @@ struct TxCfg {
     static constexpr int STAGE = 2 * PLANE + B_BYTES;
     static constexpr int TMEM_COLS = NSETS * NPD <= 256 ? 256 : 512;
     static constexpr int SMEM = STAGES * STAGE + 1024;
-    static constexpr int DRAIN_WARPS = (N == 32) ? 16 : 8;             // two / four per tensor-memory lane quarter
+    static constexpr int DRAIN_WARPS = 8;                              // two per tensor-memory lane quarter
     static constexpr int THREADS = 64 + 32 * (TX_CONV_WARPS + DRAIN_WARPS);
     static constexpr int CH = N / (DRAIN_WARPS / 4);                   // output channels per drain thread
-    // Cout = 32: the three x-taps of a set are loaded one at a time (16 live registers instead of 48) so that
-    // acc[BX][CH] + loads fit the 96 registers a 640-thread CTA leaves per thread
+    // Cout = 32 (acc[8][16] = 128 registers per drain thread): the three x-taps of a set are loaded one at a time (32
+    // live registers instead of 96), and the drain warps take registers from the producer / MMA / converter warpgroup.
+    // setmaxnreg moves registers inside the CTA's launch-time pool (384 threads x 168): 128 x 56 + 256 x 224 = 64512.
     static constexpr bool SPLIT_LD = (N == 32);
-    // ... and the drain warps take registers from the producer / MMA / converter warpgroup (setmaxnreg):
-    // 128 x 56 + 512 x 112 = 64512 <= 65536
+#ifdef CT_NO_REBALANCE
+    static constexpr bool REBALANCE = false;                           // debug build: no setmaxnreg (spills instead)
+#else
     static constexpr bool REBALANCE = (N == 32);
+#endif
     static constexpr bool POOL = (N == 16);                            // fused (2,2,1) max-pool epilogue (d0b only)
     static_assert(NSETS * NPD <= 512, "accumulators exceed tensor memory");
     static_assert(N1 % 16 == 0 && N1 <= 256 && N2 % 16 == 0, "UMMA N out of range for M = 128");
@@ -119,6 +122,11 @@ __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[CH])
     if constexpr (CH == 4) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr));
+    } else if constexpr (CH == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                      : "r"(taddr));
     } else {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -278,7 +286,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     }
     } else {
         // ---------------- drain warps: tensor memory -> registers with the x shift-add, epilogue
-        if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
         const int part = (warp - 2 - TX_CONV_WARPS) >> 2;          // which CH channels this thread owns
         const int ch0 = part * CH;

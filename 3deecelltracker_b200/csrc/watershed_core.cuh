@@ -61,6 +61,13 @@ WS_HD void atomic_min_u64(unsigned long long* p, unsigned long long v) {
     if (v < *p) *p = v;
 #endif
 }
+WS_HD void atomic_max_u64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
 WS_HD double mul_rn(double a, double b) {
 #ifdef __CUDA_ARCH__
     return __dmul_rn(a, b);
@@ -308,7 +315,7 @@ struct SeedMarkers {                             // markers = label(local_maxi) 
         if (mask[i] && peak[i]) {
             const int r = comp[i];
             const int slot = atomic_add_i(hcnt + r, 1);
-            HeapE e; e.v = -img[i]; e.age = 0; e.idx = (int)i;
+            HeapE e; e.v = -img[i]; e.age = 0; e.idx = (int)i;      // the stage floods -dist_smooth (watershed.py:44,94)
             heap[hoff[r] + slot] = e;
             lab[i] = mk[i] + 1;                  // label id = 1 + first voxel of the marker's plateau
         } else {
@@ -316,9 +323,23 @@ struct SeedMarkers {                             // markers = label(local_maxi) 
         }
     }
 };
-struct Flood {                                   // skimage.segmentation.watershed(-img, markers, mask), connectivity 1
+struct SeedLabels {                              // markers given as a label image (recalculate_cell_boundaries,
+    const uint8_t* mask; const int* markers; const int* comp; const double* img;   // watershed.py:111-151): floods +img
+    const int* hoff; int* hcnt; HeapE* heap; int* lab;
+    WS_HD void operator()(i64 i) const {
+        const int m = mask[i] ? markers[i] : 0;
+        if (m != 0) {
+            const int r = comp[i];
+            const int slot = atomic_add_i(hcnt + r, 1);
+            HeapE e; e.v = img[i]; e.age = 0; e.idx = (int)i;
+            heap[hoff[r] + slot] = e;
+        }
+        lab[i] = m;
+    }
+};
+struct Flood {                                   // skimage.segmentation.watershed(sign * img, markers, mask), connectivity 1
     Dims d; const uint8_t* mask; const int* comp; const double* img; const int* hoff; const int* hcnt;
-    HeapE* heap; int* lab; int planar;
+    HeapE* heap; int* lab; int planar; double sign;
     WS_HD void operator()(i64 i) const {
         if (!mask[i] || comp[i] != (int)i) return;
         int n = hcnt[i];
@@ -342,7 +363,7 @@ struct Flood {                                   // skimage.segmentation.watersh
                 if (!mask[j] || lab[j] != 0) continue;
                 ++age;
                 lab[j] = l;
-                HeapE e; e.v = -img[j]; e.age = age; e.idx = (int)j;
+                HeapE e; e.v = sign * img[j]; e.age = age; e.idx = (int)j;
                 h[n] = e;
                 heap_up(h, n);
                 ++n;
@@ -514,7 +535,22 @@ void flood_stage(P& pol, const Dims& d, const Buffers& b, const uint8_t* fg, con
     pol.run(CompSize{fg, b.comp, b.csize}, n);
     pol.run(HeapAlloc{fg, b.comp, b.csize, b.hoff, b.hcnt, &b.sc->heap_counter}, n);
     pol.run(SeedMarkers{fg, b.peak, b.mk, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab}, n);
-    pol.run_sparse(Flood{d, fg, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab, planar}, n);
+    pol.run_sparse(Flood{d, fg, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab, planar, -1.0}, n);
+}
+
+// watershed(img, markers, mask) per z slice with a given marker label image (recalculate_cell_boundaries).
+template <class P>
+void flood_from_labels(P& pol, const Dims& d, const Buffers& b, const uint8_t* fg, const int* markers, const double* img) {
+    const i64 n = d.n();
+    pol.run(UfInit{fg, b.comp}, n);
+    pol.run(UfLink{d, fg, b.comp, 0, 1}, n);
+    pol.run(UfFlatten{fg, b.comp}, n);
+    pol.zero(b.csize, (size_t)n * 4);
+    pol.zero(&b.sc->heap_counter, 4);
+    pol.run(CompSize{fg, b.comp, b.csize}, n);
+    pol.run(HeapAlloc{fg, b.comp, b.csize, b.hoff, b.hcnt, &b.sc->heap_counter}, n);
+    pol.run(SeedLabels{fg, markers, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab}, n);
+    pol.run_sparse(Flood{d, fg, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab, 1, 1.0}, n);
 }
 
 // The whole stage.  prob (x,y,z) float32 -> labels (x,y,z) int32, centres (2,max_cells,3) float64, scalars.
