@@ -86,6 +86,17 @@ SIGNATURES = {
     "ct_predict_one_rep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "ct_trim_mean": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "ct_watershed_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "ct_label_components_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ct_label_components": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ct_correction_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "ct_accurate_correction": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_double] + [c_void_p] * 5 + [c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ct_tracked_labels_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "ct_tracked_labels": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ct_recalculate_cell_boundaries_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ct_recalculate_cell_boundaries": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ct_watershed_segment": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

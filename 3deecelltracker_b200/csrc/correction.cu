@@ -147,3 +147,23 @@ extern "C" int ct_tracked_labels(const int16_t* vox4, const int32_t* start, cons
     ct::g_launches.fetch_add(pol.launches, std::memory_order_relaxed);
     return 0;
 }
+
+extern "C" size_t ct_recalculate_cell_boundaries_workspace_bytes(int x, int y, int z) {
+    return ws::workspace_bytes((long long)x * y * z, z, 1) + 256;
+}
+
+extern "C" int ct_recalculate_cell_boundaries(int32_t* segmentation, const int32_t* overlaps, int x, int y, int z,
+                                              int32_t* labels_out, void* wsp, size_t ws_bytes, void* stream) {
+    CT_REQUIRE(segmentation && overlaps && labels_out && wsp, "ct_recalculate_cell_boundaries: null argument");
+    CT_REQUIRE(x >= 1 && y >= 1 && z >= 1 && (long long)x * y * z < 0x7fffffffLL, "ct_recalculate_cell_boundaries: bad shape");
+    CT_REQUIRE(ws_bytes >= ct_recalculate_cell_boundaries_workspace_bytes(x, y, z), "ct_recalculate_cell_boundaries: workspace too small");
+    const ws::Dims d{x, y, z};
+    ws::Buffers wb;
+    ws::carve(wb, wsp, d.n(), z, 1);
+    ct::CorrPolicy pol;
+    pol.s = (cudaStream_t)stream;
+    corr::recalculate_cell_boundaries(pol, d, segmentation, overlaps, nullptr, labels_out, wb);
+    CT_REQUIRE(!pol.err, "ct_recalculate_cell_boundaries: a launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ct::g_launches.fetch_add(pol.launches, std::memory_order_relaxed);
+    return 0;
+}

@@ -178,16 +178,30 @@ struct CountCoverAlways {
     }
 };
 struct MarkersAndMasks {
-    const int* cover; const int* on_boundary; int* label; uint8_t* mask_image; uint8_t* overlap;
+    const int* cover; const int* on_boundary; int* label; uint8_t* mask_image; uint8_t* overlap;   // on_boundary may be null
     WS_HD void operator()(i64 i) const {
         int l = label[i];
         const bool ov = cover[i] > 1;
-        if (ov || (l > 0 && on_boundary[l - 1])) l = 0;                    // tracker.py:1395-1397
+        if (ov || (l > 0 && on_boundary && on_boundary[l - 1])) l = 0;     // tracker.py:1395-1397
         label[i] = l;
         overlap[i] = ov ? 1 : 0;
         mask_image[i] = (l > 0 || ov) ? 1 : 0;                             // watershed.py:137
     }
 };
+
+// watershed.py:111-151 for every z slice at once.  label: segmentation (modified: overlaps / boundary cells zeroed),
+// cover: cell_overlaps_mask (> 1 = overlap).  out = watershed(EDT of the overlaps, markers = label, mask = label > 0 | overlap).
+template <class P>
+void recalculate_cell_boundaries(P& pol, const ws::Dims& d, int* label, const int* cover, const int* on_boundary, int* out,
+                                 const ws::Buffers& b) {
+    const i64 n = d.n();
+    pol.run(MarkersAndMasks{cover, on_boundary, label, b.mask, b.mask2}, n);          // mask = mask_image, mask2 = overlap
+    pol.run(ws::ColDist{d, b.mask2, b.g}, (i64)d.X * d.Z);                            // distance_transform_edt(overlap, (1, 1))
+    pol.run(ws::RowDist{d, b.mask2, b.g, b.d2}, n);
+    pol.run(ws::SqrtPlane{b.d2, b.fa}, n);
+    ws::flood_from_labels(pol, d, b, b.mask, label, b.fa);
+    pol.copy_i32(out, b.lab, n);
+}
 
 template <class P>
 void accurate_correction(P& pol, const Cells& c, const ws::Dims& d, const float* prob, const void* raw, int raw_dtype,
@@ -217,13 +231,7 @@ void motion_to_image(P& pol, const Cells& c, const ws::Dims& d, const int* i_dis
     pol.zero(label, (size_t)n * 4);
     pol.run(CountCoverAlways{c, d, i_disp, cell_of, cover}, c.n_vox);
     pol.run(StampLabel{c, d, i_disp, cell_of, label}, c.n_vox);
-    pol.run(MarkersAndMasks{cover, on_boundary, label, b.mask, b.mask2}, n);          // mask = mask_image, mask2 = overlap
-    // distance_map = distance_transform_edt(overlap, sampling = (1, 1)) per slice (watershed.py:144)
-    pol.run(ws::ColDist{d, b.mask2, b.g}, (i64)d.X * d.Z);
-    pol.run(ws::RowDist{d, b.mask2, b.g, b.d2}, n);
-    pol.run(ws::SqrtPlane{b.d2, b.fa}, n);
-    ws::flood_from_labels(pol, d, b, b.mask, label, b.fa);
-    pol.copy_i32(tracked_labels, b.lab, n);
+    recalculate_cell_boundaries(pol, d, label, cover, on_boundary, tracked_labels, b);
 }
 
 }  // namespace corr

@@ -172,3 +172,23 @@ extern "C" int ct_watershed_segment(const float* prob, int x, int y, int z, doub
     ct::g_launches.fetch_add(pol.launches, std::memory_order_relaxed);
     return 0;
 }
+
+extern "C" size_t ct_label_components_workspace_bytes(int x, int y, int z) { return ct_watershed_workspace_bytes(x, y, z, 1); }
+
+extern "C" int ct_label_components(const int32_t* image, int x, int y, int z, int32_t* labels, int32_t* n_out, void* wsp,
+                                   size_t ws_bytes, void* stream) {
+    CT_REQUIRE(image && labels && n_out && wsp, "ct_label_components: null argument");
+    CT_REQUIRE(x >= 1 && y >= 1 && z >= 1 && (long long)x * y * z < 0x7fffffffLL, "ct_label_components: bad shape");
+    CT_REQUIRE(ws_bytes >= ct_label_components_workspace_bytes(x, y, z), "ct_label_components: workspace too small");
+    const long long n = (long long)x * y * z;
+    ws::Buffers b;
+    ws::carve(b, wsp, n, z, 1);
+    ct::CudaPolicy pol;
+    pol.s = (cudaStream_t)stream;
+    pol.tile_sum = reinterpret_cast<int*>(reinterpret_cast<char*>(b.thr) + 256);
+    ws::label_equal_values(pol, ws::Dims{x, y, z}, image, labels, b, &b.sc->n_cells);
+    CT_REQUIRE(!pol.err, "ct_label_components: a launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CT_CUDA(cudaMemcpyAsync(n_out, &b.sc->n_cells, 4, cudaMemcpyDeviceToDevice, pol.s));
+    ct::g_launches.fetch_add(pol.launches, std::memory_order_relaxed);
+    return 0;
+}

@@ -264,6 +264,39 @@ struct UfLink {
                 }
     }
 };
+// components of EQUAL non-zero value, full connectivity: skimage.measure.label(label image, connectivity = ndim)
+struct UfInitValue {
+    const int* val; int* L;
+    WS_HD void operator()(i64 i) const { L[i] = val[i] != 0 ? (int)i : -1; }
+};
+struct UfLinkEqual {
+    Dims d; const int* val; int* L;
+    WS_HD void operator()(i64 i) const {
+        const int v = val[i];
+        if (v == 0) return;
+        int x, y, z; d.split(i, x, y, z);
+        for (int dx = -1; dx <= 0; ++dx)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dz = -1; dz <= 1; ++dz) {
+                    if (dx == 0 && (dy > 0 || (dy == 0 && dz >= 0))) continue;
+                    const int xx = x + dx, yy = y + dy, zz = z + dz;
+                    if (xx < 0 || yy < 0 || yy >= d.Y || zz < 0 || zz >= d.Z) continue;
+                    const i64 j = ((i64)xx * d.Y + yy) * d.Z + zz;
+                    if (val[j] == v) uf_union(L, (int)i, (int)j);
+                }
+    }
+};
+struct UfFlattenValue {
+    const int* val; int* L; int* rootflag;
+    WS_HD void operator()(i64 i) const {
+        if (val[i] != 0) { const int r = uf_find(L, (int)i); L[i] = r; rootflag[i] = (r == (int)i) ? 1 : 0; }
+        else rootflag[i] = 0;
+    }
+};
+struct RankToLabel {                             // component -> 1 + number of components that start earlier in raster order
+    const int* val; const int* L; const int* rank; int* out;
+    WS_HD void operator()(i64 i) const { out[i] = val[i] != 0 ? rank[L[i]] + 1 : 0; }
+};
 struct UfFlatten {
     const uint8_t* on; int* L;
     WS_HD void operator()(i64 i) const { if (on[i]) L[i] = uf_find(L, (int)i); }
@@ -551,6 +584,17 @@ void flood_from_labels(P& pol, const Dims& d, const Buffers& b, const uint8_t* f
     pol.run(HeapAlloc{fg, b.comp, b.csize, b.hoff, b.hcnt, &b.sc->heap_counter}, n);
     pol.run(SeedLabels{fg, markers, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab}, n);
     pol.run_sparse(Flood{d, fg, b.comp, img, b.hoff, b.hcnt, b.heap, b.lab, 1, 1.0}, n);
+}
+
+// skimage.measure.label(int image, connectivity = 3): out = component ids 1..n in raster order of their first voxel
+template <class P>
+void label_equal_values(P& pol, const Dims& d, const int* val, int* out, const Buffers& b, int* n_out) {
+    const i64 n = d.n();
+    pol.run(UfInitValue{val, b.comp}, n);
+    pol.run(UfLinkEqual{d, val, b.comp}, n);
+    pol.run(UfFlattenValue{val, b.comp, b.flag}, n);
+    pol.exclusive_scan(b.flag, b.rank, n, n_out);
+    pol.run(RankToLabel{val, b.comp, b.rank, out}, n);
 }
 
 // The whole stage.  prob (x,y,z) float32 -> labels (x,y,z) int32, centres (2,max_cells,3) float64, scalars.

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import correction as _corr
 from . import io_formats
 from . import watershed as _ws
 from ._device import to_device
@@ -118,6 +119,12 @@ class Tracker:
         self.cells_on_boundary = None
         self.keep_on_device = False          # True: _segment leaves probability map and label image in HBM
         self._last_seg_device = None
+        # accurate correction (tracker.py:1044-1110): state prepared by interpolate_seg + cal_subregions
+        self.segmentation_manual_relabels = None
+        self.seg_cells_interpolated_corrected = None
+        self.Z_RANGE_INTERP = None
+        self.region_cells = None
+        self.tracked_labels = None
         self._unet_cache = {}
         self._seg_stream = None
 
@@ -234,6 +241,7 @@ class Tracker:
         host copies the reference returns (image_cell_bg, segmentation_auto) are made here because callers of the
         class API read them (set `keep_on_device` to skip the two big downloads inside `track`)."""
         image_raw = self._read_raw(vol)
+        self._last_raw = image_raw
         image_gcn = image_raw.copy() / 65536.0
         prob_dev = self._predict_cellregions_device(image_raw, vol)
         seg, n = self._watershed_device(prob_dev, method)
@@ -269,6 +277,78 @@ class Tracker:
         self.history.r_displacements.append(np.zeros((self.cell_num_t0, 3)))
         self.history.r_segmented_coordinates.append(self.r_coordinates_segment_t0)
         self.history.r_tracked_coordinates.append(self.r_coordinates_tracked_t0)
+
+    # ------------------------------------------------------------------ accurate correction (volume-1 preparation)
+    def load_manual_seg(self, segmentation=None):
+        """tracker.py:934-950: the proof-read segmentation of volume 1, from `manual_vol1/*.tif` or given directly
+        (e.g. `segresult.segmentation_auto` when no manual correction is made); relabelled sequentially."""
+        if segmentation is None:
+            files = sorted(f for f in os.listdir(self.paths.manual_segmentation_vol1) if f.lower().endswith((".tif", ".tiff")))
+            from PIL import Image
+            segmentation = np.array([np.array(Image.open(os.path.join(self.paths.manual_segmentation_vol1, f)))
+                                     for f in files]).transpose((1, 2, 0))
+        seg = np.asarray(segmentation)
+        uniq = np.unique(seg)
+        uniq = uniq[uniq != 0]
+        fw = np.zeros(int(seg.max()) + 1, dtype=np.int64)
+        fw[uniq] = np.arange(1, len(uniq) + 1)
+        self.segmentation_manual_relabels = fw[seg]
+        if self.segmentation_manual_relabels.max() > 255:
+            self.use_8_bit = False
+
+    def _interpolate(self):
+        """tracker.py:1083-1091."""
+        seg_interp, seg_cover = _corr.interpolate_labels(self.segmentation_manual_relabels, z_scaling=self.z_scaling,
+                                                         smooth_sigma=2.5)
+        corrected = _corr.recalculate_cell_boundaries(seg_interp, seg_cover)
+        return corrected[5:self.x_siz + 5, 5:self.y_siz + 5, 5:self.z_siz * self.z_scaling + 5]
+
+    def interpolate_seg(self):
+        """tracker.py:1044-1071: interpolate / smooth the cells of volume 1 along z, re-draw their boundaries, split
+        regions that fell apart, and take the cell centres as the tracked set."""
+        self.seg_cells_interpolated_corrected = self._interpolate()
+        self.Z_RANGE_INTERP = range(self.z_scaling // 2, self.seg_cells_interpolated_corrected.shape[2], self.z_scaling)
+        num_cells = np.size(np.unique(self.seg_cells_interpolated_corrected)) - 1
+        relabelled, found = _corr.label_components(self.seg_cells_interpolated_corrected)
+        if num_cells != found:
+            print(f"WARNING: {num_cells} cells were manually labeled while the program found {found} separated cells "
+                  f"and corrected it")
+        self.seg_cells_interpolated_corrected = relabelled.astype(np.int64)
+        self.segmentation_manual_relabels = self.seg_cells_interpolated_corrected[:, :, self.Z_RANGE_INTERP]
+        if self.folder_path is not None:
+            io_formats.save_img3ts(range(0, self.z_siz), self.segmentation_manual_relabels,
+                                   self.paths.track_results + "track_results_t%06i_z%04i.tif", t=1, use_8_bit=self.use_8_bit)
+        seg = _ws.segment_centres(self.segmentation_manual_relabels)
+        self.r_coordinates_tracked_t0 = self._transform_layer_to_real(seg)
+        self.cell_num_t0 = self.r_coordinates_tracked_t0.shape[0]
+
+    def cal_subregions(self):
+        """tracker.py:1093-1110: per-cell voxel lists for the quick accurate correction (device resident)."""
+        self.region_cells = _corr.CellRegions(self.seg_cells_interpolated_corrected, self.z_scaling)
+        self.region_xyz_min, self.region_width = self.region_cells.region_xyz_min, self.region_cells.region_width
+        self.pad_x, self.pad_y, self.pad_z = (int(v) for v in self.region_cells.pad)
+
+    def _transform_real_to_interpolated(self, r_disp):
+        new_disp = np.array(r_disp, dtype=np.float64).copy()                  # tracker.py:563-565
+        new_disp[:, 2] = new_disp[:, 2] * (self.z_scaling / self.z_xy_ratio)
+        return np.rint(new_disp).astype(int)
+
+    def _accurate_correction(self, cells_on_boundary_local, r_coor_predicted):
+        """tracker.py:1177-1191 (the whole repetition loop is one device call).  Needs `_segment` of the target volume
+        (probability map + raw stack on the device) and `cal_subregions`."""
+        prob_dev, _ = self._last_seg_device
+        raw_dev = _raw_to_device(self._last_raw)
+        r_disp, i_disp, _ = _corr.accurate_correction_device(
+            self.region_cells, prob_dev, raw_dev, self.z_xy_ratio, self.r_coordinates_tracked_t0,
+            self.history.r_displacements[-1], self.history.r_tracked_coordinates[-1], r_coor_predicted,
+            cells_on_boundary_local, REP_NUM_CORRECTION)
+        return r_disp.cpu().numpy(), i_disp.cpu().numpy().astype(int)
+
+    def _transform_motion_to_image(self, cells_on_boundary_local, i_disp_from_vol1_updated):
+        """tracker.py:1391-1399."""
+        lab = _corr.tracked_labels_device(self.region_cells, i_disp_from_vol1_updated, cells_on_boundary_local,
+                                          (self.x_siz, self.y_siz, self.z_siz))
+        return lab.cpu().numpy().astype(np.int64)
 
     # ------------------------------------------------------------------ FFN + PR-GLS
     def _fit_predict_batch(self, source_vols):
@@ -357,8 +437,18 @@ class Tracker:
         r_coor_predicted_mean = trim_mean_device(stack, 0.1).cpu().numpy()
         cells_bd = self._get_cells_onBoundary(r_coor_predicted_mean, self.ensemble)
         self.cells_on_boundary[cells_bd] = 1
-        r_disp_from_vol1_updated = self.history.r_displacements[-1] + \
-            (r_coor_predicted_mean - self.history.r_tracked_coordinates[-1])
+        if self.region_cells is not None:
+            # accurate correction + tracked label image (tracker.py:1512-1522), on the device
+            r_disp_from_vol1_updated, i_disp_from_vol1_updated = \
+                self._accurate_correction(self.cells_on_boundary, r_coor_predicted_mean)
+            self.tracked_labels = self._transform_motion_to_image(self.cells_on_boundary, i_disp_from_vol1_updated)
+            if self.folder_path is not None:
+                io_formats.save_img3ts(range(0, self.z_siz), self.tracked_labels,
+                                       self.paths.track_results + "track_results_t%06i_z%04i.tif", target_volume, self.use_8_bit)
+        else:
+            # without interpolate_seg + cal_subregions the positions stay those of FFN + PR-GLS
+            r_disp_from_vol1_updated = self.history.r_displacements[-1] + \
+                (r_coor_predicted_mean - self.history.r_tracked_coordinates[-1])
         if self.ensemble:
             self.cells_on_boundary = np.zeros(self.cell_num_t0).astype(int)
         self.history.r_displacements.append(r_disp_from_vol1_updated)

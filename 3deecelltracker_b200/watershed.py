@@ -82,3 +82,11 @@ def segment(image_cell_bg_xyz, z_xy_ratio, method="min_size", min_size=0, cell_n
     seg = segment_device(prob, z_xy_ratio, method, min_size, cell_num)
     n, min_size, cell_num = seg.host_scalars()
     return seg.labels.cpu().numpy(), seg.centres_host(), min_size, cell_num
+
+
+def segment_centres(labels_xyz):
+    """ndimage.center_of_mass(labels > 0, labels, range(1, max + 1)) (tracker.py:1063-1065) for a host label image."""
+    from scipy import ndimage as ndi
+    lab = np.asarray(labels_xyz)
+    n = int(lab.max())
+    return np.asarray(ndi.center_of_mass(lab > 0, lab, range(1, n + 1)), dtype=np.float64).reshape(n, 3)

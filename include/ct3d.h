@@ -238,6 +238,54 @@ int ct_watershed_segment(const float* prob, int x, int y, int z, double z_xy_rat
                          double* centres, int max_cells, int32_t* scalars_out, void* ws, size_t ws_bytes,
                          void* stream);
 
+/* skimage.measure.label(label image, connectivity = 3) as used by Tracker._relabel_separated_cells
+ * (tracker.py:1073-1081): connected components of EQUAL non-zero value, full connectivity, numbered 1..n in raster
+ * order of their first voxel.  n_out: 1 x int32 on the device. */
+size_t ct_label_components_workspace_bytes(int x, int y, int z);
+int ct_label_components(const int32_t* image, int x, int y, int z, int32_t* labels, int32_t* n_out, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Accurate correction of the tracked positions.  Replaces Tracker._accurate_correction (tracker.py:1177-1191) =
+ * up to max_rep (REP_NUM_CORRECTION = 20) x [_correction_once_interp (:1310-1350): labels of volume 1 moved by the
+ * integer displacements (_transform_cells_quick :1352-1389), overlaps and boundary cells removed, centre of mass of
+ * (probability + raw / 65536) per cell on the planes that exist in the raw stack, displacement update] with the stop
+ * rule of _evaluate_correction (:1401-1413).  All repetitions are enqueued at once; a device flag turns the ones after
+ * convergence into no-ops, the host never waits inside the loop.
+ *   Cells of volume 1 on the interpolated grid (cal_subregions, tracker.py:1093-1110; get_subregions, track.py:501-533):
+ *   vox4 (n_vox,4) int16 = x, y, z, 0 of every labelled voxel, grouped by cell; start (L+1) offsets; region_min /
+ *   region_width (L,3); pad_host = per-axis maximum of region_width (HOST); xi, yi, zi = interpolated volume extents
+ *   (= x, y, z * z_scaling).
+ *   prob (x,y,z) float32; raw (x,y,z) of raw_dtype (0 = uint16, 1 = float32, 2 = uint8);
+ *   r_tracked_t0, r_disp_prev (history.r_displacements[-1]), r_tracked_prev (history.r_tracked_coordinates[-1]),
+ *   r_pred (FFN + PR-GLS prediction): (L,3) float64; on_boundary (L) int32.
+ *   outputs: r_disp_out (L,3) float64, i_disp_out (L,3) int32, reps_out 2 x int32 (repetitions run, converged flag).
+ * ---------------------------------------------------------------------------------------------- */
+size_t ct_correction_workspace_bytes(int x, int y, int z, int n_cells, int n_vox);
+int ct_accurate_correction(const int16_t* vox4, const int32_t* start, const int32_t* region_min,
+                           const int32_t* region_width, int n_cells, int n_vox, const int32_t* pad_host,
+                           int xi, int yi, int zi, int z_scaling, const float* prob, const void* raw,
+                           int raw_dtype, int x, int y, int z, double z_xy_ratio, const double* r_tracked_t0,
+                           const double* r_disp_prev, const double* r_tracked_prev, const double* r_pred,
+                           const int32_t* on_boundary, int max_rep, double* r_disp_out, int32_t* i_disp_out,
+                           int32_t* reps_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Tracked label image of a volume.  Replaces Tracker._transform_motion_to_image (tracker.py:1391-1399): the cells of
+ * volume 1 stamped at i_disp on the planes of the raw stack, overlaps and boundary cells removed, then
+ * recalculate_cell_boundaries (watershed.py:111-151: per z slice, watershed of the distance transform of the overlap
+ * region seeded by the remaining labels).  labels_out (x,y,z) int32. */
+size_t ct_tracked_labels_workspace_bytes(int x, int y, int z, int n_cells, int n_vox);
+int ct_tracked_labels(const int16_t* vox4, const int32_t* start, const int32_t* region_min,
+                      const int32_t* region_width, int n_cells, int n_vox, const int32_t* pad_host, int xi, int yi,
+                      int zi, int z_scaling, const int32_t* i_disp, const int32_t* on_boundary, int x, int y, int z,
+                      int32_t* labels_out, void* ws, size_t ws_bytes, void* stream);
+
+/* recalculate_cell_boundaries (watershed.py:111-151) on given images: segmentation (x,y,z) int32 (MODIFIED: voxels
+ * where overlaps > 1 are zeroed, as the reference does through its view), overlaps (x,y,z) int32. */
+size_t ct_recalculate_cell_boundaries_workspace_bytes(int x, int y, int z);
+int ct_recalculate_cell_boundaries(int32_t* segmentation, const int32_t* overlaps, int x, int y, int z,
+                                   int32_t* labels_out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

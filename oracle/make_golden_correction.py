@@ -116,6 +116,7 @@ def main():
     for tag, (ratio, zs) in {"zs1": (3.0, 1), "zs3": (3.0, 3)}.items():
         seg, centres = synthetic_case(rng)
         s = make_self(ns, seg, ratio, zs)
+        interp_raw, interp_cover = ns["gaussian_filter"](seg, z_scaling=zs, smooth_sigma=2.5)
         s.interpolate_seg()
         s.cal_subregions()
         L = s.cell_num_t0
@@ -147,7 +148,7 @@ def main():
         r_disp, i_disp = s._accurate_correction(on_boundary, r_pred.copy())
         one = s._correction_once_interp(s._transform_real_to_interpolated(r_pred - s.r_coordinates_tracked_t0), on_boundary)
         labels = s._transform_motion_to_image(on_boundary, i_disp)
-        d = dict(seg_vol1=seg, z_xy_ratio=float(ratio), z_scaling=int(zs), seg_interp=s.seg_cells_interpolated_corrected,
+        d = dict(seg_vol1=seg, interp_raw=interp_raw, interp_cover=interp_cover, z_xy_ratio=float(ratio), z_scaling=int(zs), seg_interp=s.seg_cells_interpolated_corrected,
                  relabels=s.segmentation_manual_relabels, r_tracked_t0=s.r_coordinates_tracked_t0, prob=prob, raw=raw,
                  r_pred=r_pred, on_boundary=on_boundary, r_disp=r_disp, i_disp=i_disp, once_r_disp=one[0],
                  once_i_disp=one[1], once_corr=one[2], tracked_labels=labels,
