@@ -270,6 +270,116 @@ __global__ void __launch_bounds__(256) box_x_norm(const T* __restrict__ raw, con
     }
 }
 
+// ---- the reference's window (27 x 27 x 1, preprocess.py:185): radius known at compile time.  Each thread first loads
+// the LCN_R + 2 R inputs its LCN_R outputs share (independent loads: the memory system sees them all at once, the generic
+// kernels above issue one dependent load per loop trip), then every output sums ITS OWN window from the registers in
+// ascending order.  Out-of-range inputs are 0, and x + 0 is exact, so the results are bit-identical to the generic kernels.
+template <typename T, int R>
+__global__ void __launch_bounds__(256) box_y_v_r(const T* __restrict__ raw, const double* __restrict__ med_p,
+                                                 float* __restrict__ t1, int X, int Y, int Z) {
+    const int groups = (Y + LCN_R - 1) / LCN_R;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= groups * Z) return;
+    const int z = f % Z, yb = (f / Z) * LCN_R;
+    const long long plane = (long long)Y * Z;
+    const T* base = raw + (long long)blockIdx.y * plane + z;
+    float* out = t1 + (long long)blockIdx.y * plane + z;
+    const double med = *med_p;
+    float w[LCN_R + 2 * R];
+#pragma unroll
+    for (int j = 0; j < LCN_R + 2 * R; ++j) {
+        const int yy = yb - R + j;
+        w[j] = (yy >= 0 && yy < Y) ? clamped(base, (long long)yy * Z, med) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j <= 2 * R; ++j) acc += w[k + j];
+        if (yb + k < Y) out[(long long)(yb + k) * Z] = acc;
+    }
+}
+template <int R>
+__global__ void __launch_bounds__(256) box_x_avg_r(const float* __restrict__ t1, float* __restrict__ avg,
+                                                   int X, int Y, int Z, float volume) {
+    const long long plane = (long long)Y * Z;
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= plane) return;
+    const int xb = blockIdx.y * LCN_R;
+    float w[LCN_R + 2 * R];
+#pragma unroll
+    for (int j = 0; j < LCN_R + 2 * R; ++j) {
+        const int xx = xb - R + j;
+        w[j] = (xx >= 0 && xx < X) ? t1[(long long)xx * plane + f] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= 2 * R; ++j) acc += (double)w[k + j];
+        if (xb + k < X) avg[(long long)(xb + k) * plane + f] = (float)acc / volume;
+    }
+}
+template <typename T, int R>
+__global__ void __launch_bounds__(256) box_y_sq_r(const T* __restrict__ raw, const double* __restrict__ med_p,
+                                                  const float* __restrict__ avg, float* __restrict__ t2,
+                                                  int X, int Y, int Z) {
+    const int groups = (Y + LCN_R - 1) / LCN_R;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= groups * Z) return;
+    const int z = f % Z, yb = (f / Z) * LCN_R;
+    const long long plane = (long long)Y * Z;
+    const long long off = (long long)blockIdx.y * plane + z;
+    const double med = *med_p;
+    float w[LCN_R + 2 * R];
+#pragma unroll
+    for (int j = 0; j < LCN_R + 2 * R; ++j) {
+        const int yy = yb - R + j;
+        float sq = 0.f;
+        if (yy >= 0 && yy < Y) {
+            const long long i = off + (long long)yy * Z;
+            const double d = (double)clamped(raw, i, med) - (double)avg[i];
+            sq = (float)(d * d);
+        }
+        w[j] = sq;
+    }
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= 2 * R; ++j) acc += (double)w[k + j];
+        if (yb + k < Y) t2[off + (long long)(yb + k) * Z] = (float)acc;
+    }
+}
+template <typename T, int R>
+__global__ void __launch_bounds__(256) box_x_norm_r(const T* __restrict__ raw, const double* __restrict__ med_p,
+                                                    const float* __restrict__ avg, const float* __restrict__ t2,
+                                                    float* __restrict__ out, int X, int Y, int Z, float volume, float noise) {
+    const long long plane = (long long)Y * Z;
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= plane) return;
+    const int xb = blockIdx.y * LCN_R;
+    float w[LCN_R + 2 * R];
+#pragma unroll
+    for (int j = 0; j < LCN_R + 2 * R; ++j) {
+        const int xx = xb - R + j;
+        w[j] = (xx >= 0 && xx < X) ? t2[(long long)xx * plane + f] : 0.f;
+    }
+    const double med = *med_p;
+#pragma unroll
+    for (int k = 0; k < LCN_R; ++k) {
+        if (xb + k >= X) break;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= 2 * R; ++j) acc += (double)w[k + j];
+        const long long i = (long long)(xb + k) * plane + f;
+        const float sd = sqrtf((float)acc / volume);
+        const float den = sd + noise;
+        const double d = (double)clamped(raw, i, med) - (double)avg[i];
+        out[i] = (float)(d / (double)den);
+    }
+}
+
 __global__ void set_nan(double* p) { *p = __longlong_as_double(0x7ff8000000000000LL); }
 
 template <typename T>
@@ -297,6 +407,17 @@ static int normalize_impl(const T* raw, float* out, int X, int Y, int Z, float n
     dim3 grid_y((unsigned)(((long long)ygroups * Z + 255) / 256), X);       // y filters: thread = (y group, z), per x
     dim3 grid_x((unsigned)((plane + 255) / 256), xgroups);                  // x filters: thread = (y, z), per x group
     const float volume = (float)(fx * fy);
+    if (fx == 27 && fy == 27) {
+        box_y_v_r<T, 13><<<grid_y, 256, 0, s>>>(raw, med, t1, X, Y, Z);
+        CT_LAUNCHED("box_y_v");
+        box_x_avg_r<13><<<grid_x, 256, 0, s>>>(t1, avg, X, Y, Z, volume);
+        CT_LAUNCHED("box_x_avg");
+        box_y_sq_r<T, 13><<<grid_y, 256, 0, s>>>(raw, med, avg, t2, X, Y, Z);
+        CT_LAUNCHED("box_y_sq");
+        box_x_norm_r<T, 13><<<grid_x, 256, 0, s>>>(raw, med, avg, t2, out, X, Y, Z, volume, noise);
+        CT_LAUNCHED("box_x_norm");
+        return 0;
+    }
     box_y_v<T><<<grid_y, 256, 0, s>>>(raw, med, t1, X, Y, Z, fy / 2);
     CT_LAUNCHED("box_y_v");
     box_x_avg<<<grid_x, 256, 0, s>>>(t1, avg, X, Y, Z, fx / 2, volume);

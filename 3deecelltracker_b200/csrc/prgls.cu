@@ -744,10 +744,20 @@ static void bind(DevProblem& d, char* base, const Layout& o) {
 
 }  // namespace ct
 
+namespace ct {
+// prgls_grid.cu: the same EM spread over the whole GPU, for point sets too large for one CTA
+size_t grid_em_workspace_bytes(int N, int M, int L);
+int grid_em_run(const CtPrglsParams& prm, const CtPrglsProblem& q, void* ws, size_t ws_bytes, double** prior_slot, bool run,
+                cudaStream_t s, unsigned long long* launches);
+constexpr int EM_GRID_MIN_N = 1024;              // problems with at least this many reference points take the grid path
+}  // namespace ct
+
 using namespace ct;
 
 extern "C" size_t ct_prgls_workspace_bytes(int n_ref, int n_tgt, int n_tracked) {
-    return layout_for(n_ref, n_tgt, n_tracked).total + align_up(sizeof(DevProblem), 256) + 256;
+    size_t need = layout_for(n_ref, n_tgt, n_tracked).total + align_up(sizeof(DevProblem), 256) + 256;
+    if (n_ref >= EM_GRID_MIN_N) need += grid_em_workspace_bytes(n_ref, n_tgt, n_tracked) + 256;
+    return need;
 }
 
 extern "C" size_t ct_greedy_workspace_bytes(int n_ref, int n_tgt) { return ct_prgls_workspace_bytes(n_ref, n_tgt, 0); }
@@ -762,6 +772,50 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
     if (batch == 0) return 0;
     CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_prgls: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
+    // large problems: one at a time on the whole GPU (prgls_grid.cu); the rest as one batched launch, one CTA each
+    {
+        std::vector<CtPrglsProblem> small;
+        size_t used = 0;
+        bool any_large = false;
+        for (int b = 0; b < batch; ++b) any_large = any_large || problems[b].n_ref >= EM_GRID_MIN_N;
+        if (any_large) {
+            for (int b = 0; b < batch; ++b) {
+                const CtPrglsProblem& p = problems[b];
+                char* wsb = static_cast<char*>(ws) + used;
+                const size_t avail = ws_bytes - used;
+                if (p.n_ref < EM_GRID_MIN_N) {
+                    const size_t need = ct_prgls_workspace_bytes(p.n_ref, p.n_tgt, p.n_tracked);
+                    CT_REQUIRE(need <= avail, "ct_prgls: workspace too small");
+                    if (ct_prgls(prm, &p, 1, wsb, need, stream)) return 1;
+                    used += align_up(need, 256);
+                    continue;
+                }
+                CT_REQUIRE(p.n_ref >= 2 && p.n_tgt >= 1 && p.ref && p.tgt && p.corr && p.post, "ct_prgls: problem %d is malformed", b);
+                const int L = prm->mode == CT_PRGLS_LITE ? p.n_tracked : 0;
+                const size_t greedy_bytes = layout_for(p.n_ref, p.n_tgt, 0).total + align_up(sizeof(DevProblem), 256) + 256;
+                const size_t grid_bytes = grid_em_workspace_bytes(p.n_ref, p.n_tgt, L);
+                CT_REQUIRE(greedy_bytes + grid_bytes <= avail, "ct_prgls: workspace too small (%zu < %zu)", avail, greedy_bytes + grid_bytes);
+                double* prior = nullptr;
+                unsigned long long launched = 0;
+                if (grid_em_run(*prm, p, wsb + greedy_bytes, grid_bytes, &prior, false, s, nullptr)) return 1;
+                if (!p.prior_given) {
+                    DevProblem d{};
+                    d.p = p;
+                    Layout o = layout_for(p.n_ref, p.n_tgt, 0);
+                    bind(d, wsb + align_up(sizeof(DevProblem), 256), o);
+                    d.prior = prior; d.pairs = nullptr; d.n_pairs = nullptr;
+                    CT_CUDA(cudaMemcpyAsync(wsb, &d, sizeof(d), cudaMemcpyHostToDevice, s));
+                    greedy_kernel<<<1, EM_THREADS, 0, s>>>(reinterpret_cast<const DevProblem*>(wsb), prm->mode, prm->threshold);
+                    CT_LAUNCHED("greedy_kernel");
+                }
+                ProfScope prof(PROF_EM, s);
+                if (grid_em_run(*prm, p, wsb + greedy_bytes, grid_bytes, nullptr, true, s, &launched)) return 1;
+                g_launches.fetch_add(launched, std::memory_order_relaxed);
+                used += align_up(greedy_bytes + grid_bytes, 256);
+            }
+            return 0;
+        }
+    }
     std::vector<DevProblem> host(batch);
     char* base = static_cast<char*>(ws);
     size_t off = align_up((size_t)batch * sizeof(DevProblem), 256);

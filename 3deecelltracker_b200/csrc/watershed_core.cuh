@@ -208,7 +208,11 @@ struct Max1D {                                   // maximum_filter(size = 2 r + 
 struct MinReduce {                               // image.min(): per slice (2-D stage) or global (3-D stage)
     Dims d; const double* in; unsigned long long* slot; int per_slice;
     WS_HD void operator()(i64 i) const {
-        atomic_min_u64(slot + (per_slice ? (int)(i % d.Z) : 0), dbl_bits(in[i]));   // values >= +0: bit order = value order
+        unsigned long long* s = slot + (per_slice ? (int)(i % d.Z) : 0);
+        const unsigned long long b = dbl_bits(in[i]);                               // values >= +0: bit order = value order
+        // almost every voxel is background (value 0 = the minimum): only values below the slot's current content go to
+        // the atomic unit (a stale read can only cause a redundant atomic, never a missed one)
+        if (b < *reinterpret_cast<const volatile unsigned long long*>(s)) atomic_min_u64(s, b);
     }
 };
 struct Peaks {
@@ -427,15 +431,25 @@ struct Boundary2D {                              // find_boundaries(labels, conn
 };
 
 // ---------------------------------------------------------------------------------------------- sizes, relabel, centres
-struct LabelSize {                               // np.bincount(labels_ws.ravel()): slot 0 = background, 1 + root = label
-    const int* lab; int* lsize; int* bg;
-    WS_HD void operator()(i64 i) const {
-        const int l = lab[i];
-        if (l) atomic_add_i(lsize + (l - 1), 1); else atomic_add_i(bg, 1);
-    }
-};
 struct Scalars {                                 // device-resident scalars of one call
     int min_size, cell_num, n_labels, n_cells, bg_count, heap_counter, count_ge, pad;
+};
+struct LabelSize {                               // np.bincount(labels_ws.ravel()): voxels per label, kept at the label's root
+    const int* lab; int* lsize;
+    WS_HD void operator()(i64 i) const {
+        const int l = lab[i];
+        if (l) atomic_add_i(lsize + (l - 1), 1);
+    }
+};
+struct BackgroundCount {                         // bincount[0] = all voxels - labelled voxels (one atomic per label, not per voxel)
+    const uint8_t* peak; const int* mk; const int* lsize; int* labelled;
+    WS_HD void operator()(i64 i) const {
+        if (peak[i] && mk[i] == (int)i && lsize[i] > 0) atomic_add_i(labelled, lsize[i]);
+    }
+};
+struct BackgroundFinish {
+    Scalars* sc; i64 n;
+    WS_HD void operator()(i64) const { sc->bg_count = (int)(n - (i64)sc->count_ge); sc->count_ge = 0; }
 };
 struct CountGE {                                 // number of marker labels with at least `thr` voxels (roots only)
     const uint8_t* peak; const int* mk; const int* lsize; const int* thr; int* out;
@@ -641,7 +655,9 @@ void segment(P& pol, const Params& prm, const float* prob, int* labels, double* 
     int* lsize = b.csize;                                                      // reuse: voxels per marker label (at its root)
     pol.zero(lsize, (size_t)n * 4);
     pol.zero(b.sc, sizeof(Scalars));
-    pol.run(LabelSize{b.lab, lsize, &b.sc->bg_count}, n);
+    pol.run(LabelSize{b.lab, lsize}, n);
+    pol.run(BackgroundCount{b.peak, b.mk, lsize, &b.sc->count_ge}, n);
+    pol.run(BackgroundFinish{b.sc, n}, 1);
     pol.run(MinSizeBegin{b.sc, b.thr, prm.method, prm.min_size, prm.cell_num}, 1);
     if (prm.method == 0) {
         pol.run(CountGE{b.peak, b.mk, lsize, b.thr, b.thr + 1}, n);

@@ -151,6 +151,37 @@ def test_ffn_and_pr_gls_quick_at_config3_size(m):
     np.testing.assert_allclose(got[0], want[0], rtol=1e-5, atol=1e-10)
 
 
+def test_grid_em_paths_vs_oracle(m):
+    """N >= 1024 reference points run the EM as grid-wide kernels (prgls_grid.cu) instead of one CTA: both flavours
+    against the NumPy restatements, and the one-CTA kernel (N = 1000) against the grid path (N = 1030) on nested
+    problems as a sanity check of the hand-over."""
+    synth = m["synth"]
+    rng = np.random.default_rng(5)
+    for n in (1000, 1030):
+        ref = synth.random_points(n, 21, extent=(900.0, 900.0, 500.0))
+        tgt = synth.move_points(ref, 22, affine_level=0.02, noise=0.001)
+        d2 = ((ref[None] - tgt[:, None]) ** 2).sum(axis=2)
+        corr = np.clip(np.exp(-d2 / 50.0) * 0.95 + rng.random(d2.shape) * 0.3, 0, 1)
+        want = oprgls.pr_gls_quick(ref, tgt, corr, BETA=300, max_iteration=6, LAMBDA=0.1)
+        got = m["track"].pr_gls_quick(ref, tgt, corr, BETA=300, max_iteration=6, LAMBDA=0.1)
+        np.testing.assert_allclose(got[1], want[1], rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(got[0], want[0], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-4, atol=1e-7 * np.abs(want[2]).max())
+    # TrackerLite flavour on the grid path (normalised coordinates, convergence stop, tracked points)
+    n = 1100
+    ref = synth.random_points(n, 31, extent=(1.0, 1.0, 0.6)) - 0.5
+    tgt = synth.move_points(ref, 32, affine_level=0.02, noise=0.0005, drop=0.02, add=0.02)
+    d2 = ((ref[None] - tgt[:, None]) ** 2).sum(axis=2)
+    corr = np.clip(np.exp(-d2 / (2 * 0.004 ** 2)) * 0.95 + rng.random(d2.shape) * 0.05, 0, 1).astype(np.float32)
+    prior, _ = oprgls.simple_match(corr)
+    tracked = ref[:900] + rng.normal(0, 0.001, (900, 3))
+    want_pred, want_post, its = oprgls.prgls_with_two_ref(prior, tgt, ref, tracked, beta=3.0, lambda_=3.0, return_iterations=True)
+    got_pred, got_post = m["trackerlite"].prgls_with_two_ref(prior, tgt, ref, tracked, beta=3.0, lambda_=3.0)
+    assert its < 100
+    np.testing.assert_allclose(got_pred, want_pred, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(got_post, want_post, rtol=1e-6, atol=1e-13)
+
+
 def test_prgls_with_two_ref_vs_reference_golden(m):
     g = golden("trackerlite_em.npz")
     for tag in ("b3l3", "b1l01"):
