@@ -5,6 +5,9 @@
 
 namespace ct {
 
+constexpr int FLOOD_CAP = 2048;                  // watershed.cu
+__global__ void ws_flood_warp(ws::Flood f, const int* roots, const int* n_roots, const int* csize);
+
 template <class F>
 __global__ void __launch_bounds__(256) corr_pass_kernel(F f, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,6 +51,12 @@ struct CorrPolicy {
     template <class F> void run_cells(const F& f, int n_cells) {
         if (n_cells <= 0 || err) return;
         corr_cells_kernel<F><<<(n_cells + 3) / 4, 128, 0, s>>>(f, n_cells);
+        ++launches;
+        if (cudaGetLastError() != cudaSuccess) err = 1;
+    }
+    void run_flood(const ws::Flood& f, const int* roots, const int* n_roots, const int* csize, long long) {
+        if (err) return;
+        ws_flood_warp<<<148 * 6, 32, FLOOD_CAP * (int)sizeof(ws::HeapE), s>>>(f, roots, n_roots, csize);
         ++launches;
         if (cudaGetLastError() != cudaSuccess) err = 1;
     }

@@ -196,7 +196,7 @@ void recalculate_cell_boundaries(P& pol, const ws::Dims& d, int* label, const in
                                  const ws::Buffers& b) {
     const i64 n = d.n();
     pol.run(MarkersAndMasks{cover, on_boundary, label, b.mask, b.mask2}, n);          // mask = mask_image, mask2 = overlap
-    pol.run(ws::ColDist{d, b.mask2, b.g}, (i64)d.X * d.Z);                            // distance_transform_edt(overlap, (1, 1))
+    pol.run(ws::ColDist{d, b.mask2, b.g}, n);                            // distance_transform_edt(overlap, (1, 1))
     pol.run(ws::RowDist{d, b.mask2, b.g, b.d2}, n);
     pol.run(ws::SqrtPlane{b.d2, b.fa}, n);
     ws::flood_from_labels(pol, d, b, b.mask, label, b.fa);

@@ -294,19 +294,33 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         mbar_wait(&bar_acc_full[set], use_a & 1);
                         tc_fence_after();
                         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * Cfg::NPD + (uint32_t)ch0;
-                        // pair kk = (ax, px): (-1,0) (0,0) (0,1) (+1,1) -> output plane j - 1 - ax
+                        // pair kk = (ax, px): (-1,0) (0,0) (0,1) (+1,1) -> output plane j - 1 - ax.  The loads of LDG
+                        // pairs are issued in front of one wait (a wait per pair left the tensor pipe idle behind the
+                        // drain: 80 tensor-memory round trips per stage); LDG = 4 while 8 CH registers per pair fit.
+                        constexpr int LDG = (CH <= 8) ? 4 : 2;
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int ax = (kk == 0) ? -1 : (kk == 3 ? 1 : 0), px = kk >> 1;
-                            const int i = j - 1 - ax;
-                            if (i < 0 || i >= BX) continue;
-                            uint32_t v[2][CH];
-                            tu_ld_issue<CH>(t0 + kk * N, v[0]);
-                            tu_ld_issue<CH>(t0 + 4 * N + kk * N, v[1]);
+                        for (int k0 = 0; k0 < 4; k0 += LDG) {
+                            uint32_t v[LDG][2][CH];
+#pragma unroll
+                            for (int kq = 0; kq < LDG; ++kq) {
+                                const int kk = k0 + kq;
+                                const int ax = (kk == 0) ? -1 : (kk == 3 ? 1 : 0);
+                                const int i = j - 1 - ax;
+                                if (i < 0 || i >= BX) continue;
+                                tu_ld_issue<CH>(t0 + kk * N, v[kq][0]);
+                                tu_ld_issue<CH>(t0 + 4 * N + kk * N, v[kq][1]);
+                            }
                             tmem_ld_wait();
 #pragma unroll
-                            for (int ch = 0; ch < CH; ++ch)
-                                acc[i][px][py][ch] += fmaf(__uint_as_float(v[1][ch]), W2, __uint_as_float(v[0][ch]));
+                            for (int kq = 0; kq < LDG; ++kq) {
+                                const int kk = k0 + kq;
+                                const int ax = (kk == 0) ? -1 : (kk == 3 ? 1 : 0), px = kk >> 1;
+                                const int i = j - 1 - ax;
+                                if (i < 0 || i >= BX) continue;
+#pragma unroll
+                                for (int ch = 0; ch < CH; ++ch)
+                                    acc[i][px][py][ch] += fmaf(__uint_as_float(v[kq][1][ch]), W2, __uint_as_float(v[kq][0][ch]));
+                            }
                         }
                         tc_fence_before();
                         __syncwarp();

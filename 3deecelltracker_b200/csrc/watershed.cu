@@ -30,6 +30,86 @@ __global__ void __launch_bounds__(64) ws_sparse_kernel(F f, long long n) {
     if (i < n) f(i);
 }
 
+// ---- priority flood, one WARP per connected component of the foreground (roots list written by HeapAlloc).
+// The pop order is sequential, but everything around it is not: lane 0 keeps the binary heap in SHARED memory
+// (components of up to FLOOD_CAP voxels; larger ones use their slice of the global heap), and after every pop lanes 0-5
+// fetch the six neighbours (mask, label, value) at once, so a pop costs one round trip to L2 instead of eighteen.
+// Labels are read with ld.global.cg: the label a lane wrote for an earlier pop must be seen by the other lanes.
+// Same order (value, age, index) and same neighbour order as ws::Flood, so the labels are identical to it.
+constexpr int FLOOD_CAP = 2048;
+
+__global__ void __launch_bounds__(32) ws_flood_warp(ws::Flood f, const int* __restrict__ roots, const int* __restrict__ n_roots,
+                                                    const int* __restrict__ csize) {
+    extern __shared__ ws::HeapE sheap[];
+    const int lane = threadIdx.x;
+    const int total = *n_roots;
+    const ws::i64 sx = (ws::i64)f.d.Y * f.d.Z, sy = f.d.Z;
+    for (int k = blockIdx.x; k < total; k += gridDim.x) {
+        const int root = roots[k];
+        int n = f.hcnt[root];
+        if (n == 0) continue;                                        // uniform over the warp
+        ws::HeapE* gh = f.heap + f.hoff[root];
+        const bool in_smem = csize[root] <= FLOOD_CAP;
+        ws::HeapE* h = in_smem ? sheap : gh;
+        if (in_smem) {
+            for (int e = lane; e < n; e += 32) sheap[e] = gh[e];
+            __syncwarp();
+        }
+        if (lane == 0)
+            for (int e = n / 2 - 1; e >= 0; --e) ws::heap_down(h, n, e);
+        __syncwarp();
+        int age = 0;
+        while (true) {
+            n = __shfl_sync(0xffffffffu, n, 0);
+            if (n == 0) break;
+            int top_idx = 0, l = 0;
+            if (lane == 0) {
+                top_idx = h[0].idx;
+                --n;
+                if (n > 0) { h[0] = h[n]; ws::heap_down(h, n, 0); }
+                l = __ldcg(f.lab + top_idx);
+            }
+            top_idx = __shfl_sync(0xffffffffu, top_idx, 0);
+            l = __shfl_sync(0xffffffffu, l, 0);
+            int x, y, z; f.d.split(top_idx, x, y, z);
+            // C order of the neighbour offsets: x-1, y-1, z-1, z+1, y+1, x+1 (lane = position in that order)
+            ws::i64 j = -1;
+            bool ok = false;
+            switch (lane) {
+                case 0: ok = x > 0; j = top_idx - sx; break;
+                case 1: ok = y > 0; j = top_idx - sy; break;
+                case 2: ok = !f.planar && z > 0; j = (ws::i64)top_idx - 1; break;
+                case 3: ok = !f.planar && z + 1 < f.d.Z; j = (ws::i64)top_idx + 1; break;
+                case 4: ok = y + 1 < f.d.Y; j = top_idx + sy; break;
+                case 5: ok = x + 1 < f.d.X; j = top_idx + sx; break;
+                default: break;
+            }
+            double v = 0.0;
+            bool cand = false;
+            if (ok && f.mask[j]) {
+                cand = __ldcg(f.lab + j) == 0;
+                if (cand) v = f.sign * f.img[j];
+            }
+            const unsigned bits = __ballot_sync(0xffffffffu, cand);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const long long jq = __shfl_sync(0xffffffffu, (long long)j, q);
+                const double vq = __shfl_sync(0xffffffffu, v, q);
+                if (lane == 0 && ((bits >> q) & 1u)) {
+                    ++age;
+                    f.lab[jq] = l;
+                    ws::HeapE e; e.v = vq; e.age = age; e.idx = (int)jq;
+                    h[n] = e;
+                    ws::heap_up(h, n);
+                    ++n;
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void ws_fill_u64(unsigned long long* p, unsigned long long v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -114,6 +194,13 @@ struct CudaPolicy {
     template <class F> void run_sparse(const F& f, long long n) {
         if (n <= 0 || err) return;
         ws_sparse_kernel<F><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(f, n);
+        ++launches;
+        if (cudaGetLastError() != cudaSuccess) err = 1;
+    }
+    void run_flood(const ws::Flood& f, const int* roots, const int* n_roots, const int* csize, long long) {
+        if (err) return;
+        static const int smem = FLOOD_CAP * (int)sizeof(ws::HeapE);
+        ws_flood_warp<<<148 * 6, 32, smem, s>>>(f, roots, n_roots, csize);
         ++launches;
         if (cudaGetLastError() != cudaSuccess) err = 1;
     }

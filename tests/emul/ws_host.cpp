@@ -10,6 +10,7 @@
 struct HostPolicy {
     template <class F> void run(const F& f, long long n) { for (long long i = 0; i < n; ++i) f(i); }
     template <class F> void run_sparse(const F& f, long long n) { run(f, n); }
+    template <class F> void run_flood(const F& f, const int*, const int*, const int*, long long n) { run(f, n); }
     template <class F> void run_cells(const F& f, int n_cells) {
         for (int c = 0; c < n_cells; ++c) { double s[4]; f.partial(c, 0, 1, s); f.finish(c, s); }
     }
@@ -54,20 +55,20 @@ extern "C" int ws_emul_stage2d(const float* prob, int x, int y, int z, const dou
     ws::carve(b, wsp, n, z, 16);
     const ws::Dims d{x, y, z};
     HostPolicy pol;
-    ws::Gauss1D<0> gx{d, nullptr, nullptr, 8, {}};
-    ws::Gauss1D<1> gy{d, nullptr, nullptr, 8, {}};
+    ws::Gauss1D<0> gx{d, nullptr, nullptr, 8, {}, ws::ActGrid{nullptr, 0}};
+    ws::Gauss1D<1> gy{d, nullptr, nullptr, 8, {}, ws::ActGrid{nullptr, 0}};
     for (int j = 0; j < 9; ++j) { gx.w[j] = w_xy9[j]; gy.w[j] = w_xy9[j]; }
     pol.run(ws::Threshold{prob, b.mask}, n);
-    pol.run(ws::ColDist{d, b.mask, b.g}, (long long)d.X * d.Z);
+    pol.run(ws::ColDist{d, b.mask, b.g}, n);
     pol.run(ws::RowDist{d, b.mask, b.g, b.d2}, n);
     pol.run(ws::SqrtPlane{b.d2, b.fa}, n);
     gx.in = b.fa; gx.out = b.fb; pol.run(gx, n);
     gy.in = b.fb; gy.out = b.fa; pol.run(gy, n);
     pol.fill_u64(b.minslot, 0x7ff0000000000000ull, d.Z + 1);
     pol.run(ws::MinReduce{d, b.fa, b.minslot, 1}, n);
-    pol.run(ws::Max1D<0>{d, b.fa, b.fb, 7}, n);
-    pol.run(ws::Max1D<1>{d, b.fb, b.fc, 7}, n);
-    pol.run(ws::Peaks{d, b.fa, b.fc, b.minslot, 1, 7, b.peak}, n);
+    pol.run(ws::Max1D<0>{d, b.fa, b.fb, 7, ws::ActGrid{nullptr, 0}}, n);
+    pol.run(ws::Max1D<1>{d, b.fb, b.fc, 7, ws::ActGrid{nullptr, 0}}, n);
+    pol.run(ws::Peaks{d, b.fa, b.fc, b.minslot, 1, 7, b.peak, ws::ActGrid{nullptr, 0}}, n);
     ws::flood_stage(pol, d, b, b.mask, b.fa, 1);
     pol.run(ws::Boundary2D{d, b.mask, b.lab, b.mask2}, n);
     std::memcpy(lab2d, b.lab, n * 4); std::memcpy(mask2, b.mask2, n); std::memcpy(smooth, b.fa, n * 8);
