@@ -749,7 +749,8 @@ namespace ct {
 size_t grid_em_workspace_bytes(int N, int M, int L);
 int grid_em_run(const CtPrglsParams& prm, const CtPrglsProblem& q, void* ws, size_t ws_bytes, double** prior_slot, bool run,
                 cudaStream_t s, unsigned long long* launches);
-constexpr int EM_GRID_MIN_N = 1024;              // problems with at least this many reference points take the grid path
+constexpr int EM_GRID_MIN_N = 512;               // problems with at least this many reference points take the grid path
+                                                 // (one CTA: 2.85 ms per iteration at N = 512; grid: see profiles/r2_em_timings.md)
 }  // namespace ct
 
 using namespace ct;

@@ -23,7 +23,7 @@
 namespace ct {
 
 constexpr int GE_NB = 32;                         // panel width of the elimination
-constexpr int GE_TILE = 64;                       // output tile of the trailing update (64 x 64, K = GE_NB)
+constexpr int GE_TILE = 128;                      // output tile of the trailing update (128 x 128, K = GE_NB)
 
 struct GridProblem {
     const double* X; const double* Y; const double* tracked;      // (N,3) (M,3) (L,3)
@@ -225,38 +225,44 @@ __global__ void __launch_bounds__(128) ge_rowblock(GridProblem p, const GridStat
 #pragma unroll
     for (int r = 0; r < GE_NB; ++r) if (r < nb) p.S[(size_t)(k0 + r) * p.ld + c] = u[r];
 }
-// S22 -= L21 U12: 64 x 64 tile per CTA (256 threads, 4 x 4 outputs each), K = nb
+// S22 -= L21 U12: 128 x 128 tile per CTA (256 threads, 8 x 8 outputs each), K = nb in two chunks of 16.
+// 64 DFMA per 16 shared-memory doubles read: the FP64 pipe, not shared memory, is the limit (a 4 x 4 register tile was
+// shared-memory bound at 0.7 TFLOP/s).  Thread (ty, tx) owns rows ty + 16 i and columns tx + 16 j: bank-conflict free.
 __global__ void __launch_bounds__(256) ge_update(GridProblem p, const GridState* st, int k0, int nb, int cols) {
     if (st->done) return;
-    __shared__ double Ls[GE_TILE][GE_NB + 1];
-    __shared__ double Us[GE_NB][GE_TILE + 1];
+    constexpr int KC = 16;
+    __shared__ double Ls[GE_TILE][KC + 1];
+    __shared__ double Us[KC][GE_TILE + 1];
     const int r0 = k0 + nb + blockIdx.y * GE_TILE, c0 = k0 + nb + blockIdx.x * GE_TILE;
-    for (int e = threadIdx.x; e < GE_TILE * GE_NB; e += 256) {
-        const int r = e / GE_NB, k = e % GE_NB;
-        Ls[r][k] = (r0 + r < p.N && k < nb) ? p.S[(size_t)(r0 + r) * p.ld + k0 + k] : 0.0;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[8][8] = {};
+    for (int kc = 0; kc < nb; kc += KC) {
+        for (int e = threadIdx.x; e < GE_TILE * KC; e += 256) {
+            const int r = e / KC, k = e % KC;
+            Ls[r][k] = (r0 + r < p.N && kc + k < nb) ? p.S[(size_t)(r0 + r) * p.ld + k0 + kc + k] : 0.0;
+        }
+        for (int e = threadIdx.x; e < KC * GE_TILE; e += 256) {
+            const int k = e / GE_TILE, c = e % GE_TILE;
+            Us[k][c] = (c0 + c < cols && kc + k < nb) ? p.S[(size_t)(k0 + kc + k) * p.ld + c0 + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < KC; ++k) {
+            double l[8], u[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { l[i] = Ls[ty + 16 * i][k]; u[i] = Us[k][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(l[i], u[j], acc[i][j]);
+        }
+        __syncthreads();
     }
-    for (int e = threadIdx.x; e < GE_NB * GE_TILE; e += 256) {
-        const int k = e / GE_TILE, c = e % GE_TILE;
-        Us[k][c] = (c0 + c < cols && k < nb) ? p.S[(size_t)(k0 + k) * p.ld + c0 + c] : 0.0;
-    }
-    __syncthreads();
-    const int tr = (threadIdx.x >> 4) * 4, tc = (threadIdx.x & 15) * 4;
-    double acc[4][4] = {};
-#pragma unroll 8
-    for (int k = 0; k < GE_NB; ++k) {
-        double l[4], u[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { l[i] = Ls[tr + i][k]; u[i] = Us[k][tc + i]; }
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fma(l[i], u[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = r0 + tr + i, c = c0 + tc + j;
+        for (int j = 0; j < 8; ++j) {
+            const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
             if (r < p.N && c < cols) p.S[(size_t)r * p.ld + c] -= acc[i][j];
         }
 }

@@ -84,11 +84,15 @@ __global__ void __launch_bounds__(32) ws_flood_warp(ws::Flood f, const int* __re
                 case 5: ok = x + 1 < f.d.X; j = top_idx + sx; break;
                 default: break;
             }
+            // the three loads of a neighbour are independent of each other: one round trip, not three
             double v = 0.0;
             bool cand = false;
-            if (ok && f.mask[j]) {
-                cand = __ldcg(f.lab + j) == 0;
-                if (cand) v = f.sign * f.img[j];
+            if (ok) {
+                const uint8_t mk = __ldg(f.mask + j);
+                const int lb = __ldcg(f.lab + j);
+                const double im = __ldg(f.img + j);
+                cand = mk != 0 && lb == 0;
+                v = f.sign * im;
             }
             const unsigned bits = __ballot_sync(0xffffffffu, cand);
 #pragma unroll

@@ -101,8 +101,13 @@ WS_HD int vload(const int* p) { return *reinterpret_cast<const volatile int*>(p)
 struct Dims {
     int X, Y, Z;
     WS_HD i64 n() const { return (i64)X * Y * Z; }
-    WS_HD void split(i64 i, int& x, int& y, int& z) const {
-        z = (int)(i % Z); i /= Z; y = (int)(i % Y); x = (int)(i / Y);
+    WS_HD void split(i64 i, int& x, int& y, int& z) const {     // volumes have < 2^31 voxels: 32-bit division (the 64-bit
+        unsigned u = (unsigned)i;                                // one costs ~100 instructions per thread on the GPU and was
+        const unsigned q = u / (unsigned)Z;                      // the whole cost of the element-wise passes)
+        z = (int)(u - q * (unsigned)Z);
+        const unsigned r = q / (unsigned)Y;
+        y = (int)(q - r * (unsigned)Y);
+        x = (int)r;
     }
 };
 
@@ -120,7 +125,7 @@ struct ColDist {
     Dims d; const uint8_t* mask; int* g;
     WS_HD void operator()(i64 i) const {
         if (!mask[i]) { g[i] = 0; return; }
-        const int y = (int)((i / d.Z) % d.Y);
+        const int y = (int)(((unsigned)i / (unsigned)d.Z) % (unsigned)d.Y);
         int best = COL_INF;
         for (int o = 1; o < d.Y; ++o) {
             const bool lo = y - o >= 0, hi = y + o < d.Y;
@@ -243,7 +248,7 @@ struct Max1D {                                   // maximum_filter(size = 2 r + 
 struct MinReduce {                               // image.min(): per slice (2-D stage) or global (3-D stage)
     Dims d; const double* in; unsigned long long* slot; int per_slice;
     WS_HD void operator()(i64 i) const {
-        unsigned long long* s = slot + (per_slice ? (int)(i % d.Z) : 0);
+        unsigned long long* s = slot + (per_slice ? (int)((unsigned)i % (unsigned)d.Z) : 0);
         const unsigned long long b = dbl_bits(in[i]);                               // values >= +0: bit order = value order
         // almost every voxel is background (value 0 = the minimum): only values below the slot's current content go to
         // the atomic unit (a stale read can only cause a redundant atomic, never a missed one)

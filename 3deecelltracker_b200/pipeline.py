@@ -45,6 +45,7 @@ class FramePipeline:
         self._count = 0
         # raw-stack mode (step_raw): watershed results whose cell count is still on its way to the host, and the
         # point set of the last volume whose count is known
+        self._ws_stream = None
         self._segmented = collections.deque()        # (Segmentation, pinned scalars, event)
         self._prev_points = None
         self._first_points = None
@@ -157,13 +158,29 @@ class FramePipeline:
 
     def segment_cells(self, raw_dev):
         """tracker.py:605-650 on the device: LCN + U-Net + watershed + centres of mass; nothing leaves HBM except the
-        four scalars (cell count ...), which go to pinned memory asynchronously."""
+        four scalars (cell count ...), which go to pinned memory asynchronously.
+        With `overlap` the watershed runs on its own stream: its priority floods are a few hundred latency-bound warps
+        (one per connected component) that fit beside the next volume's tensor-core convolutions, exactly like the EM.
+        `seg.ready` is the event that marks the label image / centres / pinned scalars complete."""
         prob = self.segment(raw_dev)
-        seg = _ws.segment_device(prob, self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num)
-        pinned = torch.empty(4, dtype=torch.int32).pin_memory()
-        pinned.copy_(seg.scalars, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            if self._ws_stream is None:
+                self._ws_stream = torch.cuda.Stream(priority=-1)
+            produced = torch.cuda.Event()
+            produced.record(main)
+            self._ws_stream.wait_event(produced)
+            prob.record_stream(self._ws_stream)
+            stream = self._ws_stream
+        else:
+            stream = main
+        with torch.cuda.stream(stream):
+            seg = _ws.segment_device(prob, self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num)
+            pinned = torch.empty(4, dtype=torch.int32).pin_memory()
+            pinned.copy_(seg.scalars, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        seg.ready = ev
         return prob, seg, pinned, ev
 
     def _resolve_segmented(self):

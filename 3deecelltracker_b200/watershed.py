@@ -38,10 +38,13 @@ class Segmentation:
     def __init__(self, labels, centres2, scalars):
         self.labels, self.centres, self.centres_real, self.scalars = labels, centres2[0], centres2[1], scalars
         self._host = None
+        self.ready = None                # CUDA event set by callers that produce the result on a side stream
 
     def host_scalars(self):
         """(n_cells, min_size, cell_num): synchronises the current stream once."""
         if self._host is None:
+            if self.ready is not None:
+                torch.cuda.current_stream().wait_event(self.ready)
             self._host = [int(v) for v in self.scalars.cpu().tolist()]
         return self._host[0], self._host[1], self._host[2]
 

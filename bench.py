@@ -329,6 +329,8 @@ def gpu_main(args):
         ready = torch.cuda.Event()
         ready.record()
         copy_stream.wait_event(ready)
+        if seg.ready is not None:
+            copy_stream.wait_event(seg.ready)            # the label image is produced on the pipeline's watershed stream
         with torch.cuda.stream(copy_stream):
             prob_host[t % 2].copy_(prob, non_blocking=True)
             lab_host[t % 2].copy_(seg.labels, non_blocking=True)

@@ -1,0 +1,11 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_gpu_watershed.py tests/test_gpu_correction.py tests/test_gpu_pipeline.py tests/test_gpu_ffn_prgls.py -x -q 2>&1 | tail -6
+timeout 300 python scripts/ws_time.py 2>&1 | tail -2
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ws_ -c 200 --csv --log-file gpurun_out/launches_ws.csv python scripts/ws_time.py > gpurun_out/ncu_ws.log 2>&1; tail -1 gpurun_out/ncu_ws.log
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-c3 > gpurun_out/bench_r2e.json 2> gpurun_out/bench_r2e.err; python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench_r2e.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("ms_per_step", "frames_per_s", "frames_per_s_without_watershed", "stage_ms_per_step", "serial_ms_per_step")}, d["roofline"]["frac"], d["e2e"]["frames_per_s"])
+PY
+tail -3 gpurun_out/bench_r2e.err
+timeout 300 python scripts/em_time.py 2>&1 | tail -5

@@ -152,12 +152,11 @@ def test_ffn_and_pr_gls_quick_at_config3_size(m):
 
 
 def test_grid_em_paths_vs_oracle(m):
-    """N >= 1024 reference points run the EM as grid-wide kernels (prgls_grid.cu) instead of one CTA: both flavours
-    against the NumPy restatements, and the one-CTA kernel (N = 1000) against the grid path (N = 1030) on nested
-    problems as a sanity check of the hand-over."""
+    """N >= 512 reference points run the EM as grid-wide kernels (prgls_grid.cu) instead of one CTA: both flavours
+    against the NumPy restatements, on both sides of the hand-over (N = 500: one CTA, N = 520 / 1030: grid)."""
     synth = m["synth"]
     rng = np.random.default_rng(5)
-    for n in (1000, 1030):
+    for n in (500, 520, 1030):
         ref = synth.random_points(n, 21, extent=(900.0, 900.0, 500.0))
         tgt = synth.move_points(ref, 22, affine_level=0.02, noise=0.001)
         d2 = ((ref[None] - tgt[:, None]) ** 2).sum(axis=2)
