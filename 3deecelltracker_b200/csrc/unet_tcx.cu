@@ -324,13 +324,10 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                 for (int c4 = 0; c4 < CH / 4; ++c4) {
                     float o[4];
-                    float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (geo.add_partial && ok) part = d_tile[(size_t)c4 * vol + vox];       // uniform over the CTA
-                    const float pp[4] = {part.x, part.y, part.z, part.w};
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const int ch = ch0 + c4 * 4 + kk;
-                        float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch] + pp[kk]);
+                        float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch]);
                         t = t > 0.f ? t : alpha * t;
                         o[kk] = fmaf(t, ep_s[1][ch], ep_s[2][ch]);
                         if (ok) amax = fmaxf(amax, fabsf(o[kk]));
@@ -361,6 +358,26 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             for (int i = 0; i < BX; ++i)
 #pragma unroll
                 for (int ch = 0; ch < CH; ++ch) acc[i][ch] = 0.f;
+            if (geo.add_partial) {                                  // uniform over the CTA
+                // The accumulators START from the partial sums the phase kernel left in dst (decoder blocks): BX
+                // independent loads per thread at the head of the unit, hidden behind its first MMAs.  (Loading them
+                // in the per-plane epilogue put a dependent global load in front of every plane's store: ~40 % of
+                // the block's time.)  inv_scale is a power of two, so partial / inv_scale is exact.
+                const float to_acc = 1.f / inv_scale;
+#pragma unroll
+                for (int i = 0; i < BX; ++i) {
+                    const int x = un.x0 + i;
+                    if (y < geo.Y && x < geo.X) {
+                        const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
+#pragma unroll
+                        for (int c4 = 0; c4 < CH / 4; ++c4) {
+                            const float4 pv = d_tile[(size_t)c4 * vol + vox];
+                            acc[i][c4 * 4 + 0] = pv.x * to_acc; acc[i][c4 * 4 + 1] = pv.y * to_acc;
+                            acc[i][c4 * 4 + 2] = pv.z * to_acc; acc[i][c4 * 4 + 3] = pv.w * to_acc;
+                        }
+                    }
+                }
+            }
 #pragma unroll 1
             for (int c = 0; c < cin8; ++c) {
                 const bool last = (c == cin8 - 1);

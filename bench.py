@@ -306,11 +306,12 @@ def gpu_main(args):
     # one of two pinned buffers while volume t+1 computes; tracked coordinates come down at the end (rank 0).
     prob_host = [torch.empty(SHAPE, dtype=torch.float32).pin_memory() for _ in range(2)]
     lab_host = [torch.empty(SHAPE, dtype=torch.int32).pin_memory() for _ in range(2)]
-    copy_stream = torch.cuda.Stream()
+    # separate streams per direction: an upload must never queue behind a download that waits for a watershed
+    up_stream, copy_stream = torch.cuda.Stream(), torch.cuda.Stream()
     state = {"next": None, "done": []}
 
     def upload(t):
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(up_stream):
             d = frames_pinned[t].to(dev, non_blocking=True).view(torch.uint16)
             ev = torch.cuda.Event()
             ev.record()

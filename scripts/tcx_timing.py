@@ -12,14 +12,14 @@ synth = importlib.import_module("3deecelltracker_b200.synth")
 L = importlib.import_module("3deecelltracker_b200._lib")
 lib = L.lib()
 fn = C.CDLL(L.LIB_PATH).ct_debug_tcx_timers
-model = u.UNet3("a", weights=synth.unet_weights("a", 0), tiles_per_batch=15)
+model = u.UNet3("a", weights=synth.unet_weights("a", 0), tiles_per_batch=38)
 layers = u._conv_layers(u._SPECS["a"])
-sizes = {0: 160, 1: 160, 2: 80, 10: 80, 11: 80, 12: 160, 13: 160}
-names = {0: "d0a", 1: "d0b", 2: "d1a", 10: "u0a", 11: "u0b", 12: "o_m2", 13: "o_m1"}
+sizes = {1: 160, 2: 80, 3: 80, 4: 40, 9: 40, 10: 80, 11: 80, 12: 160, 13: 160}
+names = {1: "d0b", 2: "d1a", 3: "d1b", 4: "d2a", 9: "u1b", 10: "u0a", 11: "u0b", 12: "o_m2", 13: "o_m1"}
 rng = np.random.default_rng(0)
 for li, xy in sizes.items():
     cin, cout = layers[li]
-    x = torch.from_numpy(rng.normal(0, 1, (15, xy, xy, 16, cin)).astype(np.float32)).cuda()
+    x = torch.from_numpy(rng.normal(0, 1, (38, xy, xy, 16, cin)).astype(np.float32)).cuda()
     for _ in range(2):
         model.conv_block_device(li, x, "tcgen05")
     torch.cuda.synchronize()
