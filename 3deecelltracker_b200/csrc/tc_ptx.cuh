@@ -104,6 +104,54 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2): one issue slot for two IEEE operations, bit-identical to the scalar forms.
+// The drain warps are issue bound (tensor-memory loads + accumulate + epilogue on 2 warps per scheduler), so every
+// element-wise step of theirs works on channel pairs.
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n"
+        "add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n"
+        "mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
+
+// bias -> LeakyReLU / ReLU -> BatchNorm(eval) of one channel pair (unet3d.py:117-119): acc * inv_scale + bias, activation,
+// * scale + shift.  ep = shared-memory table [3][n] (bias | scale | shift), ch even.  alpha in [0, 1], so
+// t > 0 ? t : alpha t == max(t, alpha t).  Updates the running max|output|.
+__device__ __forceinline__ float2 block_epilogue(float2 acc, float inv_scale, float alpha, const float* ep, int n, int ch, float& amax) {
+    float2 t = f2_fma(acc, f2_splat(inv_scale), *reinterpret_cast<const float2*>(ep + ch));
+    const float2 ta = f2_mul(t, f2_splat(alpha));
+    t = make_float2(fmaxf(t.x, ta.x), fmaxf(t.y, ta.y));
+    const float2 o = f2_fma(t, *reinterpret_cast<const float2*>(ep + n + ch), *reinterpret_cast<const float2*>(ep + 2 * n + ch));
+    amax = fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y)));
+    return o;
+}
+// x s -> fp16 pair images hi = RN16(x s), lo' = RN16((x s - hi) 2^11); the difference and its scaling are exact
+__device__ __forceinline__ void split_pair2(float2 x, float s, uint32_t& hi, uint32_t& lo) {
+    const float2 os = f2_mul(x, f2_splat(s));
+    const __half2 h = __floats2half2_rn(os.x, os.y);
+    const float2 hf = __half22float2(h);
+    const float2 d = f2_fma(hf, f2_splat(-2048.f), f2_mul(os, f2_splat(2048.f)));
+    const __half2 l = __floats2half2_rn(d.x, d.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // shared-memory matrix descriptor, no swizzle, K-major: ((8, m), 2) : ((16 B, SBO), LBO)   [units of 16 B]
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr_bytes, uint32_t lbo16, uint32_t sbo16) {
     const uint32_t lo = ((addr_bytes >> 4) & 0x3FFFu) | ((lbo16 & 0x3FFFu) << 16);

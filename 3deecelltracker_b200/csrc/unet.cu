@@ -82,6 +82,59 @@ pool_kernel(const float4* __restrict__ slab_src, float4* __restrict__ slab_dst, 
     }
 }
 
+// MaxPooling3D(pool) between split-fp16 buffers (unet_common.cuh): planes (2 c8, 2 c8 + 1) hold the fp16 hi / lo' images of
+// 8 channels; all voxels of a tile share one scale, so the window maximum is the element with the largest
+// hi + lo' 2^-11 (exact in fp32) and its two halves are copied unchanged.  grid (c8 * DX, tiles).
+__global__ void __launch_bounds__(256)
+pool_split_kernel(const uint4* __restrict__ slab_src, uint4* __restrict__ slab_dst, size_t slab_stride4,
+                  size_t src_off4, size_t dst_off4, int src_c4off, int c8n, int SXs, int SYs, int SZs,
+                  int DX, int DY, int DZ, int px, int py, int pz, int src_slot, int dst_slot) {
+    const int t = blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float* hdr = reinterpret_cast<float*>(slab_dst + (size_t)t * slab_stride4);
+        amax_update(hdr + dst_slot, hdr[src_slot]);
+        hdr[SCALE_SLOT0 + dst_slot] = hdr[SCALE_SLOT0 + src_slot];
+    }
+    const int ck = blockIdx.x / DX, x = blockIdx.x - ck * DX;
+    const size_t dvol = (size_t)DX * DY * DZ, svol = (size_t)SXs * SYs * SZs;
+    const uint4* src = slab_src + (size_t)t * slab_stride4 + src_off4 + (size_t)(src_c4off + 2 * ck) * svol;
+    uint4* dst = slab_dst + (size_t)t * slab_stride4 + dst_off4 + (size_t)(2 * ck) * dvol + (size_t)x * DY * DZ;
+    for (int f = threadIdx.x; f < DY * DZ; f += blockDim.x) {
+        const int y = f / DZ, z = f - y * DZ;
+        float best[8];
+        uint32_t bh[4], bl[4];                           // fp16 pairs: channel 2k in the low half
+#pragma unroll
+        for (int k = 0; k < 8; ++k) best[k] = -INFINITY;
+        for (int a = 0; a < px; ++a)
+            for (int b = 0; b < py; ++b)
+                for (int c = 0; c < pz; ++c) {
+                    const size_t v = ((size_t)(x * px + a) * SYs + (y * py + b)) * SZs + (z * pz + c);
+                    const uint4 h = src[v], l = src[svol + v];
+                    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 val = unsplit_pair(hh[k], ll[k], 1.f);
+                        if ((a | b | c) == 0) {
+                            best[2 * k] = val.x; best[2 * k + 1] = val.y; bh[k] = hh[k]; bl[k] = ll[k];
+                        } else {
+                            if (val.x > best[2 * k]) {
+                                best[2 * k] = val.x;
+                                bh[k] = (bh[k] & 0xffff0000u) | (hh[k] & 0xffffu);
+                                bl[k] = (bl[k] & 0xffff0000u) | (ll[k] & 0xffffu);
+                            }
+                            if (val.y > best[2 * k + 1]) {
+                                best[2 * k + 1] = val.y;
+                                bh[k] = (bh[k] & 0xffffu) | (hh[k] & 0xffff0000u);
+                                bl[k] = (bl[k] & 0xffffu) | (ll[k] & 0xffff0000u);
+                            }
+                        }
+                    }
+                }
+        dst[f] = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+        dst[dvol + f] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+    }
+}
+
 // UpSampling3D(size) nearest, written into the first channels of the concat buffer (unet3d.py:199).  grid (c4 * SX,
 // tiles): one SOURCE x plane of one channel chunk per block; every source voxel is read once and stored px*py*pz times.
 __global__ void __launch_bounds__(256)
@@ -184,6 +237,43 @@ c4_to_ndhwc(const float4* __restrict__ src, float* __restrict__ dst, size_t vol,
     }
 }
 
+// fp32 c4-blocked <-> split-fp16 (unet_common.cuh), in place: planes (2 c8, 2 c8 + 1) of a buffer hold channels
+// [8 c8, 8 c8 + 8) either as two 4-channel fp32 planes or as the fp16 hi / lo' images.  grid (blocks, tiles).
+__global__ void __launch_bounds__(256)
+c4_to_split(float4* __restrict__ slab, size_t slab_stride4, size_t off4, int c8n, size_t vol, int slot) {
+    float* hdr = reinterpret_cast<float*>(slab + (size_t)blockIdx.y * slab_stride4);
+    const float sc = tc_operand_scale(hdr[slot]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr[SCALE_SLOT0 + slot] = sc;
+    float4* buf = slab + (size_t)blockIdx.y * slab_stride4 + off4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol * c8n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t c8 = idx / vol, v = idx - c8 * vol;
+        float4* p0 = buf + (2 * c8) * vol + v;
+        float4* p1 = p0 + vol;
+        const float4 a = *p0, b = *p1;
+        uint4 hi, lo;
+        split_pair(a.x * sc, a.y * sc, hi.x, lo.x); split_pair(a.z * sc, a.w * sc, hi.y, lo.y);
+        split_pair(b.x * sc, b.y * sc, hi.z, lo.z); split_pair(b.z * sc, b.w * sc, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(p0) = hi;
+        *reinterpret_cast<uint4*>(p1) = lo;
+    }
+}
+__global__ void __launch_bounds__(256)
+split_to_c4(float4* __restrict__ slab, size_t slab_stride4, size_t off4, int c8n, size_t vol, int slot) {
+    const float* hdr = reinterpret_cast<const float*>(slab + (size_t)blockIdx.y * slab_stride4);
+    const float inv = 1.f / hdr[SCALE_SLOT0 + slot];
+    float4* buf = slab + (size_t)blockIdx.y * slab_stride4 + off4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol * c8n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t c8 = idx / vol, v = idx - c8 * vol;
+        float4* p0 = buf + (2 * c8) * vol + v;
+        float4* p1 = p0 + vol;
+        const uint4 hi = *reinterpret_cast<const uint4*>(p0), lo = *reinterpret_cast<const uint4*>(p1);
+        const float2 a = unsplit_pair(hi.x, lo.x, inv), b = unsplit_pair(hi.y, lo.y, inv);
+        const float2 c = unsplit_pair(hi.z, lo.z, inv), d = unsplit_pair(hi.w, lo.w, inv);
+        *p0 = make_float4(a.x, a.y, b.x, b.y);
+        *p1 = make_float4(c.x, c.y, d.x, d.y);
+    }
+}
+
 static int grid_for(size_t work) {
     size_t b = (work + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
@@ -253,7 +343,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
 
     // ---- pack weights on the host into one staging vector, then one device allocation
     std::vector<float> host;
-    struct Offs { size_t wd, wt, wx, b, sc, sh, wu, ws; int c_up; float inv_u, inv_s; };
+    struct Offs { size_t wd, wt, wx, b, sc, sh, wu, ws; int c_up; float inv_u, inv_s, bp, bq; };
     std::vector<Offs> offs;
     std::vector<float> inv_scales;
     // decoder blocks that read concatenate([up, skip]): layer index -> channels of the up-sampled half
@@ -289,15 +379,22 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
             o.ws = take(tcx_weight_floats(cin - cu, cout));
             o.inv_s = tcx_pack_weights_range(p, cin, cu, cin - cu, cout, &host[o.ws]);
         }
+        std::vector<double> w1(cout, 0.0);                                   // sum of |w| per output channel
+        for (size_t i = 0; i < (size_t)27 * cin; ++i)
+            for (int co = 0; co < cout; ++co) w1[co] += std::fabs((double)p[i * cout + co]);
         p += (size_t)27 * cin * cout;
         o.b = take(cout); o.sc = take(cout); o.sh = take(cout);
         const float *bias = p, *gamma = p + cout, *beta = p + 2 * cout, *mean = p + 3 * cout, *var = p + 4 * cout;
+        double bp = 0.0, bq = 0.0;
         for (int co = 0; co < cout; ++co) {
             const float s = gamma[co] / std::sqrt(var[co] + eps);
             host[o.b + co] = bias[co];
             host[o.sc + co] = s;
             host[o.sh + co] = beta[co] - mean[co] * s;
+            bp = std::fmax(bp, std::fabs((double)s) * w1[co]);
+            bq = std::fmax(bq, std::fabs((double)s) * std::fabs((double)bias[co]) + std::fabs((double)host[o.sh + co]));
         }
+        o.bp = (float)bp; o.bq = (float)bq;
         p += 5 * (size_t)cout;
         offs.push_back(o);
     }
@@ -324,16 +421,28 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         L.w_tcu = offs[i].c_up ? net->all_dev + offs[i].wu : nullptr;
         L.w_tcx_skip = offs[i].c_up ? net->all_dev + offs[i].ws : nullptr;
         L.w_tcu_inv_scale = offs[i].inv_u; L.w_tcx_skip_inv_scale = offs[i].inv_s;
+        L.bound_p = offs[i].bp; L.bound_q = offs[i].bq;
         L.bias = net->all_dev + offs[i].b; L.scale = net->all_dev + offs[i].sc; L.shift = net->all_dev + offs[i].sh;
         net->layers.push_back(L);
     }
     net->head_w = net->all_dev + head_at;
+    // can the activation buffers between the blocks be split-fp16 (see use_split / run_plan)?
+    net->split_ok = sp->pool_x == 2 && sp->pool_y == 2 && sp->pool_z == 1 && sp->in_z % 8 == 0 &&
+                    net->layers[0].cin == 1 && net->layers[0].cout == 8;
+    for (size_t i = 1; i < net->layers.size() && net->split_ok; ++i) {
+        const ConvLayer& L = net->layers[i];
+        const bool decoder_first = c_up_of[i] > 0;
+        net->split_ok = L.cin % 8 == 0 && ((L.cout <= 32 && L.w_tcx) || (L.cout == 64 && L.w_tc)) &&
+                        (!decoder_first || (L.c_up > 0 && L.w_tcu && L.w_tcx_skip && L.cout <= 32));
+    }
+    for (int u = 0; u < sp->levels && net->split_ok; ++u)        // every up-sampling must be absorbed by a phase kernel
+        net->split_ok = c_up_of[2 * sp->levels + 2 * (u + 1)] > 0;
 
     // ---- op plan over one tile's slab
     int lx[CT_UNET_MAX_LEVELS + 1], ly[CT_UNET_MAX_LEVELS + 1], lz[CT_UNET_MAX_LEVELS + 1];
     lx[0] = sp->in_x; ly[0] = sp->in_y; lz[0] = sp->in_z;
     for (int l = 1; l <= sp->levels; ++l) { lx[l] = lx[l - 1] / sp->pool_x; ly[l] = ly[l - 1] / sp->pool_y; lz[l] = lz[l - 1] / sp->pool_z; }
-    size_t off = AMAX_SLOTS;                       // slab header: one max|value| slot per buffer
+    size_t off = HDR_FLOATS;                       // slab header: one max|value| slot and one operand-scale slot per buffer
     int n_slots = 0;
     std::vector<std::pair<size_t, int>> slot_of;  // buffer offset -> slot
     auto buf = [&](int c, int l) {
@@ -449,12 +558,13 @@ static TileGeom make_geom(const CtUNet* net, int x, int y, int z, const int cent
 
 // One convolution block on the engine the network is set to (see CtUNet::engine).
 static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t stride, int tiles, cudaStream_t s,
-                       const Op* next = nullptr, bool* next_fused = nullptr) {
+                       const Op* next = nullptr, bool* next_fused = nullptr, int fmt = 0) {
     int rc = 2;
     if (next_fused) *next_fused = false;
-    if (net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s, next, next_fused);
-    if (rc == 2 && net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s);
+    if (net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s, next, next_fused, fmt);
+    if (rc == 2 && net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s, fmt);
     if (rc == 1) return 1;
+    CT_REQUIRE(rc == 0 || fmt == 0, "unet: layer %d has no tensor-core kernel for split-fp16 buffers", op.layer);
     if (rc == 2) {
         CT_REQUIRE(net->engine == 0 || net->engine == 1,
                    "unet: tcgen05 engine forced but layer %d (cin %d, cout %d, z %d) is unsupported",
@@ -466,19 +576,35 @@ static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t str
 
 // Runs the op plan on `tiles` slabs that already hold their padded input (or, with skip_first, the output of the
 // first convolution block).
+// Split-fp16 activation buffers (unet_common.cuh) are used when every block after the first runs on a tensor-core
+// kernel that reads and writes them and the engine is one of the tensor-core mixes.
+static bool use_split(const CtUNet* net) { return net->split_ok && (net->engine == 0 || net->engine == 2 || net->engine == 4); }
+
 static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s, bool skip_first = false) {
     const size_t stride = net->slab_floats;
+    // the fused first block writes fp32; every later activation buffer is split-fp16 except the last block's output,
+    // which the 1x1x1 head reads as fp32
+    const bool split = skip_first && use_split(net);
+    const int last_layer = (int)net->layers.size() - 1;
     for (size_t idx = skip_first ? 1 : 0; idx < net->ops.size(); ++idx) {
         const Op& op = net->ops[idx];
         if (op.kind == OP_CONV) {
             bool fused = false;
             const Op* next = idx + 1 < net->ops.size() ? &net->ops[idx + 1] : nullptr;
-            if (launch_conv(net, op, slab0, stride, tiles, s, next, &fused)) return 1;
+            const int fmt = !split ? 0 : (op.layer == 1 ? 0 : FMT_SRC_SPLIT) | (op.layer == last_layer ? 0 : FMT_DST_SPLIT);
+            if (launch_conv(net, op, slab0, stride, tiles, s, next, &fused, fmt)) return 1;
             if (fused) ++idx;                      // the pooling that followed was written by the block's epilogue
         } else {
             const float4* src = reinterpret_cast<const float4*>(slab0);
             float4* dst = reinterpret_cast<float4*>(slab0);
-            if (op.kind == OP_POOL) {
+            if (op.kind == OP_POOL && split) {
+                dim3 grid((op.c / 8) * op.dx, tiles);
+                pool_split_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(slab0), reinterpret_cast<uint4*>(slab0), stride / 4,
+                                                       op.src_off / 4, op.dst_off / 4, op.src_coff / 4, op.c / 8, op.sx, op.sy,
+                                                       op.sz, op.dx, op.dy, op.dz, net->spec.pool_x, net->spec.pool_y,
+                                                       net->spec.pool_z, op.src_slot, op.dst_slot);
+                CT_LAUNCHED("pool_split_kernel");
+            } else if (op.kind == OP_POOL) {
                 dim3 grid((op.c / 4) * op.dx, tiles);
                 pool_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.src_coff / 4,
                                                  op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
@@ -491,15 +617,18 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s, 
                 if (nx && nx->kind == OP_CONV && nx->src_off == op.dst_off && (net->engine == 0 || net->engine == 2 || net->engine == 4) &&
                     net->layers[nx->layer].c_up == op.c && op.dst_coff == 0 && op.dx == 2 * op.sx && op.dy == 2 * op.sy && op.dz == op.sz) {
                     const int rc = launch_conv_tcu(net, net->layers[nx->layer], slab0, stride, tiles, op.src_off, op.src_slot,
-                                                   op.sx, op.sy, op.sz, nx->dst_off, nx->dst_coff, s);
+                                                   op.sx, op.sy, op.sz, nx->dst_off, nx->dst_coff, s, split);
                     if (rc == 1) return 1;
+                    CT_REQUIRE(rc == 0 || !split, "unet: phase kernel refused layer %d between split-fp16 buffers", nx->layer);
                     if (rc == 0) {
-                        const int rc2 = launch_conv_tcx_skip(net, *nx, slab0, stride, tiles, s);
+                        const int fmt = !split ? 0 : FMT_SRC_SPLIT | (nx->layer == last_layer ? 0 : FMT_DST_SPLIT);
+                        const int rc2 = launch_conv_tcx_skip(net, *nx, slab0, stride, tiles, s, fmt, split ? op.src_slot : -1);
                         CT_REQUIRE(rc2 == 0, "unet: skip-half convolution of layer %d failed", nx->layer);
                         ++idx;
                         continue;
                     }
                 }
+                CT_REQUIRE(!split, "unet: up-sampling op %zu has no phase kernel between split-fp16 buffers", idx);
                 dim3 grid((op.c / 4) * op.sx, tiles);
                 upsample_kernel<<<grid, 256, 0, s>>>(src, dst, stride / 4, op.src_off / 4, op.dst_off / 4, op.dst_coff / 4,
                                                      op.c / 4, op.sx, op.sy, op.sz, op.dx, op.dy, op.dz,
@@ -522,7 +651,7 @@ static int run_tiles(const CtUNet* net, const float* src, float* prob, int mode,
     for (int t0 = first; t0 < last; t0 += tiles_per_batch) {
         const int nt = (last - t0 < tiles_per_batch) ? last - t0 : tiles_per_batch;
         dim3 g(TX, nt), gh(mode == 0 ? geo.c[0] : TX, nt);
-        CT_CUDA(cudaMemset2DAsync(slab0, net->slab_floats * sizeof(float), 0, AMAX_SLOTS * sizeof(float), nt, s));
+        CT_CUDA(cudaMemset2DAsync(slab0, net->slab_floats * sizeof(float), 0, HDR_FLOATS * sizeof(float), nt, s));
         // engines 0 / 2 / 4: the first block (Cin = 1) reads the volume itself; otherwise gather, then the generic engines
         int fused = 2;
         if (net->engine != 1 && net->engine != 3)
@@ -545,7 +674,7 @@ extern "C" size_t ct_unet_conv_block_workspace_bytes(const CtUNet* net, int laye
     if (!net || layer < 0 || layer >= (int)net->layers.size() || batch < 1) return 0;
     const ConvLayer& L = net->layers[layer];
     const size_t vol = (size_t)x * y * z;
-    return (((size_t)L.cin_pad + (size_t)L.cout) * vol + AMAX_SLOTS) * sizeof(float) * (size_t)batch + 512;
+    return (((size_t)L.cin_pad + (size_t)L.cout) * vol + HDR_FLOATS) * sizeof(float) * (size_t)batch + 512;
 }
 
 extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, const float* in, float* out, int batch,
@@ -553,18 +682,22 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
     CT_REQUIRE(net && in && out && ws, "ct_unet_conv_block: null argument");
     CT_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "ct_unet_conv_block: layer %d out of range", layer);
     CT_REQUIRE(batch >= 1 && x > 0 && y > 0 && z > 0, "ct_unet_conv_block: bad shape");
-    CT_REQUIRE(engine >= 1 && engine <= 4, "ct_unet_conv_block: engine must be 1 (direct), 2 (tcgen05), 3 (tcgen05 classic) or 4 (tcgen05 x-stacked)");
+    CT_REQUIRE(engine >= 1 && engine <= 7, "ct_unet_conv_block: engine must be 1 (direct), 2 (tcgen05), 3 (tcgen05 classic), 4 (tcgen05 "
+               "x-stacked) or 5-7 (tcgen05 on split-fp16 buffers: both / destination only / source only)");
+    // engines 5-7: the block as it runs inside the network, between split-fp16 activation buffers (unet_common.cuh)
+    const int fmt = engine == 5 ? (FMT_SRC_SPLIT | FMT_DST_SPLIT) : engine == 6 ? FMT_DST_SPLIT : engine == 7 ? FMT_SRC_SPLIT : 0;
+    if (fmt) engine = 2;
     CT_REQUIRE(ws_bytes >= ct_unet_conv_block_workspace_bytes(net, layer, batch, x, y, z), "ct_unet_conv_block: workspace too small");
     CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_unet_conv_block: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const ConvLayer& L = net->layers[layer];
     const size_t vol = (size_t)x * y * z;
     // one "slab" per batch entry: [cin_pad planes | cout planes]
-    const size_t stride = ((size_t)L.cin_pad + L.cout) * vol + AMAX_SLOTS;
+    const size_t stride = ((size_t)L.cin_pad + L.cout) * vol + HDR_FLOATS;
     float* slab0 = static_cast<float*>(ws);
-    CT_CUDA(cudaMemset2DAsync(slab0, stride * sizeof(float), 0, AMAX_SLOTS * sizeof(float), batch, s));
+    CT_CUDA(cudaMemset2DAsync(slab0, stride * sizeof(float), 0, HDR_FLOATS * sizeof(float), batch, s));
     Op op{};
-    op.kind = OP_CONV; op.layer = layer; op.src_off = AMAX_SLOTS; op.dst_off = AMAX_SLOTS + (size_t)L.cin_pad * vol;
+    op.kind = OP_CONV; op.layer = layer; op.src_off = HDR_FLOATS; op.dst_off = HDR_FLOATS + (size_t)L.cin_pad * vol;
     op.src_slot = 0; op.dst_slot = 1;
     op.src_c = L.cin_pad; op.dst_c = L.cout; op.src_coff = 0; op.dst_coff = 0; op.c = L.cout;
     op.sx = op.dx = x; op.sy = op.dy = y; op.sz = op.dz = z;
@@ -579,7 +712,17 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
     {
         CtUNet view = *net;                     // shallow copy: same device arrays, engine chosen for this call
         view.engine = engine;
-        if (launch_conv(&view, op, slab0, stride, batch, s)) return 1;
+        float4* slab4 = reinterpret_cast<float4*>(slab0);
+        if (fmt & FMT_SRC_SPLIT) {
+            CT_REQUIRE(L.cin_pad % 8 == 0, "ct_unet_conv_block: a split-fp16 source needs a multiple of 8 input channels");
+            c4_to_split<<<dim3(grid_for(vol * (L.cin_pad / 8)), batch), 256, 0, s>>>(slab4, stride / 4, op.src_off / 4, L.cin_pad / 8, vol, op.src_slot);
+            CT_LAUNCHED("c4_to_split");
+        }
+        if (launch_conv(&view, op, slab0, stride, batch, s, nullptr, nullptr, fmt)) return 1;
+        if (fmt & FMT_DST_SPLIT) {
+            split_to_c4<<<dim3(grid_for(vol * (L.cout / 8)), batch), 256, 0, s>>>(slab4, stride / 4, op.dst_off / 4, L.cout / 8, vol, op.dst_slot);
+            CT_LAUNCHED("split_to_c4");
+        }
     }
     for (int b = 0; b < batch; ++b) {
         const size_t total = vol * cout4;

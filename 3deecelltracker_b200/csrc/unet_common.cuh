@@ -7,6 +7,7 @@
 // exactly one row of a no-swizzle K-major UMMA core matrix (8 rows x 16 B).
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <vector>
 
 namespace ct {
@@ -26,6 +27,9 @@ struct ConvLayer {
     float w_tcu_inv_scale;
     float* w_tcx_skip;
     float w_tcx_skip_inv_scale;
+    // a-priori bound of the block's output, |out| <= bound_p * max|in| + bound_q  (sum of |w| per output channel, bias,
+    // |alpha| <= 1, BatchNorm affine): the operand scale of a destination written in split-fp16 form is derived from it
+    float bound_p, bound_q;
     float* bias;              // device [cout]
     float* scale;             // device [cout]  gamma / sqrt(var + eps)
     float* shift;             // device [cout]  beta - mean * scale
@@ -49,6 +53,17 @@ struct Op {
 // of that tile (zeroed per batch; producers atomicMax the bit pattern, which orders like the value for floats >= 0).
 // The tensor-core convolution scales its fp16 operand images by a power of two derived from it.
 constexpr int AMAX_SLOTS = 64;
+// Split-fp16 activation buffers.  Between two tensor-core blocks an activation tensor is stored as the operand images the
+// consumer's MMAs read -- per 8 channels one 16-byte plane of fp16 `hi` and one of fp16 `lo'` with
+// x * s = hi + lo' * 2^-11 -- instead of two 4-channel fp32 planes: the same bytes at the same addresses (plane
+// 2 c8 = hi, plane 2 c8 + 1 = lo'), so TMA boxes and channel offsets are unchanged, but the consumer needs no
+// conversion pass through shared memory.  s is a power of two per tile, chosen by the PRODUCER before it has seen its
+// outputs, from the a-priori bound of ConvLayer::bound_p/q; it is published in the header's scale slot of the buffer
+// (slots [SCALE_SLOT0, SCALE_SLOT0 + AMAX_SLOTS)).  A loose bound costs nothing: hi and lo' are floating point, so
+// their relative precision holds until an element is 2^-13 / s small.
+constexpr int FMT_SRC_SPLIT = 1, FMT_DST_SPLIT = 2;
+constexpr int SCALE_SLOT0 = AMAX_SLOTS;
+constexpr int HDR_FLOATS = 2 * AMAX_SLOTS;
 
 }  // namespace ct
 
@@ -63,6 +78,7 @@ struct CtUNet {
     float* head_w;            // device [last_c]
     float head_b;
     float alpha;              // 0.3 (LeakyReLU) or 0 (ReLU)
+    bool split_ok;            // activation buffers between the blocks can be split-fp16 (unet.cu: use_split)
     int engine;               // 0 auto, 1 direct, 2 tcgen05 (stacked for Cout 8/16, else 27-tap), 3 27-tap only,
                               // 4 stacked wherever the shape allows (= 2 today)
     double flops_per_tile;
@@ -81,23 +97,25 @@ int launch_conv_direct(const CtUNet* net, const Op& op, float* slab0, size_t sla
                        cudaStream_t s);
 // implemented in unet_tc.cu (returns 2 when the layer shape is not supported by the tensor-core path)
 int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
-                   cudaStream_t s);
+                   cudaStream_t s, int fmt = 0);
 // implemented in unet_tcx.cu: x-stacked variant for Cout 8/16/32 (returns 2 when it does not take the layer)
 // `pool` = the op that follows in the plan; when it is the (2,2,1) max-pool of this block's output the kernel writes
 // the pooled copy itself and sets *pool_fused (the caller then skips that op).
+// `fmt` = FMT_SRC_SPLIT | FMT_DST_SPLIT: which of the two buffers are in split-fp16 form.
 int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles,
-                    cudaStream_t s, const Op* pool = nullptr, bool* pool_fused = nullptr);
+                    cudaStream_t s, const Op* pool = nullptr, bool* pool_fused = nullptr, int fmt = 0);
 size_t tcx_weight_floats(int cin_pad, int cout);
 float tcx_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
 // input channels [c_begin, c_begin + c_count) of the kernel only (the skip half of a decoder block)
 float tcx_pack_weights_range(const float* keras_kernel, int cin, int c_begin, int c_count, int cout, float* dst);
 // x-stacked block over the skip half of a concatenation, adding the partial sums the phase kernel left in dst
-int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s);
+int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
+                         int fmt = 0, int up_slot = -1);
 // implemented in unet_tcu.cu: convolution over the up-sampled half, on the low-resolution grid
 size_t tcu_weight_floats(int c_up, int cout);
 float tcu_pack_weights(const float* keras_kernel, int cin, int c_up, int cout, float* dst);
 int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t slab_stride, int tiles, size_t up_off,
-                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s);
+                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split = false);
 size_t tc_weight_floats(int cin_pad, int cout);
 // returns 1 / scale
 float tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);
@@ -136,6 +154,23 @@ __device__ __forceinline__ float tc_operand_scale(float am) {
     const int e = (int)((__float_as_uint(am) >> 23) & 0xffu);          // biased exponent, 0 for zero / subnormal
     const int se = (267 - e > 254) ? 254 : 267 - e;                    // 2^(13 - floor(log2 am)), clamped finite
     return (e == 0) ? 1.f : __uint_as_float((uint32_t)se << 23);
+}
+// operand scale of a block's split-fp16 output from the a-priori bound |out| <= p * max|in| + q
+__device__ __forceinline__ float split_out_scale(float am_in, float p, float q) {
+    return tc_operand_scale(fmaf(p, am_in, q) * 1.001f);
+}
+// x * s -> (hi, lo') fp16 pairs of two consecutive channels
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((a - hf.x) * 2048.f, (b - hf.y) * 2048.f);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 unsplit_pair(uint32_t hi, uint32_t lo, float inv_s) {
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+    return make_float2(fmaf(lf.x, 1.f / 2048.f, hf.x) * inv_s, fmaf(lf.y, 1.f / 2048.f, hf.y) * inv_s);
 }
 __device__ __forceinline__ void amax_update(float* slot, float v) {
     atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));

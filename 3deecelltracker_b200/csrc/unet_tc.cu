@@ -93,6 +93,10 @@ struct TcGeom {
     float* amax_dst;                             // ... of the destination buffer
     size_t slab_stride;                          // floats
     float w_inv_scale;                           // 1 / weight scale of the layer
+    // split-fp16 buffers (unet_common.cuh): header scale slots and the a-priori output bound of the block
+    const float* scale_src;
+    float* scale_dst;
+    float bound_p, bound_q;
 };
 
 struct TcUnit { int x0, y0, z0, tile; };
@@ -111,7 +115,9 @@ __device__ __forceinline__ TcUnit tc_unit(int u, const TcGeom& g, int bx) {
 // the worker warps drain into fp32 registers while the next stage's MMAs run: the tensor core adds with
 // truncation, so long in-TMEM accumulation chains would bias the result by ~(number of MMAs) * 2^-25 (measured 2e-5
 // of scale at K = 3456 with a TF32 split); register accumulation rounds to nearest.
-template <int N, int BX, int STAGES>
+// SRC_SPLIT: the source buffer already holds the fp16 hi / lo' operand images (the workers skip the conversion and the
+// MMA issuer waits for the TMA directly).  DST_SPLIT: the epilogue writes the destination in that form.
+template <int N, int BX, int STAGES, bool SRC_SPLIT, bool DST_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
                 const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -183,7 +189,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             for (int g = 0; g < n_stages; ++g) {
                 const int s = g % STAGES, use = g / STAGES, set = g & 1, use_a = g >> 1;
                 if (use_a > 0) mbar_wait(&bar_acc_empty[set], (use_a - 1) & 1);
-                mbar_wait(&bar_conv[s], use & 1);
+                mbar_wait(SRC_SPLIT ? &bar_full[s] : &bar_conv[s], use & 1);
                 tc_fence_after();
                 const uint32_t a_hi = ring16 + (uint32_t)s * (Cfg::STAGE / 16), a_lo = a_hi + Cfg::PLANE / 16;
                 const uint32_t b_base = a_hi + 2 * (Cfg::PLANE / 16);
@@ -220,7 +226,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         const int half = (warp - 2) >> 2;              // which BX/2 M tiles this thread drains
         const int row = q * 32 + lane;
         const size_t vol = (size_t)geo.X * geo.Y * geo.Z;
-        float acc[Cfg::TILES_PER_HALF][N];
+        float2 acc[Cfg::TILES_PER_HALF][N / 2];               // channel pairs: packed fp32 arithmetic (tc_ptx.cuh)
         constexpr float W2 = 1.f / 2048.f, W3 = W2 * W2;      // weights of the lo' cross terms
 
         auto drain = [&](int g, bool first) {
@@ -242,16 +248,17 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
                         tmem_ld8(t0 + i * Cfg::NPD + 24, c4);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float v = fmaf(c3[k], W3, fmaf(b2[k] + c4[k], W2, a[k]));
-                            acc[i][k] = first ? v : acc[i][k] + v;
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 v = make_float2(fmaf(c3[2 * k], W3, fmaf(b2[2 * k] + c4[2 * k], W2, a[2 * k])),
+                                                         fmaf(c3[2 * k + 1], W3, fmaf(b2[2 * k + 1] + c4[2 * k + 1], W2, a[2 * k + 1])));
+                            acc[i][k] = first ? v : f2_add(acc[i][k], v);
                         }
                     } else {
                         tmem_ld_wait();
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float v = fmaf(b2[k], W2, a[k]);
-                            acc[i][n8 * 8 + k] = first ? v : acc[i][n8 * 8 + k] + v;
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 v = f2_fma(make_float2(b2[2 * k], b2[2 * k + 1]), f2_splat(W2), make_float2(a[2 * k], a[2 * k + 1]));
+                            acc[i][n8 * 4 + k] = first ? v : f2_add(acc[i][n8 * 4 + k], v);
                         }
                     }
                 }
@@ -260,9 +267,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_acc_empty[set]);
         };
-        auto store_unit = [&](const TcUnit& un, float inv_scale) {
+        auto store_unit = [&](const TcUnit& un, float inv_scale, float s_out) {
             const int y = un.y0 + (row >> 3), z = un.z0 + (row & 7);
             float amax = 0.f;
+            if (DST_SPLIT && wt == 0) geo.scale_dst[(size_t)un.tile * geo.slab_stride] = s_out;
             if (y < geo.Y) {
                 float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)geo.dst_c4off * vol;
 #pragma unroll
@@ -270,17 +278,28 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
                     const int x = un.x0 + half * Cfg::TILES_PER_HALF + i;
                     if (x >= geo.X) break;
                     const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
+                    if constexpr (!DST_SPLIT) {
 #pragma unroll
-                    for (int c4 = 0; c4 < N / 4; ++c4) {
-                        float o[4];
+                        for (int c4 = 0; c4 < N / 4; ++c4) {
+                            float2 o[2];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float t = fmaf(acc[i][c4 * 4 + k], inv_scale, ep_s[0][c4 * 4 + k]);
-                            t = t > 0.f ? t : alpha * t;
-                            o[k] = fmaf(t, ep_s[1][c4 * 4 + k], ep_s[2][c4 * 4 + k]);
-                            amax = fmaxf(amax, fabsf(o[k]));
+                            for (int k = 0; k < 2; ++k) o[k] = block_epilogue(acc[i][c4 * 2 + k], inv_scale, alpha, &ep_s[0][0], N, c4 * 4 + 2 * k, amax);
+                            d_tile[(size_t)c4 * vol + vox] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
                         }
-                        d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+                        // plane 2 c8 = fp16 hi image of channels [8 c8, 8 c8 + 8), plane 2 c8 + 1 = lo' image
+                        uint4* d4 = reinterpret_cast<uint4*>(d_tile);
+#pragma unroll
+                        for (int c8 = 0; c8 < N / 8; ++c8) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 o = block_epilogue(acc[i][c8 * 4 + k], inv_scale, alpha, &ep_s[0][0], N, c8 * 8 + 2 * k, amax);
+                                split_pair2(o, s_out, hi[k], lo[k]);
+                            }
+                            d4[(size_t)(2 * c8) * vol + vox] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            d4[(size_t)(2 * c8 + 1) * vol + vox] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
                     }
                 }
             }
@@ -292,21 +311,25 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         int c = 0, k = 0;                              // chunk / unit ordinal of stage g
         int pc = 0;                                    // chunk of stage g - 1
         TcUnit prev{}, cur{};
-        float s_cur = 1.f, s_prev = 1.f;
+        float s_cur = 1.f, s_prev = 1.f, so_cur = 1.f, so_prev = 1.f;
         // max|x| of a unit's tile is fetched one unit ahead, so the load's latency is never in front of a conversion
         TcUnit nxt = tc_unit((int)blockIdx.x, geo, BX);
         float am_nxt = n_units > 0 ? geo.amax_src[(size_t)nxt.tile * geo.slab_stride] : 0.f;
+        float sc_nxt = (SRC_SPLIT && n_units > 0) ? geo.scale_src[(size_t)nxt.tile * geo.slab_stride] : 1.f;
         for (int g = 0; g <= n_stages; ++g) {
             if (g < n_stages) {
                 if (c == 0) {
                     cur = nxt;
-                    s_cur = tc_operand_scale(am_nxt);
+                    s_cur = SRC_SPLIT ? sc_nxt : tc_operand_scale(am_nxt);
+                    if constexpr (DST_SPLIT) so_cur = split_out_scale(am_nxt, geo.bound_p, geo.bound_q);
                     if (k + 1 < n_units) {
                         nxt = tc_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
                         am_nxt = geo.amax_src[(size_t)nxt.tile * geo.slab_stride];
+                        if constexpr (SRC_SPLIT) sc_nxt = geo.scale_src[(size_t)nxt.tile * geo.slab_stride];
                     }
                 }
                 const int s = g % STAGES, use = g / STAGES;
+                if constexpr (!SRC_SPLIT) {
                 mbar_wait(&bar_full[s], use & 1);
                 uint4* p0 = reinterpret_cast<uint4*>(ring + (size_t)s * Cfg::STAGE);
                 uint4* p1 = reinterpret_cast<uint4*>(ring + (size_t)s * Cfg::STAGE + Cfg::PLANE);
@@ -331,12 +354,13 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_conv[s]);
+                }
             }
             if (g > 0) {
                 drain(g - 1, pc == 0);
-                if (pc == cin8 - 1) store_unit(prev, geo.w_inv_scale / s_prev);
+                if (pc == cin8 - 1) store_unit(prev, geo.w_inv_scale / s_prev, so_prev);
             }
-            if (c == 0) { prev = cur; s_prev = s_cur; }
+            if (c == 0) { prev = cur; s_prev = s_cur; so_prev = so_cur; }
             pc = c;
             if (++c == cin8) { c = 0; ++k; }
         }
@@ -419,21 +443,22 @@ static int sm_count() {
     return n;
 }
 
-template <int N, int BX, int STAGES>
+template <int N, int BX, int STAGES, bool SRC_SPLIT, bool DST_SPLIT>
 static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, float4* dst, int X, int Y, int Z,
                      size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, cudaStream_t s) {
     using Cfg = TcCfg<N, BX, STAGES>;
     // per device / context attribute: set on every launch (cheap) so several GPUs in one process are correct
-    CT_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CT_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<N, BX, STAGES, SRC_SPLIT, DST_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     TcGeom g;
     g.cin8 = (L.cin_pad + 7) / 8; g.X = X; g.Y = Y; g.Z = Z;
     g.amax_src = amax_src; g.amax_dst = amax_dst; g.slab_stride = stride4 * 4; g.w_inv_scale = L.w_tc_inv_scale;
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
+    g.scale_src = amax_src + SCALE_SLOT0; g.scale_dst = amax_dst + SCALE_SLOT0; g.bound_p = L.bound_p; g.bound_q = L.bound_q;
     const int sms = sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
     const int grid = g.units < sms ? g.units : sms;
-    conv3_tc_kernel<N, BX, STAGES><<<grid, TC_THREADS, Cfg::SMEM, s>>>(map, L.w_tc, L.bias, L.scale, L.shift, alpha, dst, g);
+    conv3_tc_kernel<N, BX, STAGES, SRC_SPLIT, DST_SPLIT><<<grid, TC_THREADS, Cfg::SMEM, s>>>(map, L.w_tc, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
 }
 
@@ -454,7 +479,7 @@ int tc_make_map(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, int 
     return 0;
 }
 
-int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
+int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s, int fmt) {
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;
     if (!L.w_tc || !tc_shape_ok(L.cout) || Z % 8 != 0) return 2;
@@ -469,18 +494,26 @@ int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_st
     float* src = slab0 + op.src_off;
     const float* am_s = slab0 + op.src_slot;
     float* am_d = slab0 + op.dst_slot;
-    if (L.cout == 8) {
+    if (fmt != 0) {
+        // split-fp16 buffers: only the Cout = 64 blocks run on this kernel inside the network (unet_tcx.cu takes the rest)
+        if (L.cout != 64 || ((fmt & FMT_SRC_SPLIT) && L.cin_pad % 8 != 0)) return 2;
+        CT_REQUIRE(!(fmt & FMT_DST_SPLIT) || op.dst_coff % 8 == 0, "conv: split destination at channel offset %d", op.dst_coff);
+        if (tc_make_map(&map, src, X, Y, Z, c4, tiles, slab_stride, 2)) return 1;
+        if (fmt == FMT_SRC_SPLIT) rc = launch_tc<64, 2, 2, true, false>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+        else if (fmt == FMT_DST_SPLIT) rc = launch_tc<64, 2, 2, false, true>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+        else rc = launch_tc<64, 2, 2, true, true>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+    } else if (L.cout == 8) {
         if (tc_make_map(&map, src, X, Y, Z, c4, tiles, slab_stride, 8)) return 1;
-        rc = launch_tc<8, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+        rc = launch_tc<8, 8, 3, false, false>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     } else if (L.cout == 16) {
         if (tc_make_map(&map, src, X, Y, Z, c4, tiles, slab_stride, 8)) return 1;
-        rc = launch_tc<16, 8, 3>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+        rc = launch_tc<16, 8, 3, false, false>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     } else if (L.cout == 32) {
         if (tc_make_map(&map, src, X, Y, Z, c4, tiles, slab_stride, 4)) return 1;
-        rc = launch_tc<32, 4, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+        rc = launch_tc<32, 4, 2, false, false>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     } else {
         if (tc_make_map(&map, src, X, Y, Z, c4, tiles, slab_stride, 2)) return 1;
-        rc = launch_tc<64, 2, 2>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
+        rc = launch_tc<64, 2, 2, false, false>(map, L, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, s);
     }
     if (rc) return 1;
     CT_LAUNCHED("conv3_tc_kernel");

@@ -77,6 +77,7 @@ struct TuGeom {
     const float* amax_src;
     size_t slab_stride;
     float w_inv_scale;
+    const float* scale_src;                      // split-fp16 source: header scale slot (unet_common.cuh)
 };
 
 struct TuUnit { int x0, y0, z0, tile; };
@@ -109,7 +110,8 @@ __device__ __forceinline__ void tu_ld_issue(uint32_t taddr, uint32_t (&r)[CH]) {
 
 // Persistent CTA.  Work unit = BX x 16 x 8 LOW-resolution voxels (= 2 BX x 32 x 8 output voxels) of one tile.
 // Stage g = one 8-channel chunk of one unit; accumulator step a = (g * (BX+2) + j) * 2 + py.
-template <int N, int BX, int STAGES>
+// SRC_SPLIT: the low-resolution source already holds the fp16 hi / lo' operand images (no conversion warps).
+template <int N, int BX, int STAGES, bool SRC_SPLIT>
 __global__ void __launch_bounds__(TuCfg<N, BX, STAGES>::THREADS, 1)
 conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack, float4* __restrict__ dst,
                  const TuGeom geo) {
@@ -175,7 +177,8 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             int a = 0;
             for (int g = 0; g < n_stages; ++g) {
                 const int s = g % STAGES, use = g / STAGES;
-                mbar_wait(&bar_conv[s], use & 1);
+                mbar_wait(SRC_SPLIT ? &bar_full[s] : &bar_conv[s], use & 1);
+                if constexpr (SRC_SPLIT) tc_fence_after();
                 const uint32_t a_hi = ring16 + (uint32_t)s * (Cfg::STAGE / 16), a_lo = a_hi + Cfg::PLANE / 16;
                 const uint32_t b_base = a_hi + 2 * (Cfg::PLANE / 16);
 #pragma unroll 1
@@ -204,7 +207,7 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             }
         }
         __syncwarp();
-    } else {
+    } else if constexpr (!SRC_SPLIT) {
         // ---------------- converters: fp32 -> fp16 hi / lo' images of every landed stage, in place
         const int ct = threadIdx.x - 64;
         int g = 0;
@@ -248,17 +251,18 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         const int row = q * 32 + lane;
         const int DX = 2 * geo.X, DY = 2 * geo.Y;
         const size_t vol = (size_t)DX * DY * geo.Z;
-        float acc[BX][2][2][CH];                                   // [plane][px][py][channel]
+        float2 acc[BX][2][2][CH / 2];                              // [plane][px][py][channel pair] (packed fp32, tc_ptx.cuh)
         constexpr float W2 = 1.f / 2048.f;
         int a = 0;
         TuUnit un_next = tu_unit((int)blockIdx.x, geo, BX);
-        float am_next = n_units > 0 ? geo.amax_src[(size_t)un_next.tile * geo.slab_stride] : 0.f;
+        const float* s_slot = SRC_SPLIT ? geo.scale_src : geo.amax_src;      // split source: the scale itself
+        float am_next = n_units > 0 ? s_slot[(size_t)un_next.tile * geo.slab_stride] : 0.f;
         for (int k = 0; k < n_units; ++k) {
             const TuUnit un = un_next;
-            const float inv_scale = geo.w_inv_scale / tc_operand_scale(am_next);
+            const float inv_scale = geo.w_inv_scale / (SRC_SPLIT ? am_next : tc_operand_scale(am_next));
             if (k + 1 < n_units) {
                 un_next = tu_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
-                am_next = geo.amax_src[(size_t)un_next.tile * geo.slab_stride];
+                am_next = s_slot[(size_t)un_next.tile * geo.slab_stride];
             }
             const int yl = un.y0 + (row >> 3), z = un.z0 + (row & 7);
             float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)(geo.dst_c4off + ch0 / 4) * vol;
@@ -271,10 +275,11 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                     for (int py = 0; py < 2; ++py) {
                         const size_t vox = ((size_t)(2 * xl + px) * DY + (2 * yl + py)) * geo.Z + z;
 #pragma unroll
-                        for (int c4 = 0; c4 < CH / 4; ++c4)
-                            d_tile[(size_t)c4 * vol + vox] =
-                                make_float4(acc[i][px][py][c4 * 4 + 0] * inv_scale, acc[i][px][py][c4 * 4 + 1] * inv_scale,
-                                            acc[i][px][py][c4 * 4 + 2] * inv_scale, acc[i][px][py][c4 * 4 + 3] * inv_scale);
+                        for (int c4 = 0; c4 < CH / 4; ++c4) {
+                            const float2 lo2 = f2_mul(acc[i][px][py][c4 * 2], f2_splat(inv_scale));
+                            const float2 hi2 = f2_mul(acc[i][px][py][c4 * 2 + 1], f2_splat(inv_scale));
+                            d_tile[(size_t)c4 * vol + vox] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                        }
                     }
             };
 #pragma unroll
@@ -282,7 +287,7 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
 #pragma unroll
-                    for (int ch = 0; ch < CH; ++ch) acc[i][p >> 1][p & 1][ch] = 0.f;
+                    for (int ch = 0; ch < CH / 2; ++ch) acc[i][p >> 1][p & 1][ch] = make_float2(0.f, 0.f);
 #pragma unroll 1
             for (int c = 0; c < cin8; ++c) {
                 const bool last = (c == cin8 - 1);
@@ -318,8 +323,10 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                                 const int i = j - 1 - ax;
                                 if (i < 0 || i >= BX) continue;
 #pragma unroll
-                                for (int ch = 0; ch < CH; ++ch)
-                                    acc[i][px][py][ch] += fmaf(__uint_as_float(v[kq][1][ch]), W2, __uint_as_float(v[kq][0][ch]));
+                                for (int ch = 0; ch < CH / 2; ++ch)
+                                    acc[i][px][py][ch] = f2_add(acc[i][px][py][ch],
+                                        f2_fma(make_float2(__uint_as_float(v[kq][1][2 * ch]), __uint_as_float(v[kq][1][2 * ch + 1])), f2_splat(W2),
+                                               make_float2(__uint_as_float(v[kq][0][2 * ch]), __uint_as_float(v[kq][0][2 * ch + 1]))));
                             }
                         }
                         tc_fence_before();
@@ -400,28 +407,29 @@ float tcu_pack_weights(const float* w, int cin, int c_up, int cout, float* dst) 
     return 1.f / scale;
 }
 
-template <int N, int BX, int STAGES>
+template <int N, int BX, int STAGES, bool SRC_SPLIT>
 static int launch_tcu(const CUtensorMap& map, const float* wpack, float inv_scale, float4* dst, int X, int Y, int Z,
                       int cin8, size_t stride4, int dst_c4off, int tiles, const float* amax_src, cudaStream_t s) {
     using Cfg = TuCfg<N, BX, STAGES>;
-    CT_CUDA(cudaFuncSetAttribute(conv3_tcu_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CT_CUDA(cudaFuncSetAttribute(conv3_tcu_kernel<N, BX, STAGES, SRC_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     TuGeom g;
     g.cin8 = cin8; g.X = X; g.Y = Y; g.Z = Z;
     g.amax_src = amax_src; g.slab_stride = stride4 * 4; g.w_inv_scale = inv_scale;
+    g.scale_src = amax_src + SCALE_SLOT0;
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
     const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
     const int grid = g.units < sms ? g.units : sms;
-    conv3_tcu_kernel<N, BX, STAGES><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, wpack, dst, g);
+    conv3_tcu_kernel<N, BX, STAGES, SRC_SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, wpack, dst, g);
     return 0;
 }
 
 // Partial sums of conv block `L` over its up-sampled input half: low-resolution source `up` (c_up channels at
-// X x Y x Z, header slot up_slot) -> pre-activation sums in the block's destination buffer (2X x 2Y x Z).
-// Returns 2 when the shape is not handled.
+// X x Y x Z, header slot up_slot; fp32 or, with src_split, split-fp16) -> fp32 pre-activation sums in the block's
+// destination buffer (2X x 2Y x Z).  Returns 2 when the shape is not handled.
 int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t slab_stride, int tiles, size_t up_off,
-                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s) {
+                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split) {
     if (!L.w_tcu || Z % 8 != 0) return 2;
     CT_REQUIRE(slab_stride % 4 == 0 && up_off % 4 == 0 && dst_off % 4 == 0, "conv: misaligned slab");
     CUtensorMap map;
@@ -432,9 +440,15 @@ int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t 
     const size_t st4 = slab_stride / 4;
     const int cin8 = L.c_up / 8, co4 = dst_coff / 4;
     int rc;
-    if (L.cout == 8) rc = launch_tcu<8, 8, 3>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
-    else if (L.cout == 16) rc = launch_tcu<16, 4, 3>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
-    else rc = launch_tcu<32, 2, 3>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+    if (src_split) {
+        if (L.cout == 8) rc = launch_tcu<8, 8, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+        else rc = launch_tcu<32, 2, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+    } else {
+        if (L.cout == 8) rc = launch_tcu<8, 8, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+        else rc = launch_tcu<32, 2, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+    }
     if (rc) return 1;
     CT_LAUNCHED("conv3_tcu_kernel");
     (void)net;

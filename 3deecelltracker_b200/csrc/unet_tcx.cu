@@ -25,7 +25,9 @@
 #include "unet_common.cuh"
 #include "tc_ptx.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace ct {
 
@@ -56,7 +58,7 @@ constexpr int TX_CONV_WARPS = 2;                // operand conversion (fp32 -> f
 // + 8 warps (two per tensor-memory lane quarter, half the channels each) for accumulator drain, x shift-add, epilogue;
 // Cout = 32: two accumulator sets of 192 columns, and the drain warps take registers from warps 0-3 (setmaxnreg)
 
-template <int N, int BX, int STAGES>
+template <int N, int BX, int STAGES, int DW = 8>
 struct TxCfg {
     static constexpr bool N8 = (N == 8);
     static constexpr int NPR = 6 * N;                                  // B rows per K half
@@ -71,9 +73,17 @@ struct TxCfg {
     static constexpr int STAGE = 2 * PLANE + B_BYTES;
     static constexpr int TMEM_COLS = NSETS * NPD <= 256 ? 256 : 512;
     static constexpr int SMEM = STAGES * STAGE + 1024;
-    static constexpr int DRAIN_WARPS = 8;                              // two per tensor-memory lane quarter
+    // 8 drain warps: two per tensor-memory lane quarter, half the channels each.  16: additionally each warp owns only
+    // half of the unit's output planes (PH = 2) -- twice the warps to hide tensor-memory / shared-memory latencies
+    // behind, half the accumulator registers per thread.  Measured on B200 (38 tiles, all 13 blocks): 16 warps are
+    // 14 % SLOWER than 8 (6.51 vs 5.68 ms) -- the extra warps spin on the same accumulator barriers and take issue
+    // slots from the ones that work -- so only DW = 8 is instantiated.
+    static constexpr int DRAIN_WARPS = DW;
+    static constexpr int PH = DW / 8;                                  // plane halves
+    static constexpr int PB = BX / PH;                                 // output planes per drain thread
     static constexpr int THREADS = 64 + 32 * (TX_CONV_WARPS + DRAIN_WARPS);
-    static constexpr int CH = N / (DRAIN_WARPS / 4);                   // output channels per drain thread
+    static constexpr int CH = N / 2;                                   // output channels per drain thread
+    static_assert(DW == 8 || DW == 16, "8 or 16 drain warps");
     // Cout = 32 (acc[8][16] = 128 registers per drain thread): the three x-taps of a set are loaded one at a time (32
     // live registers instead of 96), and the drain warps take registers from the producer / MMA / converter warpgroup.
     // setmaxnreg moves registers inside the CTA's launch-time pool (384 threads x 168): 128 x 56 + 256 x 224 = 64512.
@@ -81,8 +91,10 @@ struct TxCfg {
 #ifdef CT_NO_REBALANCE
     static constexpr bool REBALANCE = false;                           // debug build: no setmaxnreg (spills instead)
 #else
-    static constexpr bool REBALANCE = (N == 32);
+    static constexpr bool REBALANCE = (N == 32) || DW == 16;
 #endif
+    // setmaxnreg targets: 384 threads x 168 -> 128 x 56 + 256 x 224; 640 threads x 96 -> 128 x 32 + 512 x 112
+    static constexpr int REG_DEC = DW == 16 ? 32 : 56, REG_INC = DW == 16 ? 112 : 224;
     static constexpr bool POOL = (N == 16);                            // fused (2,2,1) max-pool epilogue (d0b only)
     static_assert(NSETS * NPD <= 512, "accumulators exceed tensor memory");
     static_assert(N1 % 16 == 0 && N1 <= 256 && N2 % 16 == 0, "UMMA N out of range for M = 128");
@@ -104,6 +116,12 @@ struct TxGeom {
     // 1: dst already holds partial pre-activation sums of this block (the up-sampled half of a decoder block's
     // concatenated input, convolved on the low-resolution grid by unet_tcu.cu); the epilogue adds them in
     int add_partial;
+    // split-fp16 buffers (unet_common.cuh): header scale slots of the source / destination, the a-priori output bound
+    // of the block, and (decoder blocks) the max|x| slot of the up-sampled half that fed the partial sums
+    const float* scale_src;
+    float* scale_dst;
+    const float* amax_src2;
+    float bound_p, bound_q;
 };
 
 struct TxUnit { int x0, y0, z0, tile; };
@@ -139,13 +157,15 @@ __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[CH])
 // unit (ring slot g % STAGES); accumulator step a = g * (BX+2) + j = input plane j of stage g (tensor-memory set
 // a % NSETS).  Warp roles: 0 TMA producer (+ tensor-memory allocator), 1 MMA issuer, 2-3 operand conversion,
 // 4-11 accumulator drain / x shift-add / epilogue.
-template <int N, int BX, int STAGES>
-__global__ void __launch_bounds__(TxCfg<N, BX, STAGES>::THREADS, 1)
+// SRC_SPLIT: the source buffer already holds the fp16 hi / lo' operand images (no conversion warps, the MMA issuer waits
+// for the TMA directly).  DST_SPLIT: the epilogue writes the destination in that form.
+template <int N, int BX, int STAGES, int DW, bool SRC_SPLIT, bool DST_SPLIT>
+__global__ void __launch_bounds__(TxCfg<N, BX, STAGES, DW>::THREADS, 1)
 conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
                  const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                  float alpha, float4* __restrict__ dst, const TxGeom geo) {
-    using Cfg = TxCfg<N, BX, STAGES>;
-    constexpr int SXH = Cfg::SXH, CH = Cfg::CH, NSETS = Cfg::NSETS;
+    using Cfg = TxCfg<N, BX, STAGES, DW>;
+    constexpr int SXH = Cfg::SXH, CH = Cfg::CH, NSETS = Cfg::NSETS, PB = Cfg::PB;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc_full[NSETS], bar_acc_empty[NSETS];
     __shared__ uint32_t tmem_base_s;
@@ -183,7 +203,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 
     if (warp < 2 + TX_CONV_WARPS) {
     // warpgroup 0 (producer, MMA issuer, converters) gives registers to the drain warpgroups
-    if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REG_DEC));
     if (warp == 0) {
         // ---------------- TMA producer
         if (elect_one()) {
@@ -213,7 +233,8 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             long long w_conv = 0, w_acc = 0, t_begin = clock64();
             for (int g = 0; g < n_stages; ++g) {
                 const int s = g % STAGES, use = g / STAGES;
-                { TX_T0(); mbar_wait(&bar_conv[s], use & 1); TX_ACC(w_conv); }
+                { TX_T0(); mbar_wait(SRC_SPLIT ? &bar_full[s] : &bar_conv[s], use & 1); TX_ACC(w_conv); }
+                if constexpr (SRC_SPLIT) tc_fence_after();
                 const uint32_t a_hi = ring16 + (uint32_t)s * (Cfg::STAGE / 16), a_lo = a_hi + Cfg::PLANE / 16;
                 const uint32_t b_base = a_hi + 2 * (Cfg::PLANE / 16);
 #pragma unroll 1
@@ -243,7 +264,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #endif
         }
         __syncwarp();
-    } else {
+    } else if constexpr (!SRC_SPLIT) {
         // ---------------- converters: fp32 -> fp16 hi / lo' images of every landed stage, in place
         const int ct = threadIdx.x - 64;
         int g = 0;
@@ -286,78 +307,130 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     }
     } else {
         // ---------------- drain warps: tensor memory -> registers with the x shift-add, epilogue
-        if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REG_INC));
         const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
-        const int part = (warp - 2 - TX_CONV_WARPS) >> 2;          // which CH channels this thread owns
+        const int dwi = warp - 2 - TX_CONV_WARPS;                  // drain warp index
+        const int part = (dwi >> 2) & 1;                           // which CH channels this thread owns
         const int ch0 = part * CH;
         const int row = q * 32 + lane;
         const size_t vol = (size_t)geo.X * geo.Y * geo.Z;
-        float acc[BX][CH];
         constexpr float W2 = 1.f / 2048.f;                         // weight of the hi.lo' + lo'.hi column group
         constexpr int TERMS = 2;                                   // column groups per x-tap
 
+        // the body is instantiated per plane half so that every accumulator index stays a compile-time constant
+        auto run = [&](auto ph_c) {
+        constexpr int I0 = decltype(ph_c)::value * PB;             // first output plane this warp owns
+        float2 acc[PB][CH / 2];                                    // channel pairs: packed fp32 arithmetic (tc_ptx.cuh)
         int a = 0;
         long long w_accf = 0, t_epi = 0, t_begin = clock64();
-        // max|x| of the unit's tile is fetched one unit ahead: the load's latency never sits in front of the epilogue
+        // max|x| (and, for split sources, the operand scale) of the unit's tile is fetched one unit ahead: the load's
+        // latency never sits in front of the epilogue
         TxUnit un_next = tx_unit((int)blockIdx.x, geo, BX);
-        float am_next = n_units > 0 ? geo.amax_src[(size_t)un_next.tile * geo.slab_stride] : 0.f;
+        auto tile_amax = [&](int tile, float& am, float& am2) {
+            am = geo.amax_src[(size_t)tile * geo.slab_stride];
+            am2 = (DST_SPLIT && geo.amax_src2) ? geo.amax_src2[(size_t)tile * geo.slab_stride] : 0.f;
+        };
+        float am_next = 0.f, am2_next = 0.f;
+        if (n_units > 0) tile_amax(un_next.tile, am_next, am2_next);
+        float sc_next = (SRC_SPLIT && n_units > 0) ? geo.scale_src[(size_t)un_next.tile * geo.slab_stride] : 1.f;
         for (int k = 0; k < n_units; ++k) {
             const TxUnit un = un_next;
-            const float inv_scale = geo.w_inv_scale / tc_operand_scale(am_next);
+            const float s_in = SRC_SPLIT ? sc_next : tc_operand_scale(am_next);
+            const float inv_scale = geo.w_inv_scale / s_in;
+            // destination operand scale (power of two) from the a-priori bound of this block's output on this tile
+            const float s_out = DST_SPLIT ? split_out_scale(fmaxf(am_next, am2_next), geo.bound_p, geo.bound_q) : 1.f;
+            if (DST_SPLIT && warp == 2 + TX_CONV_WARPS && lane == 0) {
+                geo.scale_dst[(size_t)un.tile * geo.slab_stride] = s_out;
+                if (Cfg::POOL && geo.pool_dst != nullptr) geo.amax_pool[SCALE_SLOT0 + (size_t)un.tile * geo.slab_stride] = s_out;
+            }
             if (k + 1 < n_units) {
                 un_next = tx_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
-                am_next = geo.amax_src[(size_t)un_next.tile * geo.slab_stride];
+                tile_amax(un_next.tile, am_next, am2_next);
+                if constexpr (SRC_SPLIT) sc_next = geo.scale_src[(size_t)un_next.tile * geo.slab_stride];
             }
             const int y = un.y0 + (row >> 3), z = un.z0 + (row & 7);
-            float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)(geo.dst_c4off + ch0 / 4) * vol;
+            float4* d_base = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)geo.dst_c4off * vol;
+            float4* d_tile = d_base + (size_t)(ch0 / 4) * vol;
             float amax = 0.f;
             // epilogue of ONE output plane: scale back, bias -> activation -> BatchNorm, 16-byte channel-chunk stores.
             // Plane i is complete once input plane i + 2 of the last chunk is drained, so its stores are issued there
             // and trickle out under the remaining drains instead of bursting at the end of the unit.
             // With pooling fused, the pair of x planes (2p, 2p+1) meets in this thread and the pair of y rows sits 8
             // lanes apart (row = 8 y + z), so a 2 x 2 x 1 window is one register max and one shuffle.
-            float keep[CH];
+            // Split destination: plane 2 c8 of the buffer takes the fp16 hi image of channels [8 c8, 8 c8 + 8), plane
+            // 2 c8 + 1 the lo' image; a thread that owns 4 channels (Cout = 8) writes its 8-byte half of both.
+            float2 keep[CH / 2];
+            auto put = [&](float4* base, size_t pvol, size_t pvox, const float2 (&v)[CH / 2]) {
+                if constexpr (!DST_SPLIT) {
+#pragma unroll
+                    for (int c4 = 0; c4 < CH / 4; ++c4)
+                        base[(size_t)(ch0 / 4 + c4) * pvol + pvox] = make_float4(v[c4 * 2].x, v[c4 * 2].y, v[c4 * 2 + 1].x, v[c4 * 2 + 1].y);
+                } else {
+                    uint32_t hi[CH / 2], lo[CH / 2];
+#pragma unroll
+                    for (int h2 = 0; h2 < CH / 2; ++h2) {
+                        // x s -> hi = RN16(x s), lo' = RN16((x s - hi) 2^11): the difference and its scaling are exact
+                        const float2 os = f2_mul(v[h2], f2_splat(s_out));
+                        const __half2 h = __floats2half2_rn(os.x, os.y);
+                        const float2 hf = __half22float2(h);
+                        const float2 d = f2_fma(hf, f2_splat(-2048.f), f2_mul(os, f2_splat(2048.f)));
+                        const __half2 l = __floats2half2_rn(d.x, d.y);
+                        hi[h2] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[h2] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    if constexpr (CH >= 8) {
+                        uint4* b4 = reinterpret_cast<uint4*>(base);
+#pragma unroll
+                        for (int c8 = 0; c8 < CH / 8; ++c8) {
+                            b4[(size_t)(ch0 / 4 + 2 * c8) * pvol + pvox] = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);
+                            b4[(size_t)(ch0 / 4 + 2 * c8 + 1) * pvol + pvox] = make_uint4(lo[4 * c8], lo[4 * c8 + 1], lo[4 * c8 + 2], lo[4 * c8 + 3]);
+                        }
+                    } else {
+                        uint2* b2 = reinterpret_cast<uint2*>(base);
+                        b2[pvox * 2 + (ch0 / 4)] = make_uint2(hi[0], hi[1]);
+                        b2[(pvol + pvox) * 2 + (ch0 / 4)] = make_uint2(lo[0], lo[1]);
+                    }
+                }
+            };
             auto store_plane = [&](int i) {
                 const int x = un.x0 + i;
                 const bool ok = (y < geo.Y && x < geo.X);
                 const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
+                float2 o[CH / 2];
 #pragma unroll
-                for (int c4 = 0; c4 < CH / 4; ++c4) {
-                    float o[4];
+                for (int kk = 0; kk < CH / 2; ++kk) {
+                    const int ch = ch0 + 2 * kk;
+                    float2 t = f2_fma(acc[i - I0][kk], f2_splat(inv_scale), *reinterpret_cast<const float2*>(&ep_s[0][ch]));
+                    const float2 ta = f2_mul(t, f2_splat(alpha));      // alpha in [0, 1]: t > 0 ? t : alpha t == max(t, alpha t)
+                    t = make_float2(fmaxf(t.x, ta.x), fmaxf(t.y, ta.y));
+                    o[kk] = f2_fma(t, *reinterpret_cast<const float2*>(&ep_s[1][ch]), *reinterpret_cast<const float2*>(&ep_s[2][ch]));
+                    if (ok) amax = fmaxf(amax, fmaxf(fabsf(o[kk].x), fabsf(o[kk].y)));
+                }
+                if (ok) put(d_base, vol, vox, o);
+                if (Cfg::POOL && geo.pool_dst != nullptr) {            // uniform over the CTA
+                    if ((i & 1) == 0) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int ch = ch0 + c4 * 4 + kk;
-                        float t = fmaf(acc[i][c4 * 4 + kk], inv_scale, ep_s[0][ch]);
-                        t = t > 0.f ? t : alpha * t;
-                        o[kk] = fmaf(t, ep_s[1][ch], ep_s[2][ch]);
-                        if (ok) amax = fmaxf(amax, fabsf(o[kk]));
-                    }
-                    if (ok) d_tile[(size_t)c4 * vol + vox] = make_float4(o[0], o[1], o[2], o[3]);
-                    if (Cfg::POOL && geo.pool_dst != nullptr) {        // uniform over the CTA
-                        if ((i & 1) == 0) {
+                        for (int kk = 0; kk < CH / 2; ++kk) keep[kk] = o[kk];
+                    } else {
+                        float2 m[CH / 2];
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) keep[c4 * 4 + kk] = o[kk];
-                        } else {
-                            float m[4];
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                m[kk] = fmaxf(keep[c4 * 4 + kk], o[kk]);
-                                m[kk] = fmaxf(m[kk], __shfl_xor_sync(0xffffffffu, m[kk], 8));
-                            }
-                            if (ok && ((row >> 3) & 1) == 0) {
-                                const int PX = geo.X >> 1, PY = geo.Y >> 1;
-                                float4* p_tile = geo.pool_dst + (size_t)un.tile * geo.dst_tile_stride4 +
-                                                 (size_t)(ch0 / 4 + c4) * ((size_t)PX * PY * geo.Z);
-                                p_tile[((size_t)(x >> 1) * PY + (y >> 1)) * geo.Z + z] = make_float4(m[0], m[1], m[2], m[3]);
-                            }
+                        for (int kk = 0; kk < CH / 2; ++kk) {
+                            m[kk] = make_float2(fmaxf(keep[kk].x, o[kk].x), fmaxf(keep[kk].y, o[kk].y));
+                            m[kk].x = fmaxf(m[kk].x, __shfl_xor_sync(0xffffffffu, m[kk].x, 8));
+                            m[kk].y = fmaxf(m[kk].y, __shfl_xor_sync(0xffffffffu, m[kk].y, 8));
+                        }
+                        if (ok && ((row >> 3) & 1) == 0) {
+                            const int PX = geo.X >> 1, PY = geo.Y >> 1;
+                            put(geo.pool_dst + (size_t)un.tile * geo.dst_tile_stride4, (size_t)PX * PY * geo.Z,
+                                ((size_t)(x >> 1) * PY + (y >> 1)) * geo.Z + z, m);
                         }
                     }
                 }
             };
 #pragma unroll
-            for (int i = 0; i < BX; ++i)
+            for (int i = 0; i < PB; ++i)
 #pragma unroll
-                for (int ch = 0; ch < CH; ++ch) acc[i][ch] = 0.f;
+                for (int ch = 0; ch < CH / 2; ++ch) acc[i][ch] = make_float2(0.f, 0.f);
             if (geo.add_partial) {                                  // uniform over the CTA
                 // The accumulators START from the partial sums the phase kernel left in dst (decoder blocks): BX
                 // independent loads per thread at the head of the unit, hidden behind its first MMAs.  (Loading them
@@ -365,18 +438,21 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 // the block's time.)  inv_scale is a power of two, so partial / inv_scale is exact.
                 const float to_acc = 1.f / inv_scale;
 #pragma unroll
-                for (int i = 0; i < BX; ++i) {
-                    const int x = un.x0 + i;
+                for (int i = 0; i < PB; ++i) {
+                    const int x = un.x0 + I0 + i;
                     if (y < geo.Y && x < geo.X) {
                         const size_t vox = ((size_t)x * geo.Y + y) * geo.Z + z;
 #pragma unroll
                         for (int c4 = 0; c4 < CH / 4; ++c4) {
                             const float4 pv = d_tile[(size_t)c4 * vol + vox];
-                            acc[i][c4 * 4 + 0] = pv.x * to_acc; acc[i][c4 * 4 + 1] = pv.y * to_acc;
-                            acc[i][c4 * 4 + 2] = pv.z * to_acc; acc[i][c4 * 4 + 3] = pv.w * to_acc;
+                            acc[i][c4 * 2 + 0] = make_float2(pv.x * to_acc, pv.y * to_acc);
+                            acc[i][c4 * 2 + 1] = make_float2(pv.z * to_acc, pv.w * to_acc);
                         }
                     }
                 }
+                // Cout = 8 with a split destination: the two threads of a voxel read one fp32 partial plane each but
+                // write an 8-byte half of BOTH planes -- every partial must be read before any output is stored
+                if constexpr (DST_SPLIT && CH < 8) asm volatile("bar.sync 1, %0;" ::"n"(32 * Cfg::DRAIN_WARPS) : "memory");
             }
 #pragma unroll 1
             for (int c = 0; c < cin8; ++c) {
@@ -391,14 +467,16 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
                             const int i = j - dx;
-                            if (i < 0 || i >= BX) continue;        // output plane j - dx is fed through x-tap dx
+                            if (i < I0 || i >= I0 + PB) continue;  // output plane j - dx is fed through x-tap dx
                             uint32_t v[TERMS][CH];
 #pragma unroll
                             for (int t = 0; t < TERMS; ++t) tmem_ld_issue<CH>(t0 + t * 3 * N + dx * N, v[t]);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int ch = 0; ch < CH; ++ch)
-                                acc[i][ch] += fmaf(__uint_as_float(v[1][ch]), W2, __uint_as_float(v[0][ch]));
+                            for (int ch = 0; ch < CH / 2; ++ch)
+                                acc[i - I0][ch] = f2_add(acc[i - I0][ch],
+                                    f2_fma(make_float2(__uint_as_float(v[1][2 * ch]), __uint_as_float(v[1][2 * ch + 1])), f2_splat(W2),
+                                           make_float2(__uint_as_float(v[0][2 * ch]), __uint_as_float(v[0][2 * ch + 1]))));
                         }
                         tc_fence_before();
                         __syncwarp();
@@ -407,7 +485,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         uint32_t v[3][TERMS][CH];
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
-                            if (j - dx < 0 || j - dx >= BX) continue;  // output plane j - dx is fed through x-tap dx
+                            if (j - dx < I0 || j - dx >= I0 + PB) continue;  // output plane j - dx is fed through x-tap dx
 #pragma unroll
                             for (int t = 0; t < TERMS; ++t) tmem_ld_issue<CH>(t0 + t * 3 * N + dx * N, v[dx][t]);
                         }
@@ -418,15 +496,15 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
                             const int i = j - dx;
-                            if (i < 0 || i >= BX) continue;
+                            if (i < I0 || i >= I0 + PB) continue;
 #pragma unroll
-                            for (int ch = 0; ch < CH; ++ch) {
-                                const float hh = __uint_as_float(v[dx][0][ch]), hl = __uint_as_float(v[dx][1][ch]);
-                                acc[i][ch] += fmaf(hl, W2, hh);
-                            }
+                            for (int ch = 0; ch < CH / 2; ++ch)
+                                acc[i - I0][ch] = f2_add(acc[i - I0][ch],
+                                    f2_fma(make_float2(__uint_as_float(v[dx][1][2 * ch]), __uint_as_float(v[dx][1][2 * ch + 1])), f2_splat(W2),
+                                           make_float2(__uint_as_float(v[dx][0][2 * ch]), __uint_as_float(v[dx][0][2 * ch + 1]))));
                         }
                     }
-                    if (last && j >= 2) { TX_T0(); store_plane(j - 2); TX_ACC(t_epi); }
+                    if (last && j - 2 >= I0 && j - 2 < I0 + PB) { TX_T0(); store_plane(j - 2); TX_ACC(t_epi); }
                 }
             }
             amax = warp_max(amax);
@@ -442,6 +520,10 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #else
         (void)w_accf; (void)t_epi; (void)t_begin;
 #endif
+        };
+        if constexpr (Cfg::PH == 1) run(std::integral_constant<int, 0>{});
+        else if (dwi < 8) run(std::integral_constant<int, 0>{});
+        else run(std::integral_constant<int, 1>{});
         tc_fence_before();
     }
     __syncthreads();
@@ -504,15 +586,15 @@ float tcx_pack_weights_range(const float* w, int cin_total, int c_begin, int cin
     return 1.f / scale;
 }
 
-struct TxSource { const float* w; float inv_scale; int cin8; int add_partial; };
+struct TxSource { const float* w; float inv_scale; int cin8; int add_partial; const float* amax2; };
 
-template <int N, int BX, int STAGES>
+template <int N, int BX, int STAGES, int DW, bool SRC_SPLIT, bool DST_SPLIT>
 static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, const TxSource& src, float alpha, float4* dst, int X, int Y, int Z,
                       size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst,
                       float4* pool_dst, float* amax_pool, cudaStream_t s) {
-    using Cfg = TxCfg<N, BX, STAGES>;
+    using Cfg = TxCfg<N, BX, STAGES, DW>;
     // per device / context attribute: set on every launch (cheap) so several GPUs in one process are correct
-    CT_CUDA(cudaFuncSetAttribute(conv3_tcx_kernel<N, BX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CT_CUDA(cudaFuncSetAttribute(conv3_tcx_kernel<N, BX, STAGES, DW, SRC_SPLIT, DST_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     TxGeom g;
     g.cin8 = src.cin8; g.X = X; g.Y = Y; g.Z = Z;
     g.amax_src = amax_src; g.amax_dst = amax_dst; g.slab_stride = stride4 * 4; g.w_inv_scale = src.inv_scale;
@@ -520,20 +602,44 @@ static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, const TxSource
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
     g.pool_dst = pool_dst; g.amax_pool = amax_pool; g.add_partial = src.add_partial;
+    g.scale_src = amax_src + SCALE_SLOT0; g.scale_dst = amax_dst + SCALE_SLOT0; g.amax_src2 = src.amax2;
+    g.bound_p = L.bound_p; g.bound_q = L.bound_q;
     const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
     const int grid = g.units < sms ? g.units : sms;
-    conv3_tcx_kernel<N, BX, STAGES><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
+    conv3_tcx_kernel<N, BX, STAGES, DW, SRC_SPLIT, DST_SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
+}
+
+template <bool SRC_SPLIT, bool DST_SPLIT>
+static int launch_tcx_n(int cout, const CUtensorMap& map, const ConvLayer& L, const TxSource& src, float alpha, float4* dst, int X,
+                        int Y, int Z, size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst,
+                        float4* pool_dst, float* amax_pool, cudaStream_t s) {
+    if (cout == 8) return launch_tcx<8, 8, 3, 8, SRC_SPLIT, DST_SPLIT>(map, L, src, alpha, dst, X, Y, Z, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s);
+    if (cout == 16) return launch_tcx<16, 8, 3, 8, SRC_SPLIT, DST_SPLIT>(map, L, src, alpha, dst, X, Y, Z, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s);
+    return launch_tcx<32, 8, 2, 8, SRC_SPLIT, DST_SPLIT>(map, L, src, alpha, dst, X, Y, Z, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s);
+}
+
+static int launch_tcx_fmt(int fmt, int cout, const CUtensorMap& map, const ConvLayer& L, const TxSource& src, float alpha, float4* dst,
+                          int X, int Y, int Z, size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst,
+                          float4* pool_dst, float* amax_pool, cudaStream_t s) {
+    switch (fmt & 3) {
+    case 0: return launch_tcx_n<false, false>(cout, map, L, src, alpha, dst, X, Y, Z, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s);
+    case FMT_SRC_SPLIT: return launch_tcx_n<true, false>(cout, map, L, src, alpha, dst, X, Y, Z, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s);
+    case FMT_DST_SPLIT: return launch_tcx_n<false, true>(cout, map, L, src, alpha, dst, X, Y, Z, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s);
+    default: return launch_tcx_n<true, true>(cout, map, L, src, alpha, dst, X, Y, Z, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s);
+    }
 }
 
 // returns 2 when the layer is not handled by the stacked kernel (the caller falls back to unet_tc.cu's kernel)
 int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
-                    const Op* pool, bool* pool_fused) {
+                    const Op* pool, bool* pool_fused, int fmt) {
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;
     if (!L.w_tcx || Z % 8 != 0) return 2;
+    if ((fmt & FMT_SRC_SPLIT) && L.cin_pad % 8 != 0) return 2;
     CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
     CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
+    CT_REQUIRE(!(fmt & FMT_DST_SPLIT) || op.dst_coff % 8 == 0, "conv: split destination at channel offset %d", op.dst_coff);
     float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
     CUtensorMap map;
     ProfScope prof(PROF_CONV, s);
@@ -555,19 +661,17 @@ int launch_conv_tcx(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
         am_p = slab0 + pool->dst_slot;
         *pool_fused = true;
     }
-    const TxSource whole{L.w_tcx, L.w_tc_inv_scale, (L.cin_pad + 7) / 8, 0};
-    int rc;
-    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, whole, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
-    else if (L.cout == 16) rc = launch_tcx<16, 8, 3>(map, L, whole, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
-    else rc = launch_tcx<32, 8, 2>(map, L, whole, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s);
-    if (rc) return 1;
+    const TxSource whole{L.w_tcx, L.w_tc_inv_scale, (L.cin_pad + 7) / 8, 0, nullptr};
+    if (launch_tcx_fmt(fmt, L.cout, map, L, whole, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, pool_dst, am_p, s)) return 1;
     CT_LAUNCHED("conv3_tcx_kernel");
     return 0;
 }
 
 // The skip half of a decoder block: input channels [c_up, cin) of the concatenation buffer, partial sums of the
-// up-sampled half (unet_tcu.cu) already in the destination.
-int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s) {
+// up-sampled half (unet_tcu.cu) already in the destination.  up_slot = header slot of the low-resolution source of
+// that half (its max|x| enters the output bound of a split destination).
+int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
+                         int fmt, int up_slot) {
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;
     if (!L.w_tcx_skip || L.c_up <= 0 || Z % 8 != 0) return 2;
@@ -579,15 +683,11 @@ int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t s
     const size_t st4 = slab_stride / 4, vol = (size_t)X * Y * Z;
     float* src = slab0 + op.src_off + (size_t)L.c_up * vol;           // c4-blocked: channel chunk c starts at c * vol * 4
     if (tc_make_map(&map, src, X, Y, Z, c_skip / 4, tiles, slab_stride, 8)) return 1;
-    const TxSource skip{L.w_tcx_skip, L.w_tcx_skip_inv_scale, c_skip / 8, 1};
+    const TxSource skip{L.w_tcx_skip, L.w_tcx_skip_inv_scale, c_skip / 8, 1, up_slot >= 0 ? slab0 + up_slot : nullptr};
     const float* am_s = slab0 + op.src_slot;
     float* am_d = slab0 + op.dst_slot;
     const int co4 = op.dst_coff / 4;
-    int rc;
-    if (L.cout == 8) rc = launch_tcx<8, 8, 3>(map, L, skip, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, nullptr, nullptr, s);
-    else if (L.cout == 16) rc = launch_tcx<16, 8, 3>(map, L, skip, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, nullptr, nullptr, s);
-    else rc = launch_tcx<32, 8, 2>(map, L, skip, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, nullptr, nullptr, s);
-    if (rc) return 1;
+    if (launch_tcx_fmt(fmt, L.cout, map, L, skip, net->alpha, dst, X, Y, Z, st4, co4, tiles, am_s, am_d, nullptr, nullptr, s)) return 1;
     CT_LAUNCHED("conv3_tcx_kernel");
     return 0;
 }

@@ -25,6 +25,8 @@ _SPECS = {
 }
 
 ENGINES = {"auto": 0, "direct": 1, "tcgen05": 2, "tcgen05_classic": 3, "tcgen05_stacked": 4}
+# conv_block_device only: the tensor-core kernels between split-fp16 activation buffers, as they run inside the network
+BLOCK_ENGINES = dict(ENGINES, tcgen05_split=5, tcgen05_split_dst=6, tcgen05_split_src=7)
 
 
 def _conv_layers(spec):
@@ -183,7 +185,7 @@ class UNet3:
         out = torch.empty((b, x, y, z, cout), dtype=torch.float32, device=x_dev.device)
         ws = WORKSPACE.get("unet_block", lib.ct_unet_conv_block_workspace_bytes(self._handle, layer, b, x, y, z))
         wp = aligned_ptr(ws)
-        _lib.check(lib.ct_unet_conv_block(self._handle, int(layer), ENGINES[engine], x_dev.data_ptr(), out.data_ptr(),
+        _lib.check(lib.ct_unet_conv_block(self._handle, int(layer), BLOCK_ENGINES[engine], x_dev.data_ptr(), out.data_ptr(),
                                           b, x, y, z, wp, ws.numel() - (wp - ws.data_ptr()), stream_ptr()))
         return out
 

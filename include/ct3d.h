@@ -119,8 +119,9 @@ int ct_unet_predict_tiles(const CtUNet* net, const float* tiles, float* prob, in
                           void* ws, size_t ws_bytes, int tiles_per_batch, void* stream);
 /* One Conv3D(3, 'same') + LeakyReLU/ReLU + BatchNormalization block (unet3d.py:101-141) of the network, on
  * Keras channels-last tensors: in (B, x, y, z, Cin) float32 -> out (B, x, y, z, Cout) float32.  `layer` indexes the
- * network's conv blocks in graph order; engine 1..4 as in ct_unet_set_engine.  Any x, y; the tcgen05
- * engine needs z % 8 == 0. */
+ * network's conv blocks in graph order; engine 1..4 as in ct_unet_set_engine, or 5..7 = the tcgen05 kernels on
+ * the split-fp16 activation buffers they use inside the network (5: source and destination, 6: destination only,
+ * 7: source only; Cin resp. Cout % 8 == 0).  Any x, y; the tcgen05 engine needs z % 8 == 0. */
 size_t ct_unet_conv_block_workspace_bytes(const CtUNet* net, int layer, int batch, int x, int y, int z);
 int ct_unet_conv_block(const CtUNet* net, int layer, int engine, const float* in, float* out, int batch,
                        int x, int y, int z, void* ws, size_t ws_bytes, void* stream);

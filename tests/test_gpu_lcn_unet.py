@@ -138,6 +138,29 @@ def test_conv_block_tcgen05_and_direct_match_fp64(mods, layer):
             assert err < 2e-5, f"layer {layer} {cin}->{cout} {engine} {x}x{y}x{z}: {err:.2e}"
 
 
+@pytest.mark.parametrize("layer", list(range(14)))
+def test_conv_block_between_split_fp16_buffers(mods, layer):
+    """The tensor-core blocks as they run INSIDE the network: source and / or destination held as fp16 hi / lo' operand
+    images (csrc/unet_common.cuh) with the destination scale taken from the block's a-priori output bound.  Same
+    reference, shapes and tolerance as the fp32-buffer test above; inputs with a large and a tiny dynamic range
+    exercise the power-of-two scales."""
+    _, u, _ = mods
+    ws = ounet.random_weights("a", seed=3)
+    model = u.UNet3("a", weights=ws, tiles_per_batch=2)
+    cin, cout = u._conv_layers(u._SPECS["a"])[layer]
+    rng = np.random.default_rng(200 + layer)
+    engines = ["tcgen05_split_dst"] + (["tcgen05_split", "tcgen05_split_src"] if cin % 8 == 0 else [])
+    for b, (x, y, z), mag in [(1, (8, 16, 8), 1.0), (2, (11, 21, 16), 3e4), (1, (20, 40, 16), 2e-5)]:
+        xin = (rng.normal(0, 1, (b, x, y, z, cin)) * mag).astype(np.float32)
+        ref = _block_reference(ws, layer, xin)
+        scale = np.abs(ref).max()
+        dev = torch.from_numpy(xin).cuda()
+        for engine in engines:
+            got = model.conv_block_device(layer, dev, engine).cpu().numpy().astype(np.float64)
+            err = np.abs(got - ref).max() / scale
+            assert err < 2e-5, f"layer {layer} {cin}->{cout} {engine} {x}x{y}x{z} x{mag:g}: {err:.2e}"
+
+
 def test_tcgen05_engine_is_what_auto_runs(mods):
     """`auto` must take the tensor-core engine for every block of unet3_a (no silent CUDA-core fallback)."""
     _, u, _ = mods
