@@ -617,7 +617,7 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s, 
                 if (nx && nx->kind == OP_CONV && nx->src_off == op.dst_off && (net->engine == 0 || net->engine == 2 || net->engine == 4) &&
                     net->layers[nx->layer].c_up == op.c && op.dst_coff == 0 && op.dx == 2 * op.sx && op.dy == 2 * op.sy && op.dz == op.sz) {
                     const int rc = launch_conv_tcu(net, net->layers[nx->layer], slab0, stride, tiles, op.src_off, op.src_slot,
-                                                   op.sx, op.sy, op.sz, nx->dst_off, nx->dst_coff, s, split);
+                                                   op.sx, op.sy, op.sz, nx->dst_off, nx->dst_coff, s, split, nx->src_slot);
                     if (rc == 1) return 1;
                     CT_REQUIRE(rc == 0 || !split, "unet: phase kernel refused layer %d between split-fp16 buffers", nx->layer);
                     if (rc == 0) {

@@ -115,7 +115,8 @@ int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t s
 size_t tcu_weight_floats(int c_up, int cout);
 float tcu_pack_weights(const float* keras_kernel, int cin, int c_up, int cout, float* dst);
 int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t slab_stride, int tiles, size_t up_off,
-                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split = false);
+                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split,
+                    int skip_slot);
 size_t tc_weight_floats(int cin_pad, int cout);
 // returns 1 / scale
 float tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);

@@ -126,7 +126,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float ep_s[3][N];
+    __shared__ __align__(16) float ep_s[3][N];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

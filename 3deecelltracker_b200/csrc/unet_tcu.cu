@@ -78,6 +78,13 @@ struct TuGeom {
     size_t slab_stride;
     float w_inv_scale;
     const float* scale_src;                      // split-fp16 source: header scale slot (unet_common.cuh)
+    // The partial sums are written in the ACCUMULATOR units of the kernel that adds the skip half (unet_tcx.cu): true sum
+    // x skip operand scale (per tile: its header slot, an operand scale or -- fp32 buffers -- a max|x| bound) x
+    // post_w_scale (the skip weights' power-of-two scale).  That kernel then loads them straight into its accumulator
+    // registers: no arithmetic, so nothing waits for the loads at the head of a unit.
+    const float* post_slot;
+    int post_slot_is_scale;
+    float post_w_scale;
 };
 
 struct TuUnit { int x0, y0, z0, tile; };
@@ -259,7 +266,9 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         float am_next = n_units > 0 ? s_slot[(size_t)un_next.tile * geo.slab_stride] : 0.f;
         for (int k = 0; k < n_units; ++k) {
             const TuUnit un = un_next;
-            const float inv_scale = geo.w_inv_scale / (SRC_SPLIT ? am_next : tc_operand_scale(am_next));
+            const float post = geo.post_slot[(size_t)un.tile * geo.slab_stride];
+            const float inv_scale = geo.w_inv_scale / (SRC_SPLIT ? am_next : tc_operand_scale(am_next)) *
+                                    (geo.post_slot_is_scale ? post : tc_operand_scale(post)) * geo.post_w_scale;
             if (k + 1 < n_units) {
                 un_next = tu_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo, BX);
                 am_next = s_slot[(size_t)un_next.tile * geo.slab_stride];
@@ -409,13 +418,15 @@ float tcu_pack_weights(const float* w, int cin, int c_up, int cout, float* dst) 
 
 template <int N, int BX, int STAGES, bool SRC_SPLIT>
 static int launch_tcu(const CUtensorMap& map, const float* wpack, float inv_scale, float4* dst, int X, int Y, int Z,
-                      int cin8, size_t stride4, int dst_c4off, int tiles, const float* amax_src, cudaStream_t s) {
+                      int cin8, size_t stride4, int dst_c4off, int tiles, const float* amax_src, const float* post_slot,
+                      int post_is_scale, float post_w_scale, cudaStream_t s) {
     using Cfg = TuCfg<N, BX, STAGES>;
     CT_CUDA(cudaFuncSetAttribute(conv3_tcu_kernel<N, BX, STAGES, SRC_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     TuGeom g;
     g.cin8 = cin8; g.X = X; g.Y = Y; g.Z = Z;
     g.amax_src = amax_src; g.slab_stride = stride4 * 4; g.w_inv_scale = inv_scale;
     g.scale_src = amax_src + SCALE_SLOT0;
+    g.post_slot = post_slot; g.post_slot_is_scale = post_is_scale; g.post_w_scale = post_w_scale;
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
@@ -429,7 +440,8 @@ static int launch_tcu(const CUtensorMap& map, const float* wpack, float inv_scal
 // X x Y x Z, header slot up_slot; fp32 or, with src_split, split-fp16) -> fp32 pre-activation sums in the block's
 // destination buffer (2X x 2Y x Z).  Returns 2 when the shape is not handled.
 int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t slab_stride, int tiles, size_t up_off,
-                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split) {
+                    int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split,
+                    int skip_slot) {
     if (!L.w_tcu || Z % 8 != 0) return 2;
     CT_REQUIRE(slab_stride % 4 == 0 && up_off % 4 == 0 && dst_off % 4 == 0, "conv: misaligned slab");
     CUtensorMap map;
@@ -439,15 +451,19 @@ int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t 
     const float* am = slab0 + up_slot;
     const size_t st4 = slab_stride / 4;
     const int cin8 = L.c_up / 8, co4 = dst_coff / 4;
+    // the skip half's operand scale: its scale slot (split buffers) or max|x| slot (fp32 buffers) + the weights' scale
+    const float* post = slab0 + skip_slot + (src_split ? SCALE_SLOT0 : 0);
+    const int pis = src_split ? 1 : 0;
+    const float pw = 1.f / L.w_tcx_skip_inv_scale;
     int rc;
     if (src_split) {
-        if (L.cout == 8) rc = launch_tcu<8, 8, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
-        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
-        else rc = launch_tcu<32, 2, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+        if (L.cout == 8) rc = launch_tcu<8, 8, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
+        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
+        else rc = launch_tcu<32, 2, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
     } else {
-        if (L.cout == 8) rc = launch_tcu<8, 8, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
-        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
-        else rc = launch_tcu<32, 2, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, s);
+        if (L.cout == 8) rc = launch_tcu<8, 8, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
+        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
+        else rc = launch_tcu<32, 2, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
     }
     if (rc) return 1;
     CT_LAUNCHED("conv3_tcu_kernel");

@@ -169,7 +169,7 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc_full[NSETS], bar_acc_empty[NSETS];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float ep_s[3][N];
+    __shared__ __align__(16) float ep_s[3][N];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -432,11 +432,11 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                 for (int ch = 0; ch < CH / 2; ++ch) acc[i][ch] = make_float2(0.f, 0.f);
             if (geo.add_partial) {                                  // uniform over the CTA
-                // The accumulators START from the partial sums the phase kernel left in dst (decoder blocks): BX
-                // independent loads per thread at the head of the unit, hidden behind its first MMAs.  (Loading them
-                // in the per-plane epilogue put a dependent global load in front of every plane's store: ~40 % of
-                // the block's time.)  inv_scale is a power of two, so partial / inv_scale is exact.
-                const float to_acc = 1.f / inv_scale;
+                // The accumulators START from the partial sums the phase kernel left in dst (decoder blocks), which it
+                // wrote in this kernel's accumulator units (TuGeom::post_*): the loads land straight in the accumulator
+                // registers and are first needed by the first drain's add, so their latency hides behind the unit's
+                // first MMAs.  (Loading them in the per-plane epilogue put a dependent global load in front of every
+                // plane's store: ~40 % of the block's time; rescaling them here stalled every unit's head: ~15 %.)
 #pragma unroll
                 for (int i = 0; i < PB; ++i) {
                     const int x = un.x0 + I0 + i;
@@ -445,8 +445,8 @@ conv3_tcx_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #pragma unroll
                         for (int c4 = 0; c4 < CH / 4; ++c4) {
                             const float4 pv = d_tile[(size_t)c4 * vol + vox];
-                            acc[i][c4 * 2 + 0] = make_float2(pv.x * to_acc, pv.y * to_acc);
-                            acc[i][c4 * 2 + 1] = make_float2(pv.z * to_acc, pv.w * to_acc);
+                            acc[i][c4 * 2 + 0] = make_float2(pv.x, pv.y);
+                            acc[i][c4 * 2 + 1] = make_float2(pv.z, pv.w);
                         }
                     }
                 }

@@ -21,6 +21,21 @@ __global__ void __launch_bounds__(256) ws_pass_kernel(F f, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) f(i);
 }
+// Same pass as a resident grid-stride loop.  A pass over 9 M voxels as 36 000 one-shot blocks is bound by block turnover
+// (every block is one dependent load: ~24 us per pass on B200 however little the functor does); with a resident grid
+// the element-wise passes take 18 us and the Gaussian / min / relabel passes 20-60 % less.  The passes whose threads
+// chase pointers or walk long windows (union-find link, maximum filter, boundary test) measured 20-70 % SLOWER this way
+// and keep the one-shot form.
+constexpr int WS_PASS_BLOCKS = 148 * 8;
+template <class F>
+__global__ void __launch_bounds__(256) ws_pass_loop_kernel(F f, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+template <class F> struct ws_one_shot { static constexpr bool value = false; };
+template <> struct ws_one_shot<ws::UfLink> { static constexpr bool value = true; };
+template <> struct ws_one_shot<ws::Boundary2D> { static constexpr bool value = true; };
+template <int A> struct ws_one_shot<ws::Max1D<A>> { static constexpr bool value = true; };
 
 // Roots are sparse and their floods long: a warp that holds one root keeps its 31 other lanes idle anyway, so the flood
 // pass runs with small blocks to spread the long-running threads over all SMs' schedulers.
@@ -191,7 +206,9 @@ struct CudaPolicy {
 
     template <class F> void run(const F& f, long long n) {
         if (n <= 0 || err) return;
-        ws_pass_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(f, n);
+        const long long blocks = (n + 255) / 256;
+        if (ws_one_shot<F>::value || blocks <= WS_PASS_BLOCKS) ws_pass_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n);
+        else ws_pass_loop_kernel<F><<<WS_PASS_BLOCKS, 256, 0, s>>>(f, n);
         ++launches;
         if (cudaGetLastError() != cudaSuccess) err = 1;
     }

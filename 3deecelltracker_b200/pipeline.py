@@ -32,13 +32,18 @@ K_POINTS = 20              # tracker.py:1259
 
 class FramePipeline:
     def __init__(self, unet_model, ffn_model, noise_level, beta_tk, lambda_tk, maxiter_tk, shrink=(24, 24, 2),
-                 overlap=True, reserve_sms=8, depth=2):
+                 overlap=True, reserve_sms=8, depth=2, ws_lag=2):
         self.unet, self.ffn = unet_model, ffn_model
         self.noise_level, self.shrink = noise_level, tuple(shrink)
         self.beta_tk, self.lambda_tk, self.max_iteration = beta_tk, lambda_tk, maxiter_tk
         self.overlap = bool(overlap)
         self.reserve_sms = int(reserve_sms)
         self.depth = max(1, int(depth))
+        # raw-stack mode: how many volumes the host runs ahead of the watershed whose cell count it needs (the count sizes
+        # the fit's launches).  With a lag of 1 the host waits for the watershed of volume t-1 before it can enqueue the
+        # segmentation of volume t+1 -- and that watershed, squeezed in beside the convolutions of volume t, finishes
+        # about when they do, so the main stream runs dry; a lag of 2 keeps a whole volume of work enqueued.
+        self.ws_lag = max(1, int(ws_lag))
         self._streams = None
         self._pending = collections.deque()          # (stream, fit, tracked_prev or None)
         self._tracked = None                         # running tracked coordinates when the caller does not pass them
@@ -235,7 +240,7 @@ class FramePipeline:
                 while self._pending:
                     tracked = self._join_oldest()
             else:
-                ready = [self._segmented.popleft()] if len(self._segmented) > 1 else []
+                ready = [self._segmented.popleft()] if len(self._segmented) > self.ws_lag else []
                 keep = list(self._segmented)
                 self._segmented = collections.deque(ready)
                 pts = self._resolve_segmented()

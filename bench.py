@@ -176,7 +176,7 @@ def build_pipeline(args, overlap=True):
                                engine=args.engine)
     ffn = mod("ffn").FFN(synth.ffn_weights(0))
     pipe = mod("pipeline").FramePipeline(unet, ffn, NOISE_LEVEL, BETA_TK, LAMBDA_TK, MAXITER_TK, SHRINK,
-                                         overlap=overlap, reserve_sms=args.reserve_sms, depth=args.depth)
+                                         overlap=overlap, reserve_sms=args.reserve_sms, depth=args.depth, ws_lag=args.ws_lag)
     pipe.configure_watershed(Z_XY_RATIO, "min_size", MIN_SIZE, 0)
     return unet, ffn, pipe
 
@@ -303,9 +303,9 @@ def gpu_main(args):
 
     # ---- end-to-end arm: host buffers in, host results out, every volume.  The raw stack of volume t+1 goes up on a
     # copy stream while volume t computes; probability map + label image of volume t come down on the copy stream into
-    # one of two pinned buffers while volume t+1 computes; tracked coordinates come down at the end (rank 0).
-    prob_host = [torch.empty(SHAPE, dtype=torch.float32).pin_memory() for _ in range(2)]
-    lab_host = [torch.empty(SHAPE, dtype=torch.int32).pin_memory() for _ in range(2)]
+    # one of three pinned buffers while volumes t+1, t+2 compute; tracked coordinates come down at the end (rank 0).
+    prob_host = [torch.empty(SHAPE, dtype=torch.float32).pin_memory() for _ in range(3)]
+    lab_host = [torch.empty(SHAPE, dtype=torch.int32).pin_memory() for _ in range(3)]
     # separate streams per direction: an upload must never queue behind a download that waits for a watershed
     up_stream, copy_stream = torch.cuda.Stream(), torch.cuda.Stream()
     state = {"next": None, "done": []}
@@ -333,14 +333,14 @@ def gpu_main(args):
         if seg.ready is not None:
             copy_stream.wait_event(seg.ready)            # the label image is produced on the pipeline's watershed stream
         with torch.cuda.stream(copy_stream):
-            prob_host[t % 2].copy_(prob, non_blocking=True)
-            lab_host[t % 2].copy_(seg.labels, non_blocking=True)
+            prob_host[t % 3].copy_(prob, non_blocking=True)
+            lab_host[t % 3].copy_(seg.labels, non_blocking=True)
             done = torch.cuda.Event()
             done.record()
         prob.record_stream(copy_stream)
         seg.labels.record_stream(copy_stream)
         state["done"].append(done)
-        while len(state["done"]) > 1:
+        while len(state["done"]) > 2:                    # three pinned buffers: volume t-2's download must be complete
             state["done"].pop(0).synchronize()
 
     barrier()
@@ -695,6 +695,7 @@ def main():
     ap.add_argument("--tiles-per-batch", type=int, default=38)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="fits (FFN + PR-GLS chains) in flight on side streams")
+    ap.add_argument("--ws-lag", type=int, default=2, help="volumes the host runs ahead of the watershed it needs the cell count of")
     ap.add_argument("--reserve-sms", type=int, default=8, help="SMs kept out of the persistent conv grid while overlapping")
     ap.add_argument("--no-overlap", action="store_true", help="run segmentation and tracking back to back on one stream")
     ap.add_argument("--workload", default="c1", choices=["c1", "c3"],

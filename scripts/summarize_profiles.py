@@ -29,7 +29,7 @@ GFLOP = [0.088, 1.416, 0.708, 1.416, 0.708, 1.416, 0.708, 0.708, 2.831, 0.708, 2
 
 
 def family(name):
-    for key, fam in (("conv3_tc", "conv (tcgen05)"), ("first_conv", "conv (CUDA core, fused gather)"),
+    for key, fam in (("conv3_t", "conv (tcgen05)"), ("ws_", "watershed"), ("corr_", "accurate correction"), ("pool_split", "unet aux"), ("first_conv", "conv (CUDA core, fused gather)"),
                      ("conv3_direct", "conv (CUDA core)"), ("prgls", "PR-GLS EM"),
                      ("greedy", "PR-GLS EM"), ("predict_one_rep", "PR-GLS EM"), ("trim_mean", "PR-GLS EM"),
                      ("pool_kernel", "unet aux"), ("upsample", "unet aux"), ("gather_tiles", "unet aux"),
@@ -95,18 +95,33 @@ def raw(rep):
     return rows[0], rows[1], rows[2:]
 
 
+# one U-Net batch of unet3_a with the `auto` engine: 18 convolution launches in graph order
+# (name, algorithmic GMAC per tile, channels read, channels written, voxels per tile of the written grid, note)
+CONV_ROWS = [("d0a 1>8", 0.088, 1, 8, 409600, "CUDA cores, fused gather"), ("d0b 8>16 (+pool)", 1.416, 8, 16, 409600, "x-stacked"),
+             ("d1a 16>16", 0.708, 16, 16, 102400, "x-stacked"), ("d1b 16>32", 1.416, 16, 32, 102400, "x-stacked"),
+             ("d2a 32>32", 0.708, 32, 32, 25600, "x-stacked"), ("d2b 32>64", 1.416, 32, 64, 25600, "27-tap"),
+             ("u2a 64>64", 0.708, 64, 64, 6400, "27-tap"), ("u2b 64>64", 0.708, 64, 64, 6400, "27-tap"),
+             ("u1a up 64>32", 1.416, 16, 32, 25600, "phase kernel (low-res source)"), ("u1a skip 64>32", 1.416, 64 + 32, 32, 25600, "x-stacked + partial sums"),
+             ("u1b 32>32", 0.708, 32, 32, 25600, "x-stacked"),
+             ("u0a up 32>16", 1.416, 8, 16, 102400, "phase kernel"), ("u0a skip 32>16", 1.416, 32 + 16, 16, 102400, "x-stacked + partial sums"),
+             ("u0b 16>16", 0.708, 16, 16, 102400, "x-stacked"),
+             ("o_m2 up 16>8", 1.416, 4, 8, 409600, "phase kernel"), ("o_m2 skip 16>8", 1.416, 16 + 8, 8, 409600, "x-stacked + partial sums"),
+             ("o_m1 8>8", 0.708, 8, 8, 409600, "x-stacked, fp32 destination")]
+
+
 def conv():
     rep = os.path.join(G, f"prof_{tag}_conv_tc.ncu-rep")
     if not os.path.isfile(rep):
         return
     h, units, rows = raw(rep)
+    rows = rows[-len(CONV_ROWS):]
     idx = [(h.index(m), lab, units[h.index(m)]) for m, lab in METRICS if m in h]
     ki = h.index("Kernel Name")
     with open(os.path.join(P, f"{tag}_conv_tc.csv"), "w", newline="") as f:
         wr = csv.writer(f)
         wr.writerow(["block", "kernel"] + [f"{lab} [{u}]" for _, lab, u in idx])
-        for n, r in zip(CONV_NAMES, rows):
-            wr.writerow([n, r[ki].split("(")[0][-28:]] + [r[i] for i, _, _ in idx])
+        for (n, *_), r in zip(CONV_ROWS, rows):
+            wr.writerow([n, r[ki].split("(")[0].replace("void ", "").replace("ct::", "")[:48]] + [r[i] for i, _, _ in idx])
     t = h.index("gpu__time_duration.sum")
     dr, dw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
 
@@ -118,38 +133,43 @@ def conv():
         v = float(v.replace(",", ""))
         return {"Mbyte": v, "Gbyte": v * 1e3, "Kbyte": v / 1e3, "byte": v / 1e6}.get(u, v)
 
-    md = [f"# {tag}: convolution blocks of one U-Net batch ({TILES} tiles of 160x160x16), ncu --set full", "",
-          "One row per conv block in graph order (`first_conv_kernel` = CUDA-core Cin=1 block fused with the tile gather, "
-          "`conv3_tcx_kernel<Cout, BX, STAGES>` = x-stacked tcgen05 kernel, `conv3_tc_kernel<...>` = 27-tap tcgen05 kernel; "
-          "see the csv for which kernel ran a block); full metric table in "
-          f"`{tag}_conv_tc.csv`.  `tc pipe busy` = sm__pipe_tc_cycles_active (tensor-core pipe incl. operand fetch), "
-          "`tensor math` = sm__pipe_tensor_cycles_active, `tc smem` = l1tex__data_pipe_tc_wavefronts_mem_shared "
-          "(shared-memory wavefronts read by the tensor core, % of peak).", "",
-          "| block | ms | TFLOP/s (algorithmic) | tc pipe busy % | tensor math % | tc smem % | DRAM MB (read+write) | algorithmic MB |",
-          "|---|---:|---:|---:|---:|---:|---:|---:|"]
-    cin = [1, 8, 16, 16, 32, 32, 64, 64, 128, 32, 64, 16, 32, 8]
-    cout = [8, 16, 16, 32, 32, 64, 64, 64, 32, 32, 16, 16, 8, 8]
-    vox = [409600, 409600, 102400, 102400, 25600, 25600, 6400, 6400, 25600, 25600, 102400, 102400, 409600, 409600]
-    g = lambda m: h.index(m)
+    def pct(r, m):
+        try:
+            return f"{float(r[h.index(m)]):.1f}"
+        except (ValueError, IndexError):
+            return "-"
+
+    md = [f"# {tag}: convolution launches of one U-Net batch ({TILES} tiles of 160x160x16, engine auto), ncu --set full", "",
+          "One row per launch in graph order.  A decoder block that reads `concatenate([UpSampling3D(x), skip])` is two "
+          "launches: the phase kernel convolves the up-sampled half on the low-resolution grid (12/27 of that half's "
+          "multiply-adds) and leaves partial sums, the x-stacked kernel adds the skip half; both rows are credited with "
+          "half of the block's algorithmic FLOPs.  Activation buffers between the tensor-core blocks are split-fp16 "
+          "(DESIGN.md section 2).  `tc busy` = sm__pipe_tc_cycles_active (tensor-core unit incl. operand fetch), "
+          "`tensor math` = sm__pipe_tensor_cycles_active, `tc smem` = l1tex__data_pipe_tc_wavefronts_mem_shared (% of peak), "
+          "`issue` = smsp__issue_active.  Full metric table: "
+          f"`{tag}_conv_tc.csv`.", "",
+          "| launch | kernel | ms | TFLOP/s (algorithmic) | tc busy % | tensor math % | tc smem % | issue % | DRAM MB (r+w) | algorithmic MB |",
+          "|---|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
     tot_ms = 0.0
-    for n, r, gm, ci, co, vx in zip(CONV_NAMES, rows, GFLOP, cin, cout, vox):
+    for (n, gm, cr, cw, vx, note), r in zip(CONV_ROWS, rows):
         ms = to_ms(r[t], units[t]); tot_ms += ms
         mb = to_mb(r[dr], units[dr]) + to_mb(r[dw], units[dw])
-        alg = TILES * vx * 4 * ((1 if ci == 1 else ci) + co) / 1e6
-        md.append(f"| {n} | {ms:.3f} | {TILES * gm * 2 / ms:.1f} | "
-                  f"{float(r[g('sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed')]):.1f} | "
-                  f"{float(r[g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')]):.1f} | "
-                  f"{float(r[g('l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed')]):.1f} | "
-                  f"{mb:.0f} | {alg:.0f} |")
-    md += ["", f"Sum of the 14 blocks: {tot_ms:.3f} ms per {TILES} tiles -> {TILES * 35.573 / tot_ms:.1f} TFLOP/s algorithmic "
-           "(35.573 GFLOP/tile; per-launch times under ncu are cold-cache and serialised).  Reading: the tcgen05 blocks are "
-           "bound by the tensor core's shared-memory operand path (`tc pipe busy` >> `tensor math`: an M=128, K=16 fp16 MMA "
-           "reads a 4 KB A tile plus its B rows from shared memory at 128 B/clk, which takes longer than its math for "
-           "N <= 96), not by MMA math and not by HBM; DESIGN.md 3.2 has the arithmetic."]
+        alg = TILES * vx * 4 * (cr + cw) / 1e6
+        md.append(f"| {n} | {note} | {ms:.3f} | {TILES * gm * 2 / ms:.1f} | "
+                  f"{pct(r, 'sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed')} | "
+                  f"{pct(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')} | "
+                  f"{pct(r, 'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed')} | "
+                  f"{pct(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active')} | {mb:.0f} | {alg:.0f} |")
+    md += ["", f"Sum of the {len(CONV_ROWS)} launches: {tot_ms:.3f} ms per {TILES} tiles -> {TILES * 35.573 / tot_ms:.1f} TFLOP/s "
+           "algorithmic (35.573 GFLOP/tile; per-launch times under ncu are cold-cache and serialised).  Reading: an M = 128, "
+           "K = 16 MMA costs max(N/2, ~47 + N/6) clocks -- below N ~ 140 the shared-memory fetch of its 4 KB A tile sets the "
+           "pace, not the math -- so the Cout = 32 / 64 launches keep the tensor pipe 64-72 % active, the Cout = 16 ones "
+           "38-55 %, the Cout = 8 ones ~30 %, while the tensor-core unit itself is busy 57-79 % everywhere; and every fp32 "
+           "product costs three fp16 terms.  DESIGN.md 3.2 has the arithmetic and what would change it."]
     open(os.path.join(P, f"{tag}_conv_tc.md"), "w").write("\n".join(md) + "\n")
-    total_bytes = sum(to_mb(r[dr], units[dr]) + to_mb(r[dw], units[dw]) for r in rows[:14]) * 1e6
-    json.dump({"kernel": f"14 conv blocks of one {TILES}-tile U-Net batch (first_conv + conv3_tcx + conv3_tc)", "launches": 14,
-               "dram_bytes_per_launch_avg": total_bytes / 14, "tiles_per_batch": TILES,
+    total_bytes = sum(to_mb(r[dr], units[dr]) + to_mb(r[dw], units[dw]) for r in rows) * 1e6
+    json.dump({"kernel": f"{len(CONV_ROWS)} conv launches (14 blocks) of one {TILES}-tile U-Net batch (first_conv + conv3_tcx + conv3_tcu + conv3_tc)",
+               "launches": len(CONV_ROWS), "blocks": 14, "dram_bytes_per_launch_avg": total_bytes / len(CONV_ROWS), "tiles_per_batch": TILES,
                "source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/{tag}_conv_tc.csv"},
               open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
 
