@@ -270,8 +270,8 @@ def gpu_main(args):
     n_cells = None
     if rank == 0:
         assert len(tracked) == T - 1, f"{len(tracked)} tracking results for {T} volumes"
-        n_cells = int(tracked[-1].shape[0])
-        assert torch.isfinite(tracked[-1]).all()
+        n_cells = int(tracked[-1].shape[0]) if tracked else 0        # --steps 1: one volume, nothing to track yet
+        assert all(torch.isfinite(t).all() for t in tracked[-1:])
 
     # ---- comparison arms on one GPU: stages back to back on one stream, and the round-1 workload without watershed
     serial_ms = nows_ms = None
