@@ -343,7 +343,7 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
 
     // ---- pack weights on the host into one staging vector, then one device allocation
     std::vector<float> host;
-    struct Offs { size_t wd, wt, wx, b, sc, sh, wu, ws; int c_up; float inv_u, inv_s, bp, bq; };
+    struct Offs { size_t wd, wt, wx, b, sc, sh, wu, ws, wz, wzs; int c_up; float inv_u, inv_s, inv_z, inv_zs, bp, bq; };
     std::vector<Offs> offs;
     std::vector<float> inv_scales;
     // decoder blocks that read concatenate([up, skip]): layer index -> channels of the up-sampled half
@@ -370,6 +370,9 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         const size_t txn = tcx_weight_floats(cin_pad, cout);
         o.wx = take(txn);
         if (txn) tcx_pack_weights(p, cin, cin_pad, cout, &host[o.wx]);       // same scale as the classic image
+        const size_t tzn = tcz_weight_floats(cin, cout);                      // plane-walk image (cin % 8 == 0, Cout 8/16/32)
+        o.wz = take(tzn); o.wzs = 0; o.inv_z = o.inv_zs = 1.f;
+        if (tzn) o.inv_z = tcz_pack_weights_range(p, cin, 0, cin, cout, &host[o.wz]);
         o.c_up = 0; o.wu = o.ws = 0; o.inv_u = o.inv_s = 1.f;
         const int cu = c_up_of[offs.size()];
         if (cu > 0 && cu % 8 == 0 && (cin - cu) % 8 == 0 && tcu_weight_floats(cu, cout) && tcx_weight_floats(cin - cu, cout)) {
@@ -378,6 +381,10 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
             o.inv_u = tcu_pack_weights(p, cin, cu, cout, &host[o.wu]);
             o.ws = take(tcx_weight_floats(cin - cu, cout));
             o.inv_s = tcx_pack_weights_range(p, cin, cu, cin - cu, cout, &host[o.ws]);
+            if (tcz_weight_floats(cin - cu, cout)) {
+                o.wzs = take(tcz_weight_floats(cin - cu, cout));
+                o.inv_zs = tcz_pack_weights_range(p, cin, cu, cin - cu, cout, &host[o.wzs]);
+            }
         }
         std::vector<double> w1(cout, 0.0);                                   // sum of |w| per output channel
         for (size_t i = 0; i < (size_t)27 * cin; ++i)
@@ -421,6 +428,10 @@ extern "C" int ct_unet_create(const CtUNetSpec* sp, const float* w, size_t n_flo
         L.w_tcu = offs[i].c_up ? net->all_dev + offs[i].wu : nullptr;
         L.w_tcx_skip = offs[i].c_up ? net->all_dev + offs[i].ws : nullptr;
         L.w_tcu_inv_scale = offs[i].inv_u; L.w_tcx_skip_inv_scale = offs[i].inv_s;
+        L.w_tcz = tcz_weight_floats(L.cin, L.cout) ? net->all_dev + offs[i].wz : nullptr;
+        L.w_tcz_inv_scale = offs[i].inv_z;
+        L.w_tcz_skip = offs[i].wzs ? net->all_dev + offs[i].wzs : nullptr;
+        L.w_tcz_skip_inv_scale = offs[i].inv_zs;
         L.bound_p = offs[i].bp; L.bound_q = offs[i].bq;
         L.bias = net->all_dev + offs[i].b; L.scale = net->all_dev + offs[i].sc; L.shift = net->all_dev + offs[i].sh;
         net->layers.push_back(L);
@@ -561,7 +572,9 @@ static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t str
                        const Op* next = nullptr, bool* next_fused = nullptr, int fmt = 0) {
     int rc = 2;
     if (next_fused) *next_fused = false;
-    if (net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s, next, next_fused, fmt);
+    // auto: the plane-walk kernel wherever it applies (split-fp16 source, z = 16, Cout <= 32), then the x-stacked one
+    if (net->engine == 0) rc = launch_conv_tcz(net, op, slab0, stride, tiles, s, next, next_fused, fmt);
+    if (rc == 2 && net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s, next, next_fused, fmt);
     if (rc == 2 && net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s, fmt);
     if (rc == 1) return 1;
     CT_REQUIRE(rc == 0 || fmt == 0, "unet: layer %d has no tensor-core kernel for split-fp16 buffers", op.layer);
@@ -616,13 +629,18 @@ static int run_plan(const CtUNet* net, float* slab0, int tiles, cudaStream_t s, 
                 const Op* nx = idx + 1 < net->ops.size() ? &net->ops[idx + 1] : nullptr;
                 if (nx && nx->kind == OP_CONV && nx->src_off == op.dst_off && (net->engine == 0 || net->engine == 2 || net->engine == 4) &&
                     net->layers[nx->layer].c_up == op.c && op.dst_coff == 0 && op.dx == 2 * op.sx && op.dy == 2 * op.sy && op.dz == op.sz) {
-                    const int rc = launch_conv_tcu(net, net->layers[nx->layer], slab0, stride, tiles, op.src_off, op.src_slot,
-                                                   op.sx, op.sy, op.sz, nx->dst_off, nx->dst_coff, s, split, nx->src_slot);
+                    const ConvLayer& NL = net->layers[nx->layer];
+                    // auto: the skip half runs on the plane-walk kernel, which wants the partial sums in its P8 layout
+                    const bool zskip = net->engine == 0 && split && tcz_takes_skip(NL) && nx->sz == 16 && nx->layer != last_layer &&
+                                       nx->dst_coff % 8 == 0;
+                    const int rc = launch_conv_tcu(net, NL, slab0, stride, tiles, op.src_off, op.src_slot,
+                                                   op.sx, op.sy, op.sz, nx->dst_off, nx->dst_coff, s, split, nx->src_slot, zskip);
                     if (rc == 1) return 1;
                     CT_REQUIRE(rc == 0 || !split, "unet: phase kernel refused layer %d between split-fp16 buffers", nx->layer);
                     if (rc == 0) {
                         const int fmt = !split ? 0 : FMT_SRC_SPLIT | (nx->layer == last_layer ? 0 : FMT_DST_SPLIT);
-                        const int rc2 = launch_conv_tcx_skip(net, *nx, slab0, stride, tiles, s, fmt, split ? op.src_slot : -1);
+                        const int rc2 = zskip ? launch_conv_tcz_skip(net, *nx, slab0, stride, tiles, s, fmt, op.src_slot)
+                                              : launch_conv_tcx_skip(net, *nx, slab0, stride, tiles, s, fmt, split ? op.src_slot : -1);
                         CT_REQUIRE(rc2 == 0, "unet: skip-half convolution of layer %d failed", nx->layer);
                         ++idx;
                         continue;
@@ -682,11 +700,14 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
     CT_REQUIRE(net && in && out && ws, "ct_unet_conv_block: null argument");
     CT_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "ct_unet_conv_block: layer %d out of range", layer);
     CT_REQUIRE(batch >= 1 && x > 0 && y > 0 && z > 0, "ct_unet_conv_block: bad shape");
-    CT_REQUIRE(engine >= 1 && engine <= 7, "ct_unet_conv_block: engine must be 1 (direct), 2 (tcgen05), 3 (tcgen05 classic), 4 (tcgen05 "
-               "x-stacked) or 5-7 (tcgen05 on split-fp16 buffers: both / destination only / source only)");
-    // engines 5-7: the block as it runs inside the network, between split-fp16 activation buffers (unet_common.cuh)
-    const int fmt = engine == 5 ? (FMT_SRC_SPLIT | FMT_DST_SPLIT) : engine == 6 ? FMT_DST_SPLIT : engine == 7 ? FMT_SRC_SPLIT : 0;
-    if (fmt) engine = 2;
+    CT_REQUIRE(engine >= 1 && engine <= 9, "ct_unet_conv_block: engine must be 1 (direct), 2 (tcgen05), 3 (tcgen05 classic), 4 (tcgen05 "
+               "x-stacked), 5-7 (tcgen05 on split-fp16 buffers: both / destination only / source only) or 8-9 (the auto mix, "
+               "i.e. the plane-walk kernel where it applies, on split-fp16 buffers: both / source only)");
+    // engines 5-9: the block as it runs inside the network, between split-fp16 activation buffers (unet_common.cuh)
+    const int fmt = (engine == 5 || engine == 8) ? (FMT_SRC_SPLIT | FMT_DST_SPLIT) : engine == 6 ? FMT_DST_SPLIT
+                    : (engine == 7 || engine == 9) ? FMT_SRC_SPLIT : 0;
+    if (engine >= 8) engine = 0;
+    else if (fmt) engine = 2;
     CT_REQUIRE(ws_bytes >= ct_unet_conv_block_workspace_bytes(net, layer, batch, x, y, z), "ct_unet_conv_block: workspace too small");
     CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_unet_conv_block: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;

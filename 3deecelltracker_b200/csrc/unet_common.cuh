@@ -27,6 +27,11 @@ struct ConvLayer {
     float w_tcu_inv_scale;
     float* w_tcx_skip;
     float w_tcx_skip_inv_scale;
+    // plane-walk kernel (unet_tcz.cu): image of the whole block and of the skip half alone; null when not applicable
+    float* w_tcz;
+    float w_tcz_inv_scale;
+    float* w_tcz_skip;
+    float w_tcz_skip_inv_scale;
     // a-priori bound of the block's output, |out| <= bound_p * max|in| + bound_q  (sum of |w| per output channel, bias,
     // |alpha| <= 1, BatchNorm affine): the operand scale of a destination written in split-fp16 form is derived from it
     float bound_p, bound_q;
@@ -111,12 +116,21 @@ float tcx_pack_weights_range(const float* keras_kernel, int cin, int c_begin, in
 // x-stacked block over the skip half of a concatenation, adding the partial sums the phase kernel left in dst
 int launch_conv_tcx_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
                          int fmt = 0, int up_slot = -1);
+// implemented in unet_tcz.cu: plane-walk variant ((dx,dz) taps stacked in N, dy taps in K) for Cout 8/16/32 between
+// split-fp16 buffers of tiles with z = 16 (returns 2 when it does not take the block); same contract as launch_conv_tcx
+int launch_conv_tcz(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
+                    const Op* pool = nullptr, bool* pool_fused = nullptr, int fmt = 0);
+int launch_conv_tcz_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
+                         int fmt = 0, int up_slot = -1);
+size_t tcz_weight_floats(int cin, int cout);
+bool tcz_takes_skip(const ConvLayer& L);       // does launch_conv_tcz_skip take this decoder block?
+float tcz_pack_weights_range(const float* keras_kernel, int cin_total, int c_begin, int c_count, int cout, float* dst);
 // implemented in unet_tcu.cu: convolution over the up-sampled half, on the low-resolution grid
 size_t tcu_weight_floats(int c_up, int cout);
 float tcu_pack_weights(const float* keras_kernel, int cin, int c_up, int cout, float* dst);
 int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t slab_stride, int tiles, size_t up_off,
                     int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split,
-                    int skip_slot);
+                    int skip_slot, bool p8 = false);
 size_t tc_weight_floats(int cin_pad, int cout);
 // returns 1 / scale
 float tc_pack_weights(const float* keras_kernel, int cin, int cin_pad, int cout, float* dst);

@@ -479,6 +479,22 @@ int tc_make_map(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, int 
     return 0;
 }
 
+// same tensor (dims z*4 | y | x | 4-channel plane | tile) with a caller-chosen box
+int tc_make_map_box(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, int tiles, size_t slab_stride, const unsigned box_in[5]) {
+    EncodeTiledFn enc = encode_fn();
+    CT_REQUIRE(enc, "unet: cuTensorMapEncodeTiled is unavailable in this driver");
+    const cuuint64_t dims[5] = {(cuuint64_t)Z * 4, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)c4, (cuuint64_t)tiles};
+    const cuuint64_t strides[4] = {(cuuint64_t)Z * 16, (cuuint64_t)Y * Z * 16, (cuuint64_t)X * Y * Z * 16,
+                                   (cuuint64_t)slab_stride * 4};
+    const cuuint32_t box[5] = {box_in[0], box_in[1], box_in[2], box_in[3], box_in[4]};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CT_REQUIRE(r == CUDA_SUCCESS, "unet: cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return 0;
+}
+
 int launch_conv_tc(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s, int fmt) {
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;

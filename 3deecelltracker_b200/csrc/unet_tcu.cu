@@ -85,6 +85,10 @@ struct TuGeom {
     const float* post_slot;
     int post_slot_is_scale;
     float post_w_scale;
+    // 1: "P8" layout for the plane-walk kernel (unet_tcz.cu): of a thread's channel quadruple 4 k .. 4 k + 3 the first
+    // pair goes to plane 2 (k / 2), the second pair to plane 2 (k / 2) + 1, both at byte 8 (k % 2) of the voxel's 16 --
+    // exactly the bytes the consumer's thread that owns those channels overwrites with their fp16 hi / lo' halves
+    int post_p8;
 };
 
 struct TuUnit { int x0, y0, z0, tile; };
@@ -274,7 +278,8 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 am_next = s_slot[(size_t)un_next.tile * geo.slab_stride];
             }
             const int yl = un.y0 + (row >> 3), z = un.z0 + (row & 7);
-            float4* d_tile = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)(geo.dst_c4off + ch0 / 4) * vol;
+            float4* d_base = dst + (size_t)un.tile * geo.dst_tile_stride4 + (size_t)geo.dst_c4off * vol;
+            float4* d_tile = d_base + (size_t)(ch0 / 4) * vol;
             auto store_plane = [&](int i) {
                 const int xl = un.x0 + i;
                 if (yl >= geo.Y || xl >= geo.X) return;
@@ -287,7 +292,14 @@ conv3_tcu_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         for (int c4 = 0; c4 < CH / 4; ++c4) {
                             const float2 lo2 = f2_mul(acc[i][px][py][c4 * 2], f2_splat(inv_scale));
                             const float2 hi2 = f2_mul(acc[i][px][py][c4 * 2 + 1], f2_splat(inv_scale));
-                            d_tile[(size_t)c4 * vol + vox] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                            if (geo.post_p8) {                      // uniform over the grid
+                                const int k4 = ch0 / 4 + c4;
+                                float2* b2 = reinterpret_cast<float2*>(d_base + ((size_t)(k4 & ~1) * vol + vox)) + (k4 & 1);
+                                b2[0] = lo2;
+                                b2[vol * 2] = hi2;
+                            } else {
+                                d_tile[(size_t)c4 * vol + vox] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                            }
                         }
                     }
             };
@@ -419,14 +431,14 @@ float tcu_pack_weights(const float* w, int cin, int c_up, int cout, float* dst) 
 template <int N, int BX, int STAGES, bool SRC_SPLIT>
 static int launch_tcu(const CUtensorMap& map, const float* wpack, float inv_scale, float4* dst, int X, int Y, int Z,
                       int cin8, size_t stride4, int dst_c4off, int tiles, const float* amax_src, const float* post_slot,
-                      int post_is_scale, float post_w_scale, cudaStream_t s) {
+                      int post_is_scale, float post_w_scale, int p8, cudaStream_t s) {
     using Cfg = TuCfg<N, BX, STAGES>;
     CT_CUDA(cudaFuncSetAttribute(conv3_tcu_kernel<N, BX, STAGES, SRC_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     TuGeom g;
     g.cin8 = cin8; g.X = X; g.Y = Y; g.Z = Z;
     g.amax_src = amax_src; g.slab_stride = stride4 * 4; g.w_inv_scale = inv_scale;
     g.scale_src = amax_src + SCALE_SLOT0;
-    g.post_slot = post_slot; g.post_slot_is_scale = post_is_scale; g.post_w_scale = post_w_scale;
+    g.post_slot = post_slot; g.post_slot_is_scale = post_is_scale; g.post_w_scale = post_w_scale; g.post_p8 = p8;
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
@@ -441,7 +453,7 @@ static int launch_tcu(const CUtensorMap& map, const float* wpack, float inv_scal
 // destination buffer (2X x 2Y x Z).  Returns 2 when the shape is not handled.
 int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t slab_stride, int tiles, size_t up_off,
                     int up_slot, int X, int Y, int Z, size_t dst_off, int dst_coff, cudaStream_t s, bool src_split,
-                    int skip_slot) {
+                    int skip_slot, bool p8) {
     if (!L.w_tcu || Z % 8 != 0) return 2;
     CT_REQUIRE(slab_stride % 4 == 0 && up_off % 4 == 0 && dst_off % 4 == 0, "conv: misaligned slab");
     CUtensorMap map;
@@ -454,16 +466,18 @@ int launch_conv_tcu(const CtUNet* net, const ConvLayer& L, float* slab0, size_t 
     // the skip half's operand scale: its scale slot (split buffers) or max|x| slot (fp32 buffers) + the weights' scale
     const float* post = slab0 + skip_slot + (src_split ? SCALE_SLOT0 : 0);
     const int pis = src_split ? 1 : 0;
-    const float pw = 1.f / L.w_tcx_skip_inv_scale;
+    // the partial sums are left in the accumulator units (and, p8, the layout) of the kernel that adds the skip half
+    const float pw = 1.f / (p8 ? L.w_tcz_skip_inv_scale : L.w_tcx_skip_inv_scale);
+    const int p8i = p8 ? 1 : 0;
     int rc;
     if (src_split) {
-        if (L.cout == 8) rc = launch_tcu<8, 8, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
-        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
-        else rc = launch_tcu<32, 2, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
+        if (L.cout == 8) rc = launch_tcu<8, 8, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, p8i, s);
+        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, p8i, s);
+        else rc = launch_tcu<32, 2, 3, true>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, p8i, s);
     } else {
-        if (L.cout == 8) rc = launch_tcu<8, 8, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
-        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
-        else rc = launch_tcu<32, 2, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, s);
+        if (L.cout == 8) rc = launch_tcu<8, 8, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, p8i, s);
+        else if (L.cout == 16) rc = launch_tcu<16, 4, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, p8i, s);
+        else rc = launch_tcu<32, 2, 3, false>(map, L.w_tcu, L.w_tcu_inv_scale, dst, X, Y, Z, cin8, st4, co4, tiles, am, post, pis, pw, p8i, s);
     }
     if (rc) return 1;
     CT_LAUNCHED("conv3_tcu_kernel");

@@ -1,0 +1,640 @@
+// tcgen05 implicit-GEMM 3x3x3 convolution, "plane-walk" variant: the x- and z-taps are stacked in N, the y-taps are K.
+//
+// Same operator, operand precision and buffers as unet_tcx.cu (Conv3D 3x3x3 'same' + bias -> LeakyReLU/ReLU ->
+// BatchNorm(eval), unet3d.py:117-119 / :139-140; split-fp16 hi / lo' operand images, fp32 accumulation), but a GEMM
+// decomposition in which every MMA is wide enough to be bound by tensor math instead of by the shared-memory fetch of
+// its A tile (an M = 128, K = 16 MMA costs max(N/2, ~47 + N/6) clocks):
+//
+//     D_j[voxel (y,z), (dx, dz, co)] = sum over (dy, ci) of  in[plane j][y+dy-1, z, ci] * W[dx, dy, dz, ci, co]
+//     out[x][y, z] = sum over (dx, dz) of D_(x+dx-1)[(y, z+dz-1), (dx, dz, co)]
+//
+//   * M tile = 8 y-rows x ALL 16 z of one x-plane (TMEM lane = 16 y + z).  The z-halo of a tile is Keras' zero padding,
+//     so the z shift-add is one lane up / down inside a 16-lane group (two shuffles) with zeros at z = 0 / 15: no halo
+//     rows are computed in y or z, and Y = 40 / 20 fit the 8-row tile (the 16-row tile of unet_tcx.cu wastes 17 / 37 %).
+//   * N = 9 (dx,dz) taps x 8 output channels x (hi | lo') = 144 columns per group of 8 output channels (column =
+//     72 term + 36 (co / 4) + 4 tap + co % 4: the 36 columns a drain thread reads per term are contiguous):
+//         MMA1 = A_hi  x rows [0, 144)  -> columns [0, 72) = hi.hi, [72, 144) = hi.lo'
+//         MMA2 = A_lo' x rows [0, 80)   -> accumulated onto columns [72, 152)   (lo'.hi, same weight 2^-11; 72 is not a
+//                                          legal MMA width, the 8 extra columns are never read)
+//     Cout = 16 / 32 run 2 / 4 such groups per plane (the A tile is re-read per group, but at N = 144 the MMA is math
+//     bound, so nothing is lost).
+//   * K = 16 per MMA = two (ci-chunk, dy) taps x 8 input channels; 3 cin/8 taps -> ceil(3 cin / 16) K steps, ALL chained
+//     in tensor memory (<= 12 steps x 2 MMAs; the 27-tap kernel chains 28), one drain per (plane, group).
+//   * The CTA walks a segment of x-planes of one (tile, 8-row y-block): one shared-memory stage = ONE x-plane of all
+//     input channels (10 haloed rows x 16 z), loaded once and used by the three output planes it feeds.  The drain keeps
+//     a rolling window of three output planes in registers (12 accumulator registers per group instead of 8 planes),
+//     so there is no x-halo recomputation inside a segment: (S + 2) / S input planes per S output planes.
+//   * The packed weights of the whole block stay resident in shared memory (<= 110 KB), loaded once per CTA.
+//
+// Source buffers are split-fp16 only (unet_common.cuh); the destination is split-fp16 or fp32 c4 planes.  Decoder
+// blocks: the phase kernel (unet_tcu.cu) leaves the partial sums of the up-sampled half in the destination in the
+// "P8" layout -- the 16 bytes of a thread's four channels sit exactly where that thread later writes its hi / lo'
+// halves -- so a thread only ever reads bytes it overwrites itself.
+#include "unet_common.cuh"
+#include "tc_ptx.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace ct {
+
+int tc_sm_count();
+int tc_make_map_box(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, int tiles, size_t slab_stride, const unsigned box[5]);
+
+constexpr int TZ_Z = 16;                          // the kernel needs the whole z extent of a tile in one M tile
+constexpr int TZ_BY = 8, TZ_YH = TZ_BY + 2;       // y rows per unit, haloed
+constexpr int TZ_ROW16 = TZ_Z;                    // 16-byte units per y row of one operand image
+constexpr int TZ_IMG16 = TZ_YH * TZ_ROW16;        // one operand image (8 channels) of one plane: 160 units = 2560 B
+constexpr int TZ_CHUNK16 = 2 * TZ_IMG16;          // hi + lo'
+constexpr int TZ_NROW = 144;                      // B rows per K half: 72 hi + 72 lo'
+constexpr int TZ_WSTEP16 = 2 * TZ_NROW;           // 16-byte units per (K step, group): two K halves
+constexpr int TZ_N1 = 144, TZ_N2 = 80, TZ_D2 = 72;
+constexpr int TZ_SETCOLS = 152, TZ_NSETS = 3;
+constexpr int TZ_DRAIN_WARPS = 8;
+constexpr int TZ_THREADS = 128 + 32 * TZ_DRAIN_WARPS;      // warpgroup 0: producer + three MMA issuers
+constexpr int TZ_MAX_STAGES = 8;
+constexpr int TZ_SMEM_MAX = 232448;
+
+#ifdef TZ_TIMING
+// debug build only: cycles block 0's role warps spend waiting (scripts/tcz_timing.py)
+__device__ unsigned long long g_tz_timers[16];
+#define TZ_T0() const long long _t0 = clock64()
+#define TZ_ACC(var) var += clock64() - _t0
+#else
+#define TZ_T0()
+#define TZ_ACC(var)
+#endif
+
+struct TzGeom {
+    int cin8, nsteps, X, Y, nby, nseg, sxseg, units, stages;
+    uint32_t wbytes;
+    int dst_c4off;
+    size_t dst_tile_stride4, slab_stride;
+    const float* amax_src;
+    float* amax_dst;
+    const float* scale_src;
+    float* scale_dst;
+    const float* amax_src2;                       // decoder blocks: max|x| slot of the up-sampled half's source
+    float w_inv_scale, bound_p, bound_q;
+    int add_partial;                              // dst holds P8 partial sums of the up-sampled half (split destination only)
+    float4* pool_dst;                             // fused MaxPooling3D((2,2,1)): pooled split-fp16 copy, channel offset 0
+    float* amax_pool;
+};
+
+struct TzUnit { int x0, nout, y0, tile; };
+__device__ __forceinline__ TzUnit tz_unit(int u, const TzGeom& g) {
+    TzUnit r;
+    r.x0 = (u % g.nseg) * g.sxseg; u /= g.nseg;
+    r.nout = min(g.sxseg, g.X - r.x0);
+    r.y0 = (u % g.nby) * TZ_BY;
+    r.tile = u / g.nby;
+    return r;
+}
+
+// K-half taps of step p: tap t = (ci chunk t / 3, dy = t % 3) at t/3 chunks + t%3 rows into the plane's stage
+__host__ __device__ constexpr uint32_t tz_tap_off16(int t) { return (uint32_t)(t / 3) * TZ_CHUNK16 + (uint32_t)(t % 3) * TZ_ROW16; }
+
+__device__ __forceinline__ void tz_ld4(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
+// 32 consecutive accumulator columns of the thread's lane in one instruction: narrow tensor-memory loads are paced per
+// instruction, not per byte (18 x4 loads per set held the drain at ~1150 clocks per set)
+__device__ __forceinline__ void tz_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+
+// Persistent CTA.  Work unit = a segment of x-planes x 8 y-rows x 16 z x all Cout of one tile.  Warp roles: 0 TMA producer
+// (+ tensor-memory allocator, resident weights), 1-3 MMA issuers (one per accumulator set), 4-11 accumulator drain / shift-add / epilogue (two per
+// tensor-memory lane quarter, four of a group's eight channels each).  The drain warps take registers from warpgroup 0
+// (setmaxnreg inside the launch-time pool of 384 x 168: 128 x 56 + 256 x 224 = 64512).
+template <int CIN8, int NG, bool DST_SPLIT, bool POOL>
+__global__ void __launch_bounds__(TZ_THREADS, 1)
+conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
+                 const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                 float alpha, float4* __restrict__ dst, const TzGeom geo) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[TZ_MAX_STAGES], bar_empty[TZ_MAX_STAGES], bar_acc_full[TZ_NSETS], bar_acc_empty[TZ_NSETS], bar_w;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float ep_s[3][8 * NG];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* wsm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ring = wsm + geo.wbytes;
+    const int stages = geo.stages;
+    constexpr uint32_t stage_bytes = (uint32_t)CIN8 * (TZ_CHUNK16 * 16);
+    constexpr int NTAPS = 3 * CIN8, NSTEPS = (NTAPS + 1) / 2;
+    const int n_units = ((int)blockIdx.x < geo.units) ? (geo.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], NG < TZ_NSETS ? NG : TZ_NSETS);      // one commit per issuer that reads the plane
+        }
+#pragma unroll
+        for (int a = 0; a < TZ_NSETS; ++a) {
+            mbar_init(&bar_acc_full[a], 1);
+            mbar_init(&bar_acc_empty[a], TZ_DRAIN_WARPS);
+        }
+        mbar_init(&bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (threadIdx.x >= 128) {
+        for (int i = threadIdx.x - 128; i < 3 * 8 * NG; i += TZ_THREADS - 128)
+            ep_s[i / (8 * NG)][i % (8 * NG)] = (i < 8 * NG) ? bias[i] : (i < 16 * NG ? scale[i - 8 * NG] : shift[i - 16 * NG]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+        // ---------------- TMA producer: resident weights once, then one x-plane of all input channels per stage
+        if (elect_one()) {
+            mbar_expect_tx(&bar_w, geo.wbytes);
+            for (uint32_t o = 0; o < geo.wbytes; o += 32768u) {
+                const uint32_t n = geo.wbytes - o < 32768u ? geo.wbytes - o : 32768u;
+                bulk_load(wsm + o, reinterpret_cast<const uint8_t*>(wpack) + o, n, &bar_w);
+            }
+            int gp = 0;
+            long long w_empty = 0;
+            for (int k = 0; k < n_units; ++k) {
+                const TzUnit un = tz_unit((int)blockIdx.x + k * (int)gridDim.x, geo);
+                const int nh = un.nout + 2;
+                for (int h = 0; h < nh; ++h, ++gp) {
+                    const int s = gp % stages, use = gp / stages;
+                    if (use > 0) { TZ_T0(); mbar_wait(&bar_empty[s], (use - 1) & 1); TZ_ACC(w_empty); }
+                    mbar_expect_tx(&bar_full[s], stage_bytes);
+                    tma_load_5d(ring + (size_t)s * stage_bytes, &tmap, &bar_full[s], 0, un.y0 - 1, un.x0 - 1 + h, 0, un.tile);
+                }
+            }
+#ifdef TZ_TIMING
+            if (blockIdx.x == 0) g_tz_timers[3] = w_empty;
+#else
+            (void)w_empty;
+#endif
+        }
+        __syncwarp();
+    } else {
+        // ---------------- MMA issuers: warps 1-3, issuer i owns accumulator set i (every third (plane, group) step).
+        // A set is only 4-12 MMAs (260-800 clocks of tensor work) and the issuing thread pays ~400 clocks of latency per
+        // set around them (two mbarrier round trips, fences, commits, uniform-register moves): one issuer left the tensor
+        // pipe idle half of the time [measured: 75 % of the issuer's time outside any wait at Cin = 8].  Three issuers
+        // overlap those latencies; their MMAs target different tensor-memory columns, so their relative order is free.
+        if (elect_one()) {
+            constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(TZ_N1 >> 3) << 17) | (8u << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(TZ_N2 >> 3) << 17) | (8u << 24);
+            constexpr uint64_t sbo8_word = (uint64_t)(8u | (1u << 14)) << 32;     // 8-row groups 128 B apart (A and B)
+            const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(wsm) >> 4;
+            const int me = warp - 1;
+            const uint32_t d = tmem_base + (uint32_t)me * TZ_SETCOLS;
+            mbar_wait(&bar_w, 0);
+            int gp = 0, a3 = 0, use_me = 0;
+            long long w_full = 0, w_acc = 0, t_begin = clock64();
+            for (int k = 0; k < n_units; ++k) {
+                const TzUnit un = tz_unit((int)blockIdx.x + k * (int)gridDim.x, geo);
+                const int nh = un.nout + 2;
+                for (int h = 0; h < nh; ++h, ++gp) {
+                    const int s = gp % stages, use = gp / stages;
+                    const uint32_t a_hi = ring16 + (uint32_t)s * (stage_bytes >> 4);
+                    bool mine = false;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g, a3 = (a3 == TZ_NSETS - 1) ? 0 : a3 + 1) {
+                        if (a3 != me) continue;
+                        if (!mine) {
+                            { TZ_T0(); mbar_wait(&bar_full[s], use & 1); TZ_ACC(w_full); }
+                            mine = true;
+                        }
+                        if (use_me > 0) { TZ_T0(); mbar_wait(&bar_acc_empty[me], (use_me - 1) & 1); TZ_ACC(w_acc); }
+                        ++use_me;
+                        tc_fence_after();
+#pragma unroll
+                        for (int p = 0; p < NSTEPS; ++p) {
+                            // the last step of an odd tap count repeats the tap before it against zero weights;
+                            // every descriptor is the stage / weight base plus a compile-time constant
+                            const int t1 = (2 * p + 1 < NTAPS) ? 2 * p + 1 : NTAPS - 1;
+                            const int t0 = t1 - 1;
+                            const uint32_t o0 = tz_tap_off16(t0), lbo = (tz_tap_off16(t1) - o0) << 16;
+                            const uint32_t ah = (a_hi + o0) | lbo;
+                            const uint32_t al = (a_hi + o0 + TZ_IMG16) | lbo;
+                            const uint32_t b32 = (w16 + (uint32_t)(p * NG + g) * TZ_WSTEP16) | ((uint32_t)TZ_NROW << 16);
+                            umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b32, idesc1, p != 0);
+                            umma_f16(d + TZ_D2, sbo8_word | (uint64_t)al, sbo8_word | (uint64_t)b32, idesc2, 1u);
+                        }
+                        umma_commit(&bar_acc_full[me]);
+                    }
+                    if (mine) umma_commit(&bar_empty[s]);
+                }
+            }
+#ifdef TZ_TIMING
+            if (blockIdx.x == 0 && me == 0) { g_tz_timers[0] = w_full; g_tz_timers[1] = w_acc; g_tz_timers[2] = clock64() - t_begin; }
+#else
+            (void)w_full; (void)w_acc; (void)t_begin;
+#endif
+        }
+        __syncwarp();
+    }
+    } else {
+        // ---------------- drain warps: tensor memory -> registers, (dx, dz) shift-add, epilogue
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
+        const int part = (warp - 4) >> 2;                          // which four channels of every group
+        const int row = q * 32 + lane;
+        const int yl = row >> 4, z = row & 15;
+        const size_t vol = (size_t)geo.X * geo.Y * TZ_Z;
+        constexpr float W2 = 1.f / 2048.f;                         // weight of the hi.lo' + lo'.hi columns
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 36);
+        int a = 0;
+        long long w_accf = 0, t_ld = 0, t_fin = 0, t_begin = clock64();
+        TzUnit un_next = tz_unit((int)blockIdx.x, geo);
+        float am_next = 0.f, am2_next = 0.f, sc_next = 1.f;
+        auto tile_hdr = [&](int tile) {
+            am_next = geo.amax_src[(size_t)tile * geo.slab_stride];
+            am2_next = (DST_SPLIT && geo.amax_src2) ? geo.amax_src2[(size_t)tile * geo.slab_stride] : 0.f;
+            sc_next = geo.scale_src[(size_t)tile * geo.slab_stride];
+        };
+        if (n_units > 0) tile_hdr(un_next.tile);
+        for (int k = 0; k < n_units; ++k) {
+            const TzUnit un = un_next;
+            const float inv_scale = geo.w_inv_scale / sc_next;
+            const float s_out = DST_SPLIT ? split_out_scale(fmaxf(am_next, am2_next), geo.bound_p, geo.bound_q) : 1.f;
+            if (DST_SPLIT && warp == 4 && lane == 0) {
+                geo.scale_dst[(size_t)un.tile * geo.slab_stride] = s_out;
+                if (POOL && geo.pool_dst != nullptr) geo.amax_pool[SCALE_SLOT0 + (size_t)un.tile * geo.slab_stride] = s_out;
+            }
+            if (k + 1 < n_units) {
+                un_next = tz_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo);
+                tile_hdr(un_next.tile);
+            }
+            const int nh = un.nout + 2;
+            const int y = un.y0 + yl;
+            const bool ok_y = y < geo.Y;
+            uint8_t* d_tile = reinterpret_cast<uint8_t*>(dst + (size_t)un.tile * geo.dst_tile_stride4);
+            float amax = 0.f;
+            // accumulators of the rolling window of three output planes, kept apart per z-tap: the z shift is linear, so
+            // the two shuffles per value happen once per finished output plane instead of once per contribution
+            float2 acc[NG][3][3][2], pf[NG][2], keep[NG][2];
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+#pragma unroll
+                    for (int sl = 0; sl < 3; ++sl) acc[g][sl][0][i] = acc[g][sl][1][i] = acc[g][sl][2][i] = make_float2(0.f, 0.f);
+                    keep[g][i] = make_float2(0.f, 0.f);
+                }
+            // This thread's 8-byte halves of a voxel in a split / P8 buffer: channels 4 part .. 4 part + 3 of group g, first
+            // pair in the hi plane (2 g), second pair in the lo' plane (2 g + 1), both at byte 8 part of the voxel's 16.
+            // row_b = byte offset of (x0, y, z) inside a plane; one x-plane further = plane_b bytes.
+            const size_t plane_b = (size_t)geo.Y * TZ_Z * 16, vol_b = vol * 16;
+            uint8_t* const d_grp = d_tile + (size_t)geo.dst_c4off * vol_b + (((size_t)un.x0 * geo.Y + y) * TZ_Z + z) * 16 + (size_t)part * 8;
+            // partial sums (P8) of output plane x0 + i, fetched one plane ahead of their first use
+            auto load_partial = [&](int i) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) pf[g][0] = pf[g][1] = make_float2(0.f, 0.f);
+                if (geo.add_partial && ok_y && i < un.nout) {       // add_partial is uniform over the CTA
+                    const uint8_t* pp = d_grp + (size_t)i * plane_b;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const uint2 p0 = *reinterpret_cast<const uint2*>(pp + (size_t)(2 * g) * vol_b);
+                        const uint2 p1 = *reinterpret_cast<const uint2*>(pp + (size_t)(2 * g + 1) * vol_b);
+                        pf[g][0] = make_float2(__uint_as_float(p0.x), __uint_as_float(p0.y));
+                        pf[g][1] = make_float2(__uint_as_float(p1.x), __uint_as_float(p1.y));
+                    }
+                }
+            };
+            // pa = address of the thread's half in the group's first plane, pvol_b = bytes between channel planes
+            auto put = [&](uint8_t* pa, size_t pvol_b, const float2 (&v)[2], float so) {
+                if constexpr (!DST_SPLIT) {
+                    // fp32 c4 planes: channels 4 part .. 4 part + 3 are the whole 16 bytes of plane 2 g + part
+                    *reinterpret_cast<float4*>(pa - (size_t)part * 8 + (size_t)part * pvol_b) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+                } else {
+                    uint32_t hi[2], lo[2];
+                    split_pair2(v[0], so, hi[0], lo[0]);
+                    split_pair2(v[1], so, hi[1], lo[1]);
+                    *reinterpret_cast<uint2*>(pa) = make_uint2(hi[0], hi[1]);
+                    *reinterpret_cast<uint2*>(pa + pvol_b) = make_uint2(lo[0], lo[1]);
+                }
+            };
+            // epilogue of output plane x0 + i of group g: z shift-add of the three tap accumulators, scale back,
+            // bias -> activation -> BatchNorm, store (+ pooled copy)
+            auto finish = [&](int i, int g, const float2 (&az)[3][2]) {
+                const int x = un.x0 + i;
+                const int ch = 8 * g + 4 * part;
+                float2 av[2];
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    // out[z] takes tap dz = 0 from input row z - 1 and tap dz = 2 from input row z + 1 (zero outside the tile)
+                    float2 up = make_float2(__shfl_up_sync(0xffffffffu, az[0][kk].x, 1), __shfl_up_sync(0xffffffffu, az[0][kk].y, 1));
+                    float2 dn = make_float2(__shfl_down_sync(0xffffffffu, az[2][kk].x, 1), __shfl_down_sync(0xffffffffu, az[2][kk].y, 1));
+                    if (z == 0) up = make_float2(0.f, 0.f);
+                    if (z == TZ_Z - 1) dn = make_float2(0.f, 0.f);
+                    av[kk] = f2_add(az[1][kk], f2_add(up, dn));
+                }
+                float2 o[2];
+                float am = 0.f;
+                o[0] = block_epilogue(av[0], inv_scale, alpha, &ep_s[0][0], 8 * NG, ch, am);
+                o[1] = block_epilogue(av[1], inv_scale, alpha, &ep_s[0][0], 8 * NG, ch + 2, am);
+                if (ok_y) {
+                    amax = fmaxf(amax, am);
+                    put(d_grp + (size_t)i * plane_b + (size_t)(2 * g) * vol_b, vol_b, o, s_out);
+                }
+                if (POOL && geo.pool_dst != nullptr) {             // uniform over the CTA
+                    if ((x & 1) == 0) {
+                        keep[g][0] = o[0]; keep[g][1] = o[1];
+                    } else {
+                        float2 m[2];
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            m[kk] = make_float2(fmaxf(keep[g][kk].x, o[kk].x), fmaxf(keep[g][kk].y, o[kk].y));
+                            m[kk].x = fmaxf(m[kk].x, __shfl_xor_sync(0xffffffffu, m[kk].x, 16));     // y pair: 16 lanes apart
+                            m[kk].y = fmaxf(m[kk].y, __shfl_xor_sync(0xffffffffu, m[kk].y, 16));
+                        }
+                        if (ok_y && (yl & 1) == 0) {
+                            const int PX = geo.X >> 1, PY = geo.Y >> 1;
+                            const size_t pvol_b = (size_t)PX * PY * TZ_Z * 16;
+                            uint8_t* pb = reinterpret_cast<uint8_t*>(geo.pool_dst + (size_t)un.tile * geo.dst_tile_stride4);
+                            put(pb + (size_t)(2 * g) * pvol_b + (((size_t)(x >> 1) * PY + (y >> 1)) * TZ_Z + z) * 16 + (size_t)part * 8, pvol_b, m, s_out);
+                        }
+                    }
+                }
+            };
+            load_partial(0);
+#pragma unroll 1
+            for (int h0 = 0; h0 < nh; h0 += 3) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const int h = h0 + p;
+                    if (h >= nh) break;                                // uniform over the CTA
+                    // output plane x0 + h starts in slot p (from its partial sums), plane h - 1 continues in slot
+                    // (p + 2) % 3, plane h - 2 completes in slot (p + 1) % 3
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        acc[g][p][1][0] = pf[g][0]; acc[g][p][1][1] = pf[g][1];
+                        acc[g][p][0][0] = acc[g][p][0][1] = acc[g][p][2][0] = acc[g][p][2][1] = make_float2(0.f, 0.f);
+                    }
+                    load_partial(h + 1);
+#pragma unroll
+                    for (int g = 0; g < NG; ++g, ++a) {
+                        const int set = a % TZ_NSETS, use_a = a / TZ_NSETS;
+                        { TZ_T0(); mbar_wait(&bar_acc_full[set], use_a & 1); TZ_ACC(w_accf); }
+                        tc_fence_after();
+                        const uint32_t t0 = t_lane + (uint32_t)set * TZ_SETCOLS;
+#ifdef TZ_TIMING
+                        const long long _tl = clock64();
+#endif
+                        uint32_t v[2][36];                                    // [term][4 tap + channel]
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            tz_ld32(t0 + t * TZ_D2, &v[t][0]);
+                            tz_ld4(t0 + t * TZ_D2 + 32, &v[t][32]);
+                        }
+                        tmem_ld_wait();
+#ifdef TZ_TIMING
+                        t_ld += clock64() - _tl;
+#endif
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_acc_empty[set]);      // values are in registers: the set is free
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int slot = (p + 3 - dx) % 3;
+#pragma unroll
+                            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk)
+                                    acc[g][slot][dz][kk] = f2_add(acc[g][slot][dz][kk],
+                                        f2_fma(make_float2(__uint_as_float(v[1][(dx * 3 + dz) * 4 + 2 * kk]), __uint_as_float(v[1][(dx * 3 + dz) * 4 + 2 * kk + 1])),
+                                               f2_splat(W2),
+                                               make_float2(__uint_as_float(v[0][(dx * 3 + dz) * 4 + 2 * kk]), __uint_as_float(v[0][(dx * 3 + dz) * 4 + 2 * kk + 1]))));
+                        }
+                        if (h >= 2) { TZ_T0(); finish(h - 2, g, acc[g][(p + 1) % 3]); TZ_ACC(t_fin); }
+                    }
+                }
+            }
+            amax = warp_max(amax);
+            if (lane == 0) {
+                amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
+                if (POOL && geo.pool_dst != nullptr) amax_update(geo.amax_pool + (size_t)un.tile * geo.slab_stride, amax);
+            }
+        }
+#ifdef TZ_TIMING
+        if (blockIdx.x == 0 && warp == 4 && lane == 0) {
+            g_tz_timers[5] = w_accf; g_tz_timers[6] = t_ld; g_tz_timers[7] = t_fin; g_tz_timers[8] = clock64() - t_begin;
+        }
+#else
+        (void)w_accf; (void)t_ld; (void)t_fin; (void)t_begin;
+#endif
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int tz_steps(int cin) { return (3 * (cin / 8) + 1) / 2; }
+
+size_t tcz_weight_floats(int cin, int cout) {
+    if ((cout != 8 && cout != 16) || (cin != 8 && cin != 16 && cin != 32)) return 0;      // instantiated shapes
+    const size_t bytes = (size_t)tz_steps(cin) * (cout / 8) * TZ_WSTEP16 * 16;
+    if (bytes + 3 * (size_t)(cin / 8) * TZ_CHUNK16 * 16 + 1024 > (size_t)TZ_SMEM_MAX) return 0;     // resident weights + 3 stages
+    return bytes / 4;
+}
+
+// keras kernel (kx,ky,kz,ci,co), input channels [c_begin, c_begin + cin) -> fp16 image
+// [K step][group co/8][K half][row][ci % 8], rows 36 (co%8 / 4) + 4 (dx*3 + dz) + co%4 (hi) | 72 + the same (lo'); K half j of step p is
+// tap t = 2p + j -> (ci chunk t/3, dy = t%3); an odd tap count ends with (zero weights, last tap).  Same power-of-two
+// scale as the x-stacked image of the same channel range (max|w| in [2^13, 2^14)).  Returns 1 / scale.
+float tcz_pack_weights_range(const float* w, int cin_total, int c_begin, int cin, int cout, float* dst) {
+    const int ng = cout / 8, ntaps = 3 * (cin / 8), nsteps = tz_steps(cin);
+    std::memset(dst, 0, tcz_weight_floats(cin, cout) * sizeof(float));
+    float wmax = 0.f;
+    for (int tap = 0; tap < 27; ++tap)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int co = 0; co < cout; ++co)
+                wmax = std::fmax(wmax, std::fabs(w[((size_t)tap * cin_total + c_begin + ci) * cout + co]));
+    int e = 0;
+    if (wmax > 0.f) std::frexp(wmax, &e);
+    const float scale = std::ldexp(1.f, 14 - e);
+    __half* img = reinterpret_cast<__half*>(dst);
+    for (int p = 0; p < nsteps; ++p)
+        for (int g = 0; g < ng; ++g)
+            for (int j = 0; j < 2; ++j) {
+                int t = 2 * p + j;
+                if (2 * p + 1 >= ntaps) { if (j == 0) continue; t = ntaps - 1; }      // odd tap count: (zero weights, last tap)
+                const int c = t / 3, dy = t % 3;
+                __half* blk = img + ((((size_t)p * ng + g) * 2 + j) * TZ_NROW) * 8;
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int dz = 0; dz < 3; ++dz)
+                        for (int col = 0; col < 8; ++col)
+                            for (int qd = 0; qd < 8; ++qd) {
+                                const int ci = c * 8 + qd, tap = (dx * 3 + dy) * 3 + dz;
+                                const float v = w[((size_t)tap * cin_total + c_begin + ci) * cout + 8 * g + col] * scale;
+                                const __half hh = __float2half_rn(v);
+                                const __half ll = __float2half_rn((v - __half2float(hh)) * 2048.f);
+                                const int r = (col / 4) * 36 + (dx * 3 + dz) * 4 + col % 4;
+                                blk[(size_t)r * 8 + qd] = hh;
+                                blk[(size_t)(72 + r) * 8 + qd] = ll;
+                            }
+            }
+    return 1.f / scale;
+}
+
+struct TzSource { const float* w; float inv_scale; int cin; int add_partial; const float* amax2; };
+
+// fewest (rounds of units over the grid) x (planes per unit): segments of the x-walk trade halo planes against balance
+static void tz_segments(int X, int per_x, int grid, bool even, int* sxseg, int* nseg) {
+    long best = -1;
+    for (int n = 1; n <= (X + 3) / 4; ++n) {
+        int sx = cdiv(X, n);
+        if (even && (sx & 1)) ++sx;
+        const int ns = cdiv(X, sx);
+        const long units = (long)per_x * ns, rounds = (units + grid - 1) / grid;
+        const long cost = rounds * (sx + 3);                          // + 2 halo planes + ~1 plane of pipeline hand-over
+        if (best < 0 || cost < best) { best = cost; *sxseg = sx; *nseg = ns; }
+    }
+}
+
+template <int CIN8, int NG, bool DST_SPLIT, bool POOL>
+static int launch_tcz(const CUtensorMap& map, const ConvLayer& L, const TzSource& src, float alpha, float4* dst, int X, int Y,
+                      size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, float4* pool_dst,
+                      float* amax_pool, cudaStream_t s) {
+    TzGeom g;
+    g.cin8 = src.cin / 8; g.nsteps = tz_steps(src.cin); g.X = X; g.Y = Y;
+    g.nby = cdiv(Y, TZ_BY);
+    g.wbytes = (uint32_t)(tcz_weight_floats(src.cin, 8 * NG) * 4);
+    const size_t stage_bytes = (size_t)g.cin8 * TZ_CHUNK16 * 16;
+    int stages = (int)(((size_t)TZ_SMEM_MAX - 1024 - g.wbytes) / stage_bytes);
+    if (stages > TZ_MAX_STAGES) stages = TZ_MAX_STAGES;
+    CT_REQUIRE(stages >= 3, "conv: plane-walk kernel has no room for 3 stages (cin %d, cout %d)", src.cin, 8 * NG);
+    g.stages = stages;
+    const size_t smem = 1024 + g.wbytes + (size_t)stages * stage_bytes;
+    const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
+    tz_segments(X, tiles * g.nby, sms, POOL, &g.sxseg, &g.nseg);
+    g.units = tiles * g.nby * g.nseg;
+    g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4; g.slab_stride = stride4 * 4;
+    g.amax_src = amax_src; g.amax_dst = amax_dst;
+    g.scale_src = amax_src + SCALE_SLOT0; g.scale_dst = amax_dst + SCALE_SLOT0; g.amax_src2 = src.amax2;
+    g.w_inv_scale = src.inv_scale; g.bound_p = L.bound_p; g.bound_q = L.bound_q;
+    g.add_partial = src.add_partial; g.pool_dst = pool_dst; g.amax_pool = amax_pool;
+    // per device / context attribute: set on every launch (cheap) so several GPUs in one process are correct
+    CT_CUDA(cudaFuncSetAttribute(conv3_tcz_kernel<CIN8, NG, DST_SPLIT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = g.units < sms ? g.units : sms;
+    conv3_tcz_kernel<CIN8, NG, DST_SPLIT, POOL><<<grid, TZ_THREADS, smem, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
+    return 0;
+}
+
+static int launch_tcz_any(int cout, bool dst_split, const CUtensorMap& map, const ConvLayer& L, const TzSource& src, float alpha,
+                          float4* dst, int X, int Y, size_t stride4, int dst_c4off, int tiles, const float* amax_src,
+                          float* amax_dst, float4* pool_dst, float* amax_pool, cudaStream_t s) {
+#define TZ_GO(C8, NG, DS, PL) return launch_tcz<C8, NG, DS, PL>(map, L, src, alpha, dst, X, Y, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s)
+#define TZ_C8(NG, DS, PL) do { if (src.cin == 8) TZ_GO(1, NG, DS, PL); if (src.cin == 16) TZ_GO(2, NG, DS, PL); if (src.cin == 32) TZ_GO(4, NG, DS, PL); return 2; } while (0)
+    if (pool_dst) { if (cout == 16 && dst_split && src.cin == 8) TZ_GO(1, 2, true, true); return 2; }
+    if (cout == 8) { if (dst_split) TZ_C8(1, true, false); TZ_C8(1, false, false); }
+    if (cout == 16) { if (dst_split) TZ_C8(2, true, false); TZ_C8(2, false, false); }
+#undef TZ_C8
+#undef TZ_GO
+    return 2;
+}
+
+// Which blocks the plane-walk kernel takes in the `auto` mix [measured on B200, 38 tiles, against unet_tcx.cu]: its drain
+// (72 accumulator columns per thread and set, z shift-add, epilogue) is latency bound at two warps per scheduler, so it
+// wins where a set carries enough MMAs or the x-stacked kernel is at its worst (N = 48 at Cout = 8):
+//   skip halves of the decoder blocks (16 -> 8: 0.61 vs 0.83 ms, 32 -> 16: 0.41 vs 0.48), 8 -> 8 (0.38 vs 0.43),
+//   Cin >= 32 (32 -> 8: 0.63 vs 1.46); it loses at 16 -> 16 (0.28 vs 0.24) and 8 -> 16 (0.94 vs 0.56).
+// CT3D_TCZ_ALL=1 routes every block it can run to it (experiments, tests of the other instantiations).
+static bool tz_all() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("CT3D_TCZ_ALL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+static bool tz_takes(int cin, int cout, bool skip_half) {
+    if (cout > 16) return false;
+    return tz_all() || skip_half || (cin == 8 && cout == 8) || cin >= 32;
+}
+
+static int tz_map(CUtensorMap* map, float* src, int X, int Y, int cin, int tiles, size_t slab_stride) {
+    const unsigned box[5] = {TZ_Z * 4, TZ_YH, 1, (unsigned)(cin / 4), 1};
+    return tc_make_map_box(map, src, X, Y, TZ_Z, cin / 4, tiles, slab_stride, box);
+}
+
+bool tcz_takes_skip(const ConvLayer& L) { return L.w_tcz_skip != nullptr && L.c_up > 0 && tz_takes(L.cin - L.c_up, L.cout, true); }
+
+// returns 2 when the block is not the plane-walk kernel's (the caller falls back to unet_tcx.cu / unet_tc.cu)
+int launch_conv_tcz(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
+                    const Op* pool, bool* pool_fused, int fmt) {
+    const ConvLayer& L = net->layers[op.layer];
+    const int X = op.sx, Y = op.sy, Z = op.sz;
+    if (pool_fused) *pool_fused = false;
+    if (!L.w_tcz || Z != TZ_Z || !(fmt & FMT_SRC_SPLIT) || L.cin_pad != L.cin || !tz_takes(L.cin, L.cout, false)) return 2;
+    CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
+    CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
+    CT_REQUIRE(!(fmt & FMT_DST_SPLIT) || op.dst_coff % 8 == 0, "conv: split destination at channel offset %d", op.dst_coff);
+    float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
+    float4* pool_dst = nullptr;
+    float* am_p = nullptr;
+    if (pool && pool_fused && (fmt & FMT_DST_SPLIT) && pool->kind == OP_POOL && pool->src_off == op.dst_off &&
+        pool->src_coff == op.dst_coff && pool->c == L.cout && pool->dst_coff == 0 && pool->dst_c == L.cout &&
+        net->spec.pool_x == 2 && net->spec.pool_y == 2 && net->spec.pool_z == 1 && X % 2 == 0 && Y % 2 == 0 &&
+        pool->dx == X / 2 && pool->dy == Y / 2 && pool->dz == Z && pool->dst_off % 4 == 0 && L.cout == 16) {
+        pool_dst = reinterpret_cast<float4*>(slab0 + pool->dst_off);
+        am_p = slab0 + pool->dst_slot;
+    }
+    CUtensorMap map;
+    ProfScope prof(PROF_CONV, s);
+    if (tz_map(&map, slab0 + op.src_off, X, Y, L.cin, tiles, slab_stride)) return 1;
+    const TzSource whole{L.w_tcz, L.w_tcz_inv_scale, L.cin, 0, nullptr};
+    const int rc = launch_tcz_any(L.cout, (fmt & FMT_DST_SPLIT) != 0, map, L, whole, net->alpha, dst, X, Y, slab_stride / 4,
+                                  op.dst_coff / 4, tiles, slab0 + op.src_slot, slab0 + op.dst_slot, pool_dst, am_p, s);
+    if (rc) return rc;
+    if (pool_dst) *pool_fused = true;
+    CT_LAUNCHED("conv3_tcz_kernel");
+    return 0;
+}
+
+// The skip half of a decoder block: input channels [c_up, cin) of the concatenation buffer; the destination already holds
+// the partial sums of the up-sampled half in the P8 layout (unet_tcu.cu, post_layout 1).  Split buffers only.
+int launch_conv_tcz_skip(const CtUNet* net, const Op& op, float* slab0, size_t slab_stride, int tiles, cudaStream_t s,
+                         int fmt, int up_slot) {
+    const ConvLayer& L = net->layers[op.layer];
+    const int X = op.sx, Y = op.sy, Z = op.sz;
+    if (!tcz_takes_skip(L) || Z != TZ_Z || fmt != (FMT_SRC_SPLIT | FMT_DST_SPLIT)) return 2;
+    const int c_skip = L.cin - L.c_up;
+    CT_REQUIRE(c_skip % 8 == 0 && L.c_up % 4 == 0 && op.dst_coff % 8 == 0, "conv: skip half of layer %d has %d channels", op.layer, c_skip);
+    float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
+    CUtensorMap map;
+    ProfScope prof(PROF_CONV, s);
+    const size_t vol = (size_t)X * Y * Z;
+    if (tz_map(&map, slab0 + op.src_off + (size_t)L.c_up * vol, X, Y, c_skip, tiles, slab_stride)) return 1;
+    const TzSource skip{L.w_tcz_skip, L.w_tcz_skip_inv_scale, c_skip, 1, up_slot >= 0 ? slab0 + up_slot : nullptr};
+    const int rc = launch_tcz_any(L.cout, true, map, L, skip, net->alpha, dst, X, Y, slab_stride / 4, op.dst_coff / 4, tiles,
+                                  slab0 + op.src_slot, slab0 + op.dst_slot, nullptr, nullptr, s);
+    if (rc) return rc;
+    CT_LAUNCHED("conv3_tcz_kernel");
+    return 0;
+}
+
+}  // namespace ct
+
+#ifdef TZ_TIMING
+extern "C" int ct_debug_tcz_timers(unsigned long long* out16) {
+    return cudaMemcpyFromSymbol(out16, ct::g_tz_timers, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
