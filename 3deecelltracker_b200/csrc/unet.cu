@@ -573,13 +573,13 @@ static int launch_conv(const CtUNet* net, const Op& op, float* slab0, size_t str
     int rc = 2;
     if (next_fused) *next_fused = false;
     // auto: the plane-walk kernel wherever it applies (split-fp16 source, z = 16, Cout <= 32), then the x-stacked one
-    if (net->engine == 0) rc = launch_conv_tcz(net, op, slab0, stride, tiles, s, next, next_fused, fmt);
+    if (net->engine == 0 || net->engine == 5) rc = launch_conv_tcz(net, op, slab0, stride, tiles, s, next, next_fused, fmt);
     if (rc == 2 && net->engine != 1 && net->engine != 3) rc = launch_conv_tcx(net, op, slab0, stride, tiles, s, next, next_fused, fmt);
     if (rc == 2 && net->engine != 1) rc = launch_conv_tc(net, op, slab0, stride, tiles, s, fmt);
     if (rc == 1) return 1;
     CT_REQUIRE(rc == 0 || fmt == 0, "unet: layer %d has no tensor-core kernel for split-fp16 buffers", op.layer);
     if (rc == 2) {
-        CT_REQUIRE(net->engine == 0 || net->engine == 1,
+        CT_REQUIRE(net->engine == 0 || net->engine == 1 || net->engine == 5,
                    "unet: tcgen05 engine forced but layer %d (cin %d, cout %d, z %d) is unsupported",
                    op.layer, net->layers[op.layer].cin, net->layers[op.layer].cout, op.sz);
         if (launch_conv_direct(net, op, slab0, stride, tiles, s)) return 1;
@@ -701,12 +701,12 @@ extern "C" int ct_unet_conv_block(const CtUNet* net, int layer, int engine, cons
     CT_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "ct_unet_conv_block: layer %d out of range", layer);
     CT_REQUIRE(batch >= 1 && x > 0 && y > 0 && z > 0, "ct_unet_conv_block: bad shape");
     CT_REQUIRE(engine >= 1 && engine <= 9, "ct_unet_conv_block: engine must be 1 (direct), 2 (tcgen05), 3 (tcgen05 classic), 4 (tcgen05 "
-               "x-stacked), 5-7 (tcgen05 on split-fp16 buffers: both / destination only / source only) or 8-9 (the auto mix, "
-               "i.e. the plane-walk kernel where it applies, on split-fp16 buffers: both / source only)");
+               "x-stacked), 5-7 (tcgen05 on split-fp16 buffers: both / destination only / source only) or 8-9 (the plane-walk "
+               "kernel wherever it can run, on split-fp16 buffers: both / source only)");
     // engines 5-9: the block as it runs inside the network, between split-fp16 activation buffers (unet_common.cuh)
     const int fmt = (engine == 5 || engine == 8) ? (FMT_SRC_SPLIT | FMT_DST_SPLIT) : engine == 6 ? FMT_DST_SPLIT
                     : (engine == 7 || engine == 9) ? FMT_SRC_SPLIT : 0;
-    if (engine >= 8) engine = 0;
+    if (engine >= 8) engine = 5;            // internal: the plane-walk kernel wherever it can run, else the tcgen05 mix
     else if (fmt) engine = 2;
     CT_REQUIRE(ws_bytes >= ct_unet_conv_block_workspace_bytes(net, layer, batch, x, y, z), "ct_unet_conv_block: workspace too small");
     CT_REQUIRE(((uintptr_t)ws & 255) == 0, "ct_unet_conv_block: workspace must be 256-byte aligned");

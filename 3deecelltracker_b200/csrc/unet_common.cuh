@@ -85,7 +85,8 @@ struct CtUNet {
     float alpha;              // 0.3 (LeakyReLU) or 0 (ReLU)
     bool split_ok;            // activation buffers between the blocks can be split-fp16 (unet.cu: use_split)
     int engine;               // 0 auto, 1 direct, 2 tcgen05 (stacked for Cout 8/16, else 27-tap), 3 27-tap only,
-                              // 4 stacked wherever the shape allows (= 2 today)
+                              // 4 stacked wherever the shape allows (= 2 today); 5 (internal, ct_unet_conv_block only):
+                              // plane-walk kernel wherever it can run
     double flops_per_tile;
     float* all_dev;           // one allocation holding every device array
 };

@@ -314,6 +314,9 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             };
             // pa = address of the thread's half in the group's first plane, pvol_b = bytes between channel planes
             auto put = [&](uint8_t* pa, size_t pvol_b, const float2 (&v)[2], float so) {
+#ifdef TZ_EXP_NOSTORE
+                if (so != 12345.678f) { amax = fmaxf(amax, v[0].x + v[0].y + v[1].x + v[1].y); return; }      // experiment: no stores
+#endif
                 if constexpr (!DST_SPLIT) {
                     // fp32 c4 planes: channels 4 part .. 4 part + 3 are the whole 16 bytes of plane 2 g + part
                     *reinterpret_cast<float4*>(pa - (size_t)part * 8 + (size_t)part * pvol_b) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
@@ -340,6 +343,10 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                     if (z == TZ_Z - 1) dn = make_float2(0.f, 0.f);
                     av[kk] = f2_add(az[1][kk], f2_add(up, dn));
                 }
+#ifdef TZ_EXP_NOEPI
+                amax = fmaxf(amax, av[0].x + av[0].y + av[1].x + av[1].y);      // experiment: shuffles only
+                if (amax != 12345.678f) return;
+#endif
                 float2 o[2];
                 float am = 0.f;
                 o[0] = block_epilogue(av[0], inv_scale, alpha, &ep_s[0][0], 8 * NG, ch, am);
@@ -369,6 +376,11 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 }
             };
             load_partial(0);
+            // With two groups per plane the epilogue of a finished plane is DEFERRED into the next set's tensor-memory load:
+            // the drain of a set is one long dependency chain (barrier -> tcgen05.ld -> accumulate -> shuffles -> activation
+            // -> fp16 split -> store) on two warps per scheduler, so the previous set's epilogue runs while this set's loads
+            // are in flight [measured: 16 -> 16 0.283 -> 0.266 ms; with one group per plane it lost 5 %, so not there].
+            constexpr bool DEFER = NG >= 2;
 #pragma unroll 1
             for (int h0 = 0; h0 < nh; h0 += 3) {
 #pragma unroll
@@ -377,11 +389,9 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                     if (h >= nh) break;                                // uniform over the CTA
                     // output plane x0 + h starts in slot p (from its partial sums), plane h - 1 continues in slot
                     // (p + 2) % 3, plane h - 2 completes in slot (p + 1) % 3
+                    float2 pfc[NG][2];
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        acc[g][p][1][0] = pf[g][0]; acc[g][p][1][1] = pf[g][1];
-                        acc[g][p][0][0] = acc[g][p][0][1] = acc[g][p][2][0] = acc[g][p][2][1] = make_float2(0.f, 0.f);
-                    }
+                    for (int g = 0; g < NG; ++g) { pfc[g][0] = pf[g][0]; pfc[g][1] = pf[g][1]; }
                     load_partial(h + 1);
 #pragma unroll
                     for (int g = 0; g < NG; ++g, ++a) {
@@ -398,6 +408,14 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                             tz_ld32(t0 + t * TZ_D2, &v[t][0]);
                             tz_ld4(t0 + t * TZ_D2 + 32, &v[t][32]);
                         }
+                        // previous set: (h, g - 1) completed plane h - 2 in slot (p + 1) % 3; (h - 1, NG - 1) completed
+                        // plane h - 3 in slot p
+                        if constexpr (DEFER) {
+                            TZ_T0();
+                            if (g > 0) { if (h >= 2) finish(h - 2, g > 0 ? g - 1 : 0, acc[g > 0 ? g - 1 : 0][(p + 1) % 3]); }
+                            else if (h >= 3) finish(h - 3, NG - 1, acc[NG - 1][p]);
+                            TZ_ACC(t_fin);
+                        }
                         tmem_ld_wait();
 #ifdef TZ_TIMING
                         t_ld += clock64() - _tl;
@@ -405,6 +423,8 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_acc_empty[set]);      // values are in registers: the set is free
+                        acc[g][p][1][0] = pfc[g][0]; acc[g][p][1][1] = pfc[g][1];
+                        acc[g][p][0][0] = acc[g][p][0][1] = acc[g][p][2][0] = acc[g][p][2][1] = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
                             const int slot = (p + 3 - dx) % 3;
@@ -417,9 +437,18 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                                                f2_splat(W2),
                                                make_float2(__uint_as_float(v[0][(dx * 3 + dz) * 4 + 2 * kk]), __uint_as_float(v[0][(dx * 3 + dz) * 4 + 2 * kk + 1]))));
                         }
-                        if (h >= 2) { TZ_T0(); finish(h - 2, g, acc[g][(p + 1) % 3]); TZ_ACC(t_fin); }
+                        if constexpr (!DEFER) {
+                            if (h >= 2) { TZ_T0(); finish(h - 2, g, acc[g][(p + 1) % 3]); TZ_ACC(t_fin); }
+                        }
                     }
                 }
+            }
+            // the unit's last set (plane nh - 1, group NG - 1) completed plane nh - 3 in slot ((nh - 1) % 3 + 1) % 3
+            if constexpr (DEFER) {
+                const int pl = (nh - 1) % 3;
+                if (pl == 0) finish(nh - 3, NG - 1, acc[NG - 1][1]);
+                else if (pl == 1) finish(nh - 3, NG - 1, acc[NG - 1][2]);
+                else finish(nh - 3, NG - 1, acc[NG - 1][0]);
             }
             amax = warp_max(amax);
             if (lane == 0) {
@@ -583,7 +612,7 @@ int launch_conv_tcz(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;
     if (pool_fused) *pool_fused = false;
-    if (!L.w_tcz || Z != TZ_Z || !(fmt & FMT_SRC_SPLIT) || L.cin_pad != L.cin || !tz_takes(L.cin, L.cout, false)) return 2;
+    if (!L.w_tcz || Z != TZ_Z || !(fmt & FMT_SRC_SPLIT) || L.cin_pad != L.cin || (net->engine != 5 && !tz_takes(L.cin, L.cout, false)) || L.cout > 16) return 2;
     CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
     CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
     CT_REQUIRE(!(fmt & FMT_DST_SPLIT) || op.dst_coff % 8 == 0, "conv: split destination at channel offset %d", op.dst_coff);

@@ -27,8 +27,8 @@ _SPECS = {
 ENGINES = {"auto": 0, "direct": 1, "tcgen05": 2, "tcgen05_classic": 3, "tcgen05_stacked": 4}
 # conv_block_device only: the tensor-core kernels between split-fp16 activation buffers, as they run inside the network
 BLOCK_ENGINES = dict(ENGINES, tcgen05_split=5, tcgen05_split_dst=6, tcgen05_split_src=7,
-                     # the auto mix (plane-walk kernel where it applies) between split buffers / split source -> fp32
-                     auto_split=8, auto_split_src=9)
+                     # the plane-walk kernel (unet_tcz.cu) wherever it can run: split buffers / split source -> fp32
+                     planewalk_split=8, planewalk_split_src=9)
 
 
 def _conv_layers(spec):

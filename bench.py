@@ -317,7 +317,11 @@ def gpu_main(args):
             ev.record()
         return d, ev
 
+    trace = [] if os.environ.get("CT3D_E2E_TRACE") else None      # host timestamps per volume (debugging the e2e arm)
+
     def e2e_frame(t):
+        if trace is not None:
+            trace.append(("frame", t, time.perf_counter()))
         nxt = state["next"]
         d, ev = (nxt[0], nxt[1]) if nxt is not None and nxt[2] == t else upload(t)
         main = torch.cuda.current_stream()
@@ -327,6 +331,8 @@ def gpu_main(args):
         return d
 
     def sink(t, prob, seg):
+        if trace is not None:
+            trace.append(("sink", t, time.perf_counter()))
         ready = torch.cuda.Event()
         ready.record()
         copy_stream.wait_event(ready)
@@ -343,6 +349,24 @@ def gpu_main(args):
         while len(state["done"]) > 2:                    # three pinned buffers: volume t-2's download must be complete
             state["done"].pop(0).synchronize()
 
+    # untimed warm-up of THIS arm's own machinery (copy streams, the allocator pools of the upload stream, pinned buffers)
+    wpin = {i: w for i, w in enumerate(warm)}
+
+    def warm_frame(t):
+        with torch.cuda.stream(up_stream):
+            d = wpin[t].to(dev, non_blocking=True).view(torch.uint16)
+            ev = torch.cuda.Event()
+            ev.record()
+        torch.cuda.current_stream().wait_event(ev)
+        d.record_stream(torch.cuda.current_stream())
+        return d
+
+    tl.TimelapseTracker(pipe, 0, 1).run(warm_frame, len(warm), sink=sink)
+    for d in state["done"]:
+        d.synchronize()
+    state["done"].clear()
+    if trace is not None:
+        trace.clear()
     barrier()
     t0 = time.perf_counter()
     out = tracker.run(e2e_frame, T, sink=sink)
@@ -351,6 +375,9 @@ def gpu_main(args):
         d.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if trace is not None and rank == 0:
+        print("e2e trace (ms since start): " + " ".join(f"{k[0]}{n}@{(ts - t0) * 1e3:.1f}" for k, n, ts in trace)
+              + f" end@{e2e_s * 1e3:.1f}", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- config 3 (strong scaling of ONE 1024 x 1024 x 96 volume) on the same GPUs, same build

@@ -1,5 +1,5 @@
-"""Plane-walk conv kernel (unet_tcz.cu) bring-up: every block it takes, through ct_unet_conv_block (engines auto_split /
-auto_split_src) against fp64 torch, plus the whole network (engine auto vs tcgen05).  Prints errors, asserts nothing."""
+"""Plane-walk conv kernel (unet_tcz.cu) bring-up: every block it takes, through ct_unet_conv_block (engines planewalk_split /
+planewalk_split_src) against fp64 torch, plus the whole network (engine auto vs tcgen05).  Prints errors, asserts nothing."""
 import importlib, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +23,7 @@ for layer in only:
         ref = _block_reference(ws, layer, xin)
         scale = np.abs(ref).max()
         dev = torch.from_numpy(xin).cuda()
-        for engine in ("auto_split", "auto_split_src", "tcgen05_split"):
+        for engine in ("planewalk_split", "planewalk_split_src", "tcgen05_split"):
             try:
                 got = model.conv_block_device(layer, dev, engine).cpu().numpy().astype(np.float64)
                 torch.cuda.synchronize()

@@ -5,8 +5,10 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 csrc = os.path.join(ROOT, "3deecelltracker_b200", "csrc")
-subprocess.run(["make", "-C", csrc, "-j", "8", "NVCCFLAGS_EXTRA=-DTZ_TIMING", "BUILD=build_timing", "TARGET=../libct3d_timing.so"], check=True,
+extra = "-DTZ_TIMING " + " ".join(sys.argv[1:])            # e.g. -DTZ_EXP_NOSTORE / -DTZ_EXP_NOEPI (results are then wrong: timing only)
+subprocess.run(["make", "-C", csrc, "-j", "8", "NVCCFLAGS_EXTRA=" + extra, "BUILD=build_timing", "TARGET=../libct3d_timing.so"], check=True,
                stdout=subprocess.DEVNULL)
+print("build flags:", extra)
 os.environ["CT3D_LIB"] = os.path.join(ROOT, "3deecelltracker_b200", "libct3d_timing.so")
 u = importlib.import_module("3deecelltracker_b200.unet3d")
 synth = importlib.import_module("3deecelltracker_b200.synth")
@@ -22,7 +24,7 @@ for li, xy in sizes.items():
     cin, cout = layers[li]
     x = torch.from_numpy(rng.normal(0, 1, (38, xy, xy, 16, cin)).astype(np.float32)).cuda()
     for _ in range(2):
-        model.conv_block_device(li, x, "auto_split")
+        model.conv_block_device(li, x, "planewalk_split")
     torch.cuda.synchronize()
     out = (C.c_ulonglong * 16)()
     fn(out)
