@@ -1,4 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 400 python scripts/tcz_timing.py -DTZ_EXP_NOSTORE 2>&1 | tail -5
-rm -rf 3deecelltracker_b200/csrc/build_timing
-timeout 400 python scripts/tcz_timing.py -DTZ_EXP_NOEPI 2>&1 | tail -5
+timeout 300 python scripts/conv_layers.py 38 tcgen05_split planewalk_split 2>&1 | tail -16 | grep -E "d0b|d1a|u0b|o_m|sum"
