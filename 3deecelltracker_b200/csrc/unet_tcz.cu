@@ -11,19 +11,20 @@
 //   * M tile = 8 y-rows x ALL 16 z of one x-plane (TMEM lane = 16 y + z).  The z-halo of a tile is Keras' zero padding,
 //     so the z shift-add is one lane up / down inside a 16-lane group (two shuffles) with zeros at z = 0 / 15: no halo
 //     rows are computed in y or z, and Y = 40 / 20 fit the 8-row tile (the 16-row tile of unet_tcx.cu wastes 17 / 37 %).
-//   * N = 9 (dx,dz) taps x 8 output channels x (hi | lo') = 144 columns per group of 8 output channels (column =
-//     72 term + 36 (co / 4) + 4 tap + co % 4: the 36 columns a drain thread reads per term are contiguous):
-//         MMA1 = A_hi  x rows [0, 144)  -> columns [0, 72) = hi.hi, [72, 144) = hi.lo'
-//         MMA2 = A_lo' x rows [0, 80)   -> accumulated onto columns [72, 152)   (lo'.hi, same weight 2^-11; 72 is not a
-//                                          legal MMA width, the 8 extra columns are never read)
-//     Cout = 16 / 32 run 2 / 4 such groups per plane (the A tile is re-read per group, but at N = 144 the MMA is math
-//     bound, so nothing is lost).
-//   * K = 16 per MMA = two (ci-chunk, dy) taps x 8 input channels; 3 cin/8 taps -> ceil(3 cin / 16) K steps, ALL chained
-//     in tensor memory (<= 12 steps x 2 MMAs; the 27-tap kernel chains 28), one drain per (plane, group).
+//   * N = 3 x-taps x 48 columns = 144 per group of 8 output channels.  A block of 48 columns is ONE OUTPUT PLANE's
+//     accumulator: 3 z-taps x 8 channels x (hi.hi | hi.lo' + lo'.hi).  Output planes live in a ring of such blocks in
+//     tensor memory, and the MMA of input plane j accumulates onto the three physically consecutive blocks of output
+//     planes j-1, j, j+1 (B rows ordered dx = 2, 1, 0): the sum over the x-taps happens IN the tensor core's
+//     accumulators, and a plane is drained ONCE, when its third contribution has landed (24 columns per thread instead
+//     of 72 per input plane: the drain of the first version of this kernel, which added the x-taps in registers, took
+//     900-1100 clocks per plane and group against 260-400 clocks of MMAs).
+//         MMA1 = A_hi  x image 0 (hi | lo' rows)      MMA2 = A_lo' x image 1 (0 | hi rows), both N = 144, same columns
+//     Cout = 16 runs two such groups per plane, each with its own ring and its own issuer warp.
+//   * K = 16 per MMA = two (ci-chunk, dy) taps x 8 input channels; 3 cin/8 taps -> ceil(3 cin / 16) K steps; a plane's
+//     accumulator takes 3 x 2 x steps MMAs (<= 36; the 27-tap kernel chains 28).
 //   * The CTA walks a segment of x-planes of one (tile, 8-row y-block): one shared-memory stage = ONE x-plane of all
-//     input channels (10 haloed rows x 16 z), loaded once and used by the three output planes it feeds.  The drain keeps
-//     a rolling window of three output planes in registers (12 accumulator registers per group instead of 8 planes),
-//     so there is no x-halo recomputation inside a segment: (S + 2) / S input planes per S output planes.
+//     input channels (10 haloed rows x 16 z), loaded once and used by the three output planes it feeds: there is no
+//     x-halo recomputation inside a segment, (S + 2) / S input planes per S output planes.
 //   * The packed weights of the whole block stay resident in shared memory (<= 110 KB), loaded once per CTA.
 //
 // Source buffers are split-fp16 only (unet_common.cuh); the destination is split-fp16 or fp32 c4 planes.  Decoder
@@ -46,10 +47,15 @@ constexpr int TZ_BY = 8, TZ_YH = TZ_BY + 2;       // y rows per unit, haloed
 constexpr int TZ_ROW16 = TZ_Z;                    // 16-byte units per y row of one operand image
 constexpr int TZ_IMG16 = TZ_YH * TZ_ROW16;        // one operand image (8 channels) of one plane: 160 units = 2560 B
 constexpr int TZ_CHUNK16 = 2 * TZ_IMG16;          // hi + lo'
-constexpr int TZ_NROW = 144;                      // B rows per K half: 72 hi + 72 lo'
-constexpr int TZ_WSTEP16 = 2 * TZ_NROW;           // 16-byte units per (K step, group): two K halves
-constexpr int TZ_N1 = 144, TZ_N2 = 80, TZ_D2 = 72;
-constexpr int TZ_SETCOLS = 152, TZ_NSETS = 3;
+constexpr int TZ_BLK = 48;                        // accumulator columns of one output plane and group: (hi.hi | cross) x 3 dz x 8
+constexpr int TZ_NMMA = 3 * TZ_BLK;               // one MMA feeds three consecutive output planes (dx = 2, 1, 0)
+constexpr int TZ_NROW = TZ_NMMA;                  // B rows per K half
+constexpr int TZ_WIMG16 = 2 * TZ_NROW;            // 16-byte units of one B image (two K halves); two images per (K step, group)
+template <int NG> struct TzRing {                 // ring slots of output planes per group (+ 2 overflow blocks)
+    static constexpr int R = NG == 1 ? 8 : 3;
+    static constexpr int COLS = (R + 2) * TZ_BLK;
+    static_assert(NG <= 2 && NG * COLS <= 512, "plane ring exceeds tensor memory");
+};
 constexpr int TZ_DRAIN_WARPS = 8;
 constexpr int TZ_THREADS = 128 + 32 * TZ_DRAIN_WARPS;      // warpgroup 0: producer + three MMA issuers
 constexpr int TZ_MAX_STAGES = 8;
@@ -94,14 +100,8 @@ __device__ __forceinline__ TzUnit tz_unit(int u, const TzGeom& g) {
 // K-half taps of step p: tap t = (ci chunk t / 3, dy = t % 3) at t/3 chunks + t%3 rows into the plane's stage
 __host__ __device__ constexpr uint32_t tz_tap_off16(int t) { return (uint32_t)(t / 3) * TZ_CHUNK16 + (uint32_t)(t % 3) * TZ_ROW16; }
 
-__device__ __forceinline__ void tz_ld4(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr));
-}
-// 32 consecutive accumulator columns of the thread's lane in one instruction: narrow tensor-memory loads are paced per
-// instruction, not per byte (18 x4 loads per set held the drain at ~1150 clocks per set)
-__device__ __forceinline__ void tz_ld32(uint32_t taddr, uint32_t* r) {
+// the 48 accumulator columns of one output plane and group, of the thread's lane
+__device__ __forceinline__ void tz_ld48(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
@@ -109,19 +109,48 @@ __device__ __forceinline__ void tz_ld32(uint32_t taddr, uint32_t* r) {
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+                   "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+                 : "r"(taddr + 32));
 }
 
+__device__ __forceinline__ void tz_zero48(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+                 "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(taddr + 32), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Persistent CTA.  Work unit = a segment of x-planes x 8 y-rows x 16 z x all Cout of one tile.  Warp roles: 0 TMA producer
-// (+ tensor-memory allocator, resident weights), 1-3 MMA issuers (one per accumulator set), 4-11 accumulator drain / shift-add / epilogue (two per
-// tensor-memory lane quarter, four of a group's eight channels each).  The drain warps take registers from warpgroup 0
-// (setmaxnreg inside the launch-time pool of 384 x 168: 128 x 56 + 256 x 224 = 64512).
+// (+ tensor-memory allocator, resident weights), 1 .. NG MMA issuers (one per group of 8 output channels), 4-11 drain /
+// epilogue (two per tensor-memory lane quarter, four of a group's eight channels each).
+//
+// Output planes live in a RING of tensor-memory blocks (48 columns per plane and group).  Every plane of the CTA's
+// whole sequence of units has an id G (two pseudo ids separate consecutive units: they take the contributions that fall
+// outside a segment and are discarded); the MMA of the input plane with newest id G accumulates onto ids G-2, G-1, G
+// = three physically consecutive blocks starting at block (G-2) mod R.  Ids whose ring slot is 0 / 1 therefore receive
+// part of their sum in the two overflow blocks R / R+1 behind the ring; the drain adds the two parts.
+// The FIRST contribution to a block overwrites it (accumulate = 0), so nothing ever has to be zeroed: at K step 0 the
+// MMA is split into the 96 columns of the two older planes (accumulate) and the 48 columns of the newest one
+// (overwrite) -- or, when the three blocks are ring slots 0, 1, 2, all of which start there, issued whole with
+// accumulate = 0 (the two older ids had their earlier contributions in the overflow blocks).
+//   drain -> issuer: blk_free[g][slot]  the id that last used the slot has been read out of tensor memory
+//   issuer -> drain: blk_done[g][slot]  (tcgen05.commit after the MMAs with newest id G) id G-2 is complete
+// Drain: each warp takes WHOLE blocks (all 8 channels of a plane and group, 48 columns per thread) of every other
+// (plane, group) item -- warps 4-7 the even items, warps 8-11 the odd ones -- so two items are in flight per lane
+// quarter and the tensor-memory load latency of one (hundreds of clocks while MMAs read-modify-write their
+// accumulators) overlaps the epilogue of the other.  The block is handed back right after the load, before the epilogue.
 template <int CIN8, int NG, bool DST_SPLIT, bool POOL>
 __global__ void __launch_bounds__(TZ_THREADS, 1)
 conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
                  const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                  float alpha, float4* __restrict__ dst, const TzGeom geo) {
+    constexpr int R = TzRing<NG>::R, GCOLS = TzRing<NG>::COLS;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[TZ_MAX_STAGES], bar_empty[TZ_MAX_STAGES], bar_acc_full[TZ_NSETS], bar_acc_empty[TZ_NSETS], bar_w;
+    __shared__ uint64_t bar_full[TZ_MAX_STAGES], bar_empty[TZ_MAX_STAGES], blk_free[NG][R], blk_done[NG][R], bar_w;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float ep_s[3][8 * NG];
 
@@ -136,13 +165,15 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], NG < TZ_NSETS ? NG : TZ_NSETS);      // one commit per issuer that reads the plane
+            mbar_init(&bar_empty[s], NG);                          // one commit per issuer that reads the plane
         }
 #pragma unroll
-        for (int a = 0; a < TZ_NSETS; ++a) {
-            mbar_init(&bar_acc_full[a], 1);
-            mbar_init(&bar_acc_empty[a], TZ_DRAIN_WARPS);
-        }
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                mbar_init(&blk_free[g][r], TZ_DRAIN_WARPS / 2);
+                mbar_init(&blk_done[g][r], 1);
+            }
         mbar_init(&bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -185,55 +216,57 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #endif
         }
         __syncwarp();
-    } else {
-        // ---------------- MMA issuers: warps 1-3, issuer i owns accumulator set i (every third (plane, group) step).
-        // A set is only 4-12 MMAs (260-800 clocks of tensor work) and the issuing thread pays ~400 clocks of latency per
-        // set around them (two mbarrier round trips, fences, commits, uniform-register moves): one issuer left the tensor
-        // pipe idle half of the time [measured: 75 % of the issuer's time outside any wait at Cin = 8].  Three issuers
-        // overlap those latencies; their MMAs target different tensor-memory columns, so their relative order is free.
+    } else if (NG == 1) {
+        // ---------------- one group per plane: THREE MMA issuers, issuer i takes every third plane.  A plane is only 4-12
+        // MMAs (290-860 clocks of tensor work) and the issuing thread pays ~365 clocks of latency per plane around them
+        // (two mbarrier round trips, fence, commits) [measured: busy = 365 + 70 n clocks for n MMAs]; three issuers overlap
+        // it.  Their MMAs may execute in any order, so here every contribution ACCUMULATES onto blocks the drain has zeroed
+        // (tcgen05.st; the 8-deep ring hides that round trip), and a plane's completion is tracked per MMA: mma_done =
+        // blk_done[0][slot of the newest id], the drain waits for the three MMAs that feed an id.
         if (elect_one()) {
-            constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(TZ_N1 >> 3) << 17) | (8u << 24);
-            constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(TZ_N2 >> 3) << 17) | (8u << 24);
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TZ_NMMA >> 3) << 17) | (8u << 24);
             constexpr uint64_t sbo8_word = (uint64_t)(8u | (1u << 14)) << 32;     // 8-row groups 128 B apart (A and B)
             const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(wsm) >> 4;
             const int me = warp - 1;
-            const uint32_t d = tmem_base + (uint32_t)me * TZ_SETCOLS;
             mbar_wait(&bar_w, 0);
-            int gp = 0, a3 = 0, use_me = 0;
+            int gp = 0, turn = 0;
+            int slot = 2 % R, use = 2 / R;                          // ring slot / use count of the newest id (ids start at 2)
             long long w_full = 0, w_acc = 0, t_begin = clock64();
             for (int k = 0; k < n_units; ++k) {
                 const TzUnit un = tz_unit((int)blockIdx.x + k * (int)gridDim.x, geo);
                 const int nh = un.nout + 2;
                 for (int h = 0; h < nh; ++h, ++gp) {
-                    const int s = gp % stages, use = gp / stages;
-                    const uint32_t a_hi = ring16 + (uint32_t)s * (stage_bytes >> 4);
-                    bool mine = false;
+                    if (turn == me) {
+                        const int s = gp % stages, us = gp / stages;
+                        { TZ_T0(); mbar_wait(&bar_full[s], us & 1); TZ_ACC(w_full); }
+                        // the blocks of the three ids this plane feeds have been zeroed (the two warp sets of the drain
+                        // hand back alternate ids, in no particular order between them)
 #pragma unroll
-                    for (int g = 0; g < NG; ++g, a3 = (a3 == TZ_NSETS - 1) ? 0 : a3 + 1) {
-                        if (a3 != me) continue;
-                        if (!mine) {
-                            { TZ_T0(); mbar_wait(&bar_full[s], use & 1); TZ_ACC(w_full); }
-                            mine = true;
+                        for (int dd = 0; dd < 3; ++dd) {
+                            const int sd = slot - dd < 0 ? slot - dd + R : slot - dd, ud = slot - dd < 0 ? use - 1 : use;
+                            TZ_T0(); mbar_wait(&blk_free[0][sd], ud & 1); TZ_ACC(w_acc);
                         }
-                        if (use_me > 0) { TZ_T0(); mbar_wait(&bar_acc_empty[me], (use_me - 1) & 1); TZ_ACC(w_acc); }
-                        ++use_me;
                         tc_fence_after();
+                        const uint32_t a_hi = ring16 + (uint32_t)s * (stage_bytes >> 4);
+                        const int b = slot >= 2 ? slot - 2 : slot + R - 2;          // block of id G - 2
+                        const uint32_t d = tmem_base + (uint32_t)(b * TZ_BLK);
 #pragma unroll
                         for (int p = 0; p < NSTEPS; ++p) {
-                            // the last step of an odd tap count repeats the tap before it against zero weights;
-                            // every descriptor is the stage / weight base plus a compile-time constant
                             const int t1 = (2 * p + 1 < NTAPS) ? 2 * p + 1 : NTAPS - 1;
                             const int t0 = t1 - 1;
                             const uint32_t o0 = tz_tap_off16(t0), lbo = (tz_tap_off16(t1) - o0) << 16;
                             const uint32_t ah = (a_hi + o0) | lbo;
                             const uint32_t al = (a_hi + o0 + TZ_IMG16) | lbo;
-                            const uint32_t b32 = (w16 + (uint32_t)(p * NG + g) * TZ_WSTEP16) | ((uint32_t)TZ_NROW << 16);
-                            umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b32, idesc1, p != 0);
-                            umma_f16(d + TZ_D2, sbo8_word | (uint64_t)al, sbo8_word | (uint64_t)b32, idesc2, 1u);
+                            const uint32_t b1 = (w16 + (uint32_t)(p * 2) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                            const uint32_t b2 = (w16 + (uint32_t)(p * 2 + 1) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                            umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc, 1u);
+                            umma_f16(d, sbo8_word | (uint64_t)al, sbo8_word | (uint64_t)b2, idesc, 1u);
                         }
-                        umma_commit(&bar_acc_full[me]);
+                        umma_commit(&blk_done[0][slot]);            // the MMAs with newest id G have retired
+                        umma_commit(&bar_empty[s]);
                     }
-                    if (mine) umma_commit(&bar_empty[s]);
+                    turn = (turn == 2) ? 0 : turn + 1;
+                    if (++slot == R) { slot = 0; ++use; }
                 }
             }
 #ifdef TZ_TIMING
@@ -243,19 +276,97 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #endif
         }
         __syncwarp();
+    } else if (warp <= NG) {
+        // ---------------- two groups per plane: one MMA issuer per group, g = warp - 1
+        if (elect_one()) {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TZ_NMMA >> 3) << 17) | (8u << 24);
+            constexpr uint32_t idesc96 = (1u << 4) | ((uint32_t)((2 * TZ_BLK) >> 3) << 17) | (8u << 24);
+            constexpr uint32_t idesc48 = (1u << 4) | ((uint32_t)(TZ_BLK >> 3) << 17) | (8u << 24);
+            constexpr uint64_t sbo8_word = (uint64_t)(8u | (1u << 14)) << 32;     // 8-row groups 128 B apart (A and B)
+            const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(wsm) >> 4;
+            const int g = warp - 1;
+            const uint32_t gcol = tmem_base + (uint32_t)(g * GCOLS);
+            mbar_wait(&bar_w, 0);
+            int gp = 0;
+            int slot = 2 % R, use = 2 / R;                          // ring slot / use count of the newest id (ids start at 2)
+            long long w_full = 0, w_acc = 0, t_begin = clock64();
+            for (int k = 0; k < n_units; ++k) {
+                const TzUnit un = tz_unit((int)blockIdx.x + k * (int)gridDim.x, geo);
+                const int nh = un.nout + 2;
+                for (int h = 0; h < nh; ++h, ++gp) {
+                    const int s = gp % stages, us = gp / stages;
+                    { TZ_T0(); mbar_wait(&bar_full[s], us & 1); TZ_ACC(w_full); }
+                    if (use > 0) { TZ_T0(); mbar_wait(&blk_free[g][slot], (use - 1) & 1); TZ_ACC(w_acc); }
+                    tc_fence_after();
+                    const uint32_t a_hi = ring16 + (uint32_t)s * (stage_bytes >> 4);
+                    const int b = slot >= 2 ? slot - 2 : slot + R - 2;              // block of id G - 2
+                    const uint32_t d = gcol + (uint32_t)(b * TZ_BLK);
+#pragma unroll
+                    for (int p = 0; p < NSTEPS; ++p) {
+                        // the last step of an odd tap count repeats the tap before it against zero weights;
+                        // every descriptor is the stage / weight base plus a compile-time constant
+                        const int t1 = (2 * p + 1 < NTAPS) ? 2 * p + 1 : NTAPS - 1;
+                        const int t0 = t1 - 1;
+                        const uint32_t o0 = tz_tap_off16(t0), lbo = (tz_tap_off16(t1) - o0) << 16;
+                        const uint32_t ah = (a_hi + o0) | lbo;
+                        const uint32_t al = (a_hi + o0 + TZ_IMG16) | lbo;
+                        const uint32_t b1 = (w16 + (uint32_t)((p * NG + g) * 2) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                        const uint32_t b2 = (w16 + (uint32_t)((p * NG + g) * 2 + 1) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                        if (p == 0) {
+                            if (b == 0) {
+                                umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc, 0u);
+                            } else {
+                                umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc96, 1u);
+                                umma_f16(d + 2 * TZ_BLK, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)(b1 + 2 * TZ_BLK), idesc48, 0u);
+                            }
+                        } else {
+                            umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc, 1u);
+                        }
+                        umma_f16(d, sbo8_word | (uint64_t)al, sbo8_word | (uint64_t)b2, idesc, 1u);
+                    }
+                    umma_commit(&blk_done[g][b]);                   // id G - 2 has all three contributions
+                    umma_commit(&bar_empty[s]);
+                    if (++slot == R) { slot = 0; ++use; }
+                }
+            }
+#ifdef TZ_TIMING
+            if (blockIdx.x == 0 && g == 0) { g_tz_timers[0] = w_full; g_tz_timers[1] = w_acc; g_tz_timers[2] = clock64() - t_begin; }
+#else
+            (void)w_full; (void)w_acc; (void)t_begin;
+#endif
+        }
+        __syncwarp();
     }
     } else {
-        // ---------------- drain warps: tensor memory -> registers, (dx, dz) shift-add, epilogue
+        // ---------------- drain warps: finished planes tensor memory -> registers, z shift-add, epilogue
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int q = warp & 3;                                    // tensor-memory lane quarter this warp may read
-        const int part = (warp - 4) >> 2;                          // which four channels of every group
+        const int set = (warp - 4) >> 2;                           // which half of the (plane, group) items
         const int row = q * 32 + lane;
         const int yl = row >> 4, z = row & 15;
         const size_t vol = (size_t)geo.X * geo.Y * TZ_Z;
         constexpr float W2 = 1.f / 2048.f;                         // weight of the hi.lo' + lo'.hi columns
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 36);
-        int a = 0;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int g_mine = NG == 2 ? set : 0;                      // two groups: one per warp set; one group: alternate planes
+        const uint32_t m_up = (z == 0) ? 0u : 0xffffffffu, m_dn = (z == TZ_Z - 1) ? 0u : 0xffffffffu;
         long long w_accf = 0, t_ld = 0, t_fin = 0, t_begin = clock64();
+        if constexpr (NG == 1) {                                   // every block starts at zero; ids 0 .. R-1 are ready
+            if (set == 0) {
+#pragma unroll
+                for (int bl = 0; bl < R + 2; ++bl) tz_zero48(t_lane + (uint32_t)(bl * TZ_BLK));
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0 && set == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) mbar_arrive(&blk_free[0][r]);
+                // ids 0 and 1 have no MMA of their own (the first newest id is 2): keep the phases of their slots aligned
+                if (warp == 4) { mbar_arrive(&blk_done[0][0]); mbar_arrive(&blk_done[0][1]); }
+            }
+        }
+        int slot = 0, use = 0, idpar = 0;                          // ring slot / use count / parity of the id being drained
+        // the id sequence: two pseudo ids, then per unit its nout planes and two pseudo ids; the last two never complete
         TzUnit un_next = tz_unit((int)blockIdx.x, geo);
         float am_next = 0.f, am2_next = 0.f, sc_next = 1.f;
         auto tile_hdr = [&](int tile) {
@@ -264,6 +375,58 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             sc_next = geo.scale_src[(size_t)tile * geo.slab_stride];
         };
         if (n_units > 0) tile_hdr(un_next.tile);
+        const bool mine_all = (NG == 2);
+        // takes the finished id in (slot, use) out of tensor memory (real planes only) and hands its blocks back
+        auto take = [&](bool real, uint32_t (&v)[48]) {
+            if constexpr (NG == 1) {
+                // the three MMAs that feed this id carry the newest ids X, X + 1, X + 2 (none before id 2); the warp waited
+                // for X when it took its previous id, X - 2
+#pragma unroll
+                for (int dd = 1; dd < 3; ++dd) {
+                    const int sd = slot + dd >= R ? slot + dd - R : slot + dd, ud = slot + dd >= R ? use + 1 : use;
+                    if (ud == 0 && sd < 2) continue;
+                    TZ_T0(); mbar_wait(&blk_done[0][sd], ud & 1); TZ_ACC(w_accf);
+                }
+            } else {
+                TZ_T0(); mbar_wait(&blk_done[g_mine][slot], use & 1); TZ_ACC(w_accf);
+            }
+            tc_fence_after();
+            const uint32_t t0 = t_lane + (uint32_t)(g_mine * GCOLS + slot * TZ_BLK);
+#ifdef TZ_TIMING
+            const long long _tl = clock64();
+#endif
+            if (real) {
+                tz_ld48(t0, v);
+                if (slot < 2) {                                     // the part that landed in the overflow block
+                    uint32_t w[48];
+                    tz_ld48(t0 + R * TZ_BLK, w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 48; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+                } else {
+                    tmem_ld_wait();
+                }
+            }
+            if constexpr (NG == 1) {                                // zero the blocks for the next id of this slot
+                tz_zero48(t0);
+                if (slot < 2) tz_zero48(t0 + R * TZ_BLK);
+                tmem_st_wait();
+            }
+#ifdef TZ_TIMING
+            t_ld += clock64() - _tl;
+#endif
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&blk_free[g_mine][slot]);
+        };
+        auto next_id = [&]() { idpar ^= 1; if (++slot == R) { slot = 0; ++use; } };
+        if (n_units > 0) {
+            uint32_t dummy[48];
+            for (int e = 0; e < 2; ++e) {
+                if (mine_all || idpar == set) take(false, dummy);
+                next_id();
+            }
+        }
         for (int k = 0; k < n_units; ++k) {
             const TzUnit un = un_next;
             const float inv_scale = geo.w_inv_scale / sc_next;
@@ -276,93 +439,76 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 un_next = tz_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo);
                 tile_hdr(un_next.tile);
             }
-            const int nh = un.nout + 2;
             const int y = un.y0 + yl;
             const bool ok_y = y < geo.Y;
             uint8_t* d_tile = reinterpret_cast<uint8_t*>(dst + (size_t)un.tile * geo.dst_tile_stride4);
             float amax = 0.f;
-            // accumulators of the rolling window of three output planes, kept apart per z-tap: the z shift is linear, so
-            // the two shuffles per value happen once per finished output plane instead of once per contribution
-            float2 acc[NG][3][3][2], pf[NG][2], keep[NG][2];
+            float2 keep[4];
 #pragma unroll
-            for (int g = 0; g < NG; ++g)
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-#pragma unroll
-                    for (int sl = 0; sl < 3; ++sl) acc[g][sl][0][i] = acc[g][sl][1][i] = acc[g][sl][2][i] = make_float2(0.f, 0.f);
-                    keep[g][i] = make_float2(0.f, 0.f);
-                }
-            // This thread's 8-byte halves of a voxel in a split / P8 buffer: channels 4 part .. 4 part + 3 of group g, first
-            // pair in the hi plane (2 g), second pair in the lo' plane (2 g + 1), both at byte 8 part of the voxel's 16.
-            // row_b = byte offset of (x0, y, z) inside a plane; one x-plane further = plane_b bytes.
+            for (int kk = 0; kk < 4; ++kk) keep[kk] = make_float2(0.f, 0.f);
+            // the voxel's 16 bytes in the group's two channel planes: split buffers hold the fp16 hi image of the 8 channels
+            // in plane 2 g and the lo' image in 2 g + 1; fp32 buffers channels 0-3 / 4-7; P8 partial sums channel pairs
+            // (0,1 | 4,5) / (2,3 | 6,7)
             const size_t plane_b = (size_t)geo.Y * TZ_Z * 16, vol_b = vol * 16;
-            uint8_t* const d_grp = d_tile + (size_t)geo.dst_c4off * vol_b + (((size_t)un.x0 * geo.Y + y) * TZ_Z + z) * 16 + (size_t)part * 8;
-            // partial sums (P8) of output plane x0 + i, fetched one plane ahead of their first use
-            auto load_partial = [&](int i) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) pf[g][0] = pf[g][1] = make_float2(0.f, 0.f);
-                if (geo.add_partial && ok_y && i < un.nout) {       // add_partial is uniform over the CTA
-                    const uint8_t* pp = d_grp + (size_t)i * plane_b;
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        const uint2 p0 = *reinterpret_cast<const uint2*>(pp + (size_t)(2 * g) * vol_b);
-                        const uint2 p1 = *reinterpret_cast<const uint2*>(pp + (size_t)(2 * g + 1) * vol_b);
-                        pf[g][0] = make_float2(__uint_as_float(p0.x), __uint_as_float(p0.y));
-                        pf[g][1] = make_float2(__uint_as_float(p1.x), __uint_as_float(p1.y));
-                    }
-                }
-            };
-            // pa = address of the thread's half in the group's first plane, pvol_b = bytes between channel planes
-            auto put = [&](uint8_t* pa, size_t pvol_b, const float2 (&v)[2], float so) {
+            uint8_t* const d_grp = d_tile + (size_t)(geo.dst_c4off + 2 * g_mine) * vol_b + (((size_t)un.x0 * geo.Y + y) * TZ_Z + z) * 16;
+            auto put = [&](uint8_t* pa, size_t pvol_b, const float2 (&v)[4], float so) {
 #ifdef TZ_EXP_NOSTORE
-                if (so != 12345.678f) { amax = fmaxf(amax, v[0].x + v[0].y + v[1].x + v[1].y); return; }      // experiment: no stores
+                if (so != 12345.678f) { amax = fmaxf(amax, v[0].x + v[1].y + v[2].x + v[3].y); return; }      // experiment: no stores
 #endif
                 if constexpr (!DST_SPLIT) {
-                    // fp32 c4 planes: channels 4 part .. 4 part + 3 are the whole 16 bytes of plane 2 g + part
-                    *reinterpret_cast<float4*>(pa - (size_t)part * 8 + (size_t)part * pvol_b) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+                    *reinterpret_cast<float4*>(pa) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+                    *reinterpret_cast<float4*>(pa + pvol_b) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
                 } else {
-                    uint32_t hi[2], lo[2];
-                    split_pair2(v[0], so, hi[0], lo[0]);
-                    split_pair2(v[1], so, hi[1], lo[1]);
-                    *reinterpret_cast<uint2*>(pa) = make_uint2(hi[0], hi[1]);
-                    *reinterpret_cast<uint2*>(pa + pvol_b) = make_uint2(lo[0], lo[1]);
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) split_pair2(v[kk], so, hi[kk], lo[kk]);
+                    *reinterpret_cast<uint4*>(pa) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(pa + pvol_b) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             };
-            // epilogue of output plane x0 + i of group g: z shift-add of the three tap accumulators, scale back,
-            // bias -> activation -> BatchNorm, store (+ pooled copy)
-            auto finish = [&](int i, int g, const float2 (&az)[3][2]) {
+            // epilogue of output plane x0 + i from its 48 accumulator columns [term][dz][channel]: hi.hi + 2^-11 (hi.lo' +
+            // lo'.hi), z shift-add of the three z-taps, partial sums, scale back, bias -> activation -> BatchNorm, store
+            // (+ pooled copy)
+            auto finish = [&](int i, const uint32_t (&v)[48], const float2 (&ps)[4]) {
                 const int x = un.x0 + i;
-                const int ch = 8 * g + 4 * part;
-                float2 av[2];
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    // out[z] takes tap dz = 0 from input row z - 1 and tap dz = 2 from input row z + 1 (zero outside the tile)
-                    float2 up = make_float2(__shfl_up_sync(0xffffffffu, az[0][kk].x, 1), __shfl_up_sync(0xffffffffu, az[0][kk].y, 1));
-                    float2 dn = make_float2(__shfl_down_sync(0xffffffffu, az[2][kk].x, 1), __shfl_down_sync(0xffffffffu, az[2][kk].y, 1));
-                    if (z == 0) up = make_float2(0.f, 0.f);
-                    if (z == TZ_Z - 1) dn = make_float2(0.f, 0.f);
-                    av[kk] = f2_add(az[1][kk], f2_add(up, dn));
-                }
-#ifdef TZ_EXP_NOEPI
-                amax = fmaxf(amax, av[0].x + av[0].y + av[1].x + av[1].y);      // experiment: shuffles only
-                if (amax != 12345.678f) return;
-#endif
-                float2 o[2];
+                float2 o[4];
                 float am = 0.f;
-                o[0] = block_epilogue(av[0], inv_scale, alpha, &ep_s[0][0], 8 * NG, ch, am);
-                o[1] = block_epilogue(av[1], inv_scale, alpha, &ep_s[0][0], 8 * NG, ch + 2, am);
+                // stage by stage over the four channel pairs, so that their dependency chains interleave; the zeros at the
+                // z ends are a bit mask (a select on z compiles to a divergent branch per pair)
+                float2 c[4][3], up[4], dn[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int dz = 0; dz < 3; ++dz)
+                        c[kk][dz] = f2_fma(make_float2(__uint_as_float(v[24 + dz * 8 + 2 * kk]), __uint_as_float(v[24 + dz * 8 + 2 * kk + 1])),
+                                           f2_splat(W2),
+                                           make_float2(__uint_as_float(v[dz * 8 + 2 * kk]), __uint_as_float(v[dz * 8 + 2 * kk + 1])));
+                // out[z] takes tap dz = 0 from input row z - 1 and tap dz = 2 from input row z + 1 (zero outside the tile)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    up[kk].x = __uint_as_float(__float_as_uint(__shfl_up_sync(0xffffffffu, c[kk][0].x, 1)) & m_up);
+                    up[kk].y = __uint_as_float(__float_as_uint(__shfl_up_sync(0xffffffffu, c[kk][0].y, 1)) & m_up);
+                    dn[kk].x = __uint_as_float(__float_as_uint(__shfl_down_sync(0xffffffffu, c[kk][2].x, 1)) & m_dn);
+                    dn[kk].y = __uint_as_float(__float_as_uint(__shfl_down_sync(0xffffffffu, c[kk][2].y, 1)) & m_dn);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float2 av = f2_add(f2_add(c[kk][1], ps[kk]), f2_add(up[kk], dn[kk]));
+                    o[kk] = block_epilogue(av, inv_scale, alpha, &ep_s[0][0], 8 * NG, 8 * g_mine + 2 * kk, am);
+                }
                 if (ok_y) {
                     amax = fmaxf(amax, am);
-                    put(d_grp + (size_t)i * plane_b + (size_t)(2 * g) * vol_b, vol_b, o, s_out);
+                    put(d_grp + (size_t)i * plane_b, vol_b, o, s_out);
                 }
                 if (POOL && geo.pool_dst != nullptr) {             // uniform over the CTA
                     if ((x & 1) == 0) {
-                        keep[g][0] = o[0]; keep[g][1] = o[1];
-                    } else {
-                        float2 m[2];
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            m[kk] = make_float2(fmaxf(keep[g][kk].x, o[kk].x), fmaxf(keep[g][kk].y, o[kk].y));
+                        for (int kk = 0; kk < 4; ++kk) keep[kk] = o[kk];
+                    } else {
+                        float2 m[4];
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            m[kk] = make_float2(fmaxf(keep[kk].x, o[kk].x), fmaxf(keep[kk].y, o[kk].y));
                             m[kk].x = fmaxf(m[kk].x, __shfl_xor_sync(0xffffffffu, m[kk].x, 16));     // y pair: 16 lanes apart
                             m[kk].y = fmaxf(m[kk].y, __shfl_xor_sync(0xffffffffu, m[kk].y, 16));
                         }
@@ -370,85 +516,32 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                             const int PX = geo.X >> 1, PY = geo.Y >> 1;
                             const size_t pvol_b = (size_t)PX * PY * TZ_Z * 16;
                             uint8_t* pb = reinterpret_cast<uint8_t*>(geo.pool_dst + (size_t)un.tile * geo.dst_tile_stride4);
-                            put(pb + (size_t)(2 * g) * pvol_b + (((size_t)(x >> 1) * PY + (y >> 1)) * TZ_Z + z) * 16 + (size_t)part * 8, pvol_b, m, s_out);
+                            put(pb + (size_t)(2 * g_mine) * pvol_b + (((size_t)(x >> 1) * PY + (y >> 1)) * TZ_Z + z) * 16, pvol_b, m, s_out);
                         }
                     }
                 }
             };
-            load_partial(0);
-            // With two groups per plane the epilogue of a finished plane is DEFERRED into the next set's tensor-memory load:
-            // the drain of a set is one long dependency chain (barrier -> tcgen05.ld -> accumulate -> shuffles -> activation
-            // -> fp16 split -> store) on two warps per scheduler, so the previous set's epilogue runs while this set's loads
-            // are in flight [measured: 16 -> 16 0.283 -> 0.266 ms; with one group per plane it lost 5 %, so not there].
-            constexpr bool DEFER = NG >= 2;
+            const bool last_unit = (k == n_units - 1);
 #pragma unroll 1
-            for (int h0 = 0; h0 < nh; h0 += 3) {
+            for (int i = 0; i < un.nout + 2; ++i) {
+                const bool real = i < un.nout;
+                if (last_unit && !real) break;                      // the sequence's last two pseudo ids never complete
+                if (mine_all || idpar == set) {
+                    // partial sums (P8) of this plane: the loads fly while the warp waits for the plane to complete
+                    float2 ps[4];
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const int h = h0 + p;
-                    if (h >= nh) break;                                // uniform over the CTA
-                    // output plane x0 + h starts in slot p (from its partial sums), plane h - 1 continues in slot
-                    // (p + 2) % 3, plane h - 2 completes in slot (p + 1) % 3
-                    float2 pfc[NG][2];
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) { pfc[g][0] = pf[g][0]; pfc[g][1] = pf[g][1]; }
-                    load_partial(h + 1);
-#pragma unroll
-                    for (int g = 0; g < NG; ++g, ++a) {
-                        const int set = a % TZ_NSETS, use_a = a / TZ_NSETS;
-                        { TZ_T0(); mbar_wait(&bar_acc_full[set], use_a & 1); TZ_ACC(w_accf); }
-                        tc_fence_after();
-                        const uint32_t t0 = t_lane + (uint32_t)set * TZ_SETCOLS;
-#ifdef TZ_TIMING
-                        const long long _tl = clock64();
-#endif
-                        uint32_t v[2][36];                                    // [term][4 tap + channel]
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            tz_ld32(t0 + t * TZ_D2, &v[t][0]);
-                            tz_ld4(t0 + t * TZ_D2 + 32, &v[t][32]);
-                        }
-                        // previous set: (h, g - 1) completed plane h - 2 in slot (p + 1) % 3; (h - 1, NG - 1) completed
-                        // plane h - 3 in slot p
-                        if constexpr (DEFER) {
-                            TZ_T0();
-                            if (g > 0) { if (h >= 2) finish(h - 2, g > 0 ? g - 1 : 0, acc[g > 0 ? g - 1 : 0][(p + 1) % 3]); }
-                            else if (h >= 3) finish(h - 3, NG - 1, acc[NG - 1][p]);
-                            TZ_ACC(t_fin);
-                        }
-                        tmem_ld_wait();
-#ifdef TZ_TIMING
-                        t_ld += clock64() - _tl;
-#endif
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_acc_empty[set]);      // values are in registers: the set is free
-                        acc[g][p][1][0] = pfc[g][0]; acc[g][p][1][1] = pfc[g][1];
-                        acc[g][p][0][0] = acc[g][p][0][1] = acc[g][p][2][0] = acc[g][p][2][1] = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const int slot = (p + 3 - dx) % 3;
-#pragma unroll
-                            for (int dz = 0; dz < 3; ++dz)
-#pragma unroll
-                                for (int kk = 0; kk < 2; ++kk)
-                                    acc[g][slot][dz][kk] = f2_add(acc[g][slot][dz][kk],
-                                        f2_fma(make_float2(__uint_as_float(v[1][(dx * 3 + dz) * 4 + 2 * kk]), __uint_as_float(v[1][(dx * 3 + dz) * 4 + 2 * kk + 1])),
-                                               f2_splat(W2),
-                                               make_float2(__uint_as_float(v[0][(dx * 3 + dz) * 4 + 2 * kk]), __uint_as_float(v[0][(dx * 3 + dz) * 4 + 2 * kk + 1]))));
-                        }
-                        if constexpr (!DEFER) {
-                            if (h >= 2) { TZ_T0(); finish(h - 2, g, acc[g][(p + 1) % 3]); TZ_ACC(t_fin); }
-                        }
+                    for (int kk = 0; kk < 4; ++kk) ps[kk] = make_float2(0.f, 0.f);
+                    if (geo.add_partial && ok_y && real) {         // add_partial is uniform over the CTA
+                        const uint8_t* pp = d_grp + (size_t)i * plane_b;
+                        const float4 p0 = *reinterpret_cast<const float4*>(pp), p1 = *reinterpret_cast<const float4*>(pp + vol_b);
+                        ps[0] = make_float2(p0.x, p0.y); ps[1] = make_float2(p1.x, p1.y);
+                        ps[2] = make_float2(p0.z, p0.w); ps[3] = make_float2(p1.z, p1.w);
                     }
+                    uint32_t v[48];
+                    take(real, v);
+                    if (real) { TZ_T0(); finish(i, v, ps); TZ_ACC(t_fin); }
                 }
-            }
-            // the unit's last set (plane nh - 1, group NG - 1) completed plane nh - 3 in slot ((nh - 1) % 3 + 1) % 3
-            if constexpr (DEFER) {
-                const int pl = (nh - 1) % 3;
-                if (pl == 0) finish(nh - 3, NG - 1, acc[NG - 1][1]);
-                else if (pl == 1) finish(nh - 3, NG - 1, acc[NG - 1][2]);
-                else finish(nh - 3, NG - 1, acc[NG - 1][0]);
+                next_id();
             }
             amax = warp_max(amax);
             if (lane == 0) {
@@ -479,15 +572,18 @@ static int tz_steps(int cin) { return (3 * (cin / 8) + 1) / 2; }
 
 size_t tcz_weight_floats(int cin, int cout) {
     if ((cout != 8 && cout != 16) || (cin != 8 && cin != 16 && cin != 32)) return 0;      // instantiated shapes
-    const size_t bytes = (size_t)tz_steps(cin) * (cout / 8) * TZ_WSTEP16 * 16;
+    const size_t bytes = (size_t)tz_steps(cin) * (cout / 8) * 2 * TZ_WIMG16 * 16;       // two B images per (K step, group)
     if (bytes + 3 * (size_t)(cin / 8) * TZ_CHUNK16 * 16 + 1024 > (size_t)TZ_SMEM_MAX) return 0;     // resident weights + 3 stages
     return bytes / 4;
 }
 
-// keras kernel (kx,ky,kz,ci,co), input channels [c_begin, c_begin + cin) -> fp16 image
-// [K step][group co/8][K half][row][ci % 8], rows 36 (co%8 / 4) + 4 (dx*3 + dz) + co%4 (hi) | 72 + the same (lo'); K half j of step p is
-// tap t = 2p + j -> (ci chunk t/3, dy = t%3); an odd tap count ends with (zero weights, last tap).  Same power-of-two
-// scale as the x-stacked image of the same channel range (max|w| in [2^13, 2^14)).  Returns 1 / scale.
+// keras kernel (kx,ky,kz,ci,co), input channels [c_begin, c_begin + cin) -> fp16 images
+// [K step][group co/8][image][K half][row][ci % 8].  Row = 48 blk + 24 term + 8 dz + co%8, blk 0 / 1 / 2 =
+// x-tap dx 2 / 1 / 0 (the oldest of the three output planes an input plane feeds comes first).  Image 0 (times A_hi):
+// term 0 = hi(w), term 1 = lo'(w); image 1 (times A_lo'): term 0 = 0, term 1 = hi(w) -- so hi.lo' and lo'.hi meet in
+// the same accumulator columns.  K half j of step p is tap t = 2p + j -> (ci chunk t/3, dy = t%3); an odd tap count
+// ends with (zero weights, last tap).  Same power-of-two scale as the x-stacked image of the same channel range (max|w|
+// in [2^13, 2^14)).  Returns 1 / scale.
 float tcz_pack_weights_range(const float* w, int cin_total, int c_begin, int cin, int cout, float* dst) {
     const int ng = cout / 8, ntaps = 3 * (cin / 8), nsteps = tz_steps(cin);
     std::memset(dst, 0, tcz_weight_floats(cin, cout) * sizeof(float));
@@ -506,18 +602,20 @@ float tcz_pack_weights_range(const float* w, int cin_total, int c_begin, int cin
                 int t = 2 * p + j;
                 if (2 * p + 1 >= ntaps) { if (j == 0) continue; t = ntaps - 1; }      // odd tap count: (zero weights, last tap)
                 const int c = t / 3, dy = t % 3;
-                __half* blk = img + ((((size_t)p * ng + g) * 2 + j) * TZ_NROW) * 8;
-                for (int dx = 0; dx < 3; ++dx)
+                __half* img1 = img + (((((size_t)p * ng + g) * 2 + 0) * 2 + j) * TZ_NROW) * 8;
+                __half* img2 = img + (((((size_t)p * ng + g) * 2 + 1) * 2 + j) * TZ_NROW) * 8;
+                for (int blk = 0; blk < 3; ++blk)
                     for (int dz = 0; dz < 3; ++dz)
                         for (int col = 0; col < 8; ++col)
                             for (int qd = 0; qd < 8; ++qd) {
-                                const int ci = c * 8 + qd, tap = (dx * 3 + dy) * 3 + dz;
+                                const int dx = 2 - blk, ci = c * 8 + qd, tap = (dx * 3 + dy) * 3 + dz;
                                 const float v = w[((size_t)tap * cin_total + c_begin + ci) * cout + 8 * g + col] * scale;
                                 const __half hh = __float2half_rn(v);
                                 const __half ll = __float2half_rn((v - __half2float(hh)) * 2048.f);
-                                const int r = (col / 4) * 36 + (dx * 3 + dz) * 4 + col % 4;
-                                blk[(size_t)r * 8 + qd] = hh;
-                                blk[(size_t)(72 + r) * 8 + qd] = ll;
+                                const int r = blk * TZ_BLK + dz * 8 + col;
+                                img1[(size_t)r * 8 + qd] = hh;
+                                img1[(size_t)(r + 24) * 8 + qd] = ll;
+                                img2[(size_t)(r + 24) * 8 + qd] = hh;
                             }
             }
     return 1.f / scale;
@@ -580,12 +678,10 @@ static int launch_tcz_any(int cout, bool dst_split, const CUtensorMap& map, cons
     return 2;
 }
 
-// Which blocks the plane-walk kernel takes in the `auto` mix [measured on B200, 38 tiles, against unet_tcx.cu]: its drain
-// (72 accumulator columns per thread and set, z shift-add, epilogue) is latency bound at two warps per scheduler, so it
-// wins where a set carries enough MMAs or the x-stacked kernel is at its worst (N = 48 at Cout = 8):
-//   skip halves of the decoder blocks (16 -> 8: 0.61 vs 0.83 ms, 32 -> 16: 0.41 vs 0.48), 8 -> 8 (0.38 vs 0.43),
-//   Cin >= 32 (32 -> 8: 0.63 vs 1.46); it loses at 16 -> 16 (0.28 vs 0.24) and 8 -> 16 (0.94 vs 0.56).
-// CT3D_TCZ_ALL=1 routes every block it can run to it (experiments, tests of the other instantiations).
+// Which blocks the plane-walk kernel takes in the `auto` mix [measured on B200, 38 tiles, ms against unet_tcx.cu]: every
+// block it is instantiated for -- 16 -> 16: 0.20 vs 0.24; 8 -> 8: 0.38 vs 0.43; 32 -> 8: 0.61 vs 1.46; skip halves
+// 16 -> 8: 0.54 vs 0.83, 32 -> 16: 0.30 vs 0.48 -- except 8 -> 16 (0.62 vs 0.55: two groups on two K steps leave its
+// drain, ~350 instructions per warp and plane, as the bound).  CT3D_TCZ_ALL=1 routes that one to it as well.
 static bool tz_all() {
     static int v = -1;
     if (v < 0) {
@@ -596,7 +692,7 @@ static bool tz_all() {
 }
 static bool tz_takes(int cin, int cout, bool skip_half) {
     if (cout > 16) return false;
-    return tz_all() || skip_half || (cin == 8 && cout == 8) || cin >= 32;
+    return tz_all() || skip_half || !(cin == 8 && cout == 16);
 }
 
 static int tz_map(CUtensorMap* map, float* src, int X, int Y, int cin, int tiles, size_t slab_stride) {

@@ -103,10 +103,10 @@ CONV_ROWS = [("d0a 1>8", 0.088, 1, 8, 409600, "CUDA cores, fused gather"), ("d0b
              ("u2a 64>64", 0.708, 64, 64, 6400, "27-tap"), ("u2b 64>64", 0.708, 64, 64, 6400, "27-tap"),
              ("u1a up 64>32", 1.416, 16, 32, 25600, "phase kernel (low-res source)"), ("u1a skip 64>32", 1.416, 64 + 32, 32, 25600, "x-stacked + partial sums"),
              ("u1b 32>32", 0.708, 32, 32, 25600, "x-stacked"),
-             ("u0a up 32>16", 1.416, 8, 16, 102400, "phase kernel"), ("u0a skip 32>16", 1.416, 32 + 16, 16, 102400, "x-stacked + partial sums"),
+             ("u0a up 32>16", 1.416, 8, 16, 102400, "phase kernel"), ("u0a skip 32>16", 1.416, 32 + 16, 16, 102400, "plane-walk + partial sums"),
              ("u0b 16>16", 0.708, 16, 16, 102400, "x-stacked"),
-             ("o_m2 up 16>8", 1.416, 4, 8, 409600, "phase kernel"), ("o_m2 skip 16>8", 1.416, 16 + 8, 8, 409600, "x-stacked + partial sums"),
-             ("o_m1 8>8", 0.708, 8, 8, 409600, "x-stacked, fp32 destination")]
+             ("o_m2 up 16>8", 1.416, 4, 8, 409600, "phase kernel"), ("o_m2 skip 16>8", 1.416, 16 + 8, 8, 409600, "plane-walk + partial sums"),
+             ("o_m1 8>8", 0.708, 8, 8, 409600, "plane-walk, fp32 destination")]
 
 
 def conv():
@@ -163,12 +163,14 @@ def conv():
     md += ["", f"Sum of the {len(CONV_ROWS)} launches: {tot_ms:.3f} ms per {TILES} tiles -> {TILES * 35.573 / tot_ms:.1f} TFLOP/s "
            "algorithmic (35.573 GFLOP/tile; per-launch times under ncu are cold-cache and serialised).  Reading: an M = 128, "
            "K = 16 MMA costs max(N/2, ~47 + N/6) clocks -- below N ~ 140 the shared-memory fetch of its 4 KB A tile sets the "
-           "pace, not the math -- so the Cout = 32 / 64 launches keep the tensor pipe 64-72 % active, the Cout = 16 ones "
-           "38-55 %, the Cout = 8 ones ~30 %, while the tensor-core unit itself is busy 57-79 % everywhere; and every fp32 "
-           "product costs three fp16 terms.  DESIGN.md 3.2 has the arithmetic and what would change it."]
+           "pace, not the math -- so the x-stacked / 27-tap launches with Cout = 32 / 64 keep the tensor pipe 64-76 % active "
+           "and the Cout = 16 ones 34-55 %.  The plane-walk launches (N = 144 MMAs, math bound by construction) are bound by "
+           "their DRAIN instead: 72 accumulator columns per thread and set to add up on two warps per scheduler, so their "
+           "tensor pipe idles although each MMA is efficient.  Every fp32 product costs three fp16 terms.  DESIGN.md 3.2 has "
+           "the arithmetic, the measured wait-cycle split of the roles and what would change it."]
     open(os.path.join(P, f"{tag}_conv_tc.md"), "w").write("\n".join(md) + "\n")
     total_bytes = sum(to_mb(r[dr], units[dr]) + to_mb(r[dw], units[dw]) for r in rows) * 1e6
-    json.dump({"kernel": f"{len(CONV_ROWS)} conv launches (14 blocks) of one {TILES}-tile U-Net batch (first_conv + conv3_tcx + conv3_tcu + conv3_tc)",
+    json.dump({"kernel": f"{len(CONV_ROWS)} conv launches (14 blocks) of one {TILES}-tile U-Net batch (first_conv + conv3_tcx + conv3_tcz + conv3_tcu + conv3_tc)",
                "launches": len(CONV_ROWS), "blocks": 14, "dram_bytes_per_launch_avg": total_bytes / len(CONV_ROWS), "tiles_per_batch": TILES,
                "source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/{tag}_conv_tc.csv"},
               open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
