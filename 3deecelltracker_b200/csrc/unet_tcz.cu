@@ -51,9 +51,9 @@ constexpr int TZ_BLK = 48;                        // accumulator columns of one 
 constexpr int TZ_NMMA = 3 * TZ_BLK;               // one MMA feeds three consecutive output planes (dx = 2, 1, 0)
 constexpr int TZ_NROW = TZ_NMMA;                  // B rows per K half
 constexpr int TZ_WIMG16 = 2 * TZ_NROW;            // 16-byte units of one B image (two K halves); two images per (K step, group)
-template <int NG> struct TzRing {                 // ring slots of output planes per group (+ 2 overflow blocks)
-    static constexpr int R = NG == 1 ? 8 : 3;
-    static constexpr int COLS = (R + 2) * TZ_BLK;
+template <int NG> struct TzRing {                 // ring slots of output planes per group
+    static constexpr int R = NG == 1 ? 10 : 5;
+    static constexpr int COLS = R * TZ_BLK;
     static_assert(NG <= 2 && NG * COLS <= 512, "plane ring exceeds tensor memory");
 };
 constexpr int TZ_DRAIN_WARPS = 8;
@@ -83,8 +83,6 @@ struct TzGeom {
     const float* amax_src2;                       // decoder blocks: max|x| slot of the up-sampled half's source
     float w_inv_scale, bound_p, bound_q;
     int add_partial;                              // dst holds P8 partial sums of the up-sampled half (split destination only)
-    float4* pool_dst;                             // fused MaxPooling3D((2,2,1)): pooled split-fp16 copy, channel offset 0
-    float* amax_pool;
 };
 
 struct TzUnit { int x0, nout, y0, tile; };
@@ -115,15 +113,6 @@ __device__ __forceinline__ void tz_ld48(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr + 32));
 }
 
-__device__ __forceinline__ void tz_zero48(uint32_t taddr) {
-    const uint32_t z = 0;
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
-                 "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-                 ::"r"(taddr + 32), "r"(z) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // Persistent CTA.  Work unit = a segment of x-planes x 8 y-rows x 16 z x all Cout of one tile.  Warp roles: 0 TMA producer
 // (+ tensor-memory allocator, resident weights), 1 .. NG MMA issuers (one per group of 8 output channels), 4-11 drain /
 // epilogue (two per tensor-memory lane quarter, four of a group's eight channels each).
@@ -131,19 +120,19 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // Output planes live in a RING of tensor-memory blocks (48 columns per plane and group).  Every plane of the CTA's
 // whole sequence of units has an id G (two pseudo ids separate consecutive units: they take the contributions that fall
 // outside a segment and are discarded); the MMA of the input plane with newest id G accumulates onto ids G-2, G-1, G
-// = three physically consecutive blocks starting at block (G-2) mod R.  Ids whose ring slot is 0 / 1 therefore receive
-// part of their sum in the two overflow blocks R / R+1 behind the ring; the drain adds the two parts.
-// The FIRST contribution to a block overwrites it (accumulate = 0), so nothing ever has to be zeroed: at K step 0 the
-// MMA is split into the 96 columns of the two older planes (accumulate) and the 48 columns of the newest one
-// (overwrite) -- or, when the three blocks are ring slots 0, 1, 2, all of which start there, issued whole with
-// accumulate = 0 (the two older ids had their earlier contributions in the overflow blocks).
+// = three consecutive blocks starting at block (G-2) mod R -- issued in two pieces where the ring wraps.  The FIRST
+// contribution to a block (its id as the newest of the three) overwrites it (accumulate = 0), so nothing is ever
+// zeroed: at K step 0 the MMA is split into the 96 columns of the two older planes (accumulate) and the 48 columns of
+// the newest one (overwrite).  One thread issues all MMAs of a group in plane order, so a block always receives
+// newest -> middle -> oldest, K step by K step: the rounding of a voxel does not depend on the segment, the batch or
+// the grid (tile-sharded and spatially decomposed runs stay bit-identical to the single-GPU run).
 //   drain -> issuer: blk_free[g][slot]  the id that last used the slot has been read out of tensor memory
 //   issuer -> drain: blk_done[g][slot]  (tcgen05.commit after the MMAs with newest id G) id G-2 is complete
 // Drain: each warp takes WHOLE blocks (all 8 channels of a plane and group, 48 columns per thread) of every other
 // (plane, group) item -- warps 4-7 the even items, warps 8-11 the odd ones -- so two items are in flight per lane
 // quarter and the tensor-memory load latency of one (hundreds of clocks while MMAs read-modify-write their
 // accumulators) overlaps the epilogue of the other.  The block is handed back right after the load, before the epilogue.
-template <int CIN8, int NG, bool DST_SPLIT, bool POOL>
+template <int CIN8, int NG, bool DST_SPLIT>
 __global__ void __launch_bounds__(TZ_THREADS, 1)
 conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
                  const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -216,68 +205,9 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #endif
         }
         __syncwarp();
-    } else if (NG == 1) {
-        // ---------------- one group per plane: THREE MMA issuers, issuer i takes every third plane.  A plane is only 4-12
-        // MMAs (290-860 clocks of tensor work) and the issuing thread pays ~365 clocks of latency per plane around them
-        // (two mbarrier round trips, fence, commits) [measured: busy = 365 + 70 n clocks for n MMAs]; three issuers overlap
-        // it.  Their MMAs may execute in any order, so here every contribution ACCUMULATES onto blocks the drain has zeroed
-        // (tcgen05.st; the 8-deep ring hides that round trip), and a plane's completion is tracked per MMA: mma_done =
-        // blk_done[0][slot of the newest id], the drain waits for the three MMAs that feed an id.
-        if (elect_one()) {
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TZ_NMMA >> 3) << 17) | (8u << 24);
-            constexpr uint64_t sbo8_word = (uint64_t)(8u | (1u << 14)) << 32;     // 8-row groups 128 B apart (A and B)
-            const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(wsm) >> 4;
-            const int me = warp - 1;
-            mbar_wait(&bar_w, 0);
-            int gp = 0, turn = 0;
-            int slot = 2 % R, use = 2 / R;                          // ring slot / use count of the newest id (ids start at 2)
-            long long w_full = 0, w_acc = 0, t_begin = clock64();
-            for (int k = 0; k < n_units; ++k) {
-                const TzUnit un = tz_unit((int)blockIdx.x + k * (int)gridDim.x, geo);
-                const int nh = un.nout + 2;
-                for (int h = 0; h < nh; ++h, ++gp) {
-                    if (turn == me) {
-                        const int s = gp % stages, us = gp / stages;
-                        { TZ_T0(); mbar_wait(&bar_full[s], us & 1); TZ_ACC(w_full); }
-                        // the blocks of the three ids this plane feeds have been zeroed (the two warp sets of the drain
-                        // hand back alternate ids, in no particular order between them)
-#pragma unroll
-                        for (int dd = 0; dd < 3; ++dd) {
-                            const int sd = slot - dd < 0 ? slot - dd + R : slot - dd, ud = slot - dd < 0 ? use - 1 : use;
-                            TZ_T0(); mbar_wait(&blk_free[0][sd], ud & 1); TZ_ACC(w_acc);
-                        }
-                        tc_fence_after();
-                        const uint32_t a_hi = ring16 + (uint32_t)s * (stage_bytes >> 4);
-                        const int b = slot >= 2 ? slot - 2 : slot + R - 2;          // block of id G - 2
-                        const uint32_t d = tmem_base + (uint32_t)(b * TZ_BLK);
-#pragma unroll
-                        for (int p = 0; p < NSTEPS; ++p) {
-                            const int t1 = (2 * p + 1 < NTAPS) ? 2 * p + 1 : NTAPS - 1;
-                            const int t0 = t1 - 1;
-                            const uint32_t o0 = tz_tap_off16(t0), lbo = (tz_tap_off16(t1) - o0) << 16;
-                            const uint32_t ah = (a_hi + o0) | lbo;
-                            const uint32_t al = (a_hi + o0 + TZ_IMG16) | lbo;
-                            const uint32_t b1 = (w16 + (uint32_t)(p * 2) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
-                            const uint32_t b2 = (w16 + (uint32_t)(p * 2 + 1) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
-                            umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc, 1u);
-                            umma_f16(d, sbo8_word | (uint64_t)al, sbo8_word | (uint64_t)b2, idesc, 1u);
-                        }
-                        umma_commit(&blk_done[0][slot]);            // the MMAs with newest id G have retired
-                        umma_commit(&bar_empty[s]);
-                    }
-                    turn = (turn == 2) ? 0 : turn + 1;
-                    if (++slot == R) { slot = 0; ++use; }
-                }
-            }
-#ifdef TZ_TIMING
-            if (blockIdx.x == 0 && me == 0) { g_tz_timers[0] = w_full; g_tz_timers[1] = w_acc; g_tz_timers[2] = clock64() - t_begin; }
-#else
-            (void)w_full; (void)w_acc; (void)t_begin;
-#endif
-        }
-        __syncwarp();
     } else if (warp <= NG) {
-        // ---------------- two groups per plane: one MMA issuer per group, g = warp - 1
+        // ---------------- MMA issuer of group g = warp - 1 (one thread issues a group's MMAs, in plane order: the order in
+        // which a block receives its contributions, hence its rounding, is fixed)
         if (elect_one()) {
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TZ_NMMA >> 3) << 17) | (8u << 24);
             constexpr uint32_t idesc96 = (1u << 4) | ((uint32_t)((2 * TZ_BLK) >> 3) << 17) | (8u << 24);
@@ -308,21 +238,36 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         const int t1 = (2 * p + 1 < NTAPS) ? 2 * p + 1 : NTAPS - 1;
                         const int t0 = t1 - 1;
                         const uint32_t o0 = tz_tap_off16(t0), lbo = (tz_tap_off16(t1) - o0) << 16;
-                        const uint32_t ah = (a_hi + o0) | lbo;
-                        const uint32_t al = (a_hi + o0 + TZ_IMG16) | lbo;
-                        const uint32_t b1 = (w16 + (uint32_t)((p * NG + g) * 2) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
-                        const uint32_t b2 = (w16 + (uint32_t)((p * NG + g) * 2 + 1) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
-                        if (p == 0) {
-                            if (b == 0) {
-                                umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc, 0u);
+                        const uint64_t ah = sbo8_word | (uint64_t)((a_hi + o0) | lbo);
+                        const uint64_t al = sbo8_word | (uint64_t)((a_hi + o0 + TZ_IMG16) | lbo);
+                        const uint32_t w1 = (w16 + (uint32_t)((p * NG + g) * 2) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                        const uint32_t w2 = (w16 + (uint32_t)((p * NG + g) * 2 + 1) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                        // B rows [0, 48) feed the oldest plane (id G - 2), [48, 96) the middle one, [96, 144) the newest,
+                        // which this plane's first MMA overwrites.  Where the ring wraps the MMA is issued in two pieces.
+                        if (b <= R - 3) {
+                            if (p == 0) {
+                                umma_f16(d, ah, sbo8_word | (uint64_t)w1, idesc96, 1u);
+                                umma_f16(d + 2 * TZ_BLK, ah, sbo8_word | (uint64_t)(w1 + 2 * TZ_BLK), idesc48, 0u);
                             } else {
-                                umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc96, 1u);
-                                umma_f16(d + 2 * TZ_BLK, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)(b1 + 2 * TZ_BLK), idesc48, 0u);
+                                umma_f16(d, ah, sbo8_word | (uint64_t)w1, idesc, 1u);
                             }
-                        } else {
-                            umma_f16(d, sbo8_word | (uint64_t)ah, sbo8_word | (uint64_t)b1, idesc, 1u);
+                            umma_f16(d, al, sbo8_word | (uint64_t)w2, idesc, 1u);
+                        } else if (b == R - 2) {                    // the newest plane's block is block 0
+                            umma_f16(d, ah, sbo8_word | (uint64_t)w1, idesc96, 1u);
+                            umma_f16(gcol, ah, sbo8_word | (uint64_t)(w1 + 2 * TZ_BLK), idesc48, p == 0 ? 0u : 1u);
+                            umma_f16(d, al, sbo8_word | (uint64_t)w2, idesc96, 1u);
+                            umma_f16(gcol, al, sbo8_word | (uint64_t)(w2 + 2 * TZ_BLK), idesc48, 1u);
+                        } else {                                    // b == R - 1: the middle and newest planes are blocks 0, 1
+                            umma_f16(d, ah, sbo8_word | (uint64_t)w1, idesc48, 1u);
+                            if (p == 0) {
+                                umma_f16(gcol, ah, sbo8_word | (uint64_t)(w1 + TZ_BLK), idesc48, 1u);
+                                umma_f16(gcol + TZ_BLK, ah, sbo8_word | (uint64_t)(w1 + 2 * TZ_BLK), idesc48, 0u);
+                            } else {
+                                umma_f16(gcol, ah, sbo8_word | (uint64_t)(w1 + TZ_BLK), idesc96, 1u);
+                            }
+                            umma_f16(d, al, sbo8_word | (uint64_t)w2, idesc48, 1u);
+                            umma_f16(gcol, al, sbo8_word | (uint64_t)(w2 + TZ_BLK), idesc96, 1u);
                         }
-                        umma_f16(d, sbo8_word | (uint64_t)al, sbo8_word | (uint64_t)b2, idesc, 1u);
                     }
                     umma_commit(&blk_done[g][b]);                   // id G - 2 has all three contributions
                     umma_commit(&bar_empty[s]);
@@ -348,23 +293,8 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         constexpr float W2 = 1.f / 2048.f;                         // weight of the hi.lo' + lo'.hi columns
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         const int g_mine = NG == 2 ? set : 0;                      // two groups: one per warp set; one group: alternate planes
-        const uint32_t m_up = (z == 0) ? 0u : 0xffffffffu, m_dn = (z == TZ_Z - 1) ? 0u : 0xffffffffu;
+        const float m_up = (z == 0) ? 0.f : 1.f, m_dn = (z == TZ_Z - 1) ? 0.f : 1.f;      // zero padding at the z ends of a tile
         long long w_accf = 0, t_ld = 0, t_fin = 0, t_begin = clock64();
-        if constexpr (NG == 1) {                                   // every block starts at zero; ids 0 .. R-1 are ready
-            if (set == 0) {
-#pragma unroll
-                for (int bl = 0; bl < R + 2; ++bl) tz_zero48(t_lane + (uint32_t)(bl * TZ_BLK));
-                tmem_st_wait();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0 && set == 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) mbar_arrive(&blk_free[0][r]);
-                // ids 0 and 1 have no MMA of their own (the first newest id is 2): keep the phases of their slots aligned
-                if (warp == 4) { mbar_arrive(&blk_done[0][0]); mbar_arrive(&blk_done[0][1]); }
-            }
-        }
         int slot = 0, use = 0, idpar = 0;                          // ring slot / use count / parity of the id being drained
         // the id sequence: two pseudo ids, then per unit its nout planes and two pseudo ids; the last two never complete
         TzUnit un_next = tz_unit((int)blockIdx.x, geo);
@@ -378,39 +308,14 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         const bool mine_all = (NG == 2);
         // takes the finished id in (slot, use) out of tensor memory (real planes only) and hands its blocks back
         auto take = [&](bool real, uint32_t (&v)[48]) {
-            if constexpr (NG == 1) {
-                // the three MMAs that feed this id carry the newest ids X, X + 1, X + 2 (none before id 2); the warp waited
-                // for X when it took its previous id, X - 2
-#pragma unroll
-                for (int dd = 1; dd < 3; ++dd) {
-                    const int sd = slot + dd >= R ? slot + dd - R : slot + dd, ud = slot + dd >= R ? use + 1 : use;
-                    if (ud == 0 && sd < 2) continue;
-                    TZ_T0(); mbar_wait(&blk_done[0][sd], ud & 1); TZ_ACC(w_accf);
-                }
-            } else {
-                TZ_T0(); mbar_wait(&blk_done[g_mine][slot], use & 1); TZ_ACC(w_accf);
-            }
+            { TZ_T0(); mbar_wait(&blk_done[g_mine][slot], use & 1); TZ_ACC(w_accf); }
             tc_fence_after();
-            const uint32_t t0 = t_lane + (uint32_t)(g_mine * GCOLS + slot * TZ_BLK);
 #ifdef TZ_TIMING
             const long long _tl = clock64();
 #endif
             if (real) {
-                tz_ld48(t0, v);
-                if (slot < 2) {                                     // the part that landed in the overflow block
-                    uint32_t w[48];
-                    tz_ld48(t0 + R * TZ_BLK, w);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 48; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
-                } else {
-                    tmem_ld_wait();
-                }
-            }
-            if constexpr (NG == 1) {                                // zero the blocks for the next id of this slot
-                tz_zero48(t0);
-                if (slot < 2) tz_zero48(t0 + R * TZ_BLK);
-                tmem_st_wait();
+                tz_ld48(t_lane + (uint32_t)(g_mine * GCOLS + slot * TZ_BLK), v);
+                tmem_ld_wait();
             }
 #ifdef TZ_TIMING
             t_ld += clock64() - _tl;
@@ -433,7 +338,6 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             const float s_out = DST_SPLIT ? split_out_scale(fmaxf(am_next, am2_next), geo.bound_p, geo.bound_q) : 1.f;
             if (DST_SPLIT && warp == 4 && lane == 0) {
                 geo.scale_dst[(size_t)un.tile * geo.slab_stride] = s_out;
-                if (POOL && geo.pool_dst != nullptr) geo.amax_pool[SCALE_SLOT0 + (size_t)un.tile * geo.slab_stride] = s_out;
             }
             if (k + 1 < n_units) {
                 un_next = tz_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo);
@@ -443,9 +347,6 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             const bool ok_y = y < geo.Y;
             uint8_t* d_tile = reinterpret_cast<uint8_t*>(dst + (size_t)un.tile * geo.dst_tile_stride4);
             float amax = 0.f;
-            float2 keep[4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) keep[kk] = make_float2(0.f, 0.f);
             // the voxel's 16 bytes in the group's two channel planes: split buffers hold the fp16 hi image of the 8 channels
             // in plane 2 g and the lo' image in 2 g + 1; fp32 buffers channels 0-3 / 4-7; P8 partial sums channel pairs
             // (0,1 | 4,5) / (2,3 | 6,7)
@@ -468,13 +369,10 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             };
             // epilogue of output plane x0 + i from its 48 accumulator columns [term][dz][channel]: hi.hi + 2^-11 (hi.lo' +
             // lo'.hi), z shift-add of the three z-taps, partial sums, scale back, bias -> activation -> BatchNorm, store
-            // (+ pooled copy)
             auto finish = [&](int i, const uint32_t (&v)[48], const float2 (&ps)[4]) {
-                const int x = un.x0 + i;
                 float2 o[4];
                 float am = 0.f;
-                // stage by stage over the four channel pairs, so that their dependency chains interleave; the zeros at the
-                // z ends are a bit mask (a select on z compiles to a divergent branch per pair)
+                // stage by stage over the four channel pairs, so that their dependency chains interleave
                 float2 c[4][3], up[4], dn[4];
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
@@ -486,39 +384,19 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 // out[z] takes tap dz = 0 from input row z - 1 and tap dz = 2 from input row z + 1 (zero outside the tile)
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    up[kk].x = __uint_as_float(__float_as_uint(__shfl_up_sync(0xffffffffu, c[kk][0].x, 1)) & m_up);
-                    up[kk].y = __uint_as_float(__float_as_uint(__shfl_up_sync(0xffffffffu, c[kk][0].y, 1)) & m_up);
-                    dn[kk].x = __uint_as_float(__float_as_uint(__shfl_down_sync(0xffffffffu, c[kk][2].x, 1)) & m_dn);
-                    dn[kk].y = __uint_as_float(__float_as_uint(__shfl_down_sync(0xffffffffu, c[kk][2].y, 1)) & m_dn);
+                    up[kk] = make_float2(__shfl_up_sync(0xffffffffu, c[kk][0].x, 1), __shfl_up_sync(0xffffffffu, c[kk][0].y, 1));
+                    dn[kk] = make_float2(__shfl_down_sync(0xffffffffu, c[kk][2].x, 1), __shfl_down_sync(0xffffffffu, c[kk][2].y, 1));
                 }
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const float2 av = f2_add(f2_add(c[kk][1], ps[kk]), f2_add(up[kk], dn[kk]));
+                    // the zeros at the z ends: one packed multiply-add per neighbour (x 1 / x 0 is exact) -- a select on z
+                    // compiles to a divergent branch per pair
+                    const float2 av = f2_fma(up[kk], f2_splat(m_up), f2_fma(dn[kk], f2_splat(m_dn), f2_add(c[kk][1], ps[kk])));
                     o[kk] = block_epilogue(av, inv_scale, alpha, &ep_s[0][0], 8 * NG, 8 * g_mine + 2 * kk, am);
                 }
                 if (ok_y) {
                     amax = fmaxf(amax, am);
                     put(d_grp + (size_t)i * plane_b, vol_b, o, s_out);
-                }
-                if (POOL && geo.pool_dst != nullptr) {             // uniform over the CTA
-                    if ((x & 1) == 0) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) keep[kk] = o[kk];
-                    } else {
-                        float2 m[4];
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            m[kk] = make_float2(fmaxf(keep[kk].x, o[kk].x), fmaxf(keep[kk].y, o[kk].y));
-                            m[kk].x = fmaxf(m[kk].x, __shfl_xor_sync(0xffffffffu, m[kk].x, 16));     // y pair: 16 lanes apart
-                            m[kk].y = fmaxf(m[kk].y, __shfl_xor_sync(0xffffffffu, m[kk].y, 16));
-                        }
-                        if (ok_y && (yl & 1) == 0) {
-                            const int PX = geo.X >> 1, PY = geo.Y >> 1;
-                            const size_t pvol_b = (size_t)PX * PY * TZ_Z * 16;
-                            uint8_t* pb = reinterpret_cast<uint8_t*>(geo.pool_dst + (size_t)un.tile * geo.dst_tile_stride4);
-                            put(pb + (size_t)(2 * g_mine) * pvol_b + (((size_t)(x >> 1) * PY + (y >> 1)) * TZ_Z + z) * 16, pvol_b, m, s_out);
-                        }
-                    }
                 }
             };
             const bool last_unit = (k == n_units - 1);
@@ -546,7 +424,6 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             amax = warp_max(amax);
             if (lane == 0) {
                 amax_update(geo.amax_dst + (size_t)un.tile * geo.slab_stride, amax);
-                if (POOL && geo.pool_dst != nullptr) amax_update(geo.amax_pool + (size_t)un.tile * geo.slab_stride, amax);
             }
         }
 #ifdef TZ_TIMING
@@ -636,10 +513,9 @@ static void tz_segments(int X, int per_x, int grid, bool even, int* sxseg, int* 
     }
 }
 
-template <int CIN8, int NG, bool DST_SPLIT, bool POOL>
+template <int CIN8, int NG, bool DST_SPLIT>
 static int launch_tcz(const CUtensorMap& map, const ConvLayer& L, const TzSource& src, float alpha, float4* dst, int X, int Y,
-                      size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, float4* pool_dst,
-                      float* amax_pool, cudaStream_t s) {
+                      size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, cudaStream_t s) {
     TzGeom g;
     g.cin8 = src.cin / 8; g.nsteps = tz_steps(src.cin); g.X = X; g.Y = Y;
     g.nby = cdiv(Y, TZ_BY);
@@ -651,26 +527,25 @@ static int launch_tcz(const CUtensorMap& map, const ConvLayer& L, const TzSource
     g.stages = stages;
     const size_t smem = 1024 + g.wbytes + (size_t)stages * stage_bytes;
     const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
-    tz_segments(X, tiles * g.nby, sms, POOL, &g.sxseg, &g.nseg);
+    tz_segments(X, tiles * g.nby, sms, false, &g.sxseg, &g.nseg);
     g.units = tiles * g.nby * g.nseg;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4; g.slab_stride = stride4 * 4;
     g.amax_src = amax_src; g.amax_dst = amax_dst;
     g.scale_src = amax_src + SCALE_SLOT0; g.scale_dst = amax_dst + SCALE_SLOT0; g.amax_src2 = src.amax2;
     g.w_inv_scale = src.inv_scale; g.bound_p = L.bound_p; g.bound_q = L.bound_q;
-    g.add_partial = src.add_partial; g.pool_dst = pool_dst; g.amax_pool = amax_pool;
+    g.add_partial = src.add_partial;
     // per device / context attribute: set on every launch (cheap) so several GPUs in one process are correct
-    CT_CUDA(cudaFuncSetAttribute(conv3_tcz_kernel<CIN8, NG, DST_SPLIT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CT_CUDA(cudaFuncSetAttribute(conv3_tcz_kernel<CIN8, NG, DST_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = g.units < sms ? g.units : sms;
-    conv3_tcz_kernel<CIN8, NG, DST_SPLIT, POOL><<<grid, TZ_THREADS, smem, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
+    conv3_tcz_kernel<CIN8, NG, DST_SPLIT><<<grid, TZ_THREADS, smem, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
 }
 
 static int launch_tcz_any(int cout, bool dst_split, const CUtensorMap& map, const ConvLayer& L, const TzSource& src, float alpha,
                           float4* dst, int X, int Y, size_t stride4, int dst_c4off, int tiles, const float* amax_src,
-                          float* amax_dst, float4* pool_dst, float* amax_pool, cudaStream_t s) {
-#define TZ_GO(C8, NG, DS, PL) return launch_tcz<C8, NG, DS, PL>(map, L, src, alpha, dst, X, Y, stride4, dst_c4off, tiles, amax_src, amax_dst, pool_dst, amax_pool, s)
+                          float* amax_dst, cudaStream_t s) {
+#define TZ_GO(C8, NG, DS, PL) return launch_tcz<C8, NG, DS>(map, L, src, alpha, dst, X, Y, stride4, dst_c4off, tiles, amax_src, amax_dst, s)
 #define TZ_C8(NG, DS, PL) do { if (src.cin == 8) TZ_GO(1, NG, DS, PL); if (src.cin == 16) TZ_GO(2, NG, DS, PL); if (src.cin == 32) TZ_GO(4, NG, DS, PL); return 2; } while (0)
-    if (pool_dst) { if (cout == 16 && dst_split && src.cin == 8) TZ_GO(1, 2, true, true); return 2; }
     if (cout == 8) { if (dst_split) TZ_C8(1, true, false); TZ_C8(1, false, false); }
     if (cout == 16) { if (dst_split) TZ_C8(2, true, false); TZ_C8(2, false, false); }
 #undef TZ_C8
@@ -678,10 +553,10 @@ static int launch_tcz_any(int cout, bool dst_split, const CUtensorMap& map, cons
     return 2;
 }
 
-// Which blocks the plane-walk kernel takes in the `auto` mix [measured on B200, 38 tiles, ms against unet_tcx.cu]: every
-// block it is instantiated for -- 16 -> 16: 0.20 vs 0.24; 8 -> 8: 0.38 vs 0.43; 32 -> 8: 0.61 vs 1.46; skip halves
-// 16 -> 8: 0.54 vs 0.83, 32 -> 16: 0.30 vs 0.48 -- except 8 -> 16 (0.62 vs 0.55: two groups on two K steps leave its
-// drain, ~350 instructions per warp and plane, as the bound).  CT3D_TCZ_ALL=1 routes that one to it as well.
+// Which blocks the plane-walk kernel takes in the `auto` mix [measured on B200, 38 tiles, ms against unet_tcx.cu]:
+// 16 -> 16: 0.20 vs 0.24; 32 -> 8: 0.6 vs 1.46; skip halves 16 -> 8: 0.54 vs 0.83, 32 -> 16: 0.30 vs 0.48.  Not 8 -> 8
+// (0.42 vs 0.41: one issuer pays ~365 clocks of latency per plane around 4 MMAs) and not 8 -> 16 (0.62 vs 0.55: the
+// drain, ~350 instructions per warp and plane, is the bound).  CT3D_TCZ_ALL=1 routes those to it as well.
 static bool tz_all() {
     static int v = -1;
     if (v < 0) {
@@ -692,7 +567,7 @@ static bool tz_all() {
 }
 static bool tz_takes(int cin, int cout, bool skip_half) {
     if (cout > 16) return false;
-    return tz_all() || skip_half || !(cin == 8 && cout == 16);
+    return tz_all() || skip_half || cin != 8;
 }
 
 static int tz_map(CUtensorMap* map, float* src, int X, int Y, int cin, int tiles, size_t slab_stride) {
@@ -707,29 +582,20 @@ int launch_conv_tcz(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
                     const Op* pool, bool* pool_fused, int fmt) {
     const ConvLayer& L = net->layers[op.layer];
     const int X = op.sx, Y = op.sy, Z = op.sz;
+    (void)pool;                                  // the (2,2,1) pool after 8 -> 16 stays with unet_tcx.cu's fused epilogue
     if (pool_fused) *pool_fused = false;
     if (!L.w_tcz || Z != TZ_Z || !(fmt & FMT_SRC_SPLIT) || L.cin_pad != L.cin || (net->engine != 5 && !tz_takes(L.cin, L.cout, false)) || L.cout > 16) return 2;
     CT_REQUIRE(op.src_c == L.cin_pad, "conv: source buffer has %d channels, layer expects %d", op.src_c, L.cin_pad);
     CT_REQUIRE(slab_stride % 4 == 0 && op.src_off % 4 == 0 && op.dst_off % 4 == 0, "conv: misaligned slab");
     CT_REQUIRE(!(fmt & FMT_DST_SPLIT) || op.dst_coff % 8 == 0, "conv: split destination at channel offset %d", op.dst_coff);
     float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
-    float4* pool_dst = nullptr;
-    float* am_p = nullptr;
-    if (pool && pool_fused && (fmt & FMT_DST_SPLIT) && pool->kind == OP_POOL && pool->src_off == op.dst_off &&
-        pool->src_coff == op.dst_coff && pool->c == L.cout && pool->dst_coff == 0 && pool->dst_c == L.cout &&
-        net->spec.pool_x == 2 && net->spec.pool_y == 2 && net->spec.pool_z == 1 && X % 2 == 0 && Y % 2 == 0 &&
-        pool->dx == X / 2 && pool->dy == Y / 2 && pool->dz == Z && pool->dst_off % 4 == 0 && L.cout == 16) {
-        pool_dst = reinterpret_cast<float4*>(slab0 + pool->dst_off);
-        am_p = slab0 + pool->dst_slot;
-    }
     CUtensorMap map;
     ProfScope prof(PROF_CONV, s);
     if (tz_map(&map, slab0 + op.src_off, X, Y, L.cin, tiles, slab_stride)) return 1;
     const TzSource whole{L.w_tcz, L.w_tcz_inv_scale, L.cin, 0, nullptr};
     const int rc = launch_tcz_any(L.cout, (fmt & FMT_DST_SPLIT) != 0, map, L, whole, net->alpha, dst, X, Y, slab_stride / 4,
-                                  op.dst_coff / 4, tiles, slab0 + op.src_slot, slab0 + op.dst_slot, pool_dst, am_p, s);
+                                  op.dst_coff / 4, tiles, slab0 + op.src_slot, slab0 + op.dst_slot, s);
     if (rc) return rc;
-    if (pool_dst) *pool_fused = true;
     CT_LAUNCHED("conv3_tcz_kernel");
     return 0;
 }
@@ -750,7 +616,7 @@ int launch_conv_tcz_skip(const CtUNet* net, const Op& op, float* slab0, size_t s
     if (tz_map(&map, slab0 + op.src_off + (size_t)L.c_up * vol, X, Y, c_skip, tiles, slab_stride)) return 1;
     const TzSource skip{L.w_tcz_skip, L.w_tcz_skip_inv_scale, c_skip, 1, up_slot >= 0 ? slab0 + up_slot : nullptr};
     const int rc = launch_tcz_any(L.cout, true, map, L, skip, net->alpha, dst, X, Y, slab_stride / 4, op.dst_coff / 4, tiles,
-                                  slab0 + op.src_slot, slab0 + op.dst_slot, nullptr, nullptr, s);
+                                  slab0 + op.src_slot, slab0 + op.dst_slot, s);
     if (rc) return rc;
     CT_LAUNCHED("conv3_tcz_kernel");
     return 0;

@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 timeout 900 python -m pytest tests/test_gpu_lcn_unet.py tests/test_gpu_spatial.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -4
-timeout 300 python scripts/conv_layers.py 38 tcgen05_split planewalk_split 2>&1 | tail -16 | grep -E "d1a|u0b|o_m|sum"
+bash scripts/gpu_tczlist.sh 2>&1 | tail -2 | cut -c1-1300
 timeout 600 python bench.py --steps 20 --no-cpu-baseline --no-c3 2>gpurun_out/bench_q.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print({k:d[k] for k in ('ms_per_step','frames_per_s','serial_ms_per_step','stage_ms_per_step')}, d['e2e'], d['roofline']['frac'])"
