@@ -98,15 +98,15 @@ def raw(rep):
 # one U-Net batch of unet3_a with the `auto` engine: 18 convolution launches in graph order
 # (name, algorithmic GMAC per tile, channels read, channels written, voxels per tile of the written grid, note)
 CONV_ROWS = [("d0a 1>8", 0.088, 1, 8, 409600, "CUDA cores, fused gather"), ("d0b 8>16 (+pool)", 1.416, 8, 16, 409600, "x-stacked"),
-             ("d1a 16>16", 0.708, 16, 16, 102400, "x-stacked"), ("d1b 16>32", 1.416, 16, 32, 102400, "x-stacked"),
+             ("d1a 16>16", 0.708, 16, 16, 102400, "plane-walk"), ("d1b 16>32", 1.416, 16, 32, 102400, "x-stacked"),
              ("d2a 32>32", 0.708, 32, 32, 25600, "x-stacked"), ("d2b 32>64", 1.416, 32, 64, 25600, "27-tap"),
              ("u2a 64>64", 0.708, 64, 64, 6400, "27-tap"), ("u2b 64>64", 0.708, 64, 64, 6400, "27-tap"),
              ("u1a up 64>32", 1.416, 16, 32, 25600, "phase kernel (low-res source)"), ("u1a skip 64>32", 1.416, 64 + 32, 32, 25600, "x-stacked + partial sums"),
              ("u1b 32>32", 0.708, 32, 32, 25600, "x-stacked"),
              ("u0a up 32>16", 1.416, 8, 16, 102400, "phase kernel"), ("u0a skip 32>16", 1.416, 32 + 16, 16, 102400, "plane-walk + partial sums"),
-             ("u0b 16>16", 0.708, 16, 16, 102400, "x-stacked"),
+             ("u0b 16>16", 0.708, 16, 16, 102400, "plane-walk"),
              ("o_m2 up 16>8", 1.416, 4, 8, 409600, "phase kernel"), ("o_m2 skip 16>8", 1.416, 16 + 8, 8, 409600, "plane-walk + partial sums"),
-             ("o_m1 8>8", 0.708, 8, 8, 409600, "plane-walk, fp32 destination")]
+             ("o_m1 8>8", 0.708, 8, 8, 409600, "x-stacked, fp32 destination")]
 
 
 def conv():
@@ -164,10 +164,10 @@ def conv():
            "algorithmic (35.573 GFLOP/tile; per-launch times under ncu are cold-cache and serialised).  Reading: an M = 128, "
            "K = 16 MMA costs max(N/2, ~47 + N/6) clocks -- below N ~ 140 the shared-memory fetch of its 4 KB A tile sets the "
            "pace, not the math -- so the x-stacked / 27-tap launches with Cout = 32 / 64 keep the tensor pipe 64-76 % active "
-           "and the Cout = 16 ones 34-55 %.  The plane-walk launches (N = 144 MMAs, math bound by construction) are bound by "
-           "their DRAIN instead: 72 accumulator columns per thread and set to add up on two warps per scheduler, so their "
-           "tensor pipe idles although each MMA is efficient.  Every fp32 product costs three fp16 terms.  DESIGN.md 3.2 has "
-           "the arithmetic, the measured wait-cycle split of the roles and what would change it."]
+           "and the Cout = 16 ones 34-55 %.  The plane-walk launches (N = 144 MMAs that feed three output planes, math bound by "
+           "construction) are bound by their drain's instruction issue at Cout = 16 and by the single issuing thread's "
+           "per-plane latency at Cout = 8.  Every fp32 product costs three fp16 terms.  DESIGN.md 3.2 has "
+"the arithmetic, the measured wait-cycle split of the roles and what would change it."]
     open(os.path.join(P, f"{tag}_conv_tc.md"), "w").write("\n".join(md) + "\n")
     total_bytes = sum(to_mb(r[dr], units[dr]) + to_mb(r[dw], units[dw]) for r in rows) * 1e6
     json.dump({"kernel": f"{len(CONV_ROWS)} conv launches (14 blocks) of one {TILES}-tile U-Net batch (first_conv + conv3_tcx + conv3_tcz + conv3_tcu + conv3_tc)",
