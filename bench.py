@@ -370,7 +370,7 @@ def gpu_main(args):
     barrier()
     t0 = time.perf_counter()
     out = tracker.run(e2e_frame, T, sink=sink)
-    coords_host = None if out is None else torch.stack(out).cpu()
+    coords_host = torch.stack(out).cpu() if out else None             # --steps 1: one volume, nothing tracked yet
     for d in state["done"]:
         d.synchronize()
     barrier()
