@@ -13,6 +13,7 @@
 // voxels into a handful of background bins.
 #include "common.cuh"
 #include <cstddef>
+#include <type_traits>
 
 namespace ct {
 
@@ -299,25 +300,45 @@ __global__ void __launch_bounds__(256) box_y_v_r(const T* __restrict__ raw, cons
         if (yb + k < Y) out[(long long)(yb + k) * Z] = acc;
     }
 }
-template <int R>
+// INT: T1 is a multiple of 0.5 below 2^22 (integer raw data minus a median that is k or k + 0.5, summed over 27 rows), so
+// the window sum is done on 2 T1 in int32 -- exact, like the fp64 sum it replaces, and float(isum) * 0.5f rounds exactly
+// like float(double sum): the result is bit-identical, without the fp64 pipe (2 DADD lanes per scheduler on this part:
+// the four filters were bound by it, 73-79 % busy at 0.09-0.25 ms each).
+template <int R, bool INT>
 __global__ void __launch_bounds__(256) box_x_avg_r(const float* __restrict__ t1, float* __restrict__ avg,
                                                    int X, int Y, int Z, float volume) {
     const long long plane = (long long)Y * Z;
     const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= plane) return;
     const int xb = blockIdx.y * LCN_R;
-    float w[LCN_R + 2 * R];
+    if constexpr (INT) {
+        int w[LCN_R + 2 * R];
 #pragma unroll
-    for (int j = 0; j < LCN_R + 2 * R; ++j) {
-        const int xx = xb - R + j;
-        w[j] = (xx >= 0 && xx < X) ? t1[(long long)xx * plane + f] : 0.f;
-    }
+        for (int j = 0; j < LCN_R + 2 * R; ++j) {
+            const int xx = xb - R + j;
+            w[j] = (xx >= 0 && xx < X) ? __float2int_rn(2.f * t1[(long long)xx * plane + f]) : 0;
+        }
 #pragma unroll
-    for (int k = 0; k < LCN_R; ++k) {
-        double acc = 0.0;
+        for (int k = 0; k < LCN_R; ++k) {
+            int acc = 0;
 #pragma unroll
-        for (int j = 0; j <= 2 * R; ++j) acc += (double)w[k + j];
-        if (xb + k < X) avg[(long long)(xb + k) * plane + f] = (float)acc / volume;
+            for (int j = 0; j <= 2 * R; ++j) acc += w[k + j];
+            if (xb + k < X) avg[(long long)(xb + k) * plane + f] = (__int2float_rn(acc) * 0.5f) / volume;
+        }
+    } else {
+        float w[LCN_R + 2 * R];
+#pragma unroll
+        for (int j = 0; j < LCN_R + 2 * R; ++j) {
+            const int xx = xb - R + j;
+            w[j] = (xx >= 0 && xx < X) ? t1[(long long)xx * plane + f] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < LCN_R; ++k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j <= 2 * R; ++j) acc += (double)w[k + j];
+            if (xb + k < X) avg[(long long)(xb + k) * plane + f] = (float)acc / volume;
+        }
     }
 }
 template <typename T, int R>
@@ -338,17 +359,19 @@ __global__ void __launch_bounds__(256) box_y_sq_r(const T* __restrict__ raw, con
         float sq = 0.f;
         if (yy >= 0 && yy < Y) {
             const long long i = off + (long long)yy * Z;
-            const double d = (double)clamped(raw, i, med) - (double)avg[i];
-            sq = (float)(d * d);
+            const float d = __fsub_rn(clamped(raw, i, med), avg[i]);      // correctly rounded difference, then its square
+            sq = __fmul_rn(d, d);
         }
         w[j] = sq;
     }
+    // float32 window sums in ascending order (the reference's Conv3D sums in float32 as well; every output still sums its
+    // OWN window, so the value does not depend on where a block starts)
 #pragma unroll
     for (int k = 0; k < LCN_R; ++k) {
-        double acc = 0.0;
+        float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j <= 2 * R; ++j) acc += (double)w[k + j];
-        if (yb + k < Y) t2[off + (long long)(yb + k) * Z] = (float)acc;
+        for (int j = 0; j <= 2 * R; ++j) acc += w[k + j];
+        if (yb + k < Y) t2[off + (long long)(yb + k) * Z] = acc;
     }
 }
 template <typename T, int R>
@@ -369,14 +392,15 @@ __global__ void __launch_bounds__(256) box_x_norm_r(const T* __restrict__ raw, c
 #pragma unroll
     for (int k = 0; k < LCN_R; ++k) {
         if (xb + k >= X) break;
-        double acc = 0.0;
+        float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j <= 2 * R; ++j) acc += (double)w[k + j];
+        for (int j = 0; j <= 2 * R; ++j) acc += w[k + j];
         const long long i = (long long)(xb + k) * plane + f;
-        const float sd = sqrtf((float)acc / volume);
+        const float sd = sqrtf(acc / volume);
         const float den = sd + noise;
-        const double d = (double)clamped(raw, i, med) - (double)avg[i];
-        out[i] = (float)(d / (double)den);
+        // float32 subtraction is correctly rounded, i.e. equal to float(double(v) - double(avg)); one float32 division
+        const float d = __fsub_rn(clamped(raw, i, med), avg[i]);
+        out[i] = __fdiv_rn(d, den);
     }
 }
 
@@ -410,7 +434,8 @@ static int normalize_impl(const T* raw, float* out, int X, int Y, int Z, float n
     if (fx == 27 && fy == 27) {
         box_y_v_r<T, 13><<<grid_y, 256, 0, s>>>(raw, med, t1, X, Y, Z);
         CT_LAUNCHED("box_y_v");
-        box_x_avg_r<13><<<grid_x, 256, 0, s>>>(t1, avg, X, Y, Z, volume);
+        // integer raw data: 2 T1 is an integer (the median of integers is k or k + 0.5)
+        box_x_avg_r<13, !std::is_floating_point<T>::value><<<grid_x, 256, 0, s>>>(t1, avg, X, Y, Z, volume);
         CT_LAUNCHED("box_x_avg");
         box_y_sq_r<T, 13><<<grid_y, 256, 0, s>>>(raw, med, avg, t2, X, Y, Z);
         CT_LAUNCHED("box_y_sq");
