@@ -10,6 +10,7 @@
 // 27 x CO x 4 weights are staged in shared memory; lanes run along z so every activation LDS.128 of a
 // quarter warp touches 128 contiguous bytes, and weight reads are warp-uniform broadcasts.
 #include "unet_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace ct {
 
@@ -203,40 +204,56 @@ first_conv_kernel(const float* __restrict__ src, int mode, int tile_first, const
     __syncthreads();
     const int d1 = mode == 0 ? g.in_dim[1] : TY, d2 = mode == 0 ? g.in_dim[2] : TZ;
     const float* base = mode == 0 ? src : src + (size_t)(tile_first + tile) * vol;
-    for (int i = tid; i < (FX + 2) * (FY + 2) * (FZ + 2); i += 256) {
-        const int sz = i % (FZ + 2), r = i / (FZ + 2);
-        const int sy = r % (FY + 2), sx = r / (FY + 2);
-        const int gx = ix_s[sx], gy = iy_s[sy], gz = iz_s[sz];
-        in_s[sx][sy][sz] = (gx | gy | gz) < 0 ? 0.f : base[((size_t)gx * d1 + gy) * d2 + gz];
+    // all of a thread's 13 gathers are issued before the first is stored: with a rolled loop every trip waited for its own
+    // load (~13 L2 round trips per CTA, longer than the 1728 multiply-adds per thread that follow)
+    constexpr int N_IN = (FX + 2) * (FY + 2) * (FZ + 2), N_LD = (N_IN + 255) / 256;
+    float stage[N_LD];
+#pragma unroll
+    for (int k = 0; k < N_LD; ++k) {
+        const int i = tid + k * 256;
+        float v = 0.f;
+        if (i < N_IN) {
+            const int sz = i % (FZ + 2), r = i / (FZ + 2);
+            const int sy = r % (FY + 2), sx = r / (FY + 2);
+            const int gx = ix_s[sx], gy = iy_s[sy], gz = iz_s[sz];
+            if ((gx | gy | gz) >= 0) v = __ldg(base + ((size_t)gx * d1 + gy) * d2 + gz);
+        }
+        stage[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < N_LD; ++k) {
+        const int i = tid + k * 256;
+        if (i < N_IN) (&in_s[0][0][0])[i] = stage[k];
     }
     for (int i = tid; i < 27 * 8; i += 256) reinterpret_cast<float*>(&w_s[0][0])[i] = wts[i].x;
     __syncthreads();
 
-    float acc[FX][8];
+    // channel pairs: packed fp32 multiply-adds (FFMA2: one issue slot for two IEEE operations, bit-identical to FFMA)
+    float2 acc[FX][4];
 #pragma unroll
     for (int v = 0; v < FX; ++v)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[v][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc[v][c] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll 1
         for (int dz = 0; dz < 3; ++dz) {
-            float w[3][8];
+            float2 w[3][4];
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const float4 w0 = w_s[(dx * 3 + dy) * 3 + dz][0], w1 = w_s[(dx * 3 + dy) * 3 + dz][1];
-                w[dx][0] = w0.x; w[dx][1] = w0.y; w[dx][2] = w0.z; w[dx][3] = w0.w;
-                w[dx][4] = w1.x; w[dx][5] = w1.y; w[dx][6] = w1.z; w[dx][7] = w1.w;
+                w[dx][0] = make_float2(w0.x, w0.y); w[dx][1] = make_float2(w0.z, w0.w);
+                w[dx][2] = make_float2(w1.x, w1.y); w[dx][3] = make_float2(w1.z, w1.w);
             }
 #pragma unroll
             for (int xx = 0; xx < FX + 2; ++xx) {
-                const float a = in_s[xx][ty + dy][tz + dz];
+                const float2 a = f2_splat(in_s[xx][ty + dy][tz + dz]);
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                     const int v = xx - dx;
                     if (v < 0 || v >= FX) continue;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[v][c] = fmaf(a, w[dx][c], acc[v][c]);
+                    for (int c = 0; c < 4; ++c) acc[v][c] = f2_fma(a, w[dx][c], acc[v][c]);
                 }
             }
         }
@@ -259,7 +276,8 @@ first_conv_kernel(const float* __restrict__ src, int mode, int tile_first, const
                     float o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float t = acc[v][c4 * 4 + j] + bs[j];
+                        const float2 ap = acc[v][c4 * 2 + (j >> 1)];
+                        float t = ((j & 1) ? ap.y : ap.x) + bs[j];
                         t = t > 0.f ? t : alpha * t;
                         o[j] = fmaf(t, sc[j], sh[j]);
                     }
