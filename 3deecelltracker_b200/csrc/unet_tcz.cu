@@ -43,19 +43,22 @@ int tc_sm_count();
 int tc_make_map_box(CUtensorMap* map, float* base, int X, int Y, int Z, int c4, int tiles, size_t slab_stride, const unsigned box[5]);
 
 constexpr int TZ_Z = 16;                          // the kernel needs the whole z extent of a tile in one M tile
-constexpr int TZ_BY = 8, TZ_YH = TZ_BY + 2;       // y rows per unit, haloed
+// The CTA always runs TWO lanes, each with its own ring of output planes, MMA issuer and drain warps: at Cout = 16 the two
+// groups of 8 output channels of one 8-row M tile (NY = 1), at Cout = 8 two 8-row M tiles of the same plane (NY = 2).  Two
+// issuers overlap the ~365 clocks of latency a thread pays per plane around its MMAs; each stays in plane order.
 constexpr int TZ_ROW16 = TZ_Z;                    // 16-byte units per y row of one operand image
-constexpr int TZ_IMG16 = TZ_YH * TZ_ROW16;        // one operand image (8 channels) of one plane: 160 units = 2560 B
-constexpr int TZ_CHUNK16 = 2 * TZ_IMG16;          // hi + lo'
+__host__ __device__ constexpr int tz_by(int ny) { return 8 * ny; }                 // y rows per unit
+__host__ __device__ constexpr int tz_yh(int ny) { return 8 * ny + 2; }             // ... haloed
+__host__ __device__ constexpr int tz_img16(int ny) { return tz_yh(ny) * TZ_ROW16; } // one operand image (8 channels) of one plane
+__host__ __device__ constexpr int tz_chunk16(int ny) { return 2 * tz_img16(ny); }   // hi + lo'
 constexpr int TZ_BLK = 48;                        // accumulator columns of one output plane and group: (hi.hi | cross) x 3 dz x 8
 constexpr int TZ_NMMA = 3 * TZ_BLK;               // one MMA feeds three consecutive output planes (dx = 2, 1, 0)
 constexpr int TZ_NROW = TZ_NMMA;                  // B rows per K half
 constexpr int TZ_WIMG16 = 2 * TZ_NROW;            // 16-byte units of one B image (two K halves); two images per (K step, group)
-template <int NG> struct TzRing {                 // ring slots of output planes per group
-    static constexpr int R = NG == 1 ? 10 : 5;
-    static constexpr int COLS = R * TZ_BLK;
-    static_assert(NG <= 2 && NG * COLS <= 512, "plane ring exceeds tensor memory");
-};
+constexpr int TZ_LANES = 2;
+constexpr int TZ_R = 5;                           // ring slots of output planes per lane
+constexpr int TZ_LCOLS = TZ_R * TZ_BLK;
+static_assert(TZ_LANES * TZ_LCOLS <= 512, "plane rings exceed tensor memory");
 constexpr int TZ_DRAIN_WARPS = 8;
 constexpr int TZ_THREADS = 128 + 32 * TZ_DRAIN_WARPS;      // warpgroup 0: producer + three MMA issuers
 constexpr int TZ_MAX_STAGES = 8;
@@ -72,7 +75,7 @@ __device__ unsigned long long g_tz_timers[16];
 #endif
 
 struct TzGeom {
-    int cin8, nsteps, X, Y, nby, nseg, sxseg, units, stages;
+    int cin8, nsteps, X, Y, by, nby, nseg, sxseg, units, stages;
     uint32_t wbytes;
     int dst_c4off;
     size_t dst_tile_stride4, slab_stride;
@@ -90,13 +93,13 @@ __device__ __forceinline__ TzUnit tz_unit(int u, const TzGeom& g) {
     TzUnit r;
     r.x0 = (u % g.nseg) * g.sxseg; u /= g.nseg;
     r.nout = min(g.sxseg, g.X - r.x0);
-    r.y0 = (u % g.nby) * TZ_BY;
+    r.y0 = (u % g.nby) * g.by;
     r.tile = u / g.nby;
     return r;
 }
 
 // K-half taps of step p: tap t = (ci chunk t / 3, dy = t % 3) at t/3 chunks + t%3 rows into the plane's stage
-__host__ __device__ constexpr uint32_t tz_tap_off16(int t) { return (uint32_t)(t / 3) * TZ_CHUNK16 + (uint32_t)(t % 3) * TZ_ROW16; }
+__host__ __device__ constexpr uint32_t tz_tap_off16(int t, int chunk16) { return (uint32_t)(t / 3) * chunk16 + (uint32_t)(t % 3) * TZ_ROW16; }
 
 // the 48 accumulator columns of one output plane and group, of the thread's lane
 __device__ __forceinline__ void tz_ld48(uint32_t taddr, uint32_t* r) {
@@ -114,8 +117,8 @@ __device__ __forceinline__ void tz_ld48(uint32_t taddr, uint32_t* r) {
 }
 
 // Persistent CTA.  Work unit = a segment of x-planes x 8 y-rows x 16 z x all Cout of one tile.  Warp roles: 0 TMA producer
-// (+ tensor-memory allocator, resident weights), 1 .. NG MMA issuers (one per group of 8 output channels), 4-11 drain /
-// epilogue (two per tensor-memory lane quarter, four of a group's eight channels each).
+// (+ tensor-memory allocator, resident weights), 1-2 MMA issuers (one per lane), 4-11 drain / epilogue (one warp per lane
+// and tensor-memory lane quarter).
 //
 // Output planes live in a RING of tensor-memory blocks (48 columns per plane and group).  Every plane of the CTA's
 // whole sequence of units has an id G (two pseudo ids separate consecutive units: they take the contributions that fall
@@ -128,33 +131,36 @@ __device__ __forceinline__ void tz_ld48(uint32_t taddr, uint32_t* r) {
 // the grid (tile-sharded and spatially decomposed runs stay bit-identical to the single-GPU run).
 //   drain -> issuer: blk_free[g][slot]  the id that last used the slot has been read out of tensor memory
 //   issuer -> drain: blk_done[g][slot]  (tcgen05.commit after the MMAs with newest id G) id G-2 is complete
-// Drain: each warp takes WHOLE blocks (all 8 channels of a plane and group, 48 columns per thread) of every other
-// (plane, group) item -- warps 4-7 the even items, warps 8-11 the odd ones -- so two items are in flight per lane
-// quarter and the tensor-memory load latency of one (hundreds of clocks while MMAs read-modify-write their
-// accumulators) overlaps the epilogue of the other.  The block is handed back right after the load, before the epilogue.
-template <int CIN8, int NG, bool DST_SPLIT>
+// Drain: each warp takes WHOLE blocks (all 8 channels of a plane, 48 columns per thread) of one lane -- warps 4-7 lane 0,
+// warps 8-11 lane 1 -- so two items are in flight per tensor-memory lane quarter and the load latency of one (hundreds
+// of clocks while MMAs read-modify-write their accumulators) overlaps the epilogue of the other.  The block is handed
+// back right after the load, before the epilogue.
+template <int CIN8, int NGRP, bool DST_SPLIT>
 __global__ void __launch_bounds__(TZ_THREADS, 1)
 conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ wpack,
                  const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                  float alpha, float4* __restrict__ dst, const TzGeom geo) {
-    constexpr int R = TzRing<NG>::R, GCOLS = TzRing<NG>::COLS;
+    constexpr int R = TZ_R, GCOLS = TZ_LCOLS, NG = TZ_LANES;
+    constexpr int NY = 3 - NGRP;                                   // one channel group: two 8-row M tiles per plane
+    constexpr int IMG16 = tz_img16(NY), CHUNK16 = tz_chunk16(NY);
+    static_assert(NGRP == 1 || NGRP == 2, "one or two groups of 8 output channels");
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[TZ_MAX_STAGES], bar_empty[TZ_MAX_STAGES], blk_free[NG][R], blk_done[NG][R], bar_w;
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float ep_s[3][8 * NG];
+    __shared__ __align__(16) float ep_s[3][8 * NGRP];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* wsm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring = wsm + geo.wbytes;
     const int stages = geo.stages;
-    constexpr uint32_t stage_bytes = (uint32_t)CIN8 * (TZ_CHUNK16 * 16);
+    constexpr uint32_t stage_bytes = (uint32_t)CIN8 * (CHUNK16 * 16);
     constexpr int NTAPS = 3 * CIN8, NSTEPS = (NTAPS + 1) / 2;
     const int n_units = ((int)blockIdx.x < geo.units) ? (geo.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], NG);                          // one commit per issuer that reads the plane
+            mbar_init(&bar_empty[s], NG);                          // one commit per issuer
         }
 #pragma unroll
         for (int g = 0; g < NG; ++g)
@@ -168,8 +174,8 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (threadIdx.x >= 128) {
-        for (int i = threadIdx.x - 128; i < 3 * 8 * NG; i += TZ_THREADS - 128)
-            ep_s[i / (8 * NG)][i % (8 * NG)] = (i < 8 * NG) ? bias[i] : (i < 16 * NG ? scale[i - 8 * NG] : shift[i - 16 * NG]);
+        for (int i = threadIdx.x - 128; i < 3 * 8 * NGRP; i += TZ_THREADS - 128)
+            ep_s[i / (8 * NGRP)][i % (8 * NGRP)] = (i < 8 * NGRP) ? bias[i] : (i < 16 * NGRP ? scale[i - 8 * NGRP] : shift[i - 16 * NGRP]);
     }
     tc_fence_before();
     __syncthreads();
@@ -205,7 +211,7 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 #endif
         }
         __syncwarp();
-    } else if (warp <= NG) {
+    } else if (warp <= TZ_LANES) {
         // ---------------- MMA issuer of group g = warp - 1 (one thread issues a group's MMAs, in plane order: the order in
         // which a block receives its contributions, hence its rounding, is fixed)
         if (elect_one()) {
@@ -214,7 +220,9 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             constexpr uint32_t idesc48 = (1u << 4) | ((uint32_t)(TZ_BLK >> 3) << 17) | (8u << 24);
             constexpr uint64_t sbo8_word = (uint64_t)(8u | (1u << 14)) << 32;     // 8-row groups 128 B apart (A and B)
             const uint32_t ring16 = smem_u32(ring) >> 4, w16 = smem_u32(wsm) >> 4;
-            const int g = warp - 1;
+            const int g = warp - 1;                                 // lane: channel group (NGRP = 2) or y half (NY = 2)
+            const int gch = NGRP == 2 ? g : 0;
+            const uint32_t yoff16 = NY == 2 ? (uint32_t)(g * 8 * TZ_ROW16) : 0u;
             const uint32_t gcol = tmem_base + (uint32_t)(g * GCOLS);
             mbar_wait(&bar_w, 0);
             int gp = 0;
@@ -228,7 +236,7 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                     { TZ_T0(); mbar_wait(&bar_full[s], us & 1); TZ_ACC(w_full); }
                     if (use > 0) { TZ_T0(); mbar_wait(&blk_free[g][slot], (use - 1) & 1); TZ_ACC(w_acc); }
                     tc_fence_after();
-                    const uint32_t a_hi = ring16 + (uint32_t)s * (stage_bytes >> 4);
+                    const uint32_t a_hi = ring16 + (uint32_t)s * (stage_bytes >> 4) + yoff16;
                     const int b = slot >= 2 ? slot - 2 : slot + R - 2;              // block of id G - 2
                     const uint32_t d = gcol + (uint32_t)(b * TZ_BLK);
 #pragma unroll
@@ -237,11 +245,11 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                         // every descriptor is the stage / weight base plus a compile-time constant
                         const int t1 = (2 * p + 1 < NTAPS) ? 2 * p + 1 : NTAPS - 1;
                         const int t0 = t1 - 1;
-                        const uint32_t o0 = tz_tap_off16(t0), lbo = (tz_tap_off16(t1) - o0) << 16;
+                        const uint32_t o0 = tz_tap_off16(t0, CHUNK16), lbo = (tz_tap_off16(t1, CHUNK16) - o0) << 16;
                         const uint64_t ah = sbo8_word | (uint64_t)((a_hi + o0) | lbo);
-                        const uint64_t al = sbo8_word | (uint64_t)((a_hi + o0 + TZ_IMG16) | lbo);
-                        const uint32_t w1 = (w16 + (uint32_t)((p * NG + g) * 2) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
-                        const uint32_t w2 = (w16 + (uint32_t)((p * NG + g) * 2 + 1) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                        const uint64_t al = sbo8_word | (uint64_t)((a_hi + o0 + IMG16) | lbo);
+                        const uint32_t w1 = (w16 + (uint32_t)((p * NGRP + gch) * 2) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
+                        const uint32_t w2 = (w16 + (uint32_t)((p * NGRP + gch) * 2 + 1) * TZ_WIMG16) | ((uint32_t)TZ_NROW << 16);
                         // B rows [0, 48) feed the oldest plane (id G - 2), [48, 96) the middle one, [96, 144) the newest,
                         // which this plane's first MMA overwrites.  Where the ring wraps the MMA is issued in two pieces.
                         if (b <= R - 3) {
@@ -292,10 +300,11 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         const size_t vol = (size_t)geo.X * geo.Y * TZ_Z;
         constexpr float W2 = 1.f / 2048.f;                         // weight of the hi.lo' + lo'.hi columns
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int g_mine = NG == 2 ? set : 0;                      // two groups: one per warp set; one group: alternate planes
+        const int g_mine = set;                                    // lane of this warp set
+        const int gch = NGRP == 2 ? set : 0, yoff = NY == 2 ? 8 * set : 0;
         const float m_up = (z == 0) ? 0.f : 1.f, m_dn = (z == TZ_Z - 1) ? 0.f : 1.f;      // zero padding at the z ends of a tile
         long long w_accf = 0, t_ld = 0, t_fin = 0, t_begin = clock64();
-        int slot = 0, use = 0, idpar = 0;                          // ring slot / use count / parity of the id being drained
+        int slot = 0, use = 0;                                     // ring slot / use count of the id being drained
         // the id sequence: two pseudo ids, then per unit its nout planes and two pseudo ids; the last two never complete
         TzUnit un_next = tz_unit((int)blockIdx.x, geo);
         float am_next = 0.f, am2_next = 0.f, sc_next = 1.f;
@@ -305,7 +314,6 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             sc_next = geo.scale_src[(size_t)tile * geo.slab_stride];
         };
         if (n_units > 0) tile_hdr(un_next.tile);
-        const bool mine_all = (NG == 2);
         // takes the finished id in (slot, use) out of tensor memory (real planes only) and hands its blocks back
         auto take = [&](bool real, uint32_t (&v)[48]) {
             { TZ_T0(); mbar_wait(&blk_done[g_mine][slot], use & 1); TZ_ACC(w_accf); }
@@ -324,11 +332,11 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             __syncwarp();
             if (lane == 0) mbar_arrive(&blk_free[g_mine][slot]);
         };
-        auto next_id = [&]() { idpar ^= 1; if (++slot == R) { slot = 0; ++use; } };
+        auto next_id = [&]() { if (++slot == R) { slot = 0; ++use; } };
         if (n_units > 0) {
             uint32_t dummy[48];
             for (int e = 0; e < 2; ++e) {
-                if (mine_all || idpar == set) take(false, dummy);
+                take(false, dummy);
                 next_id();
             }
         }
@@ -343,7 +351,7 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                 un_next = tz_unit((int)blockIdx.x + (k + 1) * (int)gridDim.x, geo);
                 tile_hdr(un_next.tile);
             }
-            const int y = un.y0 + yl;
+            const int y = un.y0 + yoff + yl;
             const bool ok_y = y < geo.Y;
             uint8_t* d_tile = reinterpret_cast<uint8_t*>(dst + (size_t)un.tile * geo.dst_tile_stride4);
             float amax = 0.f;
@@ -351,7 +359,7 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             // in plane 2 g and the lo' image in 2 g + 1; fp32 buffers channels 0-3 / 4-7; P8 partial sums channel pairs
             // (0,1 | 4,5) / (2,3 | 6,7)
             const size_t plane_b = (size_t)geo.Y * TZ_Z * 16, vol_b = vol * 16;
-            uint8_t* const d_grp = d_tile + (size_t)(geo.dst_c4off + 2 * g_mine) * vol_b + (((size_t)un.x0 * geo.Y + y) * TZ_Z + z) * 16;
+            uint8_t* const d_grp = d_tile + (size_t)(geo.dst_c4off + 2 * gch) * vol_b + (((size_t)un.x0 * geo.Y + y) * TZ_Z + z) * 16;
             auto put = [&](uint8_t* pa, size_t pvol_b, const float2 (&v)[4], float so) {
 #ifdef TZ_EXP_NOSTORE
                 if (so != 12345.678f) { amax = fmaxf(amax, v[0].x + v[1].y + v[2].x + v[3].y); return; }      // experiment: no stores
@@ -392,7 +400,7 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
                     // the zeros at the z ends: one packed multiply-add per neighbour (x 1 / x 0 is exact) -- a select on z
                     // compiles to a divergent branch per pair
                     const float2 av = f2_fma(up[kk], f2_splat(m_up), f2_fma(dn[kk], f2_splat(m_dn), f2_add(c[kk][1], ps[kk])));
-                    o[kk] = block_epilogue(av, inv_scale, alpha, &ep_s[0][0], 8 * NG, 8 * g_mine + 2 * kk, am);
+                    o[kk] = block_epilogue(av, inv_scale, alpha, &ep_s[0][0], 8 * NGRP, 8 * gch + 2 * kk, am);
                 }
                 if (ok_y) {
                     amax = fmaxf(amax, am);
@@ -404,7 +412,7 @@ conv3_tcz_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
             for (int i = 0; i < un.nout + 2; ++i) {
                 const bool real = i < un.nout;
                 if (last_unit && !real) break;                      // the sequence's last two pseudo ids never complete
-                if (mine_all || idpar == set) {
+                {
                     // partial sums (P8) of this plane: the loads fly while the warp waits for the plane to complete
                     float2 ps[4];
 #pragma unroll
@@ -450,7 +458,7 @@ static int tz_steps(int cin) { return (3 * (cin / 8) + 1) / 2; }
 size_t tcz_weight_floats(int cin, int cout) {
     if ((cout != 8 && cout != 16) || (cin != 8 && cin != 16 && cin != 32)) return 0;      // instantiated shapes
     const size_t bytes = (size_t)tz_steps(cin) * (cout / 8) * 2 * TZ_WIMG16 * 16;       // two B images per (K step, group)
-    if (bytes + 3 * (size_t)(cin / 8) * TZ_CHUNK16 * 16 + 1024 > (size_t)TZ_SMEM_MAX) return 0;     // resident weights + 3 stages
+    if (bytes + 3 * (size_t)(cin / 8) * tz_chunk16(cout == 8 ? 2 : 1) * 16 + 1024 > (size_t)TZ_SMEM_MAX) return 0;     // resident weights + 3 stages
     return bytes / 4;
 }
 
@@ -513,17 +521,18 @@ static void tz_segments(int X, int per_x, int grid, bool even, int* sxseg, int* 
     }
 }
 
-template <int CIN8, int NG, bool DST_SPLIT>
+template <int CIN8, int NGRP, bool DST_SPLIT>
 static int launch_tcz(const CUtensorMap& map, const ConvLayer& L, const TzSource& src, float alpha, float4* dst, int X, int Y,
                       size_t stride4, int dst_c4off, int tiles, const float* amax_src, float* amax_dst, cudaStream_t s) {
     TzGeom g;
     g.cin8 = src.cin / 8; g.nsteps = tz_steps(src.cin); g.X = X; g.Y = Y;
-    g.nby = cdiv(Y, TZ_BY);
-    g.wbytes = (uint32_t)(tcz_weight_floats(src.cin, 8 * NG) * 4);
-    const size_t stage_bytes = (size_t)g.cin8 * TZ_CHUNK16 * 16;
+    constexpr int NY = 3 - NGRP;
+    g.by = tz_by(NY); g.nby = cdiv(Y, g.by);
+    g.wbytes = (uint32_t)(tcz_weight_floats(src.cin, 8 * NGRP) * 4);
+    const size_t stage_bytes = (size_t)g.cin8 * tz_chunk16(NY) * 16;
     int stages = (int)(((size_t)TZ_SMEM_MAX - 1024 - g.wbytes) / stage_bytes);
     if (stages > TZ_MAX_STAGES) stages = TZ_MAX_STAGES;
-    CT_REQUIRE(stages >= 3, "conv: plane-walk kernel has no room for 3 stages (cin %d, cout %d)", src.cin, 8 * NG);
+    CT_REQUIRE(stages >= 3, "conv: plane-walk kernel has no room for 3 stages (cin %d, cout %d)", src.cin, 8 * NGRP);
     g.stages = stages;
     const size_t smem = 1024 + g.wbytes + (size_t)stages * stage_bytes;
     const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
@@ -535,9 +544,9 @@ static int launch_tcz(const CUtensorMap& map, const ConvLayer& L, const TzSource
     g.w_inv_scale = src.inv_scale; g.bound_p = L.bound_p; g.bound_q = L.bound_q;
     g.add_partial = src.add_partial;
     // per device / context attribute: set on every launch (cheap) so several GPUs in one process are correct
-    CT_CUDA(cudaFuncSetAttribute(conv3_tcz_kernel<CIN8, NG, DST_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CT_CUDA(cudaFuncSetAttribute(conv3_tcz_kernel<CIN8, NGRP, DST_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = g.units < sms ? g.units : sms;
-    conv3_tcz_kernel<CIN8, NG, DST_SPLIT><<<grid, TZ_THREADS, smem, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
+    conv3_tcz_kernel<CIN8, NGRP, DST_SPLIT><<<grid, TZ_THREADS, smem, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;
 }
 
@@ -553,10 +562,10 @@ static int launch_tcz_any(int cout, bool dst_split, const CUtensorMap& map, cons
     return 2;
 }
 
-// Which blocks the plane-walk kernel takes in the `auto` mix [measured on B200, 38 tiles, ms against unet_tcx.cu]:
-// 16 -> 16: 0.20 vs 0.24; 32 -> 8: 0.6 vs 1.46; skip halves 16 -> 8: 0.54 vs 0.83, 32 -> 16: 0.30 vs 0.48.  Not 8 -> 8
-// (0.42 vs 0.41: one issuer pays ~365 clocks of latency per plane around 4 MMAs) and not 8 -> 16 (0.62 vs 0.55: the
-// drain, ~350 instructions per warp and plane, is the bound).  CT3D_TCZ_ALL=1 routes those to it as well.
+// Which blocks the plane-walk kernel takes in the `auto` mix [measured on B200, 38 tiles, ms against unet_tcx.cu]: every
+// block it is instantiated for -- 16 -> 16: 0.20 vs 0.24; 8 -> 8: 0.31 vs 0.41; 32 -> 8: 0.75 vs 1.46; skip halves
+// 16 -> 8: 0.48 vs 0.83, 32 -> 16: 0.39 vs 0.48 -- except 8 -> 16 (0.60 vs 0.55: the drain, ~350 instructions per warp
+// and plane, is the bound, and that block also carries the fused pool).  CT3D_TCZ_ALL=1 routes it there as well.
 static bool tz_all() {
     static int v = -1;
     if (v < 0) {
@@ -567,11 +576,11 @@ static bool tz_all() {
 }
 static bool tz_takes(int cin, int cout, bool skip_half) {
     if (cout > 16) return false;
-    return tz_all() || skip_half || cin != 8;
+    return tz_all() || skip_half || !(cin == 8 && cout == 16);
 }
 
-static int tz_map(CUtensorMap* map, float* src, int X, int Y, int cin, int tiles, size_t slab_stride) {
-    const unsigned box[5] = {TZ_Z * 4, TZ_YH, 1, (unsigned)(cin / 4), 1};
+static int tz_map(CUtensorMap* map, float* src, int X, int Y, int cin, int cout, int tiles, size_t slab_stride) {
+    const unsigned box[5] = {TZ_Z * 4, (unsigned)tz_yh(cout == 8 ? 2 : 1), 1, (unsigned)(cin / 4), 1};
     return tc_make_map_box(map, src, X, Y, TZ_Z, cin / 4, tiles, slab_stride, box);
 }
 
@@ -591,7 +600,7 @@ int launch_conv_tcz(const CtUNet* net, const Op& op, float* slab0, size_t slab_s
     float4* dst = reinterpret_cast<float4*>(slab0 + op.dst_off);
     CUtensorMap map;
     ProfScope prof(PROF_CONV, s);
-    if (tz_map(&map, slab0 + op.src_off, X, Y, L.cin, tiles, slab_stride)) return 1;
+    if (tz_map(&map, slab0 + op.src_off, X, Y, L.cin, L.cout, tiles, slab_stride)) return 1;
     const TzSource whole{L.w_tcz, L.w_tcz_inv_scale, L.cin, 0, nullptr};
     const int rc = launch_tcz_any(L.cout, (fmt & FMT_DST_SPLIT) != 0, map, L, whole, net->alpha, dst, X, Y, slab_stride / 4,
                                   op.dst_coff / 4, tiles, slab0 + op.src_slot, slab0 + op.dst_slot, s);
@@ -613,7 +622,7 @@ int launch_conv_tcz_skip(const CtUNet* net, const Op& op, float* slab0, size_t s
     CUtensorMap map;
     ProfScope prof(PROF_CONV, s);
     const size_t vol = (size_t)X * Y * Z;
-    if (tz_map(&map, slab0 + op.src_off + (size_t)L.c_up * vol, X, Y, c_skip, tiles, slab_stride)) return 1;
+    if (tz_map(&map, slab0 + op.src_off + (size_t)L.c_up * vol, X, Y, c_skip, L.cout, tiles, slab_stride)) return 1;
     const TzSource skip{L.w_tcz_skip, L.w_tcz_skip_inv_scale, c_skip, 1, up_slot >= 0 ? slab0 + up_slot : nullptr};
     const int rc = launch_tcz_any(L.cout, true, map, L, skip, net->alpha, dst, X, Y, slab_stride / 4, op.dst_coff / 4, tiles,
                                   slab0 + op.src_slot, slab0 + op.dst_slot, s);

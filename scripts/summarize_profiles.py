@@ -106,7 +106,7 @@ CONV_ROWS = [("d0a 1>8", 0.088, 1, 8, 409600, "CUDA cores, fused gather"), ("d0b
              ("u0a up 32>16", 1.416, 8, 16, 102400, "phase kernel"), ("u0a skip 32>16", 1.416, 32 + 16, 16, 102400, "plane-walk + partial sums"),
              ("u0b 16>16", 0.708, 16, 16, 102400, "plane-walk"),
              ("o_m2 up 16>8", 1.416, 4, 8, 409600, "phase kernel"), ("o_m2 skip 16>8", 1.416, 16 + 8, 8, 409600, "plane-walk + partial sums"),
-             ("o_m1 8>8", 0.708, 8, 8, 409600, "x-stacked, fp32 destination")]
+             ("o_m1 8>8", 0.708, 8, 8, 409600, "plane-walk, fp32 destination")]
 
 
 def conv():
