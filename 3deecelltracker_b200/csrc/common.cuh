@@ -16,7 +16,12 @@ extern std::atomic<int> g_reserved_sms;      // see ct_set_reserved_sms
 
 inline int check_cuda(cudaError_t e, const char* what) {
     if (e != cudaSuccess) {
-        set_error("%s: %s", what, cudaGetErrorString(e));
+        // The tcgen05 kernels bound every mbarrier wait (tc_ptx.cuh: trap after 4e9 clocks) so that a protocol error ends
+        // as a launch failure instead of a hung GPU; the error is sticky for the context and surfaces at a later call.
+        const bool trapped = (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction || e == cudaErrorAssert);
+        set_error("%s: %s%s", what, cudaGetErrorString(e),
+                  trapped ? " (a kernel of an EARLIER launch trapped -- a bounded mbarrier wait of a convolution kernel timed out, or a "
+                            "device-side check failed; the CUDA context is unusable from here on)" : "");
         return 1;
     }
     return 0;
