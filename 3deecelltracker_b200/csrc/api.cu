@@ -7,7 +7,7 @@
 namespace ct {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_reserved_sms{0};
+thread_local int g_reserved_sms = 0;       // per host thread: a setting is scoped to the launches of the thread that made it
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -83,7 +83,9 @@ int ct_profile_read(int tag, double* total_ms, unsigned long long* count, int re
 int ct_set_reserved_sms(int n) {
     if (n < 0) n = 0;
     if (n > 64) n = 64;
-    return ct::g_reserved_sms.exchange(n);
+    const int old = ct::g_reserved_sms;
+    ct::g_reserved_sms = n;
+    return old;
 }
 
 int ct_abi_version(void) { return CT3D_ABI_VERSION; }

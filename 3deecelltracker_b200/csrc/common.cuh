@@ -12,7 +12,7 @@ namespace ct {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
-extern std::atomic<int> g_reserved_sms;      // see ct_set_reserved_sms
+extern thread_local int g_reserved_sms;      // see ct_set_reserved_sms (per host thread)
 
 inline int check_cuda(cudaError_t e, const char* what) {
     if (e != cudaSuccess) {

@@ -456,7 +456,7 @@ static int launch_tc(const CUtensorMap& map, const ConvLayer& L, float alpha, fl
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
     g.scale_src = amax_src + SCALE_SLOT0; g.scale_dst = amax_dst + SCALE_SLOT0; g.bound_p = L.bound_p; g.bound_q = L.bound_q;
-    const int sms = sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
+    const int sms = sm_count() - g_reserved_sms;
     const int grid = g.units < sms ? g.units : sms;
     conv3_tc_kernel<N, BX, STAGES, SRC_SPLIT, DST_SPLIT><<<grid, TC_THREADS, Cfg::SMEM, s>>>(map, L.w_tc, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;

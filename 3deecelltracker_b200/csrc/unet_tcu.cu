@@ -442,7 +442,7 @@ static int launch_tcu(const CUtensorMap& map, const float* wpack, float inv_scal
     g.nbx = cdiv(X, BX); g.nby = cdiv(Y, 16); g.nbz = Z / 8;
     g.units = g.nbx * g.nby * g.nbz * tiles;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4;
-    const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
+    const int sms = tc_sm_count() - g_reserved_sms;
     const int grid = g.units < sms ? g.units : sms;
     conv3_tcu_kernel<N, BX, STAGES, SRC_SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, wpack, dst, g);
     return 0;

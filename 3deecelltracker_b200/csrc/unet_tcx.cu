@@ -604,7 +604,7 @@ static int launch_tcx(const CUtensorMap& map, const ConvLayer& L, const TxSource
     g.pool_dst = pool_dst; g.amax_pool = amax_pool; g.add_partial = src.add_partial;
     g.scale_src = amax_src + SCALE_SLOT0; g.scale_dst = amax_dst + SCALE_SLOT0; g.amax_src2 = src.amax2;
     g.bound_p = L.bound_p; g.bound_q = L.bound_q;
-    const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
+    const int sms = tc_sm_count() - g_reserved_sms;
     const int grid = g.units < sms ? g.units : sms;
     conv3_tcx_kernel<N, BX, STAGES, DW, SRC_SPLIT, DST_SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(map, src.w, L.bias, L.scale, L.shift, alpha, dst, g);
     return 0;

@@ -535,7 +535,7 @@ static int launch_tcz(const CUtensorMap& map, const ConvLayer& L, const TzSource
     CT_REQUIRE(stages >= 3, "conv: plane-walk kernel has no room for 3 stages (cin %d, cout %d)", src.cin, 8 * NGRP);
     g.stages = stages;
     const size_t smem = 1024 + g.wbytes + (size_t)stages * stage_bytes;
-    const int sms = tc_sm_count() - g_reserved_sms.load(std::memory_order_relaxed);
+    const int sms = tc_sm_count() - g_reserved_sms;
     tz_segments(X, tiles * g.nby, sms, false, &g.sxseg, &g.nseg);
     g.units = tiles * g.nby * g.nseg;
     g.dst_c4off = dst_c4off; g.dst_tile_stride4 = stride4; g.slab_stride = stride4 * 4;

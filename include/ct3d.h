@@ -37,7 +37,9 @@ unsigned long long ct_launch_count(void);
  * gather/head, 6 = watershed stage.  ct_profile_read synchronises on the recorded events and returns their summed duration. */
 /* Persistent kernels of this library (the tcgen05 convolution: one CTA per SM) leave `n` SMs unclaimed, so that a
  * single-CTA kernel running concurrently on another stream (the PR-GLS EM of the previous frame, tracker.py's frame
- * pipeline) finds a free SM instead of delaying one CTA of every convolution.  Default 0; returns the old value. */
+ * pipeline) finds a free SM instead of delaying one CTA of every convolution.  The setting belongs to the CALLING HOST
+ * THREAD (it applies to the launches that thread makes afterwards), so pipelines driven from different threads do not
+ * disturb each other.  Default 0; returns the thread's old value. */
 int ct_set_reserved_sms(int n);
 int ct_profile_enable(int on);
 int ct_profile_read(int tag, double* total_ms, unsigned long long* count, int reset);
