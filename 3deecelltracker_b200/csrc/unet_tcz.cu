@@ -1,4 +1,5 @@
-// tcgen05 implicit-GEMM 3x3x3 convolution, "plane-walk" variant: the x- and z-taps are stacked in N, the y-taps are K.
+// tcgen05 implicit-GEMM 3x3x3 convolution, "plane-walk" variant: the x- and z-taps are stacked in N, the y-taps are K, and
+// the sum over the x-taps is left in the tensor core's accumulators.
 //
 // Same operator, operand precision and buffers as unet_tcx.cu (Conv3D 3x3x3 'same' + bias -> LeakyReLU/ReLU ->
 // BatchNorm(eval), unet3d.py:117-119 / :139-140; split-fp16 hi / lo' operand images, fp32 accumulation), but a GEMM
@@ -12,25 +13,24 @@
 //     so the z shift-add is one lane up / down inside a 16-lane group (two shuffles) with zeros at z = 0 / 15: no halo
 //     rows are computed in y or z, and Y = 40 / 20 fit the 8-row tile (the 16-row tile of unet_tcx.cu wastes 17 / 37 %).
 //   * N = 3 x-taps x 48 columns = 144 per group of 8 output channels.  A block of 48 columns is ONE OUTPUT PLANE's
-//     accumulator: 3 z-taps x 8 channels x (hi.hi | hi.lo' + lo'.hi).  Output planes live in a ring of such blocks in
-//     tensor memory, and the MMA of input plane j accumulates onto the three physically consecutive blocks of output
-//     planes j-1, j, j+1 (B rows ordered dx = 2, 1, 0): the sum over the x-taps happens IN the tensor core's
-//     accumulators, and a plane is drained ONCE, when its third contribution has landed (24 columns per thread instead
-//     of 72 per input plane: the drain of the first version of this kernel, which added the x-taps in registers, took
-//     900-1100 clocks per plane and group against 260-400 clocks of MMAs).
+//     accumulator: (hi.hi | hi.lo' + lo'.hi) x 3 z-taps x 8 channels.  Output planes live in a ring of such blocks in
+//     tensor memory, and the MMA of input plane j accumulates onto the three consecutive blocks of output planes j-1, j,
+//     j+1 (B rows ordered dx = 2, 1, 0): the sum over the x-taps happens IN the accumulators, and a plane is drained
+//     ONCE, when its third contribution has landed (48 columns per thread and plane; the first version of this kernel
+//     added the x-taps in registers, 144 columns per input plane: its drain took 900-1100 clocks per plane and group
+//     against 260-400 clocks of MMAs).
 //         MMA1 = A_hi  x image 0 (hi | lo' rows)      MMA2 = A_lo' x image 1 (0 | hi rows), both N = 144, same columns
-//     Cout = 16 runs two such groups per plane, each with its own ring and its own issuer warp.
 //   * K = 16 per MMA = two (ci-chunk, dy) taps x 8 input channels; 3 cin/8 taps -> ceil(3 cin / 16) K steps; a plane's
 //     accumulator takes 3 x 2 x steps MMAs (<= 36; the 27-tap kernel chains 28).
-//   * The CTA walks a segment of x-planes of one (tile, 8-row y-block): one shared-memory stage = ONE x-plane of all
-//     input channels (10 haloed rows x 16 z), loaded once and used by the three output planes it feeds: there is no
-//     x-halo recomputation inside a segment, (S + 2) / S input planes per S output planes.
+//   * The CTA walks a segment of x-planes of one (tile, y-block): one shared-memory stage = ONE x-plane of all input
+//     channels (haloed rows x 16 z), loaded once and used by the three output planes it feeds: there is no x-halo
+//     recomputation inside a segment, (S + 2) / S input planes per S output planes.
 //   * The packed weights of the whole block stay resident in shared memory (<= 110 KB), loaded once per CTA.
 //
 // Source buffers are split-fp16 only (unet_common.cuh); the destination is split-fp16 or fp32 c4 planes.  Decoder
 // blocks: the phase kernel (unet_tcu.cu) leaves the partial sums of the up-sampled half in the destination in the
-// "P8" layout -- the 16 bytes of a thread's four channels sit exactly where that thread later writes its hi / lo'
-// halves -- so a thread only ever reads bytes it overwrites itself.
+// "P8" layout -- a thread's 2 x 16 bytes (8 channels of a voxel) sit exactly where that thread later writes its hi / lo'
+// images -- so a thread only ever reads bytes it overwrites itself.
 #include "unet_common.cuh"
 #include "tc_ptx.cuh"
 #include <cmath>
@@ -116,11 +116,11 @@ __device__ __forceinline__ void tz_ld48(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr + 32));
 }
 
-// Persistent CTA.  Work unit = a segment of x-planes x 8 y-rows x 16 z x all Cout of one tile.  Warp roles: 0 TMA producer
+// Persistent CTA.  Work unit = a segment of x-planes x 8 or 16 y-rows x 16 z x all Cout of one tile.  Warp roles: 0 TMA producer
 // (+ tensor-memory allocator, resident weights), 1-2 MMA issuers (one per lane), 4-11 drain / epilogue (one warp per lane
 // and tensor-memory lane quarter).
 //
-// Output planes live in a RING of tensor-memory blocks (48 columns per plane and group).  Every plane of the CTA's
+// Output planes live in a RING of tensor-memory blocks (48 columns per plane and lane).  Every plane of the CTA's
 // whole sequence of units has an id G (two pseudo ids separate consecutive units: they take the contributions that fall
 // outside a segment and are discarded); the MMA of the input plane with newest id G accumulates onto ids G-2, G-1, G
 // = three consecutive blocks starting at block (G-2) mod R -- issued in two pieces where the ring wraps.  The FIRST
