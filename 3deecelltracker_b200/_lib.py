@@ -85,6 +85,8 @@ SIGNATURES = {
     "ct_prgls": (c_int, [C.POINTER(CtPrglsParams), C.POINTER(CtPrglsProblem), c_int, c_void_p, c_size_t, c_void_p]),
     "ct_predict_one_rep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "ct_trim_mean": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "ct_replay_fit": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p), C.POINTER(c_int), C.POINTER(c_double),
+                            C.POINTER(c_void_p), c_double, c_void_p, c_void_p, c_void_p]),
     "ct_watershed_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ct_label_components_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ct_label_components": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

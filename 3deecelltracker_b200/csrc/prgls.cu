@@ -903,3 +903,20 @@ extern "C" int ct_trim_mean(const double* stack, int e, int count, double propor
     CT_LAUNCHED("trim_mean_kernel");
     return 0;
 }
+
+// One volume of the replay chain in one call (tracker.py:1269-1289 applied n_rep times, then the single-mode trimmed mean
+// of tracker.py:1503-1507 over a stack of one): the time-lapse driver replays hundreds of fitted transforms in volume
+// order on one rank, and six separate calls per volume were host-bound.  scratch: 2 x L x 3 doubles.
+extern "C" int ct_replay_fit(const double* pre, int L, int n_rep, const double* const* inter, const int* n_ref,
+                             const double* beta, const double* const* coef, double proportion, double* scratch,
+                             double* out, void* stream) {
+    CT_REQUIRE(pre && inter && n_ref && beta && coef && scratch && out && n_rep >= 1, "ct_replay_fit: bad argument");
+    if (L == 0) return 0;
+    const double* cur = pre;
+    for (int i = 0; i < n_rep; ++i) {
+        double* nxt = scratch + (size_t)(i & 1) * L * 3;
+        if (ct_predict_one_rep(cur, L, inter[i], n_ref[i], beta[i], coef[i], nxt, stream)) return 1;
+        cur = nxt;
+    }
+    return ct_trim_mean(cur, 1, L * 3, proportion, out, stream);
+}

@@ -24,7 +24,7 @@ import torch
 from . import _lib
 from . import watershed as _ws
 from .preprocess import normalize_image_device
-from .track import MODE_TRACK, EmProblem, predict_one_rep_device, run_em, trim_mean_device
+from .track import MODE_TRACK, EmProblem, replay_fit_device, run_em
 
 REP_NUM_PRGLS = 5          # tracker.py:45
 K_POINTS = 20              # tracker.py:1259
@@ -79,10 +79,7 @@ class FramePipeline:
 
     def replay(self, fit, tracked_prev_dev):
         """tracker.py:1269-1289 + the single-mode trimmed mean of :1503-1507: (L,3) -> (L,3)."""
-        pred = tracked_prev_dev
-        for inter, beta, coef in fit:
-            pred = predict_one_rep_device(pred, inter, beta, coef)
-        return trim_mean_device(pred[None], 0.1)
+        return replay_fit_device([(i.contiguous(), b, c.contiguous()) for i, b, c in fit], tracked_prev_dev.contiguous(), 0.1)
 
     def track(self, seg_prev_dev, seg_cur_dev, tracked_prev_dev):
         return self.replay(self.fit(seg_prev_dev, seg_cur_dev), tracked_prev_dev)

@@ -87,29 +87,31 @@ class TimelapseTracker:
     def _gather_fits(self, fits, cap, per_rank, device):
         """All fits of all ranks on every rank, in volume order: list of [(inter, beta, coef)] per volume pair."""
         n_rep = REP_NUM_PRGLS
-        # one row block per fit: [rep][0] = (count, beta, 0), then `cap` rows of inter (x,y,z) and `cap` rows of C^T
-        local = torch.zeros((per_rank, n_rep, 1 + 2 * cap, 3), dtype=torch.float64, device=device)
+        # one flat block per fit and repetition: [count, beta, 0 | inter (n,3) row-major in cap*3 | coef (3,n) row-major in
+        # cap*3] -- both arrays travel in their own memory order, so unpacking is two views, no transposes
+        blk = 3 + 6 * cap
+        local = torch.zeros((per_rank, n_rep, blk), dtype=torch.float64, device=device)
         for k, fit in enumerate(fits):
             for i, (inter, beta, coef) in enumerate(fit):
                 n = inter.shape[0]
-                local[k, i, 0, 0], local[k, i, 0, 1] = n, beta
-                local[k, i, 1:1 + n] = inter
-                local[k, i, 1 + cap:1 + cap + n] = coef.t()
+                local[k, i, 0], local[k, i, 1] = n, beta
+                local[k, i, 3:3 + 3 * n] = inter.reshape(-1)
+                local[k, i, 3 + 3 * cap:3 + 3 * cap + 3 * n] = coef.reshape(-1)
         counts = torch.tensor([len(fits)], dtype=torch.int64, device=device)
         allc = [torch.zeros_like(counts) for _ in range(self.world)]
         dist.all_gather(allc, counts)
         alld = [torch.zeros_like(local) for _ in range(self.world)]
         dist.all_gather(alld, local)
         n_fits = torch.cat(allc).cpu().tolist()                           # one small download, then no more syncs
-        heads = torch.stack([d[:, :, 0, :2] for d in alld]).cpu()       # (world, per_rank, rep, [count, beta])
+        heads = torch.stack([d[:, :, :2] for d in alld]).cpu()          # (world, per_rank, rep, [count, beta])
         out = []
         for r, d in enumerate(alld):
             for k in range(int(n_fits[r])):
                 fit = []
                 for i in range(n_rep):
                     n = int(heads[r, k, i, 0])
-                    fit.append((d[k, i, 1:1 + n].contiguous(), float(heads[r, k, i, 1]),
-                                d[k, i, 1 + cap:1 + cap + n].t().contiguous()))
+                    fit.append((d[k, i, 3:3 + 3 * n].view(n, 3), float(heads[r, k, i, 1]),
+                                d[k, i, 3 + 3 * cap:3 + 3 * cap + 3 * n].view(3, n)))
                 out.append(fit)
         return out
 

@@ -96,6 +96,22 @@ def predict_one_rep_device(pre_dev, inter_dev, beta, coef_dev):
     return post
 
 
+def replay_fit_device(fit, tracked_prev_dev, proportiontocut=0.1):
+    """tracker.py:1269-1289 for every repetition of one fitted volume pair, then the single-mode trimmed mean of
+    tracker.py:1503-1507, in ONE library call (the time-lapse driver replays every volume of the recording in order on one
+    rank; six calls per volume were host-bound).  fit: [(intermediate points (n,3), beta, coef (3,n))] per repetition."""
+    n_rep, count = len(fit), int(tracked_prev_dev.shape[0])
+    inter = (C.c_void_p * n_rep)(*[f[0].data_ptr() for f in fit])
+    coef = (C.c_void_p * n_rep)(*[f[2].data_ptr() for f in fit])
+    n_ref = (C.c_int * n_rep)(*[int(f[0].shape[0]) for f in fit])
+    beta = (C.c_double * n_rep)(*[float(f[1]) for f in fit])
+    scratch = torch.empty((2,) + tuple(tracked_prev_dev.shape), dtype=torch.float64, device=tracked_prev_dev.device)
+    out = torch.empty_like(tracked_prev_dev)
+    _lib.check(_lib.lib().ct_replay_fit(tracked_prev_dev.data_ptr(), count, n_rep, inter, n_ref, beta, coef,
+                                        float(proportiontocut), scratch.data_ptr(), out.data_ptr(), stream_ptr()))
+    return out
+
+
 def trim_mean_device(stack_dev, proportiontocut=0.1):
     """scipy.stats.trim_mean(stack, p, axis=0) for a (E, L, 3) float64 CUDA tensor."""
     e = int(stack_dev.shape[0])

@@ -219,6 +219,13 @@ int ct_predict_one_rep(const double* pre, int n_tracked, const double* inter, in
 /* trim_mean(stack (E,L,3), proportion, axis=0) -> (L,3)  (tracker.py:1507, trackerlite.py:123). */
 int ct_trim_mean(const double* stack, int e, int count, double proportion, double* out, void* stream);
 
+/* One volume of the replay chain in one call: n_rep x _predict_one_rep (tracker.py:1269-1289, repetition i with the host
+ * arrays inter[i] (n_ref[i],3), beta[i], coef[i] (3,n_ref[i]) of DEVICE pointers) followed by the single-mode trimmed mean
+ * of tracker.py:1503-1507 over a stack of one.  pre, out: (n_tracked,3); scratch: 2 x n_tracked x 3 doubles. */
+int ct_replay_fit(const double* pre, int n_tracked, int n_rep, const double* const* inter, const int* n_ref,
+                  const double* beta, const double* const* coef, double proportion, double* scratch, double* out,
+                  void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Watershed + centroid stage between the two hot paths.  Replaces Tracker._watershed (tracker.py:671-684) =
  * watershed_2d (watershed.py:16-52: per z slice threshold 0.5, distance_transform_edt, gaussian_filter(2),
