@@ -247,7 +247,13 @@ class FramePipeline:
             lib.ct_set_reserved_sms(old)
         return prob, seg, tracked
 
-    def flush_raw(self):
-        """Resolve the last segmented volume, submit its fit and join everything; tracked coordinates, oldest first."""
+    def flush_raw(self, extra_target=None):
+        """Resolve the last segmented volume, submit its fit and join everything; tracked coordinates, oldest first.
+        extra_target: a further point set (the first volume of the NEXT rank's block, timelapse.py) -- the fit from this
+        block's last volume onto it is submitted on a side stream together with the last local fit, not after it."""
         self._submit_fits(self._resolve_segmented())
+        if extra_target is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._submit_fits([(extra_target, ev)])
         return self.flush()

@@ -7,8 +7,9 @@ What depends on what in `track_one_vol` (tracker.py:1473-1536):
   * only the replay `_predict_one_rep` (tracker.py:1269-1289) and the displacement bookkeeping
     (tracker.py:1179-1180, 1525-1534) carry state from volume to volume, and they are a few tiny kernels per volume.
 So rank r takes a CONTIGUOUS block of volumes and streams it through its own FramePipeline (segmentation on the main
-stream, fits on side streams); the only data that crosses ranks is (i) the point set of the last volume of a block,
-sent to the rank that owns the next block for the one fit that straddles the boundary, and (ii) the fitted transforms
+stream, fits on side streams); the only data that crosses ranks is (i) the point set of the FIRST volume of a block,
+sent back to the rank that owns the previous block for the one fit that straddles the boundary (it runs beside that
+block's last local fit), and (ii) the fitted transforms
 (5 x (intermediate points, C) per volume, ~40 KB), gathered to rank 0, which replays them in volume order.  There is
 no collective on the data path of the volumes themselves.  The result equals the single-GPU run bit for bit: the same
 kernels see the same inputs (tests/test_timelapse_gloo.py for the plumbing, bench.py --verify-c4 on the GPUs).
@@ -34,9 +35,11 @@ class TimelapseTracker:
         self.rank = rank if rank is not None else (dist.get_rank() if _dist_on() else 0)
 
     # ---- stages (overridable)
-    def local_fits(self, frames, lo, hi, sink=None):
-        """Stream volumes lo..hi-1 through the pipeline.  Returns (first point set, last point set, fits of the pairs
-        (lo, lo+1) .. (hi-2, hi-1)).  sink(t, prob, segmentation) sees every volume's device-resident results."""
+    def local_fits(self, frames, lo, hi, sink=None, boundary=None):
+        """Stream volumes lo..hi-1 through the pipeline.  Returns (first point set, fits of the pairs (lo, lo+1) ..
+        (hi-2, hi-1) and -- when `boundary` hands back the first point set of the next rank's block -- (hi-1, hi)).
+        sink(t, prob, segmentation) sees every volume's device-resident results.  boundary(first point set) is called
+        once, before the pipeline is flushed: the straddling fit then runs beside the block's last local fit."""
         p = self.pipe
         p.reset_raw()
         p.collect_fits = True
@@ -45,8 +48,13 @@ class TimelapseTracker:
                 prob, seg, _ = p.step_raw(frames(t))
                 if sink is not None:
                     sink(t, prob, seg)
-            p.flush_raw()
-            return p._first_points, p._prev_points, list(p.collected)
+            first = p._first_points
+            if first is None:                                       # fewer volumes than the cell-count lag: resolve now
+                p._submit_fits(p._resolve_segmented())
+                first = p._first_points
+            nxt = boundary(first) if boundary is not None else None
+            p.flush_raw(extra_target=nxt)
+            return first, list(p.collected)
         finally:
             p.collect_fits = False
             p.collected = []
@@ -70,16 +78,22 @@ class TimelapseTracker:
         n = int(buf[0, 0].item())
         return buf[1:1 + n].clone()
 
-    def _boundary_exchange(self, last_pts, cap, device):
-        """Send this block's last point set to rank+1, receive rank-1's; returns the received point set or None."""
+    def _boundary_exchange(self, first_pts):
+        """Send this block's FIRST point set to rank-1, receive rank+1's; returns the received point set or None.  The
+        rank that owns volume hi-1 fits the pair (hi-1, hi): it knows the next block's first point set long before its own
+        last one, so the straddling fit overlaps the tail of its block instead of following it."""
         if self.world == 1:
             return None
+        device = first_pts.device
+        cap = torch.tensor([first_pts.shape[0]], dtype=torch.int64, device=device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        cap = int(cap.item())
         ops, recv = [], None
-        if self.rank + 1 < self.world:
-            ops.append(dist.P2POp(dist.isend, self._pack_points(last_pts, cap), self.rank + 1))
         if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, self._pack_points(first_pts, cap), self.rank - 1))
+        if self.rank + 1 < self.world:
             recv = torch.zeros((cap + 1, 3), dtype=torch.float64, device=device)
-            ops.append(dist.P2POp(dist.irecv, recv, self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, recv, self.rank + 1))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         return None if recv is None else self._unpack_points(recv)
@@ -122,19 +136,19 @@ class TimelapseTracker:
         if n_frames < self.world:
             raise ValueError(f"a time-lapse of {n_frames} volumes cannot be split over {self.world} ranks")
         lo, hi = block_for_rank(n_frames, self.rank, self.world)
-        first, last, fits = self.local_fits(frames, lo, hi) if sink is None else self.local_fits(frames, lo, hi, sink)
+        boundary = self._boundary_exchange if self.world > 1 else None
+        first, fits = (self.local_fits(frames, lo, hi, boundary=boundary) if sink is None
+                       else self.local_fits(frames, lo, hi, sink, boundary))
         device = first.device
         # padding capacity: the largest point set anywhere
-        cap_local = max([first.shape[0], last.shape[0]] + [f[0][0].shape[0] for f in fits] or [1])
+        cap_local = max([first.shape[0]] + [f[0][0].shape[0] for f in fits] or [1])
         cap = torch.tensor([cap_local], dtype=torch.int64, device=device)
         if self.world > 1:
             dist.all_reduce(cap, op=dist.ReduceOp.MAX)
         cap = int(cap.item())
-        prev_last = self._boundary_exchange(last, cap, device)
-        if prev_last is not None:
-            fits = [self.fit(prev_last, first)] + fits                  # the pair (lo-1, lo) straddles two blocks
-        per_rank = max(block_for_rank(n_frames, r, self.world)[1] - block_for_rank(n_frames, r, self.world)[0]
-                       for r in range(self.world))
+        # every rank but the last also carries the pair that straddles into the next block
+        per_rank = 1 + max(block_for_rank(n_frames, r, self.world)[1] - block_for_rank(n_frames, r, self.world)[0]
+                           for r in range(self.world))
         all_fits = fits if self.world == 1 else self._gather_fits(fits, cap, per_rank, device)
         if self.rank != 0:
             return None

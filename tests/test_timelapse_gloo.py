@@ -2,7 +2,8 @@
 The GPU stages (segmentation + watershed, FFN + PR-GLS fit, replay) are replaced by deterministic CPU stand-ins
 with the same data flow (a volume -> a point set whose size varies; a pair of point sets -> 5 x (points, beta, C);
 replay = state carried from volume to volume), so what is tested is the sharding itself: contiguous blocks, the
-boundary exchange of one point set per rank, the padded all-gather of the fitted transforms and the sequential
+boundary exchange of one point set per rank (a block's first point set travels back to the rank before it, which
+fits the straddling pair), the padded all-gather of the fitted transforms and the sequential
 replay on rank 0 -- the result must equal the single-process run bit for bit."""
 import importlib
 import os
@@ -32,9 +33,13 @@ def _make_tracker(rank, world):
     tl = importlib.import_module("3deecelltracker_b200.timelapse")
 
     class Stub(tl.TimelapseTracker):
-        def local_fits(self, frames, lo, hi):
+        def local_fits(self, frames, lo, hi, sink=None, boundary=None):
             pts = [frames(t) for t in range(lo, hi)]
-            return pts[0], pts[-1], [self.fit(a, b) for a, b in zip(pts, pts[1:])]
+            fits = [self.fit(a, b) for a, b in zip(pts, pts[1:])]
+            nxt = boundary(pts[0]) if boundary is not None else None      # first point set of the next rank's block
+            if nxt is not None:
+                fits.append(self.fit(pts[-1], nxt))
+            return pts[0], fits
 
         def fit(self, prev_pts, cur_pts):
             out, inter = [], prev_pts
