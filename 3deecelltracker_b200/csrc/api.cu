@@ -15,6 +15,50 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+// ---------------------------------------------------------------------------------------------
+// pinned staging ring for small uploads (see common.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct StageRing {
+    static constexpr int SLOTS = 64;
+    static constexpr size_t SLOT_BYTES = 8192;
+    char* base = nullptr;
+    cudaEvent_t ev[SLOTS] = {};
+    bool used[SLOTS] = {};
+    int next = 0;
+    int device = -1;
+};
+thread_local StageRing t_ring;
+}  // namespace
+
+int stage_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    StageRing& r = t_ring;
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+    if (bytes > StageRing::SLOT_BYTES)                                   // rare (very large batches): the pageable path
+        return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync(descriptors)");
+    if (r.base == nullptr || r.device != dev) {                          // first use on this thread / device
+        if (r.base == nullptr &&
+            check_cuda(cudaHostAlloc(reinterpret_cast<void**>(&r.base), StageRing::SLOTS * StageRing::SLOT_BYTES, cudaHostAllocDefault),
+                       "cudaHostAlloc(staging ring)")) return 1;
+        for (int i = 0; i < StageRing::SLOTS; ++i) {
+            if (r.ev[i]) { cudaEventSynchronize(r.ev[i]); cudaEventDestroy(r.ev[i]); r.ev[i] = nullptr; }
+            if (check_cuda(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming), "cudaEventCreate")) return 1;
+            r.used[i] = false;
+        }
+        r.device = dev;
+    }
+    const int i = r.next;
+    r.next = (r.next + 1) % StageRing::SLOTS;
+    if (r.used[i] && check_cuda(cudaEventSynchronize(r.ev[i]), "cudaEventSynchronize(staging slot)")) return 1;   // 64 uploads ago
+    char* slot = r.base + (size_t)i * StageRing::SLOT_BYTES;
+    memcpy(slot, src, bytes);
+    if (check_cuda(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync(descriptors)")) return 1;
+    if (check_cuda(cudaEventRecord(r.ev[i], s), "cudaEventRecord")) return 1;
+    r.used[i] = true;
+    return 0;
+}
 }  // namespace ct
 
 // ---------------------------------------------------------------------------------------------

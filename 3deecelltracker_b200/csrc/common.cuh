@@ -58,6 +58,12 @@ struct ProfScope {
     cudaEvent_t a_;
 };
 
+// Small host -> device uploads (problem descriptors) through a per-thread ring of PINNED staging slots.  A
+// cudaMemcpyAsync from pageable memory is staged by the driver and "might be synchronous with respect to the host": in
+// the frame pipeline the five descriptor uploads of a fit (one per PR-GLS repetition) tied the host to the EM chain and
+// produced 60-140 ms gaps in its launch loop [measured].  From pinned memory the copy is a plain stream operation.
+int stage_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s);
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -805,7 +805,7 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
                     Layout o = layout_for(p.n_ref, p.n_tgt, 0);
                     bind(d, wsb + align_up(sizeof(DevProblem), 256), o);
                     d.prior = prior; d.pairs = nullptr; d.n_pairs = nullptr;
-                    CT_CUDA(cudaMemcpyAsync(wsb, &d, sizeof(d), cudaMemcpyHostToDevice, s));
+                    if (stage_h2d(wsb, &d, sizeof(d), s)) return 1;
                     greedy_kernel<<<1, EM_THREADS, 0, s>>>(reinterpret_cast<const DevProblem*>(wsb), prm->mode, prm->threshold);
                     CT_LAUNCHED("greedy_kernel");
                 }
@@ -835,7 +835,7 @@ extern "C" int ct_prgls(const CtPrglsParams* prm, const CtPrglsProblem* problems
         if (p.n_ref > max_n) max_n = p.n_ref;
     }
     CT_REQUIRE(off <= ws_bytes, "ct_prgls: workspace too small (%zu < %zu)", ws_bytes, off);
-    CT_CUDA(cudaMemcpyAsync(ws, host.data(), (size_t)batch * sizeof(DevProblem), cudaMemcpyHostToDevice, s));
+    if (stage_h2d(ws, host.data(), (size_t)batch * sizeof(DevProblem), s)) return 1;
     // every CTA carves its own plan out of the same allocation: size it for the most demanding problem
     size_t smem = 0;
     for (int b = 0; b < batch; ++b) {
@@ -879,7 +879,7 @@ extern "C" int ct_greedy_prior(const void* corr, int corr_is_f64, int n_tgt, int
     d.prior = prior;
     d.pairs = pairs;
     d.n_pairs = n_pairs;
-    CT_CUDA(cudaMemcpyAsync(ws, &d, sizeof(d), cudaMemcpyHostToDevice, s));
+    if (stage_h2d(ws, &d, sizeof(d), s)) return 1;
     greedy_kernel<<<1, EM_THREADS, 0, s>>>(static_cast<const DevProblem*>(ws), mode, threshold);
     CT_LAUNCHED("greedy_kernel");
     return 0;

@@ -26,6 +26,9 @@ from . import watershed as _ws
 from .preprocess import normalize_image_device
 from .track import MODE_TRACK, EmProblem, replay_fit_device, run_em
 
+import os as _os
+
+BLOCKING_WAITS = bool(_os.environ.get("CT3D_BLOCKING_WAITS"))     # experiment: the host sleeps instead of spinning in ev.synchronize()
 REP_NUM_PRGLS = 5          # tracker.py:45
 K_POINTS = 20              # tracker.py:1259
 
@@ -43,7 +46,7 @@ class FramePipeline:
         # the fit's launches).  With a lag of 1 the host waits for the watershed of volume t-1 before it can enqueue the
         # segmentation of volume t+1 -- and that watershed, squeezed in beside the convolutions of volume t, finishes
         # about when they do, so the main stream runs dry; a lag of 2 keeps a whole volume of work enqueued.
-        self.ws_lag = max(1, int(ws_lag))
+        self.ws_lag = min(max(1, int(ws_lag)), 6)
         self._streams = None
         self._pending = collections.deque()          # (stream, fit, tracked_prev or None)
         self._tracked = None                         # running tracked coordinates when the caller does not pass them
@@ -57,6 +60,8 @@ class FramePipeline:
         self.collect_fits = False                    # True: joined fits are kept in `collected` instead of replayed
         self.collected = []                          # (timelapse.py replays them on the rank that owns the state)
         self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num = 1.0, "min_size", 0, 0
+        self.trace = None                            # debugging: a list collects the host's waits for the cell counts (s)
+        self._pinned_ring, self._pinned_next = None, 0  # pinned cell-count scalars, reused every 8 volumes (lag <= 3)
 
     # ---- the stages, each on the current stream
     def segment(self, raw_dev):
@@ -153,6 +158,19 @@ class FramePipeline:
             out.append(self._join_oldest())
         return out
 
+    def reserve_small_blocks(self, megabytes=64):
+        """Grow the caching allocator's small-block pools of the pipeline's streams now.  A time-lapse keeps every fitted
+        transform (5 x (points, coefficients) per volume) until the replay, so those pools grow while it runs, 2 MB
+        segment by segment, and each cudaMalloc is an implicit synchronisation of the whole device: the host then stalls
+        for the 2-3 volumes of work it has queued [measured: 50-140 ms gaps every few volumes in one run out of three].
+        Call once after the first volumes (the streams exist by then)."""
+        streams = [torch.cuda.current_stream()] + list(self._streams or []) + ([self._ws_stream] if self._ws_stream else [])
+        n = max(1, int(megabytes))
+        for st in streams:
+            with torch.cuda.stream(st):
+                held = [torch.empty(1 << 20, dtype=torch.uint8, device="cuda") for _ in range(n)]
+            del held
+
     # ---- raw-stack mode: segmentation -> watershed -> centres -> fit, the whole Tracker.track_one_vol chain
     def configure_watershed(self, z_xy_ratio, method="min_size", min_size=0, cell_num=0):
         """Parameters of Tracker._watershed (tracker.py:671-684) for `step_raw`."""
@@ -178,9 +196,15 @@ class FramePipeline:
             stream = main
         with torch.cuda.stream(stream):
             seg = _ws.segment_device(prob, self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num)
-            pinned = torch.empty(4, dtype=torch.int32).pin_memory()
+            # A page-locked allocation is an implicit synchronisation point of the whole device (and the caching host
+            # allocator does allocate whenever its few cached blocks are still tied to unfinished watersheds): one in the
+            # loop stalled the host for 40-140 ms every few volumes [measured].  The scalars land in a ring allocated once.
+            if self._pinned_ring is None:
+                self._pinned_ring = [torch.empty(4, dtype=torch.int32).pin_memory() for _ in range(8)]
+            pinned = self._pinned_ring[self._pinned_next % len(self._pinned_ring)]
+            self._pinned_next += 1
             pinned.copy_(seg.scalars, non_blocking=True)
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(blocking=BLOCKING_WAITS)
             ev.record(stream)
         seg.ready = ev
         return prob, seg, pinned, ev
@@ -191,7 +215,13 @@ class FramePipeline:
         out = []
         while self._segmented:
             seg, pinned, ev = self._segmented.popleft()
-            ev.synchronize()
+            if self.trace is not None:
+                import time
+                t0 = time.perf_counter()
+                ev.synchronize()
+                self.trace.append(time.perf_counter() - t0)
+            else:
+                ev.synchronize()
             n = int(pinned[0])
             if n > _ws.MAX_CELLS:
                 raise ValueError(f"watershed found {n} cells; at most {_ws.MAX_CELLS} are supported")

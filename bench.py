@@ -31,6 +31,7 @@ if "--impl" in sys.argv and "reference" in sys.argv:
         os.environ[_v] = str(os.cpu_count() or 1)
 
 import argparse
+import gc
 import importlib
 import json
 import os
@@ -97,6 +98,8 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("CT3D_NO_SAMPLER"):                          # debugging only: the contract wants the samples
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -222,7 +225,11 @@ def gpu_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    dev_trace = [] if os.environ.get("CT3D_E2E_TRACE") else None  # host timestamps per volume (debugging)
+
     def resident(t):
+        if dev_trace is not None:
+            dev_trace.append(time.perf_counter())
         flush.zero_()                                    # flush L2 between timed iterations (inside the region)
         return frames_dev[t]
 
@@ -251,6 +258,15 @@ def gpu_main(args):
     # per GPU through segmentation + watershed + fit, the boundary exchange, the gather and the replay on rank 0
     wdev = [w.to(dev).view(torch.uint16) for w in warm]
     tl.TimelapseTracker(pipe, 0, 1).run(lambda t: wdev[t], len(wdev))
+    pipe.reserve_small_blocks(64)                      # no cudaMalloc (a device-wide implicit sync) inside the timed regions
+    # The host enqueues ~150 launches per volume from Python; a generation-2 pass of the cyclic garbage collector over the
+    # interpreter's ~10^6 tracked objects (torch, numpy ...) stalls it for 40-140 ms [measured: host gaps of that size
+    # between volumes, not spent in any CUDA wait], which empties the GPU's queues.  Everything allocated so far is moved
+    # to the permanent generation and the collector is off while the timed regions run (reference counting still frees
+    # every tensor at once).
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -259,6 +275,9 @@ def gpu_main(args):
     read_profile(lib)
     launches0 = lib.ct_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dev_trace is not None:
+        pipe.trace = []
+        mem0 = dict(torch.cuda.memory_stats())
     e0.record()
     tracked = tracker.run(resident, T)
     e1.record()
@@ -266,6 +285,14 @@ def gpu_main(args):
     launches = lib.ct_launch_count() - launches0
     lib.ct_profile_enable(0)
     dev_ms = e0.elapsed_time(e1)
+    if dev_trace is not None and rank == 0:
+        print("device-arm host trace (ms between volumes): " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(dev_trace, dev_trace[1:]))
+              + f" | total {dev_ms:.1f}", file=sys.stderr)
+        mem1 = torch.cuda.memory_stats()
+        print("  waits for cell counts (ms): " + " ".join(f"{w * 1e3:.1f}" for w in pipe.trace), file=sys.stderr)
+        print("  allocator: " + ", ".join(f"{k} +{mem1[k] - mem0.get(k, 0)}" for k in ("num_device_alloc", "num_device_free", "num_alloc_retries",
+                                                                                "reserved_bytes.all.current", "allocation.all.allocated")), file=sys.stderr)
+        pipe.trace = None
     prof = read_profile(lib)
     n_cells = None
     if rank == 0:
@@ -383,6 +410,7 @@ def gpu_main(args):
     # ---- config 3 (strong scaling of ONE 1024 x 1024 x 96 volume) on the same GPUs, same build
     c3 = None if args.no_c3 else c3_measure(args, unet, rank, world, dev, barrier)
 
+    gc.enable()
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -598,7 +626,11 @@ def gpu_spatial_main(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    gc.collect()
+    gc.freeze()
+    gc.disable()                                      # see gpu_main: no collector pauses inside the timed steps
     res = c3_measure(args, unet, rank, world, dev, barrier, steps=args.steps, warmup=max(args.warmup, 3), verify=args.verify)
+    gc.enable()
     if rank == 0:
         res.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic",
                     "dtype": "fp16 hi/lo split, fp32 accumulate (U-Net conv); f32 (LCN)",
