@@ -26,9 +26,6 @@ from . import watershed as _ws
 from .preprocess import normalize_image_device
 from .track import MODE_TRACK, EmProblem, replay_fit_device, run_em
 
-import os as _os
-
-BLOCKING_WAITS = bool(_os.environ.get("CT3D_BLOCKING_WAITS"))     # experiment: the host sleeps instead of spinning in ev.synchronize()
 REP_NUM_PRGLS = 5          # tracker.py:45
 K_POINTS = 20              # tracker.py:1259
 
@@ -204,7 +201,7 @@ class FramePipeline:
             pinned = self._pinned_ring[self._pinned_next % len(self._pinned_ring)]
             self._pinned_next += 1
             pinned.copy_(seg.scalars, non_blocking=True)
-            ev = torch.cuda.Event(blocking=BLOCKING_WAITS)
+            ev = torch.cuda.Event()
             ev.record(stream)
         seg.ready = ev
         return prob, seg, pinned, ev
