@@ -59,6 +59,7 @@ class FramePipeline:
         self.z_xy_ratio, self.ws_method, self.min_size, self.cell_num = 1.0, "min_size", 0, 0
         self.trace = None                            # debugging: a list collects the host's waits for the cell counts (s)
         self._pinned_ring, self._pinned_next = None, 0  # pinned cell-count scalars, reused every 8 volumes (lag <= 3)
+        self._reserved = False                       # reserve_small_blocks has run
 
     # ---- the stages, each on the current stream
     def segment(self, raw_dev):
@@ -161,6 +162,7 @@ class FramePipeline:
         segment by segment, and each cudaMalloc is an implicit synchronisation of the whole device: the host then stalls
         for the 2-3 volumes of work it has queued [measured: 50-140 ms gaps every few volumes in one run out of three].
         Call once after the first volumes (the streams exist by then)."""
+        self._reserved = True
         streams = [torch.cuda.current_stream()] + list(self._streams or []) + ([self._ws_stream] if self._ws_stream else [])
         n = max(1, int(megabytes))
         for st in streams:

@@ -48,6 +48,8 @@ class TimelapseTracker:
                 prob, seg, _ = p.step_raw(frames(t))
                 if sink is not None:
                     sink(t, prob, seg)
+                if t - lo == 3 and not p._reserved:              # all of the pipeline's streams exist by now
+                    p.reserve_small_blocks()
             first = p._first_points
             if first is None:                                       # fewer volumes than the cell-count lag: resolve now
                 p._submit_fits(p._resolve_segmented())
