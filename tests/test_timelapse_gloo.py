@@ -75,7 +75,7 @@ def _worker(rank, world, port, n_frames, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_frames", [(2, 9), (3, 8), (2, 2)])
+@pytest.mark.parametrize("world,n_frames", [(2, 9), (3, 8), (2, 2), (3, 3)])
 def test_timelapse_sharding_equals_single_process(world, n_frames):
     load_pkg()
     want = _make_tracker(0, 1).run(_points, n_frames)
